@@ -1,0 +1,75 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map encoding and launch.
+#include "gemm_tcgen05.cuh"
+#include "internal.h"
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols] with leading dimension ld (elements); box = 64 cols x box_rows,
+// 128-byte swizzle; out-of-bounds elements read as zero (that is how M/N/K tails are handled).
+int make_tmap_bf16_2d(b200clip_handle* h, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                      uint64_t ld, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return b200_fail(h, B200CLIP_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
+        return b200_fail(h, B200CLIP_E_SHAPE, "TMA operand must be 16-byte aligned with a 16-byte multiple pitch");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return b200_fail(h, B200CLIP_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+template <int BLOCK_N>
+static int launch_gemm_bn(b200clip_handle* h, const bf16* a, int lda, const bf16* w, int ldw, bf16* out, int ldc,
+                          int M, int N, int K, const b200::GemmEpilogue& ep, cudaStream_t st) {
+    using Cfg = b200::GemmCfg<BLOCK_N>;
+    CUtensorMap ta, tw;
+    int rc;
+    if ((rc = make_tmap_bf16_2d(h, &ta, a, M, K, lda, b200::GEMM_BLOCK_M, b200::GEMM_BLOCK_K,
+                                CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    if ((rc = make_tmap_bf16_2d(h, &tw, w, N, K, ldw, BLOCK_N, b200::GEMM_BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    static bool attr_set = false;
+    auto kern = b200::gemm_bf16_tcgen05_kernel<BLOCK_N>;
+    if (!attr_set) {
+        B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int m_blocks = (M + b200::GEMM_BLOCK_M - 1) / b200::GEMM_BLOCK_M;
+    const int n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
+    const int tiles = m_blocks * n_blocks;
+    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
+    kern<<<grid, b200::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tw, out, ldc, M, N, K, ep);
+    h->launches++;
+    B200_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+int launch_gemm(b200clip_handle* h, const bf16* a, int lda, const bf16* w, int ldw, bf16* out, int ldc, int M, int N,
+                int K, const b200::GemmEpilogue& ep, cudaStream_t st) {
+    if (M <= 0 || N <= 0 || K <= 0) return b200_fail(h, B200CLIP_E_ARG, "gemm: empty problem %dx%dx%d", M, N, K);
+    if (N % 32 != 0 || K % 8 != 0 || ldc % 8 != 0)
+        return b200_fail(h, B200CLIP_E_SHAPE, "gemm: N must be a multiple of 32, K and ldc of 8 (N=%d K=%d ldc=%d)", N,
+                         K, ldc);
+    if (N % 256 == 0 || N > 1024) return launch_gemm_bn<256>(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
+    return launch_gemm_bn<128>(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
+}

@@ -1,0 +1,240 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] . W[N,K]^T)
+//
+//   * A (activations, token rows) and W (nn.Linear weight [out,in]) are both K-major, so both
+//     operands are fed to tcgen05.mma straight from 128B-swizzled shared memory tiles that TMA
+//     fills (box 64 x rows, bf16) -- no transposes anywhere.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
+//     warps 2..5 = epilogue (each owns the 32 TMEM lanes its warp-id % 4 may read).
+//   * the fp32 accumulator lives in TMEM, double buffered (2 x BLOCK_N columns) so the epilogue of
+//     tile i overlaps the main loop of tile i+1; one CTA per SM loops over tiles (grid = #SMs).
+//   * fused epilogues: +bias, +bias+QuickGELU / erf-GELU, +bias+residual (in place), and the
+//     patch-embed variant (row remap 49->50 tokens per image, + positional-embedding row).
+//
+// Replaces the cuBLAS/cuDNN calls eager PyTorch makes inside open_clip's VisionTransformer.forward
+// (reference call site: src/models/openclip_model.py:177,196 -> model.encode_image).
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+
+struct GemmEpilogue {
+    const float* bias;          // [N] or nullptr
+    const __nv_bfloat16* resid; // [rows_out, ldc] added to the result, or nullptr (may alias out)
+    const float* rowtab;        // [t_out, N] fp32 row table added by token position, or nullptr
+    int act;                    // 0 none, 1 QuickGELU x*sigmoid(1.702x), 2 GELU(erf)
+    int t_in, t_out, row_off;   // out_row = (r / t_in) * t_out + r % t_in + row_off   (t_in == 0: identity)
+};
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
+constexpr int GEMM_UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;  // 6 warps
+
+template <int BLOCK_N>
+struct GemmCfg {
+    static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == 1) {
+        // QuickGELU: x * sigmoid(1.702 x)
+        return __fdividef(x, 1.0f + __expf(-1.702f * x));
+    } else if (act == 2) {
+        return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    }
+    return x;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                         __nv_bfloat16* out, int ldc, int M, int N, int K, GemmEpilogue ep) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                      // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;            // [STAGES]
+    uint64_t* tmem_full_bar = bars + 2 * STAGES;    // [2]
+    uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int m_blocks = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+    const int n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = m_blocks * n_blocks;
+    const int k_blocks = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full_bar[s], 1);
+            mbar_init(&tmem_empty_bar[s], 4);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc<1>(tmem_slot, Cfg::TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / n_blocks;
+                const int n_blk = tile - m_blk * n_blocks;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K,
+                                m_blk * GEMM_BLOCK_M);
+                    tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_w, &full_bar[stage], kb * GEMM_BLOCK_K,
+                                n_blk * BLOCK_N);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1, 2);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, 3);
+                    tc_fence_after();
+                    const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::A_BYTES));
+                    const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
+                        // advance 16 bf16 = 32 B inside the swizzle row: +2 in the (>>4) address field
+                        umma_bf16<1>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full_bar[as]);     // accumulator complete -> epilogue
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (2..5) =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / n_blocks;
+            const int n_blk = tile - m_blk * n_blocks;
+            const int row = m_blk * GEMM_BLOCK_M + q * 32 + lane;
+            const bool row_ok = row < M;
+            long out_row = row;
+            int tpos = 0;
+            if (ep.t_in > 0) {
+                const int img = row / ep.t_in;
+                tpos = row - img * ep.t_in + ep.row_off;
+                out_row = static_cast<long>(img) * ep.t_out + tpos;
+            }
+            __nv_bfloat16* out_ptr = out + out_row * ldc;
+            const __nv_bfloat16* res_ptr = ep.resid ? ep.resid + out_row * ldc : nullptr;
+            const float* tab_ptr = ep.rowtab ? ep.rowtab + static_cast<long>(tpos) * N : nullptr;
+
+            mbar_wait(&tmem_full_bar[as], aphase, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                const int n0 = n_blk * BLOCK_N + c;
+                if (n0 >= N) break;  // warp-uniform
+                uint32_t acc[32];
+                tmem_ld_32x32(taddr + c, acc);
+                tmem_ld_wait();
+                if (row_ok) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+                    if (ep.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                        }
+                    }
+                    if (tab_ptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(tab_ptr + n0 + j));
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                        }
+                    }
+                    if (ep.act) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+                    }
+                    if (res_ptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            const uint4 r = *reinterpret_cast<const uint4*>(res_ptr + n0 + j);
+                            float2 f;
+                            f = unpack_bf16x2(r.x); v[j] += f.x; v[j + 1] += f.y;
+                            f = unpack_bf16x2(r.y); v[j + 2] += f.x; v[j + 3] += f.y;
+                            f = unpack_bf16x2(r.z); v[j + 4] += f.x; v[j + 5] += f.y;
+                            f = unpack_bf16x2(r.w); v[j + 6] += f.x; v[j + 7] += f.y;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 o;
+                        o.x = pack_bf16x2(v[j], v[j + 1]);
+                        o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                        o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                        o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                        *reinterpret_cast<uint4*>(out_ptr + n0 + j) = o;
+                    }
+                }
+            }
+            // this warp is done reading the accumulator stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace b200

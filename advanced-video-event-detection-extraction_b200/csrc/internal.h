@@ -1,0 +1,104 @@
+// Internal declarations shared by the translation units of libb200clip.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200clip.h"
+
+typedef __nv_bfloat16 bf16;
+
+struct b200clip_handle {
+    b200clip_config cfg;
+    int device = 0;
+    int num_sms = 148;
+    bool finalized = false;
+    mutable std::string err;
+    int64_t launches = 0;
+
+    // ---- packed weights (device) ----
+    struct Block {
+        float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+        bf16 *w_qkv = nullptr, *w_out = nullptr, *w_fc = nullptr, *w_proj = nullptr;
+        float *b_qkv = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_proj = nullptr;
+    };
+    struct Tower {
+        int width = 0, layers = 0, heads = 0, mlp = 0;
+        std::vector<Block> blocks;
+    };
+    Tower vis, txt;
+    // vision stem / head
+    bf16* w_patch = nullptr;      // [width, patch_k] (conv1.weight flattened, K padded to 64)
+    float* pos_emb = nullptr;     // [tokens, width] fp32
+    float* cls_pos0 = nullptr;    // [width] = class_embedding + positional_embedding[0]
+    float *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr, *ln_post_b = nullptr;
+    bf16* vis_proj = nullptr;     // [width, embed] row-major (x @ proj)
+    // text stem / head
+    bf16* tok_emb = nullptr;      // [vocab, text_width]
+    float* txt_pos = nullptr;     // [ctx, text_width]
+    float *ln_final_g = nullptr, *ln_final_b = nullptr;
+    bf16* txt_proj = nullptr;     // [text_width, embed]
+    std::map<std::string, bool> have;
+    std::vector<void*> allocs;    // everything cudaMalloc'ed for weights
+
+    // ---- derived geometry ----
+    int grid = 0;       // patches per side
+    int tokens = 0;     // grid^2 + 1
+    int patch_k = 0;    // 3*P*P padded to a multiple of 64
+
+    // ---- persistent workspace ----
+    int ws_images = 0, ws_texts = 0;
+    bf16 *ws_x = nullptr, *ws_y = nullptr, *ws_qkv = nullptr, *ws_h = nullptr, *ws_patches = nullptr;
+    uint8_t* ws_stage_dev[2] = {nullptr, nullptr};   // device staging for host-frame calls
+    uint8_t* ws_stage_host[2] = {nullptr, nullptr};  // pinned
+    size_t ws_stage_bytes = 0;
+    float* ws_emb = nullptr;       // [ws_images, embed] device scratch for host-output calls
+    size_t ws_emb_elems = 0;
+    uint8_t* ws_pre = nullptr;     // preprocess intermediates
+    size_t ws_pre_bytes = 0;
+    void* ws_topk = nullptr;       // sim/top-k partial candidates
+    size_t ws_topk_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+};
+
+// error helpers (api.cu)
+int b200_fail(const b200clip_handle* h, int code, const char* fmt, ...);
+#define B200_CUDA(h, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return b200_fail(h, B200CLIP_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                             __FILE__, __LINE__);                                                   \
+    } while (0)
+
+// ---- kernel launchers (return cudaError_t-free int codes via handle) ----
+namespace b200 {
+struct GemmEpilogue;
+}
+int launch_gemm(b200clip_handle* h, const bf16* a, int lda, const bf16* w, int ldw, bf16* out, int ldc, int M, int N,
+                int K, const b200::GemmEpilogue& ep, cudaStream_t st);
+int launch_layernorm(b200clip_handle* h, const bf16* x, const float* g, const float* b, bf16* y, int64_t rows,
+                     int width, float eps, int t_per_img, const float* cls_row, cudaStream_t st);
+int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, int t, int heads, int causal,
+                     cudaStream_t st);
+int launch_head(b200clip_handle* h, const bf16* x, int64_t row_stride, const int32_t* row_index, const float* g,
+                const float* b, const bf16* proj, int n, int width, int embed, float eps, void* out, int out_dtype,
+                int l2norm, cudaStream_t st);
+int launch_patchify_chw(b200clip_handle* h, const float* chw, int n, bf16* patches, cudaStream_t st);
+int launch_text_embed(b200clip_handle* h, const int64_t* tokens, int q, bf16* x, int32_t* eot_rows, cudaStream_t st);
+int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
+                      int64_t row_stride, int mode, bf16* patches, float* chw, cudaStream_t st);
+int launch_sim_topk(b200clip_handle* h, const void* img, int dtype, int64_t n, int e, const float* txt, int q, int k,
+                    float thr, const float* ts, int64_t index_base, float clip_dur, float vid_dur, float* top_scores,
+                    int64_t* top_idx, float* intervals, int32_t* counts, cudaStream_t st);
+int launch_similarity(b200clip_handle* h, const void* img, int dtype, int64_t n, int e, const float* txt, int q,
+                      float* scores, cudaStream_t st);
+int launch_topk_merge(b200clip_handle* h, const float* cs, const int64_t* ci, int g, int q, int k, float thr,
+                      const float* ts, int64_t n_total, float clip_dur, float vid_dur, float* top_scores,
+                      int64_t* top_idx, float* intervals, int32_t* counts, cudaStream_t st);

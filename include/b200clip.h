@@ -1,0 +1,166 @@
+/*
+ * b200clip.h -- C ABI of libb200clip.so: the B200 (sm_100a) implementation of the phase1_mvp
+ * natural-language query hot path of nb-hmd/Advanced-Video-Event-Detection-Extraction.
+ *
+ * The reference is pure Python; what a maintainer would bind is the object protocol its wrapper uses
+ * on the third-party `open_clip` model (see INTEGRATION.md for the ctypes stub).  Every entry point
+ * below names the reference interface (file:line under the reference tree) it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `*_dev` pointers are CUDA device pointers on the handle's device,
+ *     `*_host` pointers are host memory (pageable or pinned).
+ *   - every function returns 0 on success or a negative B200CLIP_E_* code; b200clip_last_error()
+ *     returns a human-readable message for the last failure on that handle (or globally when h == NULL).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are asynchronous
+ *     on that stream unless they take/return host buffers, in which case they return after the result
+ *     is in the host buffer.
+ *   - a handle is not re-entrant: one in-flight call per handle.  One handle per GPU / rank.
+ *   - there is no CPU fallback anywhere: on a device that is not sm_100 every call fails with
+ *     B200CLIP_E_ARCH.
+ */
+#ifndef B200CLIP_H_
+#define B200CLIP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CLIP_OK 0
+#define B200CLIP_E_ARG (-1)    /* null pointer / bad enum / bad size */
+#define B200CLIP_E_SHAPE (-2)  /* unsupported shape (e.g. width not a multiple of 64) */
+#define B200CLIP_E_CUDA (-3)   /* a CUDA runtime / driver call failed */
+#define B200CLIP_E_ARCH (-4)   /* device is not compute capability 10.x */
+#define B200CLIP_E_STATE (-5)  /* weights missing / handle not finalized */
+#define B200CLIP_E_NOMEM (-6)
+
+typedef struct b200clip_handle b200clip_handle;
+
+/* Model geometry == open_clip model_configs/{ViT-B-32,ViT-L-14}.json. */
+typedef struct b200clip_config {
+    int32_t image_size;  /* 224 */
+    int32_t patch;       /* 32 (B/32) or 14 (L/14) */
+    int32_t width;       /* 768 / 1024 */
+    int32_t layers;      /* 12 / 24 */
+    int32_t heads;       /* width / 64 */
+    int32_t mlp_dim;     /* 4 * width */
+    int32_t embed_dim;   /* 512 / 768 */
+    int32_t act;         /* 0 = QuickGELU (pretrained="openai", src/utils/config.py:25-26), 1 = erf GELU */
+    float ln_eps;        /* 1e-5 */
+    int32_t text_ctx;    /* 77 */
+    int32_t text_vocab;  /* 49408 */
+    int32_t text_width;  /* 512 / 768 */
+    int32_t text_heads;  /* 8 / 12 */
+    int32_t text_layers; /* 12 */
+    int32_t text_mlp_dim;
+} b200clip_config;
+
+/* resize modes of the frame preprocess kernel */
+#define B200CLIP_RESIZE_REFERENCE 0 /* bit-exact reference chain: cv2 INTER_AREA (<=512^2) -> Pillow bicubic(aa) -> crop */
+#define B200CLIP_RESIZE_BILINEAR_AA 1 /* single-pass antialiased triangle filter (fast mode) */
+
+/* element types for embedding buffers */
+#define B200CLIP_F32 0
+#define B200CLIP_BF16 1
+
+const char* b200clip_version(void);
+const char* b200clip_last_error(const b200clip_handle* h);
+
+/* ---- life cycle.  Replaces OpenCLIPModel.__init__/load_model (src/models/openclip_model.py:14-150),
+ *      i.e. open_clip.create_model_and_transforms(...) + model.eval(). */
+int b200clip_create(const b200clip_config* cfg, int device, b200clip_handle** out);
+int b200clip_destroy(b200clip_handle* h);
+/* One tensor of the open_clip state dict (key names of SURVEY.md Appendix A, e.g.
+ * "visual.transformer.resblocks.3.attn.in_proj_weight"), fp32, host memory, row-major.  The library
+ * converts to its own bf16 / fp32 device layouts; the caller keeps ownership of `data_host`. */
+int b200clip_set_weight(b200clip_handle* h, const char* name, const float* data_host, const int64_t* shape,
+                        int ndim);
+/* Verifies that every tensor the config needs was supplied; after this the encode calls are legal. */
+int b200clip_finalize(b200clip_handle* h);
+/* Pre-sizes the persistent activation workspace (otherwise grown on first use). */
+int b200clip_reserve(b200clip_handle* h, int max_images, int max_texts);
+
+/* ---- K1: frame preprocess.  Replaces MemoryManager.resize_frame_for_memory
+ *      (src/utils/memory_manager.py:299-322) + open_clip image_transform (PIL Resize(bicubic) /
+ *      CenterCrop / ToTensor / Normalize; call sites src/models/openclip_model.py:165-174,188-193).
+ *      frames_dev: uint8 RGB HWC, frame i at frames_dev + i*frame_stride, rows row_stride bytes apart.
+ *      patches_out_dev: bf16 [n * grid^2, patch_k] patch-major rows, col = c*P*P + y*P + x
+ *      (patch_k = 3*P*P rounded up to a multiple of 64, zero padded). */
+int b200clip_preprocess_u8(b200clip_handle* h, const uint8_t* frames_dev, int n, int height, int width,
+                           int64_t frame_stride, int64_t row_stride, int resize_mode, void* patches_out_dev,
+                           void* stream);
+/* The normalised image itself, fp32 [n,3,S,S] (what open_clip's `preprocess` returns, stacked). */
+int b200clip_preprocess_u8_chw(b200clip_handle* h, const uint8_t* frames_dev, int n, int height, int width,
+                               int64_t frame_stride, int64_t row_stride, int resize_mode, float* chw_out_dev,
+                               void* stream);
+
+/* ---- K2+K3: image tower.  Replaces model.encode_image(x[B,3,S,S]) (+ the L2 normalisation at
+ *      src/models/openclip_model.py:177-178,196-197 when l2norm != 0).
+ *      emb_out_dev: [n, embed_dim] of out_dtype (B200CLIP_F32 / B200CLIP_BF16). */
+int b200clip_encode_patches(b200clip_handle* h, const void* patches_dev, int n, void* emb_out_dev, int out_dtype,
+                            int l2norm, void* stream);
+int b200clip_encode_image_chw(b200clip_handle* h, const float* chw_dev, int n, void* emb_out_dev, int out_dtype,
+                              int l2norm, void* stream);
+/* Fused K1 -> K3 on device-resident frames. */
+int b200clip_encode_frames_u8(b200clip_handle* h, const uint8_t* frames_dev, int n, int height, int width,
+                              int64_t frame_stride, int64_t row_stride, int resize_mode, void* emb_out_dev,
+                              int out_dtype, int l2norm, void* stream);
+/* Reference-facing call: OpenCLIPModel.encode_images(np.ndarray[N,H,W,3] uint8) -> float32[N,E]
+ * (src/models/openclip_model.py:152-198).  HOST buffers in and out: frames are staged through pinned
+ * double buffers (H2D overlapped with compute), embeddings are copied back; returns when emb_out_host is
+ * complete. */
+int b200clip_encode_frames_u8_host(b200clip_handle* h, const uint8_t* frames_host, int n, int height, int width,
+                                   int resize_mode, float* emb_out_host, int l2norm, void* stream);
+
+/* ---- text tower.  Replaces model.encode_text(tokens[Q,77]) (+ L2 norm, openclip_model.py:200-210). */
+int b200clip_encode_text(b200clip_handle* h, const int64_t* tokens_dev, int q, float* emb_out_dev, int l2norm,
+                         void* stream);
+int b200clip_encode_text_host(b200clip_handle* h, const int64_t* tokens_host, int q, float* emb_out_host,
+                              int l2norm, void* stream);
+
+/* ---- K4: similarity + top-k + threshold + clip intervals.  Replaces
+ *      OpenCLIPModel.compute_similarity (np.dot, openclip_model.py:212-214),
+ *      np.argsort(s)[::-1][:top_k] + threshold (src/pipeline/phase1_mvp.py:145-155; ties -> higher index
+ *      first) and ClipExtractor.extract_clip_with_padding / extract_clip interval arithmetic
+ *      (src/services/clip_extractor.py:175-183, 94-111).
+ *      img_emb_dev [n,e] (emb_dtype), txt_emb_dev fp32 [q,e].
+ *      timestamps_dev: fp32 [n] or NULL (then timestamp = index).  index_base is added to every row
+ *      index (global index of this shard's first row).  video_duration <= 0 means unknown.
+ *      Outputs (device): top_scores fp32 [q,k], top_idx int64 [q,k] (-1 past count),
+ *      intervals fp32 [q,k,2] (start,end seconds), counts int32 [q] = hits with score >= threshold. */
+int b200clip_sim_topk(b200clip_handle* h, const void* img_emb_dev, int emb_dtype, int64_t n, int e,
+                      const float* txt_emb_dev, int q, int k, float threshold, const float* timestamps_dev,
+                      int64_t index_base, float clip_duration, float video_duration, float* top_scores_dev,
+                      int64_t* top_idx_dev, float* intervals_dev, int32_t* counts_dev, void* stream);
+/* Dense scores fp32 [n,q] (compute_similarity itself). */
+int b200clip_similarity(b200clip_handle* h, const void* img_emb_dev, int emb_dtype, int64_t n, int e,
+                        const float* txt_emb_dev, int q, float* scores_out_dev, void* stream);
+/* k-way merge of g candidate lists (e.g. after an all-gather over ranks): cand_scores fp32 [g,q,k],
+ * cand_idx int64 [g,q,k] (-1 = empty).  timestamps are looked up by global index. */
+int b200clip_topk_merge(b200clip_handle* h, const float* cand_scores_dev, const int64_t* cand_idx_dev, int g, int q,
+                        int k, float threshold, const float* timestamps_dev, int64_t n_total, float clip_duration,
+                        float video_duration, float* top_scores_dev, int64_t* top_idx_dev, float* intervals_dev,
+                        int32_t* counts_dev, void* stream);
+
+/* ---- building blocks, exported for the parity tests and micro-benchmarks ---- */
+/* out[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ resid); bf16 in/out, fp32 accumulate. act: 0 none,
+ * 1 QuickGELU, 2 erf GELU.  bias fp32 [N] or NULL, resid bf16 [M,N] or NULL (may equal out). */
+int b200clip_gemm_bf16(b200clip_handle* h, const void* a_dev, const void* w_dev, void* out_dev, int m, int n, int k,
+                       const float* bias_dev, const void* resid_dev, int act, void* stream);
+/* rows of `width` bf16 -> bf16, fp32 statistics. */
+int b200clip_layernorm_bf16(b200clip_handle* h, const void* x_dev, const float* gamma_dev, const float* beta_dev,
+                            void* y_dev, int64_t rows, int width, float eps, void* stream);
+/* qkv bf16 [n_seq*t, 3*heads*64] -> out bf16 [n_seq*t, heads*64]; softmax(q k^T / 8) v per (seq, head). */
+int b200clip_attention_bf16(b200clip_handle* h, const void* qkv_dev, void* out_dev, int n_seq, int t, int heads,
+                            int causal, void* stream);
+
+/* Counts kernel launches issued through this handle since the last reset (bench.py's gpu_launches). */
+int64_t b200clip_launch_count(const b200clip_handle* h);
+void b200clip_reset_launch_count(b200clip_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CLIP_H_ */
