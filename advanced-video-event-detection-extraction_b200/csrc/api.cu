@@ -1,6 +1,7 @@
 // C ABI of libb200clip.so: handle life cycle, weight packing, workspace, tower orchestration.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -91,9 +92,10 @@ extern "C" int b200clip_destroy(b200clip_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    preprocess_free_plans(h);
     for (void* p : h->allocs) cudaFree(p);
     cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_qkv); cudaFree(h->ws_h); cudaFree(h->ws_patches);
-    cudaFree(h->ws_emb); cudaFree(h->ws_pre); cudaFree(h->ws_topk);
+    cudaFree(h->ws_emb); cudaFree(h->ws_pre); cudaFree(h->ws_topk); cudaFree(h->ws_eot); cudaFree(h->ws_tokens);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->ws_stage_dev[i]);
         if (h->ws_stage_host[i]) cudaFreeHost(h->ws_stage_host[i]);
@@ -105,17 +107,528 @@ extern "C" int b200clip_destroy(b200clip_handle* h) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------- weights
+static int upload_f32(b200clip_handle* h, const float* src, size_t count, float** dst) {
+    void* d = nullptr;
+    B200_CUDA(h, cudaMalloc(&d, count * sizeof(float)));
+    h->allocs.push_back(d);
+    B200_CUDA(h, cudaMemcpy(d, src, count * sizeof(float), cudaMemcpyHostToDevice));
+    *dst = static_cast<float*>(d);
+    return 0;
+}
+
+// fp32 [rows, cols] -> bf16 [rows, ld] (ld >= cols, zero padded), round to nearest even
+static int upload_bf16(b200clip_handle* h, const float* src, size_t rows, size_t cols, size_t ld, bf16** dst) {
+    std::vector<bf16> tmp(rows * ld, __float2bfloat16(0.f));
+    for (size_t r = 0; r < rows; ++r)
+        for (size_t c = 0; c < cols; ++c) tmp[r * ld + c] = __float2bfloat16(src[r * cols + c]);
+    void* d = nullptr;
+    B200_CUDA(h, cudaMalloc(&d, tmp.size() * sizeof(bf16)));
+    h->allocs.push_back(d);
+    B200_CUDA(h, cudaMemcpy(d, tmp.data(), tmp.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+    *dst = static_cast<bf16*>(d);
+    return 0;
+}
+
+static bool shape_is(const int64_t* shape, int ndim, std::initializer_list<int64_t> want) {
+    if (ndim != static_cast<int>(want.size())) return false;
+    int i = 0;
+    for (int64_t w : want)
+        if (shape[i++] != w) return false;
+    return true;
+}
+
+#define WANT_SHAPE(...)                                                                        \
+    if (!shape_is(shape, ndim, {__VA_ARGS__}))                                                 \
+        return b200_fail(h, B200CLIP_E_SHAPE, "set_weight(%s): unexpected shape for this config", name)
+
+static int set_block_weight(b200clip_handle* h, b200clip_handle::Tower& tw, const char* name, const char* rest,
+                            const float* data, const int64_t* shape, int ndim) {
+    // rest = "<i>.<param>"
+    char* end = nullptr;
+    const long li = strtol(rest, &end, 10);
+    if (end == rest || *end != '.' || li < 0 || li >= tw.layers)
+        return b200_fail(h, B200CLIP_E_ARG, "set_weight(%s): bad block index", name);
+    b200clip_handle::Block& b = tw.blocks[li];
+    const std::string p(end + 1);
+    const int64_t W = tw.width, F = tw.mlp;
+    if (p == "ln_1.weight") { WANT_SHAPE(W); return upload_f32(h, data, W, &b.ln1_g); }
+    if (p == "ln_1.bias") { WANT_SHAPE(W); return upload_f32(h, data, W, &b.ln1_b); }
+    if (p == "ln_2.weight") { WANT_SHAPE(W); return upload_f32(h, data, W, &b.ln2_g); }
+    if (p == "ln_2.bias") { WANT_SHAPE(W); return upload_f32(h, data, W, &b.ln2_b); }
+    if (p == "attn.in_proj_weight") { WANT_SHAPE(3 * W, W); return upload_bf16(h, data, 3 * W, W, W, &b.w_qkv); }
+    if (p == "attn.in_proj_bias") { WANT_SHAPE(3 * W); return upload_f32(h, data, 3 * W, &b.b_qkv); }
+    if (p == "attn.out_proj.weight") { WANT_SHAPE(W, W); return upload_bf16(h, data, W, W, W, &b.w_out); }
+    if (p == "attn.out_proj.bias") { WANT_SHAPE(W); return upload_f32(h, data, W, &b.b_out); }
+    if (p == "mlp.c_fc.weight") { WANT_SHAPE(F, W); return upload_bf16(h, data, F, W, W, &b.w_fc); }
+    if (p == "mlp.c_fc.bias") { WANT_SHAPE(F); return upload_f32(h, data, F, &b.b_fc); }
+    if (p == "mlp.c_proj.weight") { WANT_SHAPE(W, F); return upload_bf16(h, data, W, F, F, &b.w_proj); }
+    if (p == "mlp.c_proj.bias") { WANT_SHAPE(W); return upload_f32(h, data, W, &b.b_proj); }
+    return b200_fail(h, B200CLIP_E_ARG, "set_weight(%s): unknown block parameter", name);
+}
+
+extern "C" int b200clip_set_weight(b200clip_handle* h, const char* name, const float* data, const int64_t* shape,
+                                   int ndim) {
+    if (!h || !name || !data || !shape) return b200_fail(h, B200CLIP_E_ARG, "set_weight: null argument");
+    B200_CUDA(h, cudaSetDevice(h->device));
+    const b200clip_config& c = h->cfg;
+    const std::string n(name);
+    const int64_t W = c.width, E = c.embed_dim, TW = c.text_width;
+    int rc = 0;
+    static const char* kVis = "visual.transformer.resblocks.";
+    static const char* kTxt = "transformer.resblocks.";
+    if (n.rfind(kVis, 0) == 0) rc = set_block_weight(h, h->vis, name, name + strlen(kVis), data, shape, ndim);
+    else if (n.rfind(kTxt, 0) == 0) rc = set_block_weight(h, h->txt, name, name + strlen(kTxt), data, shape, ndim);
+    else if (n == "visual.conv1.weight") {
+        WANT_SHAPE(W, 3, c.patch, c.patch);
+        rc = upload_bf16(h, data, W, 3 * c.patch * c.patch, h->patch_k, &h->w_patch);
+    } else if (n == "visual.class_embedding") {
+        WANT_SHAPE(W);
+        h->host_cls.assign(data, data + W);
+    } else if (n == "visual.positional_embedding") {
+        WANT_SHAPE(h->tokens, W);
+        h->host_pos0.assign(data, data + W);
+        rc = upload_f32(h, data, static_cast<size_t>(h->tokens) * W, &h->pos_emb);
+    } else if (n == "visual.ln_pre.weight") { WANT_SHAPE(W); rc = upload_f32(h, data, W, &h->ln_pre_g); }
+    else if (n == "visual.ln_pre.bias") { WANT_SHAPE(W); rc = upload_f32(h, data, W, &h->ln_pre_b); }
+    else if (n == "visual.ln_post.weight") { WANT_SHAPE(W); rc = upload_f32(h, data, W, &h->ln_post_g); }
+    else if (n == "visual.ln_post.bias") { WANT_SHAPE(W); rc = upload_f32(h, data, W, &h->ln_post_b); }
+    else if (n == "visual.proj") { WANT_SHAPE(W, E); rc = upload_bf16(h, data, W, E, E, &h->vis_proj); }
+    else if (n == "token_embedding.weight") {
+        WANT_SHAPE(c.text_vocab, TW);
+        rc = upload_f32(h, data, static_cast<size_t>(c.text_vocab) * TW, &h->tok_emb);
+    } else if (n == "positional_embedding") {
+        WANT_SHAPE(c.text_ctx, TW);
+        rc = upload_f32(h, data, static_cast<size_t>(c.text_ctx) * TW, &h->txt_pos);
+    } else if (n == "ln_final.weight") { WANT_SHAPE(TW); rc = upload_f32(h, data, TW, &h->ln_final_g); }
+    else if (n == "ln_final.bias") { WANT_SHAPE(TW); rc = upload_f32(h, data, TW, &h->ln_final_b); }
+    else if (n == "text_projection") { WANT_SHAPE(TW, E); rc = upload_bf16(h, data, TW, E, E, &h->txt_proj); }
+    else if (n == "logit_scale") { return 0; /* unused by the reference (plain cosine) */ }
+    else return b200_fail(h, B200CLIP_E_ARG, "set_weight: unknown tensor name '%s'", name);
+    if (rc == 0) h->have[n] = true;
+    return rc;
+}
+
+extern "C" int b200clip_finalize(b200clip_handle* h) {
+    if (!h) return b200_fail(h, B200CLIP_E_ARG, "finalize: null handle");
+    B200_CUDA(h, cudaSetDevice(h->device));
+    std::vector<std::string> need = {"visual.conv1.weight", "visual.class_embedding", "visual.positional_embedding",
+                                     "visual.ln_pre.weight", "visual.ln_pre.bias", "visual.ln_post.weight",
+                                     "visual.ln_post.bias", "visual.proj", "token_embedding.weight",
+                                     "positional_embedding", "ln_final.weight", "ln_final.bias", "text_projection"};
+    static const char* per_block[] = {"ln_1.weight", "ln_1.bias", "ln_2.weight", "ln_2.bias", "attn.in_proj_weight",
+                                      "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias",
+                                      "mlp.c_fc.weight", "mlp.c_fc.bias", "mlp.c_proj.weight", "mlp.c_proj.bias"};
+    for (int i = 0; i < h->cfg.layers; ++i)
+        for (const char* p : per_block) need.push_back("visual.transformer.resblocks." + std::to_string(i) + "." + p);
+    for (int i = 0; i < h->cfg.text_layers; ++i)
+        for (const char* p : per_block) need.push_back("transformer.resblocks." + std::to_string(i) + "." + p);
+    for (const std::string& k : need)
+        if (!h->have.count(k)) return b200_fail(h, B200CLIP_E_STATE, "finalize: weight '%s' was never set", k.c_str());
+    std::vector<float> cp(h->cfg.width);
+    for (int i = 0; i < h->cfg.width; ++i) cp[i] = h->host_cls[i] + h->host_pos0[i];
+    int rc = upload_f32(h, cp.data(), cp.size(), &h->cls_pos0);
+    if (rc) return rc;
+    h->finalized = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- workspace
+static int ensure_workspace(b200clip_handle* h, int images, int texts, cudaStream_t st) {
+    if (images <= h->ws_images && texts <= h->ws_texts) return 0;
+    const int ni = images > h->ws_images ? images : h->ws_images;
+    const int nt = texts > h->ws_texts ? texts : h->ws_texts;
+    B200_CUDA(h, cudaStreamSynchronize(st));
+    const b200clip_config& c = h->cfg;
+    const size_t mv = static_cast<size_t>(ni) * h->tokens, mt = static_cast<size_t>(nt) * c.text_ctx;
+    auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
+    const size_t x_el = mx(mv * c.width, mt * c.text_width);
+    const size_t qkv_el = 3 * x_el;
+    const size_t h_el = mx(mv * c.mlp_dim, mt * c.text_mlp_dim);
+    const size_t p_el = static_cast<size_t>(ni) * h->grid * h->grid * h->patch_k;
+    cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_qkv); cudaFree(h->ws_h); cudaFree(h->ws_patches);
+    cudaFree(h->ws_eot); cudaFree(h->ws_tokens);
+    h->ws_x = h->ws_y = h->ws_qkv = h->ws_h = h->ws_patches = nullptr;
+    h->ws_eot = nullptr; h->ws_tokens = nullptr;
+    h->ws_images = h->ws_texts = 0;
+    B200_CUDA(h, cudaMalloc(&h->ws_x, mx(x_el, 8) * 2));
+    B200_CUDA(h, cudaMalloc(&h->ws_y, mx(x_el, 8) * 2));
+    B200_CUDA(h, cudaMalloc(&h->ws_qkv, mx(qkv_el, 8) * 2));
+    B200_CUDA(h, cudaMalloc(&h->ws_h, mx(h_el, 8) * 2));
+    B200_CUDA(h, cudaMalloc(&h->ws_patches, mx(p_el, 8) * 2));
+    B200_CUDA(h, cudaMalloc(&h->ws_eot, mx(nt, 1) * sizeof(int32_t)));
+    B200_CUDA(h, cudaMalloc(&h->ws_tokens, mx(mt, 1) * sizeof(int64_t)));
+    h->ws_images = ni;
+    h->ws_texts = nt;
+    return 0;
+}
+
+static const int kDefaultChunk = 1024;  // images per pass of the tower when the caller reserved nothing
+
+extern "C" int b200clip_reserve(b200clip_handle* h, int max_images, int max_texts) {
+    if (!h || max_images < 0 || max_texts < 0) return b200_fail(h, B200CLIP_E_ARG, "reserve: bad argument");
+    B200_CUDA(h, cudaSetDevice(h->device));
+    return ensure_workspace(h, max_images, max_texts, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------- towers
+static int run_blocks(b200clip_handle* h, b200clip_handle::Tower& tw, int n_seq, int T, int causal, cudaStream_t st) {
+    const int M = n_seq * T;
+    const int W = tw.width, F = tw.mlp;
+    const int act = h->cfg.act == 0 ? 1 : 2;
+    const float eps = h->cfg.ln_eps;
+    int rc;
+    for (int l = 0; l < tw.layers; ++l) {
+        const b200clip_handle::Block& b = tw.blocks[l];
+        b200::GemmEpilogue ep{};
+        if ((rc = launch_layernorm(h, h->ws_x, b.ln1_g, b.ln1_b, h->ws_y, M, W, eps, 0, nullptr, st))) return rc;
+        ep = {}; ep.bias = b.b_qkv;
+        if ((rc = launch_gemm(h, h->ws_y, W, b.w_qkv, W, h->ws_qkv, 3 * W, M, 3 * W, W, ep, st))) return rc;
+        if ((rc = launch_attention(h, h->ws_qkv, h->ws_y, n_seq, T, tw.heads, causal, st))) return rc;
+        ep = {}; ep.bias = b.b_out; ep.resid = h->ws_x;
+        if ((rc = launch_gemm(h, h->ws_y, W, b.w_out, W, h->ws_x, W, M, W, W, ep, st))) return rc;
+        if ((rc = launch_layernorm(h, h->ws_x, b.ln2_g, b.ln2_b, h->ws_y, M, W, eps, 0, nullptr, st))) return rc;
+        ep = {}; ep.bias = b.b_fc; ep.act = act;
+        if ((rc = launch_gemm(h, h->ws_y, W, b.w_fc, W, h->ws_h, F, M, F, W, ep, st))) return rc;
+        ep = {}; ep.bias = b.b_proj; ep.resid = h->ws_x;
+        if ((rc = launch_gemm(h, h->ws_h, F, b.w_proj, F, h->ws_x, W, M, W, F, ep, st))) return rc;
+    }
+    return 0;
+}
+
+// patches (device, [n*g*g, patch_k]) -> embeddings; n <= ws_images
+static int encode_patches_chunk(b200clip_handle* h, const bf16* patches, int n, void* out, int out_dtype, int l2norm,
+                                cudaStream_t st) {
+    const b200clip_config& c = h->cfg;
+    const int g2 = h->grid * h->grid;
+    int rc;
+    b200::GemmEpilogue ep{};
+    ep.rowtab = h->pos_emb; ep.t_in = g2; ep.t_out = h->tokens; ep.row_off = 1;
+    if ((rc = launch_gemm(h, patches, h->patch_k, h->w_patch, h->patch_k, h->ws_y, c.width, n * g2, c.width, h->patch_k,
+                          ep, st)))
+        return rc;
+    if ((rc = launch_layernorm(h, h->ws_y, h->ln_pre_g, h->ln_pre_b, h->ws_x, static_cast<int64_t>(n) * h->tokens,
+                               c.width, c.ln_eps, h->tokens, h->cls_pos0, st)))
+        return rc;
+    if ((rc = run_blocks(h, h->vis, n, h->tokens, 0, st))) return rc;
+    return launch_head(h, h->ws_x, static_cast<int64_t>(h->tokens) * c.width, nullptr, h->ln_post_g, h->ln_post_b,
+                       h->vis_proj, n, c.width, c.embed_dim, c.ln_eps, out, out_dtype, l2norm, st);
+}
+
+static int check_ready(b200clip_handle* h, const char* what) {
+    if (!h) return b200_fail(h, B200CLIP_E_ARG, "%s: null handle", what);
+    if (!h->finalized) return b200_fail(h, B200CLIP_E_STATE, "%s: handle not finalized (weights missing)", what);
+    if (cudaSetDevice(h->device) != cudaSuccess) return b200_fail(h, B200CLIP_E_CUDA, "%s: cudaSetDevice failed", what);
+    return 0;
+}
+
+static size_t out_elem(int dt) { return dt == B200CLIP_BF16 ? 2 : 4; }
+
+static int chunk_images(b200clip_handle* h, int n) {
+    if (h->ws_images > 0) return h->ws_images;
+    return n < kDefaultChunk ? n : kDefaultChunk;
+}
+
+extern "C" int b200clip_encode_patches(b200clip_handle* h, const void* patches_dev, int n, void* emb_out_dev,
+                                       int out_dtype, int l2norm, void* stream) {
+    int rc = check_ready(h, "encode_patches");
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!patches_dev || !emb_out_dev))) return b200_fail(h, B200CLIP_E_ARG, "encode_patches: bad argument");
+    if (out_dtype != B200CLIP_F32 && out_dtype != B200CLIP_BF16) return b200_fail(h, B200CLIP_E_ARG, "bad out_dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int chunk = chunk_images(h, n);
+    if (n > 0 && (rc = ensure_workspace(h, chunk, 0, st))) return rc;
+    const size_t prow = static_cast<size_t>(h->grid) * h->grid * h->patch_k;
+    for (int i = 0; i < n; i += chunk) {
+        const int nc = (n - i) < chunk ? (n - i) : chunk;
+        rc = encode_patches_chunk(h, static_cast<const bf16*>(patches_dev) + i * prow, nc,
+                                  static_cast<uint8_t*>(emb_out_dev) + static_cast<size_t>(i) * h->cfg.embed_dim * out_elem(out_dtype),
+                                  out_dtype, l2norm, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int b200clip_encode_image_chw(b200clip_handle* h, const float* chw_dev, int n, void* emb_out_dev,
+                                         int out_dtype, int l2norm, void* stream) {
+    int rc = check_ready(h, "encode_image_chw");
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!chw_dev || !emb_out_dev))) return b200_fail(h, B200CLIP_E_ARG, "encode_image_chw: bad argument");
+    if (out_dtype != B200CLIP_F32 && out_dtype != B200CLIP_BF16) return b200_fail(h, B200CLIP_E_ARG, "bad out_dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int chunk = chunk_images(h, n);
+    if (n > 0 && (rc = ensure_workspace(h, chunk, 0, st))) return rc;
+    const size_t S = h->cfg.image_size;
+    for (int i = 0; i < n; i += chunk) {
+        const int nc = (n - i) < chunk ? (n - i) : chunk;
+        if ((rc = launch_patchify_chw(h, chw_dev + static_cast<size_t>(i) * 3 * S * S, nc, h->ws_patches, st))) return rc;
+        rc = encode_patches_chunk(h, h->ws_patches, nc,
+                                  static_cast<uint8_t*>(emb_out_dev) + static_cast<size_t>(i) * h->cfg.embed_dim * out_elem(out_dtype),
+                                  out_dtype, l2norm, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int b200clip_preprocess_u8(b200clip_handle* h, const uint8_t* frames_dev, int n, int height, int width,
+                                      int64_t frame_stride, int64_t row_stride, int resize_mode, void* patches_out_dev,
+                                      void* stream) {
+    if (!h) return b200_fail(h, B200CLIP_E_ARG, "preprocess: null handle");
+    if (n < 0 || (n > 0 && (!frames_dev || !patches_out_dev))) return b200_fail(h, B200CLIP_E_ARG, "preprocess: bad argument");
+    B200_CUDA(h, cudaSetDevice(h->device));
+    return launch_preprocess(h, frames_dev, n, height, width, frame_stride, row_stride, resize_mode,
+                             static_cast<bf16*>(patches_out_dev), nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200clip_preprocess_u8_chw(b200clip_handle* h, const uint8_t* frames_dev, int n, int height, int width,
+                                          int64_t frame_stride, int64_t row_stride, int resize_mode,
+                                          float* chw_out_dev, void* stream) {
+    if (!h) return b200_fail(h, B200CLIP_E_ARG, "preprocess: null handle");
+    if (n < 0 || (n > 0 && (!frames_dev || !chw_out_dev))) return b200_fail(h, B200CLIP_E_ARG, "preprocess: bad argument");
+    B200_CUDA(h, cudaSetDevice(h->device));
+    return launch_preprocess(h, frames_dev, n, height, width, frame_stride, row_stride, resize_mode, nullptr,
+                             chw_out_dev, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200clip_encode_frames_u8(b200clip_handle* h, const uint8_t* frames_dev, int n, int height, int width,
+                                         int64_t frame_stride, int64_t row_stride, int resize_mode, void* emb_out_dev,
+                                         int out_dtype, int l2norm, void* stream) {
+    int rc = check_ready(h, "encode_frames_u8");
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!frames_dev || !emb_out_dev))) return b200_fail(h, B200CLIP_E_ARG, "encode_frames_u8: bad argument");
+    if (out_dtype != B200CLIP_F32 && out_dtype != B200CLIP_BF16) return b200_fail(h, B200CLIP_E_ARG, "bad out_dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int chunk = chunk_images(h, n);
+    if (n > 0 && (rc = ensure_workspace(h, chunk, 0, st))) return rc;
+    for (int i = 0; i < n; i += chunk) {
+        const int nc = (n - i) < chunk ? (n - i) : chunk;
+        if ((rc = launch_preprocess(h, frames_dev + static_cast<int64_t>(i) * frame_stride, nc, height, width,
+                                    frame_stride, row_stride, resize_mode, h->ws_patches, nullptr, st)))
+            return rc;
+        rc = encode_patches_chunk(h, h->ws_patches, nc,
+                                  static_cast<uint8_t*>(emb_out_dev) + static_cast<size_t>(i) * h->cfg.embed_dim * out_elem(out_dtype),
+                                  out_dtype, l2norm, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// HOST frames -> HOST embeddings.  Device staging is double buffered: the copy stream uploads chunk i+1 while the
+// compute stream runs preprocess + tower on chunk i.  Pinned caller memory is copied directly; pageable memory
+// goes through pinned bounce buffers.
+extern "C" int b200clip_encode_frames_u8_host(b200clip_handle* h, const uint8_t* frames_host, int n, int height,
+                                              int width, int resize_mode, float* emb_out_host, int l2norm,
+                                              void* stream) {
+    int rc = check_ready(h, "encode_frames_u8_host");
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!frames_host || !emb_out_host))) return b200_fail(h, B200CLIP_E_ARG, "encode_frames_u8_host: bad argument");
+    if (n == 0) return 0;
+    if (height <= 0 || width <= 0) return b200_fail(h, B200CLIP_E_ARG, "encode_frames_u8_host: bad frame size");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t fbytes = static_cast<size_t>(height) * width * 3;
+    int chunk = chunk_images(h, n);
+    const size_t budget = size_t(1) << 30;  // ~1 GiB of frames per staging buffer
+    if (static_cast<size_t>(chunk) * fbytes > budget) chunk = static_cast<int>(budget / fbytes);
+    if (chunk < 1) chunk = 1;
+    if ((rc = ensure_workspace(h, chunk, 0, st))) return rc;
+    cudaPointerAttributes attr{};
+    bool pinned = cudaPointerGetAttributes(&attr, frames_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const size_t sbytes = static_cast<size_t>(chunk) * fbytes;
+    if (sbytes > h->ws_stage_bytes || (!pinned && !h->ws_stage_host[0])) {
+        B200_CUDA(h, cudaStreamSynchronize(st));
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(h->ws_stage_dev[i]); h->ws_stage_dev[i] = nullptr;
+            if (h->ws_stage_host[i]) { cudaFreeHost(h->ws_stage_host[i]); h->ws_stage_host[i] = nullptr; }
+        }
+        const size_t nb = sbytes > h->ws_stage_bytes ? sbytes : h->ws_stage_bytes;
+        h->ws_stage_bytes = 0;
+        for (int i = 0; i < 2; ++i) {
+            B200_CUDA(h, cudaMalloc(&h->ws_stage_dev[i], nb));
+            if (!pinned) B200_CUDA(h, cudaMallocHost(&h->ws_stage_host[i], nb));
+        }
+        h->ws_stage_bytes = nb;
+    }
+    if (!h->copy_stream) {
+        B200_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            B200_CUDA(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+            B200_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    // the result buffer may be host memory (reference behaviour: numpy out) or device memory (keeps the
+    // embeddings resident for K4)
+    cudaPointerAttributes oattr{};
+    const bool out_on_device = cudaPointerGetAttributes(&oattr, emb_out_host) == cudaSuccess &&
+                               (oattr.type == cudaMemoryTypeDevice || oattr.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    const size_t emb_el = static_cast<size_t>(n) * h->cfg.embed_dim;
+    if (!out_on_device && emb_el > h->ws_emb_elems) {
+        B200_CUDA(h, cudaStreamSynchronize(st));
+        cudaFree(h->ws_emb); h->ws_emb = nullptr; h->ws_emb_elems = 0;
+        B200_CUDA(h, cudaMalloc(&h->ws_emb, emb_el * sizeof(float)));
+        h->ws_emb_elems = emb_el;
+    }
+    float* emb_dev = out_on_device ? emb_out_host : h->ws_emb;
+    // the copy stream must not overwrite a staging buffer the compute stream of a previous call still reads
+    cudaEvent_t& e0 = h->ev_done[0];
+    B200_CUDA(h, cudaEventRecord(e0, st));
+    B200_CUDA(h, cudaStreamWaitEvent(h->copy_stream, e0, 0));
+    const int nchunks = (n + chunk - 1) / chunk;
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int b = ci & 1;
+        const int i0 = ci * chunk;
+        const int nc = (n - i0) < chunk ? (n - i0) : chunk;
+        const uint8_t* src = frames_host + static_cast<size_t>(i0) * fbytes;
+        if (ci >= 2) B200_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));
+        if (!pinned) {
+            if (ci >= 2) B200_CUDA(h, cudaEventSynchronize(h->ev_h2d[b]));  // bounce buffer b is free again
+            memcpy(h->ws_stage_host[b], src, static_cast<size_t>(nc) * fbytes);
+            src = h->ws_stage_host[b];
+        }
+        B200_CUDA(h, cudaMemcpyAsync(h->ws_stage_dev[b], src, static_cast<size_t>(nc) * fbytes, cudaMemcpyHostToDevice,
+                                     h->copy_stream));
+        B200_CUDA(h, cudaEventRecord(h->ev_h2d[b], h->copy_stream));
+        B200_CUDA(h, cudaStreamWaitEvent(st, h->ev_h2d[b], 0));
+        if ((rc = launch_preprocess(h, h->ws_stage_dev[b], nc, height, width, static_cast<int64_t>(fbytes),
+                                    static_cast<int64_t>(width) * 3, resize_mode, h->ws_patches, nullptr, st)))
+            return rc;
+        if ((rc = encode_patches_chunk(h, h->ws_patches, nc, emb_dev + static_cast<size_t>(i0) * h->cfg.embed_dim,
+                                       B200CLIP_F32, l2norm, st)))
+            return rc;
+        B200_CUDA(h, cudaEventRecord(h->ev_done[b], st));
+    }
+    if (out_on_device) {
+        // frames_host may be reused by the caller once the uploads are done; compute stays asynchronous on `st`
+        B200_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+        return 0;
+    }
+    B200_CUDA(h, cudaMemcpyAsync(emb_out_host, h->ws_emb, emb_el * sizeof(float), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- text
+static int encode_text_dev(b200clip_handle* h, const int64_t* tokens_dev, int q, float* out_dev, int l2norm,
+                           cudaStream_t st) {
+    const b200clip_config& c = h->cfg;
+    int rc;
+    int chunk = h->ws_texts > 0 ? h->ws_texts : (q < 256 ? q : 256);
+    if ((rc = ensure_workspace(h, 0, chunk, st))) return rc;
+    for (int i = 0; i < q; i += chunk) {
+        const int nc = (q - i) < chunk ? (q - i) : chunk;
+        if ((rc = launch_text_embed(h, tokens_dev + static_cast<size_t>(i) * c.text_ctx, nc, h->ws_x, h->ws_eot, st)))
+            return rc;
+        if ((rc = run_blocks(h, h->txt, nc, c.text_ctx, 1, st))) return rc;
+        if ((rc = launch_head(h, h->ws_x, c.text_width, h->ws_eot, h->ln_final_g, h->ln_final_b, h->txt_proj, nc,
+                              c.text_width, c.embed_dim, c.ln_eps, out_dev + static_cast<size_t>(i) * c.embed_dim,
+                              B200CLIP_F32, l2norm, st)))
+            return rc;
+    }
+    return 0;
+}
+
+extern "C" int b200clip_encode_text(b200clip_handle* h, const int64_t* tokens_dev, int q, float* emb_out_dev,
+                                    int l2norm, void* stream) {
+    int rc = check_ready(h, "encode_text");
+    if (rc) return rc;
+    if (q < 0 || (q > 0 && (!tokens_dev || !emb_out_dev))) return b200_fail(h, B200CLIP_E_ARG, "encode_text: bad argument");
+    if (q == 0) return 0;
+    return encode_text_dev(h, tokens_dev, q, emb_out_dev, l2norm, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200clip_encode_text_host(b200clip_handle* h, const int64_t* tokens_host, int q, float* emb_out_host,
+                                         int l2norm, void* stream) {
+    int rc = check_ready(h, "encode_text_host");
+    if (rc) return rc;
+    if (q < 0 || (q > 0 && (!tokens_host || !emb_out_host))) return b200_fail(h, B200CLIP_E_ARG, "encode_text_host: bad argument");
+    if (q == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const b200clip_config& c = h->cfg;
+    int64_t* tok_dev = nullptr;
+    float* emb_dev = nullptr;
+    B200_CUDA(h, cudaMalloc(&tok_dev, static_cast<size_t>(q) * c.text_ctx * sizeof(int64_t)));
+    if (cudaMalloc(&emb_dev, static_cast<size_t>(q) * c.embed_dim * sizeof(float)) != cudaSuccess) {
+        cudaFree(tok_dev);
+        return b200_fail(h, B200CLIP_E_NOMEM, "encode_text_host: out of device memory");
+    }
+    cudaError_t e = cudaMemcpyAsync(tok_dev, tokens_host, static_cast<size_t>(q) * c.text_ctx * sizeof(int64_t),
+                                    cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        rc = encode_text_dev(h, tok_dev, q, emb_dev, l2norm, st);
+        if (rc == 0)
+            e = cudaMemcpyAsync(emb_out_host, emb_dev, static_cast<size_t>(q) * c.embed_dim * sizeof(float),
+                                cudaMemcpyDeviceToHost, st);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(tok_dev);
+    cudaFree(emb_dev);
+    if (rc) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess)
+        return b200_fail(h, B200CLIP_E_CUDA, "encode_text_host: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- K4
+extern "C" int b200clip_sim_topk(b200clip_handle* h, const void* img_emb_dev, int emb_dtype, int64_t n, int e,
+                                 const float* txt_emb_dev, int q, int k, float threshold, const double* timestamps_dev,
+                                 int64_t index_base, double clip_duration, double video_duration,
+                                 float* top_scores_dev, int64_t* top_idx_dev, double* intervals_dev,
+                                 int32_t* counts_dev, void* stream) {
+    if (!h) return b200_fail(h, B200CLIP_E_ARG, "sim_topk: null handle");
+    B200_CUDA(h, cudaSetDevice(h->device));
+    return launch_sim_topk(h, img_emb_dev, emb_dtype, n, e, txt_emb_dev, q, k, threshold, timestamps_dev, index_base,
+                           clip_duration, video_duration, top_scores_dev, top_idx_dev, intervals_dev, counts_dev,
+                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200clip_similarity(b200clip_handle* h, const void* img_emb_dev, int emb_dtype, int64_t n, int e,
+                                   const float* txt_emb_dev, int q, float* scores_out_dev, void* stream) {
+    if (!h || !scores_out_dev) return b200_fail(h, B200CLIP_E_ARG, "similarity: null argument");
+    B200_CUDA(h, cudaSetDevice(h->device));
+    return launch_similarity(h, img_emb_dev, emb_dtype, n, e, txt_emb_dev, q, scores_out_dev,
+                             static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200clip_topk_merge(b200clip_handle* h, const float* cand_scores_dev, const int64_t* cand_idx_dev, int g,
+                                   int q, int k, float threshold, const double* timestamps_dev, double clip_duration,
+                                   double video_duration, float* top_scores_dev, int64_t* top_idx_dev,
+                                   double* intervals_dev, int32_t* counts_dev, void* stream) {
+    if (!h) return b200_fail(h, B200CLIP_E_ARG, "topk_merge: null handle");
+    B200_CUDA(h, cudaSetDevice(h->device));
+    return launch_topk_merge(h, cand_scores_dev, cand_idx_dev, g, q, k, threshold, timestamps_dev, clip_duration,
+                             video_duration, top_scores_dev, top_idx_dev, intervals_dev, counts_dev,
+                             static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------- building blocks
 extern "C" int b200clip_gemm_bf16(b200clip_handle* h, const void* a_dev, const void* w_dev, void* out_dev, int m,
                                   int n, int k, const float* bias_dev, const void* resid_dev, int act,
                                   void* stream) {
     if (!h || !a_dev || !w_dev || !out_dev) return b200_fail(h, B200CLIP_E_ARG, "gemm: null argument");
     if (act < 0 || act > 2) return b200_fail(h, B200CLIP_E_ARG, "gemm: act must be 0, 1 or 2");
+    B200_CUDA(h, cudaSetDevice(h->device));
     b200::GemmEpilogue ep{};
     ep.bias = bias_dev;
     ep.resid = static_cast<const bf16*>(resid_dev);
-    ep.rowtab = nullptr;
     ep.act = act;
-    ep.t_in = 0; ep.t_out = 0; ep.row_off = 0;
     return launch_gemm(h, static_cast<const bf16*>(a_dev), k, static_cast<const bf16*>(w_dev), k,
                        static_cast<bf16*>(out_dev), n, m, n, k, ep, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200clip_layernorm_bf16(b200clip_handle* h, const void* x_dev, const float* gamma_dev,
+                                       const float* beta_dev, void* y_dev, int64_t rows, int width, float eps,
+                                       void* stream) {
+    if (!h || !x_dev || !gamma_dev || !beta_dev || !y_dev) return b200_fail(h, B200CLIP_E_ARG, "layernorm: null argument");
+    B200_CUDA(h, cudaSetDevice(h->device));
+    return launch_layernorm(h, static_cast<const bf16*>(x_dev), gamma_dev, beta_dev, static_cast<bf16*>(y_dev), rows,
+                            width, eps, 0, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200clip_attention_bf16(b200clip_handle* h, const void* qkv_dev, void* out_dev, int n_seq, int t,
+                                       int heads, int causal, void* stream) {
+    if (!h || !qkv_dev || !out_dev) return b200_fail(h, B200CLIP_E_ARG, "attention: null argument");
+    B200_CUDA(h, cudaSetDevice(h->device));
+    return launch_attention(h, static_cast<const bf16*>(qkv_dev), static_cast<bf16*>(out_dev), n_seq, t, heads, causal,
+                            static_cast<cudaStream_t>(stream));
 }

@@ -39,11 +39,12 @@ struct b200clip_handle {
     float *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr, *ln_post_b = nullptr;
     bf16* vis_proj = nullptr;     // [width, embed] row-major (x @ proj)
     // text stem / head
-    bf16* tok_emb = nullptr;      // [vocab, text_width]
+    float* tok_emb = nullptr;     // [vocab, text_width] fp32 (one rounding after + positional)
     float* txt_pos = nullptr;     // [ctx, text_width]
     float *ln_final_g = nullptr, *ln_final_b = nullptr;
     bf16* txt_proj = nullptr;     // [text_width, embed]
     std::map<std::string, bool> have;
+    std::vector<float> host_cls, host_pos0;   // kept until finalize builds cls_pos0
     std::vector<void*> allocs;    // everything cudaMalloc'ed for weights
 
     // ---- derived geometry ----
@@ -57,8 +58,12 @@ struct b200clip_handle {
     uint8_t* ws_stage_dev[2] = {nullptr, nullptr};   // device staging for host-frame calls
     uint8_t* ws_stage_host[2] = {nullptr, nullptr};  // pinned
     size_t ws_stage_bytes = 0;
-    float* ws_emb = nullptr;       // [ws_images, embed] device scratch for host-output calls
+    int32_t* ws_eot = nullptr;     // [ws_texts] row of the EOT token per text
+    int64_t* ws_tokens = nullptr;  // [ws_texts * ctx]
+    float* ws_emb = nullptr;       // device scratch for host-output calls
     size_t ws_emb_elems = 0;
+    void* pre_plans = nullptr;     // preprocess.cu: cached resize tables per frame geometry
+    float* pre_lut = nullptr;      // [3][256] ToTensor+Normalize lookup
     uint8_t* ws_pre = nullptr;     // preprocess intermediates
     size_t ws_pre_bytes = 0;
     void* ws_topk = nullptr;       // sim/top-k partial candidates
@@ -95,10 +100,11 @@ int launch_text_embed(b200clip_handle* h, const int64_t* tokens, int q, bf16* x,
 int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
                       int64_t row_stride, int mode, bf16* patches, float* chw, cudaStream_t st);
 int launch_sim_topk(b200clip_handle* h, const void* img, int dtype, int64_t n, int e, const float* txt, int q, int k,
-                    float thr, const float* ts, int64_t index_base, float clip_dur, float vid_dur, float* top_scores,
-                    int64_t* top_idx, float* intervals, int32_t* counts, cudaStream_t st);
+                    float thr, const double* ts, int64_t index_base, double clip_dur, double vid_dur,
+                    float* top_scores, int64_t* top_idx, double* intervals, int32_t* counts, cudaStream_t st);
 int launch_similarity(b200clip_handle* h, const void* img, int dtype, int64_t n, int e, const float* txt, int q,
                       float* scores, cudaStream_t st);
 int launch_topk_merge(b200clip_handle* h, const float* cs, const int64_t* ci, int g, int q, int k, float thr,
-                      const float* ts, int64_t n_total, float clip_dur, float vid_dur, float* top_scores,
-                      int64_t* top_idx, float* intervals, int32_t* counts, cudaStream_t st);
+                      const double* ts, double clip_dur, double vid_dur, float* top_scores, int64_t* top_idx,
+                      double* intervals, int32_t* counts, cudaStream_t st);
+void preprocess_free_plans(b200clip_handle* h);

@@ -1,0 +1,569 @@
+// K1: uint8 HWC frames -> normalised bf16 patch rows (or fp32 CHW), bit-exact with the reference chain
+//   MemoryManager.resize_frame_for_memory (cv2.resize INTER_AREA to fit 512x512; src/utils/memory_manager.py:299-322)
+//   -> open_clip image_transform: PIL Resize(224, BICUBIC, antialias) -> CenterCrop(224) -> ToTensor -> Normalize
+//      (applied at src/models/openclip_model.py:165-174,188-193)
+// restated in oracle/preprocess_ref.py.  Three small kernels, each computing only what the crop needs:
+//   A  area shrink      (fp32 taps, x pass then y pass, rint)            frame  -> mid1 uint8
+//   B  horizontal pass  (Pillow 22-bit fixed point, uint8 intermediate)  mid1   -> mid2 uint8 [rows, S, 3]
+//   C  vertical pass + ToTensor/Normalize lookup + patch-major bf16 (or fp32 CHW) store
+// The coefficient tables are built on the host with the same double-precision arithmetic as
+// OpenCV's computeResizeAreaTab and Pillow's precompute_coeffs, cached per frame geometry.
+#include <math.h>
+
+#include <vector>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+using namespace b200;
+
+namespace {
+
+struct AxisTaps {          // generic "dst <- sum of src taps" table for one axis
+    std::vector<int> start;   // [n_out] first source index
+    std::vector<int> cnt;     // [n_out]
+    std::vector<float> wf;    // [n_out * stride] float weights (area)
+    std::vector<int> wi;      // [n_out * stride] fixed-point weights (Pillow)
+    int stride = 0;
+};
+
+// OpenCV computeResizeAreaTab (modules/imgproc/src/resize.cpp)
+AxisTaps area_taps(int ssize, int dsize) {
+    AxisTaps t;
+    const double inv_scale = dsize / static_cast<double>(ssize);
+    const double scale = 1.0 / inv_scale;
+    t.stride = static_cast<int>(ceil(scale)) + 2;
+    t.start.assign(dsize, 0);
+    t.cnt.assign(dsize, 0);
+    t.wf.assign(static_cast<size_t>(dsize) * t.stride, 0.f);
+    for (int dx = 0; dx < dsize; ++dx) {
+        const double fsx1 = dx * scale;
+        const double fsx2 = fsx1 + scale;
+        const double cell = fmin(scale, ssize - fsx1);
+        int sx1 = static_cast<int>(ceil(fsx1)), sx2 = static_cast<int>(floor(fsx2));
+        sx2 = sx2 < ssize - 1 ? sx2 : ssize - 1;
+        sx1 = sx1 < sx2 ? sx1 : sx2;
+        int n = 0;
+        float* w = &t.wf[static_cast<size_t>(dx) * t.stride];
+        int first = -1;
+        if (sx1 - fsx1 > 1e-3) {
+            first = sx1 - 1;
+            w[n++] = static_cast<float>((sx1 - fsx1) / cell);
+        }
+        for (int sx = sx1; sx < sx2; ++sx) {
+            if (first < 0) first = sx;
+            w[n++] = static_cast<float>(1.0 / cell);
+        }
+        if (fsx2 - sx2 > 1e-3) {
+            if (first < 0) first = sx2;
+            w[n++] = static_cast<float>(fmin(fmin(fsx2 - sx2, 1.0), cell) / cell);
+        }
+        t.start[dx] = first < 0 ? 0 : first;
+        t.cnt[dx] = n;
+    }
+    return t;
+}
+
+double bicubic_filter(double x) {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+}
+double triangle_filter(double x) {
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return 1.0 - x;
+    return 0.0;
+}
+
+// Pillow precompute_coeffs + normalize_coeffs_8bpc (src/libImaging/Resample.c), full-image box.
+AxisTaps pillow_taps(int in_size, int out_size, bool bicubic) {
+    AxisTaps t;
+    const double fsupport = bicubic ? 2.0 : 1.0;
+    const double scale = static_cast<double>(in_size) / out_size;
+    double filterscale = scale;
+    if (filterscale < 1.0) filterscale = 1.0;
+    const double support = fsupport * filterscale;
+    const int ksize = static_cast<int>(ceil(support)) * 2 + 1;
+    t.stride = ksize;
+    t.start.assign(out_size, 0);
+    t.cnt.assign(out_size, 0);
+    t.wi.assign(static_cast<size_t>(out_size) * ksize, 0);
+    std::vector<double> k(ksize);
+    const double ss = 1.0 / filterscale;
+    for (int xx = 0; xx < out_size; ++xx) {
+        const double center = (xx + 0.5) * scale;
+        double ww = 0.0;
+        int xmin = static_cast<int>(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = static_cast<int>(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        for (int x = 0; x < xmax; ++x) {
+            const double arg = (x + xmin - center + 0.5) * ss;
+            const double w = bicubic ? bicubic_filter(arg) : triangle_filter(arg);
+            k[x] = w;
+            ww += w;
+        }
+        for (int x = 0; x < xmax; ++x) {
+            if (ww != 0.0) k[x] /= ww;
+        }
+        int* wi = &t.wi[static_cast<size_t>(xx) * ksize];
+        for (int x = 0; x < xmax; ++x) {
+            if (k[x] < 0)
+                wi[x] = static_cast<int>(-0.5 + k[x] * (1 << 22));
+            else
+                wi[x] = static_cast<int>(0.5 + k[x] * (1 << 22));
+        }
+        t.start[xx] = xmin;
+        t.cnt[xx] = xmax;
+    }
+    return t;
+}
+
+// Device-side view of one axis table, restricted to outputs [o0, o0+n).
+struct DevTaps {
+    const int* start;
+    const int* cnt;
+    const float* wf;
+    const int* wi;
+    int stride;
+};
+
+struct Plan {
+    int H = 0, W = 0, mode = 0;
+    bool has_a = false, has_b = false, has_c = false;
+    bool a_fast = false;     // integer scale factors in both axes (OpenCV ResizeAreaFast path)
+    int a_fx = 1, a_fy = 1;
+    int h1 = 0, w1 = 0;      // size after the area shrink
+    int nw = 0, nh = 0;      // size after the Pillow resize
+    int left = 0, top = 0;   // centre crop
+    int ry0 = 0, ry1 = 0;    // rows of the stage-B input/outputs that stage C needs
+    int rx0 = 0, rx1 = 0;    // columns of the stage-A output that stage B needs
+    DevTaps ax{}, ay{}, bx{}, cy{};
+    size_t mid1_per_frame = 0, mid2_per_frame = 0;
+    std::vector<void*> dev;  // device allocations holding the tables
+};
+
+template <class T>
+const T* upload(b200clip_handle* h, Plan& p, const std::vector<T>& v, int& rc) {
+    if (v.empty()) return nullptr;
+    void* d = nullptr;
+    if (cudaMalloc(&d, v.size() * sizeof(T)) != cudaSuccess) { rc = B200CLIP_E_NOMEM; return nullptr; }
+    if (cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+        rc = B200CLIP_E_CUDA;
+        return nullptr;
+    }
+    p.dev.push_back(d);
+    h->allocs.push_back(d);
+    return static_cast<const T*>(d);
+}
+
+DevTaps upload_taps(b200clip_handle* h, Plan& p, const AxisTaps& t, int& rc) {
+    DevTaps d{};
+    d.start = upload(h, p, t.start, rc);
+    d.cnt = upload(h, p, t.cnt, rc);
+    d.wf = upload(h, p, t.wf, rc);
+    d.wi = upload(h, p, t.wi, rc);
+    d.stride = t.stride;
+    return d;
+}
+
+void taps_range(const AxisTaps& t, int o0, int o1, int& lo, int& hi) {
+    lo = 1 << 30; hi = 0;
+    for (int o = o0; o < o1; ++o) {
+        lo = t.start[o] < lo ? t.start[o] : lo;
+        const int e = t.start[o] + t.cnt[o];
+        hi = e > hi ? e : hi;
+    }
+}
+
+std::map<uint64_t, Plan>& plans(b200clip_handle* h) {
+    if (!h->pre_plans) h->pre_plans = new std::map<uint64_t, Plan>();
+    return *static_cast<std::map<uint64_t, Plan>*>(h->pre_plans);
+}
+
+int py_round_half_even(double v) {  // Python round()
+    return static_cast<int>(nearbyint(v));
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- kernels
+// A: area shrink.  One thread per output pixel (3 channels); taps accumulated in OpenCV's order with
+// unfused fp32 multiply/add.
+__global__ void area_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride,
+                            uint8_t* __restrict__ dst, int64_t dst_frame_stride, int n, int oy0, int ny, int ox0,
+                            int nx, DevTaps ax, DevTaps ay) {
+    const int64_t total = static_cast<int64_t>(n) * ny * nx;
+    for (int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; id < total;
+         id += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(id % nx);
+        const int64_t r = id / nx;
+        const int y = static_cast<int>(r % ny);
+        const int64_t f = r / ny;
+        const int dx = ox0 + x, dy = oy0 + y;
+        const int sx0 = ax.start[dx], cx = ax.cnt[dx];
+        const int sy0 = ay.start[dy], cy = ay.cnt[dy];
+        const float* wx = ax.wf + static_cast<int64_t>(dx) * ax.stride;
+        const float* wy = ay.wf + static_cast<int64_t>(dy) * ay.stride;
+        const uint8_t* base = src + f * frame_stride + static_cast<int64_t>(sx0) * 3;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int j = 0; j < cy; ++j) {
+            const uint8_t* row = base + static_cast<int64_t>(sy0 + j) * row_stride;
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+            for (int i = 0; i < cx; ++i) {
+                const float a = wx[i];
+                b0 = __fadd_rn(b0, __fmul_rn(static_cast<float>(row[i * 3 + 0]), a));
+                b1 = __fadd_rn(b1, __fmul_rn(static_cast<float>(row[i * 3 + 1]), a));
+                b2 = __fadd_rn(b2, __fmul_rn(static_cast<float>(row[i * 3 + 2]), a));
+            }
+            const float beta = wy[j];
+            if (j == 0) {
+                s0 = __fmul_rn(beta, b0); s1 = __fmul_rn(beta, b1); s2 = __fmul_rn(beta, b2);
+            } else {
+                s0 = __fadd_rn(s0, __fmul_rn(beta, b0));
+                s1 = __fadd_rn(s1, __fmul_rn(beta, b1));
+                s2 = __fadd_rn(s2, __fmul_rn(beta, b2));
+            }
+        }
+        uint8_t* o = dst + f * dst_frame_stride + (static_cast<int64_t>(y) * nx + x) * 3;
+        o[0] = static_cast<uint8_t>(min(max(__float2int_rn(s0), 0), 255));
+        o[1] = static_cast<uint8_t>(min(max(__float2int_rn(s1), 0), 255));
+        o[2] = static_cast<uint8_t>(min(max(__float2int_rn(s2), 0), 255));
+    }
+}
+
+// A (integer scale factors): OpenCV ResizeAreaFast -- integer box sum times float(1/area), rint;
+// the 2x2 uint8 case is (a+b+c+d+2)>>2.
+__global__ void area_fast_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride,
+                                 uint8_t* __restrict__ dst, int64_t dst_frame_stride, int n, int oy0, int ny, int ox0,
+                                 int nx, int fx, int fy) {
+    const int64_t total = static_cast<int64_t>(n) * ny * nx;
+    const float inv_area = 1.0f / static_cast<float>(fx * fy);
+    for (int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; id < total;
+         id += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(id % nx);
+        const int64_t r = id / nx;
+        const int y = static_cast<int>(r % ny);
+        const int64_t f = r / ny;
+        const uint8_t* base = src + f * frame_stride + static_cast<int64_t>(oy0 + y) * fy * row_stride +
+                              static_cast<int64_t>(ox0 + x) * fx * 3;
+        int s0 = 0, s1 = 0, s2 = 0;
+        for (int j = 0; j < fy; ++j) {
+            const uint8_t* row = base + j * row_stride;
+            for (int i = 0; i < fx; ++i) { s0 += row[i * 3]; s1 += row[i * 3 + 1]; s2 += row[i * 3 + 2]; }
+        }
+        uint8_t* o = dst + f * dst_frame_stride + (static_cast<int64_t>(y) * nx + x) * 3;
+        if (fx == 2 && fy == 2) {
+            o[0] = static_cast<uint8_t>((s0 + 2) >> 2);
+            o[1] = static_cast<uint8_t>((s1 + 2) >> 2);
+            o[2] = static_cast<uint8_t>((s2 + 2) >> 2);
+        } else {
+            o[0] = static_cast<uint8_t>(min(max(__float2int_rn(__fmul_rn(static_cast<float>(s0), inv_area)), 0), 255));
+            o[1] = static_cast<uint8_t>(min(max(__float2int_rn(__fmul_rn(static_cast<float>(s1), inv_area)), 0), 255));
+            o[2] = static_cast<uint8_t>(min(max(__float2int_rn(__fmul_rn(static_cast<float>(s2), inv_area)), 0), 255));
+        }
+    }
+}
+
+__device__ __forceinline__ uint8_t clip8(int v) {
+    v >>= 22;
+    return static_cast<uint8_t>(min(max(v, 0), 255));
+}
+
+// B: Pillow horizontal pass for output columns [ocol0, ocol0+S) on rows [0, ny) of the (possibly compacted)
+// source whose column 0 is absolute column src_x0.
+__global__ void hpass_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride, int src_x0,
+                             uint8_t* __restrict__ dst, int64_t dst_frame_stride, int n, int ny, int ocol0, int S,
+                             DevTaps bx) {
+    const int64_t total = static_cast<int64_t>(n) * ny * S;
+    for (int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; id < total;
+         id += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(id % S);
+        const int64_t r = id / S;
+        const int y = static_cast<int>(r % ny);
+        const int64_t f = r / ny;
+        const int ox = ocol0 + x;
+        const int lo = bx.start[ox], cnt = bx.cnt[ox];
+        const int* k = bx.wi + static_cast<int64_t>(ox) * bx.stride;
+        const uint8_t* p = src + f * frame_stride + static_cast<int64_t>(y) * row_stride +
+                           static_cast<int64_t>(lo - src_x0) * 3;
+        int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+        for (int i = 0; i < cnt; ++i) {
+            const int kk = k[i];
+            a0 += kk * p[i * 3]; a1 += kk * p[i * 3 + 1]; a2 += kk * p[i * 3 + 2];
+        }
+        uint8_t* o = dst + f * dst_frame_stride + (static_cast<int64_t>(y) * S + x) * 3;
+        o[0] = clip8(a0); o[1] = clip8(a1); o[2] = clip8(a2);
+    }
+}
+
+// C: vertical pass (or plain crop) + ToTensor/Normalize lookup + store.  One thread per 8 output pixels of one
+// output row (all 3 channels): 24 contiguous source bytes per tap.  Output either bf16 patch-major rows
+// (col = c*P*P + y*P + x, patch_k padded) or fp32 CHW.
+__global__ void vpass_store_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride,
+                                   int src_y0, int src_x0, int has_v, int top, DevTaps cy, int n, int S, int P,
+                                   int grid, int patch_k, const float* __restrict__ lut /*[3][256]*/,
+                                   bf16* __restrict__ patches, float* __restrict__ chw) {
+    __shared__ float s_lut[768];
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+    __syncthreads();
+    const int xchunks = (S + 7) >> 3;
+    const int64_t total = static_cast<int64_t>(n) * S * xchunks;
+    for (int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; id < total;
+         id += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int xc = static_cast<int>(id % xchunks);
+        const int64_t r = id / xchunks;
+        const int oy = static_cast<int>(r % S);
+        const int64_t f = r / S;
+        const int x0 = xc << 3;
+        const int npx = min(8, S - x0);
+        uint8_t u[24];
+        const uint8_t* fbase = src + f * frame_stride + static_cast<int64_t>(x0 - src_x0) * 3;
+        if (has_v) {
+            const int o = top + oy;
+            const int lo = cy.start[o], cnt = cy.cnt[o];
+            const int* k = cy.wi + static_cast<int64_t>(o) * cy.stride;
+            int acc[24];
+#pragma unroll
+            for (int j = 0; j < 24; ++j) acc[j] = 1 << 21;
+            for (int i = 0; i < cnt; ++i) {
+                const uint8_t* p = fbase + static_cast<int64_t>(lo + i - src_y0) * row_stride;
+                const int kk = k[i];
+#pragma unroll
+                for (int j = 0; j < 24; ++j)
+                    if (j < npx * 3) acc[j] += kk * p[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 24; ++j) u[j] = clip8(acc[j]);
+        } else {
+            const uint8_t* p = fbase + static_cast<int64_t>(top + oy - src_y0) * row_stride;
+#pragma unroll
+            for (int j = 0; j < 24; ++j) u[j] = (j < npx * 3) ? p[j] : 0;
+        }
+        if (patches) {
+            const int py = oy / P, yy = oy - py * P;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                // the 8 pixels may straddle a patch boundary when P is not a multiple of 8 -> element stores
+                const int px0 = x0 / P;
+                const bool one_patch = (npx == 8) && ((x0 + 7) / P == px0) && (((x0 - px0 * P) & 7) == 0) && ((P & 7) == 0);
+                if (one_patch) {
+                    uint4 o;
+                    o.x = pack_bf16x2(s_lut[c * 256 + u[0 * 3 + c]], s_lut[c * 256 + u[1 * 3 + c]]);
+                    o.y = pack_bf16x2(s_lut[c * 256 + u[2 * 3 + c]], s_lut[c * 256 + u[3 * 3 + c]]);
+                    o.z = pack_bf16x2(s_lut[c * 256 + u[4 * 3 + c]], s_lut[c * 256 + u[5 * 3 + c]]);
+                    o.w = pack_bf16x2(s_lut[c * 256 + u[6 * 3 + c]], s_lut[c * 256 + u[7 * 3 + c]]);
+                    const int64_t row = (f * grid + py) * grid + px0;
+                    *reinterpret_cast<uint4*>(patches + row * patch_k + c * P * P + yy * P + (x0 - px0 * P)) = o;
+                } else {
+                    for (int j = 0; j < npx; ++j) {
+                        const int x = x0 + j;
+                        const int px = x / P, xx = x - px * P;
+                        if (px < grid && py < grid) {
+                            const int64_t row = (f * grid + py) * grid + px;
+                            patches[row * patch_k + c * P * P + yy * P + xx] =
+                                __float2bfloat16(s_lut[c * 256 + u[j * 3 + c]]);
+                        }
+                    }
+                }
+            }
+        }
+        if (chw) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float* o = chw + ((f * 3 + c) * S + oy) * S + x0;
+                for (int j = 0; j < npx; ++j) o[j] = s_lut[c * 256 + u[j * 3 + c]];
+            }
+        }
+    }
+}
+
+// zero the K padding columns of the patch rows (only when 3*P*P is not a multiple of 64, e.g. P = 14)
+__global__ void zero_pad_kernel(bf16* __restrict__ patches, int64_t rows, int kk, int patch_k) {
+    const int pad = patch_k - kk;
+    const int64_t total = rows * pad;
+    for (int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; id < total;
+         id += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = id / pad;
+        patches[r * patch_k + kk + (id - r * pad)] = __float2bfloat16(0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+static int build_plan(b200clip_handle* h, int H, int W, int mode, Plan& p) {
+    const int S = h->cfg.image_size;
+    p.H = H; p.W = W; p.mode = mode;
+    int rc = 0;
+    // stage A geometry (reference mode only): memory_manager.py:304-312
+    int h1 = H, w1 = W;
+    if (mode == B200CLIP_RESIZE_REFERENCE) {
+        const double sw = 512.0 / W, sh = 512.0 / H;
+        double scale = sw < sh ? sw : sh;
+        if (scale > 1.0) scale = 1.0;
+        if (scale < 1.0) {
+            w1 = static_cast<int>(W * scale);
+            h1 = static_cast<int>(H * scale);
+            p.has_a = true;
+        }
+    }
+    if (h1 <= 0 || w1 <= 0) return b200_fail(h, B200CLIP_E_SHAPE, "preprocess: degenerate frame %dx%d", W, H);
+    p.h1 = h1; p.w1 = w1;
+    // torchvision Resize(S): shortest side -> S, long side int(S * long / short)
+    if (w1 <= h1) { p.nw = S; p.nh = static_cast<int>(static_cast<double>(S) * h1 / w1); }
+    else { p.nh = S; p.nw = static_cast<int>(static_cast<double>(S) * w1 / h1); }
+    p.left = py_round_half_even((p.nw - S) / 2.0);
+    p.top = py_round_half_even((p.nh - S) / 2.0);
+    p.has_b = p.nw != w1;
+    p.has_c = p.nh != h1;
+    const bool bicubic = mode != B200CLIP_RESIZE_BILINEAR_AA;
+    AxisTaps bx, cy, ax, ay;
+    if (p.has_c) {
+        cy = pillow_taps(h1, p.nh, bicubic);
+        taps_range(cy, p.top, p.top + S, p.ry0, p.ry1);
+    } else {
+        p.ry0 = p.top; p.ry1 = p.top + S;
+    }
+    if (p.has_b) {
+        bx = pillow_taps(w1, p.nw, bicubic);
+        taps_range(bx, p.left, p.left + S, p.rx0, p.rx1);
+    } else {
+        p.rx0 = p.left; p.rx1 = p.left + S;
+    }
+    if (p.has_a) {
+        const double scx = 1.0 / (w1 / static_cast<double>(W)), scy = 1.0 / (h1 / static_cast<double>(H));
+        const int ix = static_cast<int>(scx), iy = static_cast<int>(scy);
+        p.a_fast = fabs(scx - ix) < 2.220446049250313e-16 && fabs(scy - iy) < 2.220446049250313e-16;
+        p.a_fx = ix; p.a_fy = iy;
+        if (!p.a_fast) {
+            ax = area_taps(W, w1);
+            ay = area_taps(H, h1);
+        }
+    }
+    p.ax = upload_taps(h, p, ax, rc);
+    p.ay = upload_taps(h, p, ay, rc);
+    p.bx = upload_taps(h, p, bx, rc);
+    p.cy = upload_taps(h, p, cy, rc);
+    if (rc) return b200_fail(h, rc, "preprocess: uploading resize tables failed");
+    p.mid1_per_frame = p.has_a ? static_cast<size_t>(p.ry1 - p.ry0) * (p.rx1 - p.rx0) * 3 : 0;
+    p.mid2_per_frame = p.has_b ? static_cast<size_t>(p.ry1 - p.ry0) * S * 3 : 0;
+    // 16-byte align the per-frame strides
+    p.mid1_per_frame = (p.mid1_per_frame + 15) & ~size_t(15);
+    p.mid2_per_frame = (p.mid2_per_frame + 15) & ~size_t(15);
+    return 0;
+}
+
+void preprocess_free_plans(b200clip_handle* h) {
+    // the device tables themselves are owned by h->allocs
+    delete static_cast<std::map<uint64_t, Plan>*>(h->pre_plans);
+    h->pre_plans = nullptr;
+}
+
+static float* get_lut(b200clip_handle* h) {
+    if (h->pre_lut) return h->pre_lut;
+    // ToTensor (/255) then Normalize ((x - mean) / std) in fp32, exactly as torch evaluates it
+    const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+    const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+    std::vector<float> t(768);
+    for (int c = 0; c < 3; ++c)
+        for (int u = 0; u < 256; ++u) {
+            volatile float x = static_cast<float>(u) / 255.0f;
+            volatile float d = x - mean[c];
+            t[c * 256 + u] = d / stdv[c];
+        }
+    float* d = nullptr;
+    if (cudaMalloc(&d, 768 * sizeof(float)) != cudaSuccess) return nullptr;
+    cudaMemcpy(d, t.data(), 768 * sizeof(float), cudaMemcpyHostToDevice);
+    h->allocs.push_back(d);
+    h->pre_lut = d;
+    return d;
+}
+
+static unsigned grid_for(b200clip_handle* h, int64_t total, int threads) {
+    int64_t b = (total + threads - 1) / threads;
+    const int64_t cap = static_cast<int64_t>(h->num_sms) * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<unsigned>(b);
+}
+
+int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
+                      int64_t row_stride, int mode, bf16* patches, float* chw, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (mode != B200CLIP_RESIZE_REFERENCE && mode != B200CLIP_RESIZE_BILINEAR_AA && mode != B200CLIP_RESIZE_BICUBIC)
+        return b200_fail(h, B200CLIP_E_ARG, "preprocess: unknown resize mode %d", mode);
+    if (H <= 0 || W <= 0 || row_stride < static_cast<int64_t>(W) * 3 || frame_stride < row_stride * H)
+        return b200_fail(h, B200CLIP_E_ARG, "preprocess: bad frame geometry %dx%d strides %lld/%lld", W, H,
+                         (long long)row_stride, (long long)frame_stride);
+    const int S = h->cfg.image_size, P = h->cfg.patch;
+    const uint64_t key = (static_cast<uint64_t>(H) << 34) | (static_cast<uint64_t>(W) << 4) | static_cast<uint64_t>(mode);
+    auto& pl = plans(h);
+    auto it = pl.find(key);
+    if (it == pl.end()) {
+        Plan p;
+        int rc = build_plan(h, H, W, mode, p);
+        if (rc) return rc;
+        it = pl.emplace(key, std::move(p)).first;
+    }
+    const Plan& p = it->second;
+    float* lut = get_lut(h);
+    if (!lut) return b200_fail(h, B200CLIP_E_NOMEM, "preprocess: LUT allocation failed");
+    // intermediates
+    const size_t need = (p.mid1_per_frame + p.mid2_per_frame) * static_cast<size_t>(n);
+    if (need > h->ws_pre_bytes) {
+        B200_CUDA(h, cudaStreamSynchronize(st));
+        if (h->ws_pre) cudaFree(h->ws_pre);
+        h->ws_pre = nullptr; h->ws_pre_bytes = 0;
+        B200_CUDA(h, cudaMalloc(&h->ws_pre, need));
+        h->ws_pre_bytes = need;
+    }
+    uint8_t* mid1 = h->ws_pre;
+    uint8_t* mid2 = h->ws_pre + p.mid1_per_frame * static_cast<size_t>(n);
+
+    const uint8_t* cur = frames;
+    int64_t cur_fs = frame_stride, cur_rs = row_stride;
+    int cur_x0 = 0, cur_y0 = 0;  // absolute (stage-coordinate) position of cur's element (0,0)
+    if (p.has_a) {
+        const int ny = p.ry1 - p.ry0, nx = p.rx1 - p.rx0;
+        const int64_t total = static_cast<int64_t>(n) * ny * nx;
+        if (p.a_fast)
+            area_fast_kernel<<<grid_for(h, total, 256), 256, 0, st>>>(cur, cur_fs, cur_rs, mid1, p.mid1_per_frame, n,
+                                                                      p.ry0, ny, p.rx0, nx, p.a_fx, p.a_fy);
+        else
+            area_kernel<<<grid_for(h, total, 256), 256, 0, st>>>(cur, cur_fs, cur_rs, mid1, p.mid1_per_frame, n, p.ry0,
+                                                                 ny, p.rx0, nx, p.ax, p.ay);
+        h->launches++;
+        cur = mid1; cur_fs = p.mid1_per_frame; cur_rs = static_cast<int64_t>(nx) * 3;
+        cur_x0 = p.rx0; cur_y0 = p.ry0;
+    }
+    if (p.has_b) {
+        const int ny = p.ry1 - p.ry0;
+        // rows [ry0, ry1) of cur: shift the base pointer so that row 0 of the kernel == row ry0
+        const uint8_t* base = cur + static_cast<int64_t>(p.ry0 - cur_y0) * cur_rs;
+        const int64_t total = static_cast<int64_t>(n) * ny * S;
+        hpass_kernel<<<grid_for(h, total, 256), 256, 0, st>>>(base, cur_fs, cur_rs, cur_x0, mid2, p.mid2_per_frame, n,
+                                                              ny, p.left, S, p.bx);
+        h->launches++;
+        cur = mid2; cur_fs = p.mid2_per_frame; cur_rs = static_cast<int64_t>(S) * 3;
+        cur_x0 = 0 /* column 0 of mid2 is output column `left`, handled below */; cur_y0 = p.ry0;
+    }
+    {
+        // stage C reads output-column x0 at cur column (x0 + xoff - cur_x0): after B the crop is already applied
+        const int src_x0 = p.has_b ? 0 : cur_x0 - p.left;  // so that (x0 - src_x0) = x0 + left - cur_x0
+        const int64_t total = static_cast<int64_t>(n) * S * ((S + 7) >> 3);
+        vpass_store_kernel<<<grid_for(h, total, 128), 128, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, src_x0, p.has_c ? 1 : 0,
+                                                                    p.top, p.cy, n, S, P, h->grid, h->patch_k, lut,
+                                                                    patches, chw);
+        h->launches++;
+    }
+    if (patches && h->patch_k != 3 * P * P) {
+        const int64_t rows = static_cast<int64_t>(n) * h->grid * h->grid;
+        zero_pad_kernel<<<grid_for(h, rows * (h->patch_k - 3 * P * P), 256), 256, 0, st>>>(patches, rows, 3 * P * P,
+                                                                                          h->patch_k);
+        h->launches++;
+    }
+    B200_CUDA(h, cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,329 @@
+// K4: image x text cosine scores fused with top-k, threshold and clip-interval emission.
+//
+// Replaces (reference file:line)
+//   OpenCLIPModel.compute_similarity          src/models/openclip_model.py:212-214   (np.dot)
+//   np.argsort(s)[::-1][:top_k] + threshold   src/pipeline/phase1_mvp.py:145-155     (ties -> higher index first)
+//   extract_clip_with_padding / extract_clip  src/services/clip_extractor.py:175-183, 94-111 (interval clamps)
+// restated in oracle/phase1_ref.py.
+//
+// This is the HBM-bound form (few queries): every embedding row is streamed once with 128-bit loads, each
+// warp keeps a sorted top-k list per query (entries spread over lanes, inserted with ballot + shuffle), lists
+// are merged per CTA and then by a final kernel that also applies the threshold and writes the intervals.
+// The same final kernel merges candidate lists gathered from other ranks (multi-GPU path).
+#include <math.h>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+using namespace b200;
+
+constexpr int SIM_WARPS = 8;
+constexpr int SIM_QTILE = 16;   // queries per pass of the streaming kernel
+constexpr int SIM_MAXK = 32;
+
+__device__ __forceinline__ bool beats(float sa, int ia, float sb, int ib) {
+    // descending score; equal scores -> higher index first (np.argsort(...)[::-1])
+    return sa > sb || (sa == sb && ia > ib);
+}
+
+// Insert (s, i) into a sorted list of k entries held in shared memory; lane j owns entry j.
+__device__ __forceinline__ void warp_insert(float* ls, int* li, int k, float s, int i, int lane) {
+    const float es = lane < k ? ls[lane] : 0.f;
+    const int ei = lane < k ? li[lane] : 0;
+    const bool ahead = lane < k && beats(es, ei, s, i);
+    const int p = __popc(__ballot_sync(0xffffffffu, ahead));  // entries that stay in front
+    const float ps = __shfl_up_sync(0xffffffffu, es, 1);
+    const int pi = __shfl_up_sync(0xffffffffu, ei, 1);
+    if (lane < k) {
+        if (lane == p) { ls[lane] = s; li[lane] = i; }
+        else if (lane > p) { ls[lane] = ps; li[lane] = pi; }
+    }
+    __syncwarp();
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(SIM_WARPS * 32)
+sim_stream_kernel(const void* __restrict__ img, int64_t n, int e, const float* __restrict__ txt, int q0, int qn,
+                  int q_total, int k, float* __restrict__ scores_out, float* __restrict__ part_s,
+                  int* __restrict__ part_i) {
+    extern __shared__ __align__(16) float sm[];
+    float* sq = sm;                                                  // [qn][e]
+    float* ls = sq + static_cast<size_t>(qn) * e;                    // [SIM_WARPS][qn][k]
+    int* li = reinterpret_cast<int*>(ls + static_cast<size_t>(SIM_WARPS) * qn * k);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < qn * e; i += blockDim.x) sq[i] = txt[static_cast<size_t>(q0) * e + i];
+    for (int i = threadIdx.x; i < SIM_WARPS * qn * k; i += blockDim.x) { ls[i] = -INFINITY; li[i] = -1; }
+    __syncthreads();
+    float* wls = ls + static_cast<size_t>(warp) * qn * k;
+    int* wli = li + static_cast<size_t>(warp) * qn * k;
+
+    constexpr int VEC = BF16 ? 8 : 4;
+    const int chunks = e / VEC;                  // 16-byte chunks per row
+    const int64_t warps_total = static_cast<int64_t>(gridDim.x) * SIM_WARPS;
+    const int64_t wid = static_cast<int64_t>(blockIdx.x) * SIM_WARPS + warp;
+    constexpr int MAXC = BF16 ? 4 : 8;           // e <= 1024
+    for (int64_t row = wid * 2; row < n; row += warps_total * 2) {
+        // two rows in flight per warp
+        uint4 d0[MAXC], d1[MAXC];
+        const bool has1 = row + 1 < n;
+        const uint4* r0 = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(img) +
+                                                         row * static_cast<int64_t>(e) * (BF16 ? 2 : 4));
+        const uint4* r1 = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(img) +
+                                                         (row + (has1 ? 1 : 0)) * static_cast<int64_t>(e) * (BF16 ? 2 : 4));
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) {
+            const int c = lane + j * 32;
+            if (c < chunks) { d0[j] = __ldg(r0 + c); d1[j] = __ldg(r1 + c); }
+        }
+        for (int qi = 0; qi < qn; ++qi) {
+            const float* qv = sq + static_cast<size_t>(qi) * e;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < MAXC; ++j) {
+                const int c = lane + j * 32;
+                if (c < chunks) {
+                    const float4 t0 = *reinterpret_cast<const float4*>(qv + c * VEC);
+                    if (BF16) {
+                        const float4 t1 = *reinterpret_cast<const float4*>(qv + c * VEC + 4);
+                        float2 f;
+                        f = unpack_bf16x2(d0[j].x); a0 = fmaf(f.x, t0.x, a0); a0 = fmaf(f.y, t0.y, a0);
+                        f = unpack_bf16x2(d0[j].y); a0 = fmaf(f.x, t0.z, a0); a0 = fmaf(f.y, t0.w, a0);
+                        f = unpack_bf16x2(d0[j].z); a0 = fmaf(f.x, t1.x, a0); a0 = fmaf(f.y, t1.y, a0);
+                        f = unpack_bf16x2(d0[j].w); a0 = fmaf(f.x, t1.z, a0); a0 = fmaf(f.y, t1.w, a0);
+                        f = unpack_bf16x2(d1[j].x); a1 = fmaf(f.x, t0.x, a1); a1 = fmaf(f.y, t0.y, a1);
+                        f = unpack_bf16x2(d1[j].y); a1 = fmaf(f.x, t0.z, a1); a1 = fmaf(f.y, t0.w, a1);
+                        f = unpack_bf16x2(d1[j].z); a1 = fmaf(f.x, t1.x, a1); a1 = fmaf(f.y, t1.y, a1);
+                        f = unpack_bf16x2(d1[j].w); a1 = fmaf(f.x, t1.z, a1); a1 = fmaf(f.y, t1.w, a1);
+                    } else {
+                        a0 = fmaf(__uint_as_float(d0[j].x), t0.x, a0); a0 = fmaf(__uint_as_float(d0[j].y), t0.y, a0);
+                        a0 = fmaf(__uint_as_float(d0[j].z), t0.z, a0); a0 = fmaf(__uint_as_float(d0[j].w), t0.w, a0);
+                        a1 = fmaf(__uint_as_float(d1[j].x), t0.x, a1); a1 = fmaf(__uint_as_float(d1[j].y), t0.y, a1);
+                        a1 = fmaf(__uint_as_float(d1[j].z), t0.z, a1); a1 = fmaf(__uint_as_float(d1[j].w), t0.w, a1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            }
+            if (scores_out && lane == 0) {
+                scores_out[row * q_total + q0 + qi] = a0;
+                if (has1) scores_out[(row + 1) * q_total + q0 + qi] = a1;
+            }
+            if (k > 0) {
+                float* l_s = wls + qi * k;
+                int* l_i = wli + qi * k;
+                if (beats(a0, static_cast<int>(row), l_s[k - 1], l_i[k - 1]))
+                    warp_insert(l_s, l_i, k, a0, static_cast<int>(row), lane);
+                if (has1 && beats(a1, static_cast<int>(row + 1), l_s[k - 1], l_i[k - 1]))
+                    warp_insert(l_s, l_i, k, a1, static_cast<int>(row + 1), lane);
+            }
+        }
+    }
+    if (k == 0) return;
+    __syncthreads();
+    // merge the SIM_WARPS lists of each query into warp 0's slot, queries round-robin over warps
+    for (int qi = warp; qi < qn; qi += SIM_WARPS) {
+        float* dst_s = ls + qi * k;   // warp 0's list for query qi
+        int* dst_i = li + qi * k;
+        for (int w = 1; w < SIM_WARPS; ++w) {
+            const float* src_s = ls + (static_cast<size_t>(w) * qn + qi) * k;
+            const int* src_i = li + (static_cast<size_t>(w) * qn + qi) * k;
+            for (int j = 0; j < k; ++j) {
+                const float s = src_s[j];
+                const int i = src_i[j];
+                if (i < 0) break;
+                if (!beats(s, i, dst_s[k - 1], dst_i[k - 1])) break;  // sorted: nothing further can enter
+                warp_insert(dst_s, dst_i, k, s, i, lane);
+            }
+        }
+        if (lane < k) {
+            part_s[(static_cast<size_t>(blockIdx.x) * q_total + q0 + qi) * k + lane] = dst_s[lane];
+            part_i[(static_cast<size_t>(blockIdx.x) * q_total + q0 + qi) * k + lane] = dst_i[lane];
+        }
+    }
+}
+
+// Final merge: one CTA per query merges g sorted candidate lists, applies the threshold and emits intervals.
+// IDX64: candidates carry int64 global indices (multi-GPU merge) instead of int32 local ones.
+template <bool IDX64>
+__global__ void __launch_bounds__(SIM_WARPS * 32)
+topk_final_kernel(const float* __restrict__ cand_s, const void* __restrict__ cand_i, int g, int q_total, int k,
+                  float thr, const double* __restrict__ ts, int64_t index_base, double clip_dur, double vid_dur,
+                  float* __restrict__ top_s, int64_t* __restrict__ top_i, double* __restrict__ intervals,
+                  int32_t* __restrict__ counts) {
+    __shared__ float ls[SIM_WARPS][SIM_MAXK];
+    __shared__ long long gi[SIM_WARPS][SIM_MAXK];  // candidate index, the tie-break key
+    const int q = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < k) { ls[warp][lane] = -INFINITY; gi[warp][lane] = -1; }
+    __syncwarp();
+    auto cand_index = [&](int list, int j) -> long long {
+        const size_t off = (static_cast<size_t>(list) * q_total + q) * k + j;
+        return IDX64 ? static_cast<const long long*>(cand_i)[off] : static_cast<long long>(static_cast<const int*>(cand_i)[off]);
+    };
+    // 64-bit aware insert (tie-break on the global index)
+    auto insert = [&](int w, float s, long long idx) {
+        const float es = lane < k ? ls[w][lane] : 0.f;
+        const long long ei = lane < k ? gi[w][lane] : 0;
+        const bool ahead = lane < k && (es > s || (es == s && ei > idx));
+        const int p = __popc(__ballot_sync(0xffffffffu, ahead));
+        const float ps = __shfl_up_sync(0xffffffffu, es, 1);
+        const long long pi = __shfl_up_sync(0xffffffffu, ei, 1);
+        if (lane < k) {
+            if (lane == p) { ls[w][lane] = s; gi[w][lane] = idx; }
+            else if (lane > p) { ls[w][lane] = ps; gi[w][lane] = pi; }
+        }
+        __syncwarp();
+    };
+    for (int list = warp; list < g; list += SIM_WARPS) {
+        for (int j = 0; j < k; ++j) {
+            const float s = cand_s[(static_cast<size_t>(list) * q_total + q) * k + j];
+            const long long idx = cand_index(list, j);
+            if (idx < 0) break;
+            const float ws = ls[warp][k - 1];
+            const long long wi = gi[warp][k - 1];
+            if (!(s > ws || (s == ws && idx > wi))) break;
+            insert(warp, s, idx);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < SIM_WARPS; ++w) {
+            for (int j = 0; j < k; ++j) {
+                const float s = ls[w][j];
+                const long long idx = gi[w][j];
+                if (idx < 0) break;
+                const float ws = ls[0][k - 1];
+                const long long wi = gi[0][k - 1];
+                if (!(s > ws || (s == ws && idx > wi))) break;
+                insert(0, s, idx);
+            }
+        }
+        if (lane < k) {
+            const float s = ls[0][lane];
+            const long long idx = gi[0][lane];
+            const long long gidx = idx < 0 ? -1 : idx + index_base;
+            const size_t o = static_cast<size_t>(q) * k + lane;
+            top_s[o] = s;
+            top_i[o] = gidx;
+            double start = 0.0, end = 0.0;
+            if (gidx >= 0) {
+                // clip_extractor.py:175-183 then :94-111
+                const double t = ts ? ts[gidx] : static_cast<double>(gidx);
+                start = fmax(0.0, t - clip_dur / 2);
+                end = t + clip_dur / 2;
+                if (end <= start) end = start + 5.0;
+                if (vid_dur > 0.0) {
+                    if (start >= vid_dur) { start = fmax(0.0, vid_dur - 5.0); end = vid_dur; }
+                    else if (end > vid_dur) end = vid_dur;
+                }
+            }
+            if (intervals) { intervals[o * 2] = start; intervals[o * 2 + 1] = end; }
+        }
+        const bool pass = lane < k && gi[0][lane] >= 0 && ls[0][lane] >= thr;
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (lane == 0 && counts) counts[q] = __popc(m);
+    }
+}
+
+static int sim_grid(b200clip_handle* h, int64_t n) {
+    int64_t g = (n + SIM_WARPS * 2 - 1) / (SIM_WARPS * 2);
+    const int64_t cap = static_cast<int64_t>(h->num_sms) * 4;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+static int run_stream(b200clip_handle* h, const void* img, int dtype, int64_t n, int e, const float* txt, int q,
+                      int k, float* scores, float* part_s, int* part_i, int grid, cudaStream_t st) {
+    for (int q0 = 0; q0 < q; q0 += SIM_QTILE) {
+        const int qn = (q - q0) < SIM_QTILE ? (q - q0) : SIM_QTILE;
+        const size_t smem = static_cast<size_t>(qn) * e * 4 + static_cast<size_t>(SIM_WARPS) * qn * (k > 0 ? k : 0) * 8;
+        if (dtype == B200CLIP_BF16) {
+            static bool set = false;
+            if (!set) {
+                B200_CUDA(h, cudaFuncSetAttribute(sim_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  160 * 1024));
+                set = true;
+            }
+            sim_stream_kernel<true><<<grid, SIM_WARPS * 32, smem, st>>>(img, n, e, txt, q0, qn, q, k, scores, part_s, part_i);
+        } else {
+            static bool set = false;
+            if (!set) {
+                B200_CUDA(h, cudaFuncSetAttribute(sim_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  160 * 1024));
+                set = true;
+            }
+            sim_stream_kernel<false><<<grid, SIM_WARPS * 32, smem, st>>>(img, n, e, txt, q0, qn, q, k, scores, part_s, part_i);
+        }
+        h->launches++;
+    }
+    B200_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+static int check_sim_args(b200clip_handle* h, const void* img, int dtype, int64_t n, int e, const float* txt, int q) {
+    if ((!img && n > 0) || !txt) return b200_fail(h, B200CLIP_E_ARG, "similarity: null embedding pointer");
+    if (dtype != B200CLIP_F32 && dtype != B200CLIP_BF16) return b200_fail(h, B200CLIP_E_ARG, "similarity: bad dtype");
+    if (n < 0 || n >= (int64_t(1) << 31)) return b200_fail(h, B200CLIP_E_SHAPE, "similarity: n out of range");
+    if (e <= 0 || e % 8 != 0 || e > 1024) return b200_fail(h, B200CLIP_E_SHAPE, "similarity: e must be a multiple of 8, <= 1024");
+    if (q <= 0) return b200_fail(h, B200CLIP_E_ARG, "similarity: q must be positive");
+    return 0;
+}
+
+int launch_similarity(b200clip_handle* h, const void* img, int dtype, int64_t n, int e, const float* txt, int q,
+                      float* scores, cudaStream_t st) {
+    int rc = check_sim_args(h, img, dtype, n, e, txt, q);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    return run_stream(h, img, dtype, n, e, txt, q, 0, scores, nullptr, nullptr, sim_grid(h, n), st);
+}
+
+int launch_sim_topk(b200clip_handle* h, const void* img, int dtype, int64_t n, int e, const float* txt, int q, int k,
+                    float thr, const double* ts, int64_t index_base, double clip_dur, double vid_dur,
+                    float* top_scores, int64_t* top_idx, double* intervals, int32_t* counts, cudaStream_t st) {
+    int rc = check_sim_args(h, img, dtype, n, e, txt, q);
+    if (rc) return rc;
+    if (k <= 0 || k > SIM_MAXK) return b200_fail(h, B200CLIP_E_SHAPE, "sim_topk: k must be in [1, %d]", SIM_MAXK);
+    if (!top_scores || !top_idx) return b200_fail(h, B200CLIP_E_ARG, "sim_topk: null output");
+    const int grid = sim_grid(h, n > 0 ? n : 1);
+    const size_t need = static_cast<size_t>(grid) * q * k * 8;
+    if (need > h->ws_topk_bytes) {
+        B200_CUDA(h, cudaStreamSynchronize(st));
+        if (h->ws_topk) cudaFree(h->ws_topk);
+        h->ws_topk = nullptr; h->ws_topk_bytes = 0;
+        B200_CUDA(h, cudaMalloc(&h->ws_topk, need));
+        h->ws_topk_bytes = need;
+    }
+    float* part_s = static_cast<float*>(h->ws_topk);
+    int* part_i = reinterpret_cast<int*>(part_s + static_cast<size_t>(grid) * q * k);
+    int g = grid;
+    if (n == 0) {
+        // no rows: one empty list
+        B200_CUDA(h, cudaMemsetAsync(part_i, 0xff, static_cast<size_t>(q) * k * 4, st));
+        B200_CUDA(h, cudaMemsetAsync(part_s, 0, static_cast<size_t>(q) * k * 4, st));
+        g = 1;
+    } else {
+        rc = run_stream(h, img, dtype, n, e, txt, q, k, nullptr, part_s, part_i, grid, st);
+        if (rc) return rc;
+    }
+    topk_final_kernel<false><<<q, SIM_WARPS * 32, 0, st>>>(part_s, part_i, g, q, k, thr, ts, index_base, clip_dur,
+                                                          vid_dur, top_scores, top_idx, intervals, counts);
+    h->launches++;
+    B200_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+int launch_topk_merge(b200clip_handle* h, const float* cs, const int64_t* ci, int g, int q, int k, float thr,
+                      const double* ts, double clip_dur, double vid_dur, float* top_scores, int64_t* top_idx,
+                      double* intervals, int32_t* counts, cudaStream_t st) {
+    if (!cs || !ci || !top_scores || !top_idx) return b200_fail(h, B200CLIP_E_ARG, "topk_merge: null argument");
+    if (g <= 0 || q <= 0 || k <= 0 || k > SIM_MAXK) return b200_fail(h, B200CLIP_E_SHAPE, "topk_merge: bad g/q/k");
+    topk_final_kernel<true><<<q, SIM_WARPS * 32, 0, st>>>(cs, ci, g, q, k, thr, ts, 0, clip_dur, vid_dur, top_scores,
+                                                         top_idx, intervals, counts);
+    h->launches++;
+    B200_CUDA(h, cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,521 @@
+// Non-GEMM kernels of the ViT / text towers: LayerNorm, small-sequence attention, the fused
+// ln_post + projection + L2-normalise head, fp32-CHW patchify and the text token embedding.
+// Semantics follow open_clip's VisionTransformer / TextTransformer as restated in oracle/clip_ref.py
+// (reference call sites: src/models/openclip_model.py:177-178,196-197,205-209).
+#include "internal.h"
+#include "ptx.cuh"
+
+using namespace b200;
+
+// ============================================================================ LayerNorm
+// One warp per row, row kept in registers (width <= 1024, multiple of 8), fp32 statistics
+// (biased variance, eps inside the sqrt -- torch.nn.functional.layer_norm).
+// If t_per_img > 0, rows with row % t_per_img == 0 take their input from cls_row (fp32 [width]):
+// that is how `class_embedding + positional_embedding[0]` enters the sequence without a concat.
+constexpr int LN_WARPS = 8;
+constexpr int LN_MAXV = 4;  // uint4 (8 bf16) per lane
+
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 bf16* __restrict__ y, int64_t rows, int width, float eps, int t_per_img,
+                 const float* __restrict__ cls_row) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int nvec = width >> 3;
+    float v[LN_MAXV][8];
+    const bool from_cls = t_per_img > 0 && (row % t_per_img) == 0;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * width);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < nvec) {
+            if (from_cls) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(cls_row) + idx * 2);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(cls_row) + idx * 2 + 1);
+                v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+                v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+            } else {
+                const uint4 u = xr[idx];
+                float2 f;
+                f = unpack_bf16x2(u.x); v[i][0] = f.x; v[i][1] = f.y;
+                f = unpack_bf16x2(u.y); v[i][2] = f.x; v[i][3] = f.y;
+                f = unpack_bf16x2(u.z); v[i][4] = f.x; v[i][5] = f.y;
+                f = unpack_bf16x2(u.w); v[i][6] = f.x; v[i][7] = f.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum += v[i][j];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / width;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        if (lane + i * 32 < nvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = v[i][j] - mean;
+                sq += d * d;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / width + eps);
+    uint4* yr = reinterpret_cast<uint4*>(y + row * width);
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < nvec) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + idx * 2);
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + idx * 2 + 1);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + idx * 2);
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + idx * 2 + 1);
+            uint4 o;
+            o.x = pack_bf16x2((v[i][0] - mean) * rstd * g0.x + b0.x, (v[i][1] - mean) * rstd * g0.y + b0.y);
+            o.y = pack_bf16x2((v[i][2] - mean) * rstd * g0.z + b0.z, (v[i][3] - mean) * rstd * g0.w + b0.w);
+            o.z = pack_bf16x2((v[i][4] - mean) * rstd * g1.x + b1.x, (v[i][5] - mean) * rstd * g1.y + b1.y);
+            o.w = pack_bf16x2((v[i][6] - mean) * rstd * g1.z + b1.z, (v[i][7] - mean) * rstd * g1.w + b1.w);
+            yr[idx] = o;
+        }
+    }
+}
+
+int launch_layernorm(b200clip_handle* h, const bf16* x, const float* g, const float* b, bf16* y, int64_t rows,
+                     int width, float eps, int t_per_img, const float* cls_row, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    if (width % 8 != 0 || width > LN_MAXV * 256)
+        return b200_fail(h, B200CLIP_E_SHAPE, "layernorm: width %d must be a multiple of 8 and <= %d", width,
+                         LN_MAXV * 256);
+    const int64_t blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+    layernorm_kernel<<<static_cast<unsigned>(blocks), LN_WARPS * 32, 0, st>>>(x, g, b, y, rows, width, eps, t_per_img,
+                                                                             cls_row);
+    h->launches++;
+    B200_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+// ============================================================================ attention
+// softmax(q k^T / sqrt(64)) v for head_dim 64 and short sequences (T = 50 / 77 / 257), one CTA per
+// (64-query tile, head, sequence).  Q/K/V tiles are staged with cp.async into XOR-swizzled shared memory,
+// S = Q K^T and O = P V run on the tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate), the softmax is
+// an fp32 online softmax over 64-key blocks held in registers (no T x T matrix ever reaches memory).
+constexpr int ATT_BQ = 64, ATT_BK = 64, ATT_D = 64, ATT_THREADS = 128;
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                                  uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// byte offset of 16-byte chunk `c` (0..7) of row `r` in a [rows][64] bf16 tile with XOR swizzle
+__device__ __forceinline__ uint32_t sw_off(int r, int c) { return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ void load_tile_async(uint8_t* smem_tile, const bf16* base, int64_t row_stride, int row0,
+                                                int rows_valid) {
+    // 64 rows x 8 chunks of 16 B; 128 threads -> 4 chunks each
+    const uint32_t sbase = smem_u32(smem_tile);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int id = threadIdx.x + i * ATT_THREADS;
+        const int r = id >> 3, c = id & 7;
+        const bool ok = (row0 + r) < rows_valid;
+        const bf16* src = base + static_cast<int64_t>(ok ? row0 + r : 0) * row_stride + c * 8;
+        cp_async_16(sbase + sw_off(r, c), src, ok);
+    }
+}
+
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int heads, int causal) {
+    __shared__ __align__(128) uint8_t sQ[ATT_BQ * 128];
+    __shared__ __align__(128) uint8_t sK[ATT_BK * 128];
+    __shared__ __align__(128) uint8_t sV[ATT_BK * 128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int q0 = blockIdx.x * ATT_BQ;
+    const int head = blockIdx.y;
+    const int64_t seq = blockIdx.z;
+    const int D = heads * ATT_D;
+    const int64_t ld = 3 * static_cast<int64_t>(D);
+    const bf16* qbase = qkv + seq * T * ld + head * ATT_D;
+    const bf16* kbase = qbase + D;
+    const bf16* vbase = qbase + 2 * D;
+
+    load_tile_async(sQ, qbase, ld, q0, T);
+    cp_async_commit();
+
+    float o_acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o_acc[j][0] = o_acc[j][1] = o_acc[j][2] = o_acc[j][3] = 0.f; }
+    float m_run[2] = {-INFINITY, -INFINITY};
+    float l_run[2] = {0.f, 0.f};
+    uint32_t qf[4][4];  // Q fragments for the 4 k-steps over d
+    const float scale_log2 = 0.125f * 1.4426950408889634f;
+
+    const int kv_end = causal ? min(T, q0 + ATT_BQ) : T;
+    bool q_loaded = false;
+    for (int k0 = 0; k0 < kv_end; k0 += ATT_BK) {
+        __syncthreads();  // previous iteration's readers of sK/sV are done
+        load_tile_async(sK, kbase, ld, k0, T);
+        load_tile_async(sV, vbase, ld, k0, T);
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+        if (!q_loaded) {
+            const uint32_t qb = smem_u32(sQ);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int r = warp * 16 + (lane & 15);
+                const int c = ks * 2 + (lane >> 4);
+                ldmatrix_x4(qb + sw_off(r, c), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+            }
+            q_loaded = true;
+        }
+        // ---- S = Q K^T for this warp's 16 rows x 64 keys
+        float s[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+        const uint32_t kb = smem_u32(sK);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-key tiles
+                uint32_t b0, b1, b2, b3;
+                const int r = jp * 16 + (lane & 7) + ((lane >> 4) << 3);
+                const int c = ks * 2 + ((lane >> 3) & 1);
+                ldmatrix_x4(kb + sw_off(r, c), b0, b1, b2, b3);
+                mma_bf16_16816(s[jp * 2], qf[ks], b0, b1);
+                mma_bf16_16816(s[jp * 2 + 1], qf[ks], b2, b3);
+            }
+        }
+        // ---- mask + online softmax (rows g and g+8 of this warp's 16)
+        const int qrow0 = q0 + warp * 16 + g;
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int key = k0 + j * 8 + t4 * 2 + (e & 1);
+                const int qr = qrow0 + ((e >> 1) << 3);
+                const bool ok = key < T && (!causal || key <= qr);
+                s[j][e] = ok ? s[j][e] * scale_log2 : -INFINITY;
+                mx[e >> 1] = fmaxf(mx[e >> 1], s[j][e]);
+            }
+        }
+        float corr[2], m_use[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float m_new = fmaxf(m_run[r], mx[r]);
+            m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;  // fully masked row so far
+            corr[r] = exp2f(m_run[r] - m_use[r]);
+            m_run[r] = m_new;
+        }
+        float rs[2] = {0.f, 0.f};
+        uint32_t pf[4][4];  // P as A fragments for 4 k-steps over keys
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float p0 = exp2f(s[j][0] - m_use[0]);
+            const float p1 = exp2f(s[j][1] - m_use[0]);
+            const float p2 = exp2f(s[j][2] - m_use[1]);
+            const float p3 = exp2f(s[j][3] - m_use[1]);
+            rs[0] += p0 + p1;
+            rs[1] += p2 + p3;
+            pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+            pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            o_acc[j][0] *= corr[0]; o_acc[j][1] *= corr[0];
+            o_acc[j][2] *= corr[1]; o_acc[j][3] *= corr[1];
+        }
+        // ---- O += P V
+        const uint32_t vb = smem_u32(sV);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {       // 16 keys per step
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {   // pairs of 8-wide d tiles
+                uint32_t b0, b1, b2, b3;
+                const int r = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+                const int c = jp * 2 + (lane >> 4);
+                ldmatrix_x4_trans(vb + sw_off(r, c), b0, b1, b2, b3);
+                mma_bf16_16816(o_acc[jp * 2], pf[ks], b0, b1);
+                mma_bf16_16816(o_acc[jp * 2 + 1], pf[ks], b2, b3);
+            }
+        }
+    }
+    // ---- finalize: row sums across the quad, normalise, stage through sQ (this warp's own rows), store
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
+    const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int r0 = warp * 16 + g;
+        // element columns j*8 + t4*2, +1 -> chunk j, byte offset t4*4 inside the 16-byte chunk
+        *reinterpret_cast<uint32_t*>(sQ + sw_off(r0, j) + t4 * 4) = pack_bf16x2(o_acc[j][0] * inv0, o_acc[j][1] * inv0);
+        *reinterpret_cast<uint32_t*>(sQ + sw_off(r0 + 8, j) + t4 * 4) =
+            pack_bf16x2(o_acc[j][2] * inv1, o_acc[j][3] * inv1);
+    }
+    __syncwarp();
+    bf16* obase = out + seq * T * static_cast<int64_t>(D) + head * ATT_D;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int id = lane + i * 32;      // 16 rows x 8 chunks
+        const int r = warp * 16 + (id >> 3), c = id & 7;
+        if (q0 + r < T) {
+            const uint4 v = *reinterpret_cast<const uint4*>(sQ + sw_off(r, c));
+            *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(q0 + r) * D + c * 8) = v;
+        }
+    }
+}
+
+int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, int t, int heads, int causal,
+                     cudaStream_t st) {
+    if (n_seq <= 0) return 0;
+    if (t <= 0 || heads <= 0) return b200_fail(h, B200CLIP_E_ARG, "attention: bad t/heads");
+    if (n_seq > 65535 * 64) return b200_fail(h, B200CLIP_E_SHAPE, "attention: too many sequences");
+    // gridDim.z is limited to 65535: split long batches
+    const int64_t per_seq_in = static_cast<int64_t>(t) * 3 * heads * ATT_D;
+    const int64_t per_seq_out = static_cast<int64_t>(t) * heads * ATT_D;
+    for (int s0 = 0; s0 < n_seq; s0 += 65535) {
+        const int ns = (n_seq - s0) < 65535 ? (n_seq - s0) : 65535;
+        dim3 grid((t + ATT_BQ - 1) / ATT_BQ, heads, ns);
+        attention_kernel<<<grid, ATT_THREADS, 0, st>>>(qkv + s0 * per_seq_in, out + s0 * per_seq_out, t, heads, causal);
+        h->launches++;
+    }
+    B200_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+// ============================================================================ head (K3)
+// For each selected row: LayerNorm (ln_post / ln_final) -> @ proj[width, embed] -> optional L2 normalise.
+// HEAD_IMGS rows per CTA share one pass over the projection matrix.
+constexpr int HEAD_IMGS = 8, HEAD_THREADS = 256, HEAD_MAXCOL = 4;  // embed <= 1024
+
+__global__ void __launch_bounds__(HEAD_THREADS)
+head_kernel(const bf16* __restrict__ x, int64_t row_stride, const int32_t* __restrict__ row_index,
+            const float* __restrict__ gamma, const float* __restrict__ beta, const bf16* __restrict__ proj, int n,
+            int width, int embed, float eps, void* __restrict__ out, int out_dtype, int l2norm) {
+    extern __shared__ float hs[];  // [HEAD_IMGS][width] normalised rows, then [HEAD_IMGS] norms
+    float* xs = hs;
+    float* red = hs + HEAD_IMGS * width;  // [HEAD_IMGS][HEAD_THREADS/32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int img0 = blockIdx.x * HEAD_IMGS;
+    // (1) LayerNorm: warp w handles image img0 + w
+    {
+        const int img = img0 + warp;
+        float* dst = xs + warp * width;
+        if (img < n) {
+            const int64_t r = row_index ? static_cast<int64_t>(row_index[img]) : static_cast<int64_t>(img);
+            const bf16* xr = x + r * row_stride;
+            float sum = 0.f;
+            for (int i = lane; i < width; i += 32) {
+                const float v = __bfloat162float(xr[i]);
+                dst[i] = v;
+                sum += v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float mean = sum / width;
+            float sq = 0.f;
+            for (int i = lane; i < width; i += 32) {
+                const float d = dst[i] - mean;
+                sq += d * d;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            const float rstd = rsqrtf(sq / width + eps);
+            for (int i = lane; i < width; i += 32) dst[i] = (dst[i] - mean) * rstd * gamma[i] + beta[i];
+        } else {
+            for (int i = lane; i < width; i += 32) dst[i] = 0.f;
+        }
+    }
+    __syncthreads();
+    // (2) projection: thread owns columns threadIdx.x + c*HEAD_THREADS
+    float acc[HEAD_MAXCOL][HEAD_IMGS];
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXCOL; ++c)
+#pragma unroll
+        for (int i = 0; i < HEAD_IMGS; ++i) acc[c][i] = 0.f;
+    for (int d = 0; d < width; ++d) {
+        float w[HEAD_MAXCOL];
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXCOL; ++c) {
+            const int col = threadIdx.x + c * HEAD_THREADS;
+            w[c] = col < embed ? __bfloat162float(proj[static_cast<int64_t>(d) * embed + col]) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < HEAD_IMGS; ++i) {
+            const float xv = xs[i * width + d];
+#pragma unroll
+            for (int c = 0; c < HEAD_MAXCOL; ++c) acc[c][i] = fmaf(xv, w[c], acc[c][i]);
+        }
+    }
+    // (3) L2 norm per image
+    float inv[HEAD_IMGS];
+    if (l2norm) {
+#pragma unroll
+        for (int i = 0; i < HEAD_IMGS; ++i) {
+            float sq = 0.f;
+#pragma unroll
+            for (int c = 0; c < HEAD_MAXCOL; ++c) sq += acc[c][i] * acc[c][i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            if (lane == 0) red[i * (HEAD_THREADS / 32) + warp] = sq;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < HEAD_IMGS; ++i) {
+            float tot = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < HEAD_THREADS / 32; ++wv) tot += red[i * (HEAD_THREADS / 32) + wv];
+            inv[i] = 1.0f / sqrtf(tot);  // reference divides by the norm with no epsilon
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < HEAD_IMGS; ++i) inv[i] = 1.f;
+    }
+#pragma unroll
+    for (int i = 0; i < HEAD_IMGS; ++i) {
+        const int img = img0 + i;
+        if (img >= n) break;
+#pragma unroll
+        for (int c = 0; c < HEAD_MAXCOL; ++c) {
+            const int col = threadIdx.x + c * HEAD_THREADS;
+            if (col < embed) {
+                const float v = acc[c][i] * inv[i];
+                if (out_dtype == B200CLIP_F32)
+                    static_cast<float*>(out)[static_cast<int64_t>(img) * embed + col] = v;
+                else
+                    static_cast<bf16*>(out)[static_cast<int64_t>(img) * embed + col] = __float2bfloat16(v);
+            }
+        }
+    }
+}
+
+int launch_head(b200clip_handle* h, const bf16* x, int64_t row_stride, const int32_t* row_index, const float* g,
+                const float* b, const bf16* proj, int n, int width, int embed, float eps, void* out, int out_dtype,
+                int l2norm, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (embed > HEAD_MAXCOL * HEAD_THREADS) return b200_fail(h, B200CLIP_E_SHAPE, "head: embed_dim %d too large", embed);
+    const size_t smem = (static_cast<size_t>(HEAD_IMGS) * width + HEAD_IMGS * (HEAD_THREADS / 32)) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        B200_CUDA(h, cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    const int blocks = (n + HEAD_IMGS - 1) / HEAD_IMGS;
+    head_kernel<<<blocks, HEAD_THREADS, smem, st>>>(x, row_stride, row_index, g, b, proj, n, width, embed, eps, out,
+                                                    out_dtype, l2norm);
+    h->launches++;
+    B200_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+// ============================================================================ patchify (fp32 CHW -> bf16 patch rows)
+// The open_clip-surface entry (model.encode_image(x[B,3,S,S])) gets normalised fp32 images; conv1 with
+// kernel = stride = P is a GEMM over rows [c*P*P + y*P + x] -- this kernel builds those rows.
+__global__ void patchify_chw_kernel(const float* __restrict__ chw, bf16* __restrict__ patches, int n, int S, int P,
+                                    int grid, int patch_k) {
+    const int64_t chunks_per_row = patch_k >> 3;
+    const int64_t total = static_cast<int64_t>(n) * grid * grid * chunks_per_row;
+    const int kk = 3 * P * P;
+    for (int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; id < total;
+         id += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t row = id / chunks_per_row;
+        const int k0 = static_cast<int>(id - row * chunks_per_row) << 3;
+        const int img = static_cast<int>(row / (grid * grid));
+        const int pr = static_cast<int>(row - static_cast<int64_t>(img) * grid * grid);
+        const int py = pr / grid, px = pr - py * grid;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + j;
+            if (k < kk) {
+                const int c = k / (P * P);
+                const int rem = k - c * P * P;
+                const int y = rem / P, xx = rem - y * P;
+                v[j] = chw[((static_cast<int64_t>(img) * 3 + c) * S + (py * P + y)) * S + (px * P + xx)];
+            } else {
+                v[j] = 0.f;
+            }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(patches + row * patch_k + k0) = o;
+    }
+}
+
+int launch_patchify_chw(b200clip_handle* h, const float* chw, int n, bf16* patches, cudaStream_t st) {
+    if (n <= 0) return 0;
+    const int64_t total = static_cast<int64_t>(n) * h->grid * h->grid * (h->patch_k >> 3);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > h->num_sms * 32) blocks = h->num_sms * 32;
+    patchify_chw_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(chw, patches, n, h->cfg.image_size,
+                                                                       h->cfg.patch, h->grid, h->patch_k);
+    h->launches++;
+    B200_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+// ============================================================================ text embedding
+// x[q*ctx + t] = token_embedding[ids[q,t]] + positional_embedding[t]; eot_rows[q] = q*ctx + argmax_t ids[q,t]
+// (first maximum, as torch.argmax).
+__global__ void text_embed_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ tok_emb,
+                                  const float* __restrict__ pos, bf16* __restrict__ x, int32_t* __restrict__ eot_rows,
+                                  int q, int ctx, int width, int vocab) {
+    const int row = blockIdx.x;  // q*ctx + t
+    const int qi = row / ctx, t = row - qi * ctx;
+    int64_t id = tokens[row];
+    if (id < 0) id = 0;
+    if (id >= vocab) id = vocab - 1;
+    const float* e = tok_emb + id * width;
+    for (int i = threadIdx.x; i < width; i += blockDim.x)
+        x[static_cast<int64_t>(row) * width + i] = __float2bfloat16(e[i] + pos[t * width + i]);
+    if (t == 0 && threadIdx.x == 0) {
+        int best = 0;
+        int64_t bv = tokens[static_cast<int64_t>(qi) * ctx];
+        for (int j = 1; j < ctx; ++j) {
+            const int64_t v = tokens[static_cast<int64_t>(qi) * ctx + j];
+            if (v > bv) { bv = v; best = j; }
+        }
+        eot_rows[qi] = qi * ctx + best;
+    }
+}
+
+int launch_text_embed(b200clip_handle* h, const int64_t* tokens, int q, bf16* x, int32_t* eot_rows, cudaStream_t st) {
+    if (q <= 0) return 0;
+    text_embed_kernel<<<q * h->cfg.text_ctx, 128, 0, st>>>(tokens, h->tok_emb, h->txt_pos, x, eot_rows, q,
+                                                          h->cfg.text_ctx, h->cfg.text_width, h->cfg.text_vocab);
+    h->launches++;
+    B200_CUDA(h, cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,90 @@
+"""FrameExtractor: the window / timestamp semantics of /root/reference/src/services/frame_extractor.py that the
+query path depends on (:66-104 sampling + timestamps, :237-273 sliding windows).  Decoding itself (Decord / OpenCV,
+CPU codec libraries) is outside the accelerated path: `extract_frames` uses OpenCV when it is installed and returns
+RAW decoded frames -- the <=512x512 INTER_AREA shrink the reference applies here
+(memory_manager.py:299-322) is folded into the K1 kernel (resize mode REFERENCE), so no CPU resize runs."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+from ..utils.config import settings
+from ..utils.logger import get_logger
+
+logger = get_logger(__name__)
+
+
+class FrameExtractor:
+    def __init__(self):
+        self.sample_rate = settings.FRAME_SAMPLE_RATE
+        self.window_size = settings.WINDOW_SIZE
+        self.window_stride = settings.WINDOW_STRIDE
+
+    def sample_indices(self, total_frames: int) -> List[int]:
+        """frame_extractor.py:66-74: every `sample_rate`-th frame, capped at 1000 frames by uniform sub-sampling."""
+        idx = list(range(0, total_frames, self.sample_rate))
+        cap = settings.MAX_SAMPLED_FRAMES
+        if len(idx) > cap:
+            step = len(idx) // cap
+            idx = idx[::step][:cap]
+        return idx
+
+    def extract_frames(self, video_path: str) -> Tuple[np.ndarray, List[float]]:
+        """Decode + sample; timestamps = frame_index / fps (frame_extractor.py:104).  Returns raw RGB frames."""
+        try:
+            import cv2
+        except ImportError as e:  # pragma: no cover
+            raise RuntimeError("video decoding needs OpenCV; pass frames to Phase1MVP.process_frames instead") from e
+        cap = cv2.VideoCapture(video_path)
+        if not cap.isOpened():
+            raise ValueError(f"Cannot open video: {video_path}")
+        total = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        fps = cap.get(cv2.CAP_PROP_FPS) or 30.0
+        frames, stamps = [], []
+        for i in self.sample_indices(total):
+            cap.set(cv2.CAP_PROP_POS_FRAMES, i)
+            ok, frame = cap.read()
+            if not ok:
+                continue
+            frames.append(cv2.cvtColor(frame, cv2.COLOR_BGR2RGB))
+            stamps.append(i / fps)
+        cap.release()
+        if not frames:
+            raise ValueError(f"No frames extracted from video: {video_path}")
+        return np.stack(frames), stamps
+
+    def window_middles(self, n_frames: int, timestamps: List[float]) -> Tuple[List[int], List[float]]:
+        """Index of the frame Phase 1 embeds for every sliding window (`window[len(window)//2]`,
+        phase1_mvp.py:80) and the window timestamp (frame_extractor.py:237-273) -- without materialising the
+        [m,16,H,W,3] window copy the reference builds."""
+        if n_frames != len(timestamps):
+            raise ValueError(f"Frames and timestamps length mismatch: {n_frames} vs {len(timestamps)}")
+        if n_frames < self.window_size:
+            logger.warning(f"Not enough frames ({n_frames}) for window size ({self.window_size})")
+            if n_frames > 0:
+                return [n_frames // 2], [timestamps[len(timestamps) // 2]]
+            return [], []
+        idx, ts = [], []
+        for i in range(0, n_frames - self.window_size + 1, self.window_stride):
+            mid = i + self.window_size // 2
+            if mid >= len(timestamps):
+                mid = len(timestamps) - 1
+            idx.append(i + self.window_size // 2)
+            ts.append(timestamps[mid])
+        return idx, ts
+
+    def create_sliding_windows(self, frames: np.ndarray, timestamps: List[float]):
+        """Same return value as the reference (windows array + timestamps), for callers that want it."""
+        if len(frames) != len(timestamps):
+            raise ValueError(f"Frames and timestamps length mismatch: {len(frames)} vs {len(timestamps)}")
+        if len(frames) < self.window_size:
+            if len(frames) > 0:
+                return np.array([frames]), [timestamps[len(timestamps) // 2]]
+            return np.array([]), []
+        windows, stamps = [], []
+        for i in range(0, len(frames) - self.window_size + 1, self.window_stride):
+            windows.append(frames[i:i + self.window_size])
+            mid = min(i + self.window_size // 2, len(timestamps) - 1)
+            stamps.append(timestamps[mid])
+        return np.array(windows), stamps

@@ -58,8 +58,12 @@ typedef struct b200clip_config {
 } b200clip_config;
 
 /* resize modes of the frame preprocess kernel */
-#define B200CLIP_RESIZE_REFERENCE 0 /* bit-exact reference chain: cv2 INTER_AREA (<=512^2) -> Pillow bicubic(aa) -> crop */
-#define B200CLIP_RESIZE_BILINEAR_AA 1 /* single-pass antialiased triangle filter (fast mode) */
+#define B200CLIP_RESIZE_REFERENCE 0   /* decoded frame -> bit-exact reference chain: cv2 INTER_AREA shrink to fit
+                                         512x512 (FrameExtractor) -> Pillow bicubic(aa) Resize(S) -> CenterCrop */
+#define B200CLIP_RESIZE_BILINEAR_AA 1 /* Pillow antialiased BILINEAR Resize(S) -> CenterCrop straight from the frame
+                                         (no 512 shrink, cheaper taps; not the reference's filter) */
+#define B200CLIP_RESIZE_BICUBIC 2     /* open_clip's transform only (what `preprocess(PIL)` does): Pillow bicubic(aa)
+                                         Resize(S) -> CenterCrop, no 512 shrink */
 
 /* element types for embedding buffers */
 #define B200CLIP_F32 0
@@ -110,7 +114,8 @@ int b200clip_encode_frames_u8(b200clip_handle* h, const uint8_t* frames_dev, int
 /* Reference-facing call: OpenCLIPModel.encode_images(np.ndarray[N,H,W,3] uint8) -> float32[N,E]
  * (src/models/openclip_model.py:152-198).  HOST buffers in and out: frames are staged through pinned
  * double buffers (H2D overlapped with compute), embeddings are copied back; returns when emb_out_host is
- * complete. */
+ * complete.  emb_out_host may also be a DEVICE pointer: the embeddings then stay resident (no D2H), the call
+ * returns once all uploads are done and the compute remains asynchronous on `stream`. */
 int b200clip_encode_frames_u8_host(b200clip_handle* h, const uint8_t* frames_host, int n, int height, int width,
                                    int resize_mode, float* emb_out_host, int l2norm, void* stream);
 
@@ -126,22 +131,26 @@ int b200clip_encode_text_host(b200clip_handle* h, const int64_t* tokens_host, in
  *      first) and ClipExtractor.extract_clip_with_padding / extract_clip interval arithmetic
  *      (src/services/clip_extractor.py:175-183, 94-111).
  *      img_emb_dev [n,e] (emb_dtype), txt_emb_dev fp32 [q,e].
- *      timestamps_dev: fp32 [n] or NULL (then timestamp = index).  index_base is added to every row
- *      index (global index of this shard's first row).  video_duration <= 0 means unknown.
- *      Outputs (device): top_scores fp32 [q,k], top_idx int64 [q,k] (-1 past count),
- *      intervals fp32 [q,k,2] (start,end seconds), counts int32 [q] = hits with score >= threshold. */
+ *      timestamps_dev: float64 [index_base + n] indexed by GLOBAL row index, or NULL (then timestamp =
+ *      global index).  index_base is added to every row index (global index of this shard's first row).
+ *      video_duration <= 0 means unknown.  Timestamps and intervals are float64 because the reference
+ *      computes them with Python floats.
+ *      Outputs (device): top_scores fp32 [q,k] and top_idx int64 [q,k] = the k best rows in descending
+ *      order BEFORE thresholding (-1 marks an empty slot when n < k); counts int32 [q] = length of the
+ *      prefix with score >= threshold (the reference's result list); intervals float64 [q,k,2]
+ *      (start,end seconds) for every non-empty slot.  intervals_dev / counts_dev may be NULL. */
 int b200clip_sim_topk(b200clip_handle* h, const void* img_emb_dev, int emb_dtype, int64_t n, int e,
-                      const float* txt_emb_dev, int q, int k, float threshold, const float* timestamps_dev,
-                      int64_t index_base, float clip_duration, float video_duration, float* top_scores_dev,
-                      int64_t* top_idx_dev, float* intervals_dev, int32_t* counts_dev, void* stream);
+                      const float* txt_emb_dev, int q, int k, float threshold, const double* timestamps_dev,
+                      int64_t index_base, double clip_duration, double video_duration, float* top_scores_dev,
+                      int64_t* top_idx_dev, double* intervals_dev, int32_t* counts_dev, void* stream);
 /* Dense scores fp32 [n,q] (compute_similarity itself). */
 int b200clip_similarity(b200clip_handle* h, const void* img_emb_dev, int emb_dtype, int64_t n, int e,
                         const float* txt_emb_dev, int q, float* scores_out_dev, void* stream);
-/* k-way merge of g candidate lists (e.g. after an all-gather over ranks): cand_scores fp32 [g,q,k],
- * cand_idx int64 [g,q,k] (-1 = empty).  timestamps are looked up by global index. */
+/* k-way merge of g sorted candidate lists (e.g. after an all-gather over ranks): cand_scores fp32 [g,q,k],
+ * cand_idx int64 [g,q,k] global indices (-1 = empty).  Same outputs as b200clip_sim_topk. */
 int b200clip_topk_merge(b200clip_handle* h, const float* cand_scores_dev, const int64_t* cand_idx_dev, int g, int q,
-                        int k, float threshold, const float* timestamps_dev, int64_t n_total, float clip_duration,
-                        float video_duration, float* top_scores_dev, int64_t* top_idx_dev, float* intervals_dev,
+                        int k, float threshold, const double* timestamps_dev, double clip_duration,
+                        double video_duration, float* top_scores_dev, int64_t* top_idx_dev, double* intervals_dev,
                         int32_t* counts_dev, void* stream);
 
 /* ---- building blocks, exported for the parity tests and micro-benchmarks ---- */

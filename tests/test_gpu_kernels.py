@@ -1,0 +1,92 @@
+"""GPU parity of the building-block kernels through the C ABI (b200clip_gemm_bf16 / layernorm / attention)
+against plain PyTorch fp32 references of the same op on the same seeded inputs."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handle():
+    from b200clip import capi
+    from b200clip.model_configs import MODEL_CONFIGS, to_capi_config
+
+    h = capi.Handle(to_capi_config(MODEL_CONFIGS["ViT-B-32"]), 0)
+    yield h
+    h.close()
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("m,n,k,bias,resid,act", [
+    (128, 256, 64, 0, 0, 0), (200, 768, 768, 1, 1, 0), (1000, 3072, 768, 1, 0, 1), (1000, 768, 3072, 1, 1, 0),
+    (333, 2304, 768, 1, 0, 2), (77, 512, 512, 1, 0, 0), (130, 384, 512, 1, 0, 0), (50, 64, 64, 1, 0, 0),
+    (5000, 768, 3072, 0, 0, 0), (1, 768, 768, 1, 0, 0), (12544, 1024, 640, 0, 0, 0),
+])
+def test_gemm_matches_torch(handle, m, n, k, bias, resid, act):
+    from b200clip import capi
+
+    torch.manual_seed(m + n + k)
+    a = (torch.randn(m, k, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(n, k, device="cuda") * 0.05).bfloat16()
+    b = torch.randn(n, device="cuda") if bias else None
+    r = torch.randn(m, n, device="cuda").bfloat16() if resid else None
+    out = torch.full((m, n), float("nan"), device="cuda", dtype=torch.bfloat16)
+    if resid:
+        out.copy_(r)
+    handle.call("b200clip_gemm_bf16", capi._p(a), capi._p(w), capi._p(out), m, n, k, capi._p(b),
+                capi._p(out if resid else None), act, _stream())
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t()
+    if bias:
+        ref = ref + b
+    if act == 1:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    elif act == 2:
+        ref = torch.nn.functional.gelu(ref)
+    if resid:
+        ref = ref + r.float()
+    err = (out.float() - ref).abs()
+    tol = 0.02 + 0.01 * ref.abs()   # bf16 output rounding (2^-9 relative) + accumulation order
+    assert not torch.isnan(out.float()).any()
+    assert bool((err <= tol).all()), f"max err {float(err.max())}"
+
+
+@pytest.mark.parametrize("rows,width", [(1000, 768), (77, 512), (257, 1024), (5, 128), (9, 64)])
+def test_layernorm_matches_torch(handle, rows, width):
+    from b200clip import capi
+
+    torch.manual_seed(rows)
+    x = (torch.randn(rows, width, device="cuda") * 3 + 0.5).bfloat16()
+    g = torch.randn(width, device="cuda") * 0.2 + 1
+    b = torch.randn(width, device="cuda") * 0.1
+    y = torch.empty_like(x)
+    handle.call("b200clip_layernorm_bf16", capi._p(x), capi._p(g), capi._p(b), capi._p(y), rows, width, 1e-5, _stream())
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.float(), (width,), g, b, 1e-5)
+    assert float((y.float() - ref).abs().max()) <= 0.02 + 0.008 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("n_seq,t,heads,causal", [(3, 50, 12, 0), (2, 77, 8, 1), (2, 257, 16, 0), (5, 5, 2, 0),
+                                                    (1, 16, 1, 1), (70, 50, 12, 0), (1, 64, 2, 1), (1, 65, 2, 0)])
+def test_attention_matches_torch(handle, n_seq, t, heads, causal):
+    from b200clip import capi
+
+    torch.manual_seed(t * heads)
+    d = heads * 64
+    qkv = (torch.randn(n_seq * t, 3 * d, device="cuda") * 1.5).bfloat16()
+    out = torch.full((n_seq * t, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    handle.call("b200clip_attention_bf16", capi._p(qkv), capi._p(out), n_seq, t, heads, causal, _stream())
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(n_seq, t, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    if causal:
+        s = s + torch.full((t, t), float("-inf"), device="cuda").triu_(1)
+    ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(n_seq * t, d)
+    assert not torch.isnan(out.float()).any()
+    # P is rounded to bf16 before the PV product and the output is bf16
+    assert float((out.float() - ref).abs().max()) <= 0.03

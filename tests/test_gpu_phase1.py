@@ -1,0 +1,103 @@
+"""End-to-end phase1_mvp parity against tests/golden/phase1_cfg1.json = the reference's own
+Phase1MVP.process_video (512 synthetic frames -> 63 windows, top_k=5) with decode replaced by the same frames."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from parity import SCORE_TOL, assert_topk_equivalent
+from synth import structured_frames
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def phase1(oracle_sd_b32):
+    from b200clip.models.openclip_model import OpenCLIPModel
+    from b200clip.pipeline.phase1_mvp import Phase1MVP
+    from b200clip.utils.config import settings
+
+    settings.B200_MAX_IMAGES_PER_PASS = 128
+    return Phase1MVP(clip_model=OpenCLIPModel(state_dict=oracle_sd_b32))
+
+
+def test_process_frames_matches_reference_phase1(phase1, golden_dir):
+    from b200clip.services.video_processor import VideoProcessor
+    from b200clip.utils.config import settings
+
+    g = json.load(open(os.path.join(golden_dir, "phase1_cfg1.json")))
+    video = structured_frames(g["n_frames"], 224, 224, seed=g["frames_seed"])
+    ts = [i / g["fps"] for i in range(len(video))]
+    vp = VideoProcessor(phase1=phase1)
+    assert vp.preprocess_query(g["query"]) == g["processed_query"]
+    ref_sims = np.array(g["similarities"], np.float32)
+
+    settings.CONFIDENCE_THRESHOLD = -1.0
+    res, debug = phase1.process_frames(video, ts, g["processed_query"], top_k=5, debug_mode=True)
+    phase1.debug_mode = False
+    assert len(debug) == 63 and [d["timestamp"] for d in debug] == g["window_timestamps"]
+    sims = np.array([d["similarity"] for d in debug], np.float32)
+    print(f"\n[parity] phase1 max |dscore| over 63 windows: {np.abs(sims - ref_sims).max():.5f}; "
+          f"reference top-5 {[r['window_index'] for r in g['top5']]} ours {[r['window_index'] for r in res]}")
+    assert np.abs(sims - ref_sims).max() <= SCORE_TOL
+    assert len(res) == 5 and all(r["phase"] == "phase1_mvp" for r in res)
+    assert [r["confidence"] for r in res] == sorted([r["confidence"] for r in res], reverse=True)
+    assert_topk_equivalent(ref_sims, [r["window_index"] for r in res], [r["confidence"] for r in res], 5)
+    for r in res:
+        assert r["timestamp"] == g["window_timestamps"][r["window_index"]]
+    # the tight check the 1e-2 rule cannot give on clustered scores: same set and order as the oracle applied to
+    # OUR scores (i.e. the top-k / tie / threshold logic itself is exact)
+    from oracle.phase1_ref import topk_threshold
+
+    want = topk_threshold(sims, g["window_timestamps"], 5, -1.0)
+    assert [r["window_index"] for r in res] == [r["window_index"] for r in want]
+
+    # thresholded run: the reference kept exactly 3 hits at this threshold
+    thr = g["threshold_case"]["threshold"]
+    settings.CONFIDENCE_THRESHOLD = thr
+    res_thr = phase1.process_frames(video, ts, g["processed_query"], top_k=5)
+    want_thr = topk_threshold(sims, g["window_timestamps"], 5, thr)
+    assert [r["window_index"] for r in res_thr] == [r["window_index"] for r in want_thr]
+    assert abs(len(res_thr) - len(g["threshold_case"]["results"])) <= 1   # a score within 1e-2 of thr may flip
+    settings.CONFIDENCE_THRESHOLD = 0.25
+    assert phase1.process_frames(video, ts, g["processed_query"], top_k=5) == []   # default 0.25: nothing passes
+
+
+def test_short_and_empty_videos(phase1):
+    from b200clip.utils.config import settings
+
+    settings.CONFIDENCE_THRESHOLD = -1.0
+    video = structured_frames(10, 224, 224, seed=1)          # fewer than WINDOW_SIZE frames -> one window
+    res = phase1.process_frames(video, [i / 10 for i in range(10)], "red car", top_k=5)
+    assert len(res) == 1 and res[0]["window_index"] == 0 and res[0]["timestamp"] == 0.5
+    with pytest.raises(ValueError):
+        phase1.process_frames(video[:0], [], "red car")
+    with pytest.raises(ValueError):
+        phase1.process_frames(video, [0.0], "red car")
+    settings.CONFIDENCE_THRESHOLD = 0.25
+
+
+def test_process_query_contract(phase1, tmp_path):
+    from b200clip.services.video_processor import VideoProcessor
+    from b200clip.utils.config import settings
+
+    vp = VideoProcessor(phase1=phase1)
+    out = vp.process_query(str(tmp_path / "missing.mp4"), "a dog jumps")
+    assert out["status"] == "error" and out["results"] == []
+    bad = tmp_path / "x.txt"
+    bad.write_text("x")
+    assert vp.process_query(str(bad), "a dog")["status"] == "error"
+    # a real file path; decode replaced by synthetic frames like the golden generator does
+    f = tmp_path / "v.mp4"
+    f.write_bytes(b"0")
+    video = structured_frames(64, 224, 224, seed=2)
+    phase1.frame_extractor.extract_frames = lambda _p: (video, [i / 8 for i in range(64)])
+    settings.CONFIDENCE_THRESHOLD = -1.0
+    out = vp.process_query(str(f), "A dog  jumps", top_k=3, threshold=-1.0)
+    settings.CONFIDENCE_THRESHOLD = 0.25
+    assert out["status"] == "success" and out["processed_query"] == "dog jumping" and out["total_found"] == 3
+    for r in out["results"]:
+        assert r["clip_start"] == max(0, r["timestamp"] - 15) and r["clip_end"] == r["timestamp"] + 15
+    with pytest.raises(ValueError):
+        vp.process_query(str(f), "dog", mode="nope")

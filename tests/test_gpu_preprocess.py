@@ -1,0 +1,106 @@
+"""K1 parity (byte-exact): the CUDA preprocess kernel against the numpy oracle (oracle/preprocess_ref.py) on seeded
+frames, and against tests/golden/*.npz produced by the real cv2 / Pillow / torchvision through the reference's own
+MemoryManager.resize_frame_for_memory + open_clip transform."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from synth import noise_frames, structured_frames
+
+pytestmark = pytest.mark.gpu
+
+
+def _u8_from_chw(chw: np.ndarray) -> np.ndarray:
+    """invert the ToTensor/Normalize lookup: nearest table entry per channel -> uint8 HWC."""
+    from oracle.preprocess_ref import normalize_table
+
+    tab = normalize_table()
+    out = np.stack([np.abs(tab[c][None, None, :] - chw[c][..., None]).argmin(-1) for c in range(3)], -1)
+    return out.astype(np.uint8)
+
+
+@pytest.mark.parametrize("w,h", [(224, 224), (512, 288), (1920, 1080), (1280, 720), (640, 480), (300, 300),
+                                 (288, 512), (399, 224), (1024, 1024), (800, 600), (2048, 1024), (225, 400)])
+def test_reference_mode_bit_exact_vs_oracle(model_b32, w, h):
+    from b200clip import capi
+    from oracle import preprocess_ref as P
+
+    frames = np.concatenate([noise_frames(1, h, w, seed=w + h), structured_frames(1, h, w, seed=w * 3 + h)])
+    dev = torch.from_numpy(frames).cuda()
+    chw = model_b32.preprocess_u8(dev, capi.RESIZE_REFERENCE, chw=True).cpu().numpy()
+    patches = model_b32.preprocess_u8(dev, capi.RESIZE_REFERENCE, chw=False).float().cpu().numpy()
+    for i in range(len(frames)):
+        want_u8 = P.reference_preprocess_u8(frames[i])
+        want = P.to_chw_normalized(want_u8)
+        assert np.array_equal(chw[i].view(np.uint32), want.view(np.uint32)), \
+            f"{w}x{h} frame {i}: {(chw[i] != want).sum()} of {want.size} values differ"
+        want_patches = torch.from_numpy(P.patchify(want, 32)).bfloat16().float().numpy()
+        assert np.array_equal(patches[i * 49:(i + 1) * 49], want_patches)
+
+
+@pytest.mark.parametrize("w,h", [(512, 288), (640, 480), (1000, 700)])
+def test_transform_only_mode_matches_pil(model_b32, w, h):
+    """RESIZE_BICUBIC == open_clip's transform alone (no 512 shrink), checked against the real torchvision/Pillow."""
+    from PIL import Image
+
+    from b200clip import capi
+    from oracle.open_clip_shim import image_transform
+
+    frame = noise_frames(1, h, w, seed=5)[0]
+    want = image_transform(224)(Image.fromarray(frame)).numpy()
+    got = model_b32.preprocess_u8(torch.from_numpy(frame[None]).cuda(), capi.RESIZE_BICUBIC, chw=True)[0].cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_bilinear_mode_matches_pil_bilinear(model_b32):
+    from PIL import Image
+
+    from b200clip import capi
+    from oracle import preprocess_ref as P
+
+    frame = noise_frames(1, 1080, 1920, seed=6)[0]
+    nw, nh = P.resize_output_size(1920, 1080)
+    r = np.asarray(Image.fromarray(frame).resize((nw, nh), Image.BILINEAR))
+    left, top = P.center_crop_box(nw, nh)
+    want = P.to_chw_normalized(r[top:top + 224, left:left + 224])
+    got = model_b32.preprocess_u8(torch.from_numpy(frame[None]).cuda(), capi.RESIZE_BILINEAR_AA, chw=True)[0].cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_golden_1080p_and_geometries(model_b32, golden_dir):
+    """Fixtures made by the real libraries in the reference's own call chain."""
+    from b200clip import capi
+
+    g = np.load(os.path.join(golden_dir, "vitb32_1080p.npz"))
+    hd = np.concatenate([structured_frames(4, 1080, 1920, seed=7), noise_frames(2, 1080, 1920, seed=8)])
+    chw = model_b32.preprocess_u8(torch.from_numpy(hd).cuda(), capi.RESIZE_REFERENCE, chw=True).cpu().numpy()
+    for i in range(len(hd)):
+        assert np.array_equal(_u8_from_chw(chw[i]), g["pre_u8"][i]), f"1080p frame {i}"
+    geo = np.load(os.path.join(golden_dir, "preprocess_geometries.npz"))
+    for key in geo.files:
+        dims, seed = key.split("_s")
+        w, h = (int(v) for v in dims.split("x"))
+        f = noise_frames(1, h, w, seed=int(seed))
+        got = model_b32.preprocess_u8(torch.from_numpy(f).cuda(), capi.RESIZE_REFERENCE, chw=True)[0].cpu().numpy()
+        assert np.array_equal(_u8_from_chw(got), geo[key]), key
+
+
+def test_strided_frames_and_empty(model_b32):
+    """row/frame strides larger than the packed size (a crop of a bigger buffer), and n = 0."""
+    from b200clip import capi
+    from oracle import preprocess_ref as P
+
+    big = noise_frames(2, 300, 400, seed=21)
+    view = big[:, 10:250, 20:340]            # 240 x 320 window
+    dev = torch.from_numpy(big).cuda()
+    out = torch.empty(2, 3, 224, 224, device="cuda")
+    base = dev.data_ptr() + (10 * 400 + 20) * 3
+    model_b32.handle.call("b200clip_preprocess_u8_chw", capi._p(base), 2, 240, 320, 300 * 400 * 3, 400 * 3,
+                          capi.RESIZE_REFERENCE, capi._p(out), model_b32._stream())
+    for i in range(2):
+        want = P.to_chw_normalized(P.reference_preprocess_u8(np.ascontiguousarray(view[i])))
+        assert np.array_equal(out[i].cpu().numpy(), want)
+    model_b32.handle.call("b200clip_preprocess_u8_chw", capi._p(None), 0, 240, 320, 0, 0, capi.RESIZE_REFERENCE,
+                          capi._p(None), model_b32._stream())
