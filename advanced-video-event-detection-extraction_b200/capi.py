@@ -69,6 +69,8 @@ SIGNATURES = {
     "b200clip_layernorm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float,
                                         c_void_p]),
     "b200clip_attention_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200clip_profile_enable": (c_int, [c_void_p, c_int]),
+    "b200clip_profile_read": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_double), POINTER(c_int64), c_int]),
     "b200clip_launch_count": (c_int64, [c_void_p]),
     "b200clip_reset_launch_count": (None, [c_void_p]),
 }
@@ -156,6 +158,21 @@ class Handle:
 
     def reserve(self, max_images: int, max_texts: int = 0):
         self.call("b200clip_reserve", int(max_images), int(max_texts))
+
+    PROFILE_CLASSES = ("gemm", "attention", "layernorm", "preprocess", "head", "sim_topk", "misc")
+
+    def profile_enable(self, on: bool = True):
+        self.call("b200clip_profile_enable", int(on))
+
+    def profile_read(self, reset: bool = True) -> dict:
+        """{class: {"ms", "work", "launches"}} summed over the timed launches since the last reset."""
+        out = {}
+        for i, name in enumerate(self.PROFILE_CLASSES):
+            ms, work, n = c_double(), c_double(), c_int64()
+            last = i == len(self.PROFILE_CLASSES) - 1
+            self.call("b200clip_profile_read", i, byref(ms), byref(work), byref(n), int(reset and last))
+            out[name] = {"ms": ms.value, "work": work.value, "launches": n.value}
+        return out
 
     @property
     def launches(self) -> int:

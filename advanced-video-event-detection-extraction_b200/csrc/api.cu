@@ -39,6 +39,57 @@ extern "C" void b200clip_reset_launch_count(b200clip_handle* h) {
     if (h) h->launches = 0;
 }
 
+// ------------------------------------------------------------------------------------------- profiler
+static cudaEvent_t prof_get_event(b200clip_handle* h) {
+    if (!h->prof_pool.empty()) {
+        cudaEvent_t e = h->prof_pool.back();
+        h->prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+ProfScope::ProfScope(b200clip_handle* h_, int cls, double work, cudaStream_t st_) : h(h_), st(st_), idx(-1) {
+    if (!h || !h->prof_on) return;
+    b200clip_handle::ProfRec r{prof_get_event(h), prof_get_event(h), cls, work};
+    if (!r.a || !r.b) return;
+    cudaEventRecord(r.a, st);
+    h->prof_recs.push_back(r);
+    idx = static_cast<int>(h->prof_recs.size()) - 1;
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(h->prof_recs[idx].b, st);
+}
+
+extern "C" int b200clip_profile_enable(b200clip_handle* h, int on) {
+    if (!h) return b200_fail(h, B200CLIP_E_ARG, "profile_enable: null handle");
+    h->prof_on = on != 0;
+    return 0;
+}
+
+extern "C" int b200clip_profile_read(b200clip_handle* h, int cls, double* ms_out, double* work_out,
+                                     int64_t* launches_out, int reset) {
+    if (!h || cls < 0 || cls >= PROF_NCLS) return b200_fail(h, B200CLIP_E_ARG, "profile_read: bad argument");
+    B200_CUDA(h, cudaSetDevice(h->device));
+    B200_CUDA(h, cudaDeviceSynchronize());
+    double ms = 0, work = 0;
+    int64_t n = 0;
+    for (const auto& r : h->prof_recs) {
+        if (r.cls != cls) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms += t; work += r.work; ++n; }
+    }
+    if (ms_out) *ms_out = ms;
+    if (work_out) *work_out = work;
+    if (launches_out) *launches_out = n;
+    if (reset) {
+        for (const auto& r : h->prof_recs) { h->prof_pool.push_back(r.a); h->prof_pool.push_back(r.b); }
+        h->prof_recs.clear();
+    }
+    return 0;
+}
+
 static int check_cfg(const b200clip_config* c) {
     if (c->image_size <= 0 || c->patch <= 0 || c->image_size % c->patch != 0)
         return b200_fail(nullptr, B200CLIP_E_SHAPE, "image_size %d must be a positive multiple of patch %d",
@@ -93,6 +144,8 @@ extern "C" int b200clip_destroy(b200clip_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     preprocess_free_plans(h);
+    for (const auto& r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
     cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_qkv); cudaFree(h->ws_h); cudaFree(h->ws_patches);
     cudaFree(h->ws_emb); cudaFree(h->ws_pre); cudaFree(h->ws_topk); cudaFree(h->ws_eot); cudaFree(h->ws_tokens);

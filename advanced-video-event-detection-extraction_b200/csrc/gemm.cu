@@ -58,7 +58,10 @@ static int launch_gemm_bn(b200clip_handle* h, const bf16* a, int lda, const bf16
     const int n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
     const int tiles = m_blocks * n_blocks;
     const int grid = tiles < h->num_sms ? tiles : h->num_sms;
-    kern<<<grid, b200::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tw, out, ldc, M, N, K, ep);
+    {
+        ProfScope ps(h, PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
+        kern<<<grid, b200::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tw, out, ldc, M, N, K, ep);
+    }
     h->launches++;
     B200_CUDA(h, cudaGetLastError());
     return 0;

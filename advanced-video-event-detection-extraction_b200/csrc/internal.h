@@ -21,6 +21,12 @@ struct b200clip_handle {
     mutable std::string err;
     int64_t launches = 0;
 
+    // ---- opt-in per-class kernel timing (CUDA events on the launching stream; bench.py's roofline numbers)
+    struct ProfRec { cudaEvent_t a, b; int cls; double work; };
+    bool prof_on = false;
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+
     // ---- packed weights (device) ----
     struct Block {
         float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
@@ -70,6 +76,15 @@ struct b200clip_handle {
     size_t ws_topk_bytes = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+};
+
+// kernel classes for the profiler
+enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_PRE = 3, PROF_HEAD = 4, PROF_SIM = 5, PROF_MISC = 6, PROF_NCLS = 7 };
+// RAII bracket: records an event pair around the launches made in its scope when profiling is on
+struct ProfScope {
+    b200clip_handle* h; cudaStream_t st; int idx;
+    ProfScope(b200clip_handle* h_, int cls, double work, cudaStream_t st_);
+    ~ProfScope();
 };
 
 // error helpers (api.cu)

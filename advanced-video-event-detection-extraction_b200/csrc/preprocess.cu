@@ -522,6 +522,10 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
     uint8_t* mid1 = h->ws_pre;
     uint8_t* mid2 = h->ws_pre + p.mid1_per_frame * static_cast<size_t>(n);
 
+    // algorithmic bytes: the whole frame in, the patch rows (or fp32 CHW) out
+    ProfScope ps(h, PROF_PRE, static_cast<double>(n) * (static_cast<double>(H) * W * 3.0 +
+                 (patches ? static_cast<double>(h->grid) * h->grid * h->patch_k * 2.0 : 0.0) +
+                 (chw ? 3.0 * S * S * 4.0 : 0.0)), st);
     const uint8_t* cur = frames;
     int64_t cur_fs = frame_stride, cur_rs = row_stride;
     int cur_x0 = 0, cur_y0 = 0;  // absolute (stage-coordinate) position of cur's element (0,0)

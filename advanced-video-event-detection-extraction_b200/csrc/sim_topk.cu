@@ -278,6 +278,7 @@ int launch_similarity(b200clip_handle* h, const void* img, int dtype, int64_t n,
     int rc = check_sim_args(h, img, dtype, n, e, txt, q);
     if (rc) return rc;
     if (n == 0) return 0;
+    ProfScope ps(h, PROF_SIM, static_cast<double>(n) * e * (dtype == B200CLIP_BF16 ? 2.0 : 4.0) + static_cast<double>(n) * q * 4.0, st);
     return run_stream(h, img, dtype, n, e, txt, q, 0, scores, nullptr, nullptr, sim_grid(h, n), st);
 }
 
@@ -289,6 +290,7 @@ int launch_sim_topk(b200clip_handle* h, const void* img, int dtype, int64_t n, i
     if (k <= 0 || k > SIM_MAXK) return b200_fail(h, B200CLIP_E_SHAPE, "sim_topk: k must be in [1, %d]", SIM_MAXK);
     if (!top_scores || !top_idx) return b200_fail(h, B200CLIP_E_ARG, "sim_topk: null output");
     const int grid = sim_grid(h, n > 0 ? n : 1);
+    ProfScope ps(h, PROF_SIM, static_cast<double>(n) * e * (dtype == B200CLIP_BF16 ? 2.0 : 4.0) + static_cast<double>(q) * (e * 4.0 + k * 12.0), st);
     const size_t need = static_cast<size_t>(grid) * q * k * 8;
     if (need > h->ws_topk_bytes) {
         B200_CUDA(h, cudaStreamSynchronize(st));

@@ -91,6 +91,7 @@ int launch_layernorm(b200clip_handle* h, const bf16* x, const float* g, const fl
         return b200_fail(h, B200CLIP_E_SHAPE, "layernorm: width %d must be a multiple of 8 and <= %d", width,
                          LN_MAXV * 256);
     const int64_t blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+    ProfScope ps(h, PROF_LN, static_cast<double>(rows) * width * 4.0, st);
     layernorm_kernel<<<static_cast<unsigned>(blocks), LN_WARPS * 32, 0, st>>>(x, g, b, y, rows, width, eps, t_per_img,
                                                                              cls_row);
     h->launches++;
@@ -307,6 +308,8 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
     for (int s0 = 0; s0 < n_seq; s0 += 65535) {
         const int ns = (n_seq - s0) < 65535 ? (n_seq - s0) : 65535;
         dim3 grid((t + ATT_BQ - 1) / ATT_BQ, heads, ns);
+        // work = algorithmic bytes (qkv read + out write); FLOPs are 4*t*t*64 per (seq, head)
+        ProfScope ps(h, PROF_ATTN, static_cast<double>(ns) * t * heads * ATT_D * 2.0 * 4.0, st);
         attention_kernel<<<grid, ATT_THREADS, 0, st>>>(qkv + s0 * per_seq_in, out + s0 * per_seq_out, t, heads, causal);
         h->launches++;
     }
@@ -432,6 +435,7 @@ int launch_head(b200clip_handle* h, const bf16* x, int64_t row_stride, const int
         attr_set = true;
     }
     const int blocks = (n + HEAD_IMGS - 1) / HEAD_IMGS;
+    ProfScope ps(h, PROF_HEAD, static_cast<double>(n) * (width * 2.0 + embed * 4.0) + static_cast<double>(width) * embed * 2.0, st);
     head_kernel<<<blocks, HEAD_THREADS, smem, st>>>(x, row_stride, row_index, g, b, proj, n, width, embed, eps, out,
                                                     out_dtype, l2norm);
     h->launches++;
@@ -479,6 +483,7 @@ int launch_patchify_chw(b200clip_handle* h, const float* chw, int n, bf16* patch
     const int64_t total = static_cast<int64_t>(n) * h->grid * h->grid * (h->patch_k >> 3);
     int64_t blocks = (total + 255) / 256;
     if (blocks > h->num_sms * 32) blocks = h->num_sms * 32;
+    ProfScope ps(h, PROF_MISC, static_cast<double>(total) * 8 * 6.0, st);
     patchify_chw_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(chw, patches, n, h->cfg.image_size,
                                                                        h->cfg.patch, h->grid, h->patch_k);
     h->launches++;
@@ -513,6 +518,7 @@ __global__ void text_embed_kernel(const int64_t* __restrict__ tokens, const floa
 
 int launch_text_embed(b200clip_handle* h, const int64_t* tokens, int q, bf16* x, int32_t* eot_rows, cudaStream_t st) {
     if (q <= 0) return 0;
+    ProfScope ps(h, PROF_MISC, static_cast<double>(q) * h->cfg.text_ctx * h->cfg.text_width * 10.0, st);
     text_embed_kernel<<<q * h->cfg.text_ctx, 128, 0, st>>>(tokens, h->tok_emb, h->txt_pos, x, eot_rows, q,
                                                           h->cfg.text_ctx, h->cfg.text_width, h->cfg.text_vocab);
     h->launches++;

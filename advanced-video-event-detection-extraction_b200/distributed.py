@@ -33,7 +33,7 @@ def allgather_candidates(scores: torch.Tensor, idx: torch.Tensor, group=None) ->
         return scores.unsqueeze(0), idx.unsqueeze(0)
     msg = torch.stack([scores.contiguous().view(torch.int32).to(torch.int64), idx.to(torch.int64)], dim=-1).contiguous()
     out = torch.empty((world,) + tuple(msg.shape), dtype=msg.dtype, device=msg.device)
-    dist.all_gather_into_tensor(out, msg, group=group)
+    dist.all_gather(list(out.unbind(0)), msg, group=group)   # one collective; works on NCCL and gloo
     cs = out[..., 0].to(torch.int32).view(torch.float32)
     ci = out[..., 1]
     return cs.contiguous(), ci.contiguous()
