@@ -1,5 +1,7 @@
 // Host side of the tcgen05 GEMM: TMA tensor-map encoding and launch.
-#include "gemm_tcgen05.cuh"
+#include "gemm_tcgen05_2cta.cuh"
+#include <stdlib.h>
+
 #include "internal.h"
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -67,12 +69,47 @@ static int launch_gemm_bn(b200clip_handle* h, const bf16* a, int lda, const bf16
     return 0;
 }
 
+static int launch_gemm_2cta(b200clip_handle* h, const bf16* a, int lda, const bf16* w, int ldw, bf16* out, int ldc,
+                            int M, int N, int K, const b200::GemmEpilogue& ep, cudaStream_t st) {
+    CUtensorMap ta, tw;
+    int rc;
+    if ((rc = make_tmap_bf16_2d(h, &ta, a, M, K, lda, b200::GEMM_BLOCK_M, b200::GEMM_BLOCK_K,
+                                CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    if ((rc = make_tmap_bf16_2d(h, &tw, w, N, K, ldw, b200::G2_HALF_N, b200::GEMM_BLOCK_K,
+                                CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200_CUDA(h, cudaFuncSetAttribute(b200::gemm_bf16_tcgen05_2cta_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, b200::G2_SMEM_BYTES));
+        attr_set = true;
+    }
+    const int m_blocks = (M + 2 * b200::GEMM_BLOCK_M - 1) / (2 * b200::GEMM_BLOCK_M);
+    const int n_blocks = (N + b200::G2_BLOCK_N - 1) / b200::G2_BLOCK_N;
+    const int tiles = m_blocks * n_blocks;
+    int clusters = h->num_sms / 2;
+    if (tiles < clusters) clusters = tiles;
+    {
+        ProfScope ps(h, PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
+        b200::gemm_bf16_tcgen05_2cta_kernel<<<2 * clusters, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, st>>>(
+            ta, tw, out, ldc, M, N, K, ep);
+    }
+    h->launches++;
+    B200_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
 int launch_gemm(b200clip_handle* h, const bf16* a, int lda, const bf16* w, int ldw, bf16* out, int ldc, int M, int N,
                 int K, const b200::GemmEpilogue& ep, cudaStream_t st) {
     if (M <= 0 || N <= 0 || K <= 0) return b200_fail(h, B200CLIP_E_ARG, "gemm: empty problem %dx%dx%d", M, N, K);
     if (N % 32 != 0 || K % 8 != 0 || ldc % 8 != 0)
         return b200_fail(h, B200CLIP_E_SHAPE, "gemm: N must be a multiple of 32, K and ldc of 8 (N=%d K=%d ldc=%d)", N,
                          K, ldc);
+    // large-M problems: CTA pairs (256x256 tiles, half the B traffic per CTA); B200CLIP_GEMM_1CTA=1 forces the
+    // single-CTA kernel (used by the parity tests to cover both)
+    static const bool force_1cta = getenv("B200CLIP_GEMM_1CTA") != nullptr;
+    if (!force_1cta && N % 256 == 0 && M >= 2048) return launch_gemm_2cta(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
     if (N % 256 == 0 || N > 1024) return launch_gemm_bn<256>(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
     return launch_gemm_bn<128>(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
 }

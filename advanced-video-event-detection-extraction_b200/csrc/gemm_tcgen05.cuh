@@ -4,7 +4,8 @@
 //     operands are fed to tcgen05.mma straight from 128B-swizzled shared memory tiles that TMA
 //     fills (box 64 x rows, bf16) -- no transposes anywhere.
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
-//     warps 2..5 = epilogue (each owns the 32 TMEM lanes its warp-id % 4 may read).
+//     warps 2..9 = epilogue (each may read the 32 TMEM lanes of its warp-id % 4; two warps split the
+//     columns of a lane quarter), TMEM loads software-pipelined against the epilogue math.
 //   * the fp32 accumulator lives in TMEM, double buffered (2 x BLOCK_N columns) so the epilogue of
 //     tile i overlaps the main loop of tile i+1; one CTA per SM loops over tiles (grid = #SMs).
 //   * fused epilogues: +bias, +bias+QuickGELU / erf-GELU, +bias+residual (in place), and the
@@ -28,7 +29,8 @@ struct GemmEpilogue {
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int GEMM_UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;  // 6 warps
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + GEMM_EPI_WARPS * 32;  // TMA warp + MMA warp + epilogue warps
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -86,7 +88,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty_bar[s], GEMM_EPI_WARPS);  // one arrive per epilogue warp
         }
         fence_mbar_init();
     }
@@ -147,8 +149,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
         }
     } else {
-        // ===================== epilogue warps (2..5) =====================
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        // ===================== epilogue warps (2..2+GEMM_EPI_WARPS) =====================
+        // warp w may read TMEM lanes [32*(w%4), +32); two warps share each lane quarter and split the columns.
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int COLS_PER_WARP = BLOCK_N / (GEMM_EPI_WARPS / 4);
+        constexpr int NCH = COLS_PER_WARP / 32;
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -166,59 +172,68 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             __nv_bfloat16* out_ptr = out + out_row * ldc;
             const __nv_bfloat16* res_ptr = ep.resid ? ep.resid + out_row * ldc : nullptr;
             const float* tab_ptr = ep.rowtab ? ep.rowtab + static_cast<long>(tpos) * N : nullptr;
+            const int col0 = n_blk * BLOCK_N + half * COLS_PER_WARP;
+
+            auto process = [&](uint32_t (&acc)[32], int n0) {
+                if (!row_ok || n0 >= N) return;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+                if (ep.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                    }
+                }
+                if (tab_ptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(tab_ptr + n0 + j));
+                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                    }
+                }
+                if (ep.act) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+                }
+                if (res_ptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        const uint4 r = *reinterpret_cast<const uint4*>(res_ptr + n0 + j);
+                        float2 f;
+                        f = unpack_bf16x2(r.x); v[j] += f.x; v[j + 1] += f.y;
+                        f = unpack_bf16x2(r.y); v[j + 2] += f.x; v[j + 3] += f.y;
+                        f = unpack_bf16x2(r.z); v[j + 4] += f.x; v[j + 5] += f.y;
+                        f = unpack_bf16x2(r.w); v[j + 6] += f.x; v[j + 7] += f.y;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint4 o;
+                    o.x = pack_bf16x2(v[j], v[j + 1]);
+                    o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                    o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                    o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                    *reinterpret_cast<uint4*>(out_ptr + n0 + j) = o;
+                }
+            };
 
             mbar_wait(&tmem_full_bar[as], aphase, 4);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
-                const int n0 = n_blk * BLOCK_N + c;
-                if (n0 >= N) break;  // warp-uniform
-                uint32_t acc[32];
-                tmem_ld_32x32(taddr + c, acc);
-                tmem_ld_wait();
-                if (row_ok) {
-                    float v[32];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + half * COLS_PER_WARP;
+            // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
+            uint32_t acc_a[32], acc_b[32];
+            tmem_ld_32x32(taddr, acc_a);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-                    if (ep.bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
-                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                        }
-                    }
-                    if (tab_ptr) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(tab_ptr + n0 + j));
-                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                        }
-                    }
-                    if (ep.act) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-                    }
-                    if (res_ptr) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            const uint4 r = *reinterpret_cast<const uint4*>(res_ptr + n0 + j);
-                            float2 f;
-                            f = unpack_bf16x2(r.x); v[j] += f.x; v[j + 1] += f.y;
-                            f = unpack_bf16x2(r.y); v[j + 2] += f.x; v[j + 3] += f.y;
-                            f = unpack_bf16x2(r.z); v[j + 4] += f.x; v[j + 5] += f.y;
-                            f = unpack_bf16x2(r.w); v[j + 6] += f.x; v[j + 7] += f.y;
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 o;
-                        o.x = pack_bf16x2(v[j], v[j + 1]);
-                        o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                        o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                        o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                        *reinterpret_cast<uint4*>(out_ptr + n0 + j) = o;
-                    }
+            for (int c = 0; c < NCH; c += 2) {
+                tmem_ld_wait_regs(acc_a);
+                if (c + 1 < NCH) tmem_ld_32x32(taddr + (c + 1) * 32, acc_b);
+                process(acc_a, col0 + c * 32);
+                if (c + 1 < NCH) {
+                    tmem_ld_wait_regs(acc_b);
+                    if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, acc_a);
+                    process(acc_b, col0 + (c + 1) * 32);
                 }
             }
             // this warp is done reading the accumulator stage

@@ -1,0 +1,222 @@
+// 2-CTA (cta_group::2) variant of the persistent tcgen05 GEMM: a cluster of two CTAs on one TPC computes a
+// 256 x 256 output tile.  Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 weight
+// rows), so per output FLOP only 2/3 of the shared-memory fill traffic of the 1-CTA 128x256 kernel crosses
+// L2 -> SM (128 vs 85 FLOP per byte) -- the 1-CTA kernel is L2-bandwidth bound on the K=768 ViT GEMMs.
+//
+//   rank 0 (leader): TMA producer, the single MMA-issuing thread (UMMA 256x256x16, cta_group::2), epilogue
+//   rank 1         : TMA producer (signals the leader's full barrier), epilogue for its own 128 rows
+// Barrier plumbing: full[s] lives in the leader (expects both CTAs' bytes); empty[s] and tmem_full[a] exist in
+// both CTAs and are signalled by multicast tcgen05.commit; tmem_empty[a] lives in the leader and collects the
+// epilogue warps of BOTH CTAs (remote mbarrier.arrive through mapa).
+#pragma once
+#include "gemm_tcgen05.cuh"
+
+namespace b200 {
+
+constexpr int G2_BLOCK_N = 256;
+constexpr int G2_HALF_N = 128;
+constexpr int G2_STAGES = 6;
+constexpr int G2_A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB: this CTA's 128 rows of A
+constexpr int G2_B_BYTES = G2_HALF_N * GEMM_BLOCK_K * 2;      // 16 KB: this CTA's half of B
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 256 + 1024;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster barrier address
+
+// one 32-column chunk of the epilogue (shared by the 1-CTA and 2-CTA kernels)
+__device__ __forceinline__ void epilogue_chunk(uint32_t (&acc)[32], int n0, int N, bool row_ok, const GemmEpilogue& ep,
+                                               __nv_bfloat16* out_ptr, const __nv_bfloat16* res_ptr,
+                                               const float* tab_ptr) {
+    if (!row_ok || n0 >= N) return;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+    if (ep.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+    }
+    if (tab_ptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(tab_ptr + n0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+    }
+    if (ep.act) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+    }
+    if (res_ptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            const uint4 r = *reinterpret_cast<const uint4*>(res_ptr + n0 + j);
+            float2 f;
+            f = unpack_bf16x2(r.x); v[j] += f.x; v[j + 1] += f.y;
+            f = unpack_bf16x2(r.y); v[j + 2] += f.x; v[j + 3] += f.y;
+            f = unpack_bf16x2(r.z); v[j + 4] += f.x; v[j + 5] += f.y;
+            f = unpack_bf16x2(r.w); v[j + 6] += f.x; v[j + 7] += f.y;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        uint4 o;
+        o.x = pack_bf16x2(v[j], v[j + 1]);
+        o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+        o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(out_ptr + n0 + j) = o;
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                              __nv_bfloat16* out, int ldc, int M, int N, int K, GemmEpilogue ep) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + G2_STAGES * G2_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+    uint64_t* full_bar = bars;                           // [STAGES]  (used in the leader)
+    uint64_t* empty_bar = bars + G2_STAGES;              // [STAGES]  (both CTAs)
+    uint64_t* tmem_full_bar = bars + 2 * G2_STAGES;      // [2]       (both CTAs)
+    uint64_t* tmem_empty_bar = bars + 2 * G2_STAGES + 2; // [2]       (used in the leader)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+
+    const int m_blocks = (M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
+    const int n_blocks = (N + G2_BLOCK_N - 1) / G2_BLOCK_N;
+    const int num_tiles = m_blocks * n_blocks;
+    const int k_blocks = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+        for (int s = 0; s < G2_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full_bar[s], 1);
+            mbar_init(&tmem_empty_bar[s], 2 * GEMM_EPI_WARPS);  // epilogue warps of both CTAs
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<2>(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();   // barriers of BOTH CTAs are initialised before anyone signals across the pair
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m_blk = tile / n_blocks;
+                const int n_blk = tile - m_blk * n_blocks;
+                const int m0 = m_blk * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M;
+                const int n0 = n_blk * G2_BLOCK_N + static_cast<int>(rank) * G2_HALF_N;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 11);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+                    const uint32_t bar = smem_u32(&full_bar[stage]) & kPeerBitMask;  // always the leader's barrier
+                    tma_load_2d_cg2(smem_a + stage * G2_A_BYTES, &tmap_a, bar, kb * GEMM_BLOCK_K, m0);
+                    tma_load_2d_cg2(smem_b + stage * G2_B_BYTES, &tmap_w, bar, kb * GEMM_BLOCK_K, n0);
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BLOCK_M, G2_BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1, 12);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * G2_BLOCK_N;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, 13);
+                    tc_fence_after();
+                    const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smem_a + stage * G2_A_BYTES));
+                    const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smem_b + stage * G2_B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k)
+                        umma_bf16<2>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_cg2(&empty_bar[stage], 0b11);   // frees the stage in both CTAs
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_cg2(&tmem_full_bar[as], 0b11);      // accumulator ready in both CTAs
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (both CTAs, own 128 rows) =====================
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int COLS_PER_WARP = G2_BLOCK_N / (GEMM_EPI_WARPS / 4);
+        constexpr int NCH = COLS_PER_WARP / 32;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int m_blk = tile / n_blocks;
+            const int n_blk = tile - m_blk * n_blocks;
+            const int row = m_blk * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M + q * 32 + lane;
+            const bool row_ok = row < M;
+            long out_row = row;
+            int tpos = 0;
+            if (ep.t_in > 0) {
+                const int img = row / ep.t_in;
+                tpos = row - img * ep.t_in + ep.row_off;
+                out_row = static_cast<long>(img) * ep.t_out + tpos;
+            }
+            __nv_bfloat16* out_ptr = out + out_row * ldc;
+            const __nv_bfloat16* res_ptr = ep.resid ? ep.resid + out_row * ldc : nullptr;
+            const float* tab_ptr = ep.rowtab ? ep.rowtab + static_cast<long>(tpos) * N : nullptr;
+            const int col0 = n_blk * G2_BLOCK_N + half * COLS_PER_WARP;
+
+            mbar_wait(&tmem_full_bar[as], aphase, 14);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * G2_BLOCK_N + half * COLS_PER_WARP;
+            uint32_t acc_a[32], acc_b[32];
+            tmem_ld_32x32(taddr, acc_a);
+#pragma unroll
+            for (int c = 0; c < NCH; c += 2) {
+                tmem_ld_wait_regs(acc_a);
+                if (c + 1 < NCH) tmem_ld_32x32(taddr + (c + 1) * 32, acc_b);
+                epilogue_chunk(acc_a, col0 + c * 32, N, row_ok, ep, out_ptr, res_ptr, tab_ptr);
+                if (c + 1 < NCH) {
+                    tmem_ld_wait_regs(acc_b);
+                    if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, acc_a);
+                    epilogue_chunk(acc_b, col0 + (c + 1) * 32, N, row_ok, ep, out_ptr, res_ptr, tab_ptr);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);  // the leader's barrier
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer may still signal / read
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<2>(tmem_base, 512);
+    }
+}
+
+}  // namespace b200

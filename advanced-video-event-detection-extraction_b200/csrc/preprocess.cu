@@ -135,6 +135,7 @@ struct Plan {
     int H = 0, W = 0, mode = 0;
     bool has_a = false, has_b = false, has_c = false;
     bool a_fast = false;     // integer scale factors in both axes (OpenCV ResizeAreaFast path)
+    int a_max_cx = 0;        // largest horizontal tap count of the area stage
     int a_fx = 1, a_fy = 1;
     int h1 = 0, w1 = 0;      // size after the area shrink
     int nw = 0, nh = 0;      // size after the Pillow resize
@@ -218,6 +219,71 @@ __global__ void area_kernel(const uint8_t* __restrict__ src, int64_t frame_strid
                 b0 = __fadd_rn(b0, __fmul_rn(static_cast<float>(row[i * 3 + 0]), a));
                 b1 = __fadd_rn(b1, __fmul_rn(static_cast<float>(row[i * 3 + 1]), a));
                 b2 = __fadd_rn(b2, __fmul_rn(static_cast<float>(row[i * 3 + 2]), a));
+            }
+            const float beta = wy[j];
+            if (j == 0) {
+                s0 = __fmul_rn(beta, b0); s1 = __fmul_rn(beta, b1); s2 = __fmul_rn(beta, b2);
+            } else {
+                s0 = __fadd_rn(s0, __fmul_rn(beta, b0));
+                s1 = __fadd_rn(s1, __fmul_rn(beta, b1));
+                s2 = __fadd_rn(s2, __fmul_rn(beta, b2));
+            }
+        }
+        uint8_t* o = dst + f * dst_frame_stride + (static_cast<int64_t>(y) * nx + x) * 3;
+        o[0] = static_cast<uint8_t>(min(max(__float2int_rn(s0), 0), 255));
+        o[1] = static_cast<uint8_t>(min(max(__float2int_rn(s1), 0), 255));
+        o[2] = static_cast<uint8_t>(min(max(__float2int_rn(s2), 0), 255));
+    }
+}
+
+// A, fast path for <= 5 horizontal taps (scale <= 4, e.g. 1080p/720p -> 512 wide): per source row the <= 15 source
+// bytes are fetched as five aligned 32-bit words and realigned with funnel shifts, the tap weights live in
+// registers (zero padded: adding +0.0f leaves the fp32 accumulator bit-identical), so a thread issues ~30 loads
+// instead of ~100.  Accumulation order and rounding are exactly those of area_kernel.
+__global__ void __launch_bounds__(256)
+area_kernel_w5(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride, uint8_t* __restrict__ dst,
+               int64_t dst_frame_stride, int n, int oy0, int ny, int ox0, int nx, DevTaps ax, DevTaps ay) {
+    const int64_t total = static_cast<int64_t>(n) * ny * nx;
+    for (int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; id < total;
+         id += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(id % nx);
+        const int64_t r = id / nx;
+        const int y = static_cast<int>(r % ny);
+        const int64_t f = r / ny;
+        const int dx = ox0 + x, dy = oy0 + y;
+        const int sx0 = ax.start[dx], cx = ax.cnt[dx];
+        const int sy0 = ay.start[dy], cy = ay.cnt[dy];
+        const float* wxp = ax.wf + static_cast<int64_t>(dx) * ax.stride;
+        const float* wy = ay.wf + static_cast<int64_t>(dy) * ay.stride;
+        float wx[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) wx[i] = i < cx ? wxp[i] : 0.f;
+        const uint8_t* base = src + f * frame_stride + static_cast<int64_t>(sx0) * 3;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int j = 0; j < cy; ++j) {
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(base + static_cast<int64_t>(sy0 + j) * row_stride);
+            const uint32_t sh = static_cast<uint32_t>(addr & 3) * 8;
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(addr & ~uintptr_t(3));
+            // last word that holds a needed byte: never read past it (bytes beyond only meet zero weights)
+            const int last = static_cast<int>(((addr & 3) + static_cast<uintptr_t>(cx) * 3 - 1) >> 2);
+            uint32_t w[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) w[k] = __ldg(wp + (k < last ? k : last));
+            uint32_t u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[k] = __funnelshift_r(w[k], w[k + 1], sh);
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int n0 = i * 3, n1 = i * 3 + 1, n2 = i * 3 + 2;
+                // uint8 -> float without the quarter-rate I2F: splice the byte into the mantissa of 2^23 and
+                // subtract 2^23 (exact)
+                const float p0 = __fadd_rn(__uint_as_float(__byte_perm(u[n0 >> 2], 0x4B000000u, 0x7650u | (n0 & 3))), -8388608.0f);
+                const float p1 = __fadd_rn(__uint_as_float(__byte_perm(u[n1 >> 2], 0x4B000000u, 0x7650u | (n1 & 3))), -8388608.0f);
+                const float p2 = __fadd_rn(__uint_as_float(__byte_perm(u[n2 >> 2], 0x4B000000u, 0x7650u | (n2 & 3))), -8388608.0f);
+                b0 = __fadd_rn(b0, __fmul_rn(p0, wx[i]));
+                b1 = __fadd_rn(b1, __fmul_rn(p1, wx[i]));
+                b2 = __fadd_rn(b2, __fmul_rn(p2, wx[i]));
             }
             const float beta = wy[j];
             if (j == 0) {
@@ -440,6 +506,7 @@ static int build_plan(b200clip_handle* h, int H, int W, int mode, Plan& p) {
         if (!p.a_fast) {
             ax = area_taps(W, w1);
             ay = area_taps(H, h1);
+            for (int c : ax.cnt) p.a_max_cx = c > p.a_max_cx ? c : p.a_max_cx;
         }
     }
     p.ax = upload_taps(h, p, ax, rc);
@@ -535,6 +602,9 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         if (p.a_fast)
             area_fast_kernel<<<grid_for(h, total, 256), 256, 0, st>>>(cur, cur_fs, cur_rs, mid1, p.mid1_per_frame, n,
                                                                       p.ry0, ny, p.rx0, nx, p.a_fx, p.a_fy);
+        else if (p.a_max_cx <= 5)
+            area_kernel_w5<<<grid_for(h, total, 256), 256, 0, st>>>(cur, cur_fs, cur_rs, mid1, p.mid1_per_frame, n,
+                                                                    p.ry0, ny, p.rx0, nx, p.ax, p.ay);
         else
             area_kernel<<<grid_for(h, total, 256), 256, 0, st>>>(cur, cur_fs, cur_rs, mid1, p.mid1_per_frame, n, p.ry0,
                                                                  ny, p.rx0, nx, p.ax, p.ay);

@@ -367,6 +367,7 @@ head_kernel(const bf16* __restrict__ x, int64_t row_stride, const int32_t* __res
     for (int c = 0; c < HEAD_MAXCOL; ++c)
 #pragma unroll
         for (int i = 0; i < HEAD_IMGS; ++i) acc[c][i] = 0.f;
+#pragma unroll 8
     for (int d = 0; d < width; ++d) {
         float w[HEAD_MAXCOL];
 #pragma unroll

@@ -26,6 +26,9 @@ def _stream():
     (128, 256, 64, 0, 0, 0), (200, 768, 768, 1, 1, 0), (1000, 3072, 768, 1, 0, 1), (1000, 768, 3072, 1, 1, 0),
     (333, 2304, 768, 1, 0, 2), (77, 512, 512, 1, 0, 0), (130, 384, 512, 1, 0, 0), (50, 64, 64, 1, 0, 0),
     (5000, 768, 3072, 0, 0, 0), (1, 768, 768, 1, 0, 0), (12544, 1024, 640, 0, 0, 0),
+    # M >= 2048 and N % 256 == 0 -> the 2-CTA (cta_group::2) kernel; tails in M, every epilogue
+    (4096, 2304, 768, 1, 0, 0), (2049, 768, 768, 1, 1, 0), (3000, 3072, 768, 1, 0, 1), (2304, 256, 64, 0, 0, 2),
+    (20000, 768, 3072, 1, 1, 0), (2048, 512, 2048, 1, 1, 0),
 ])
 def test_gemm_matches_torch(handle, m, n, k, bias, resid, act):
     from b200clip import capi
