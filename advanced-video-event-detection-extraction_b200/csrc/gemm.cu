@@ -79,6 +79,16 @@ static int launch_gemm_2cta(b200clip_handle* h, const bf16* a, int lda, const bf
     if ((rc = make_tmap_bf16_2d(h, &tw, w, N, K, ldw, b200::G2_HALF_N, b200::GEMM_BLOCK_K,
                                 CU_TENSOR_MAP_SWIZZLE_128B)))
         return rc;
+    // staged (TMA store) epilogue whenever the output rows are an affine image of the accumulator rows
+    const int use_tma_epi = ep.t_in == 0 && ep.rowtab == nullptr && (ldc % 8 == 0) ? 1 : 0;
+    CUtensorMap to, tr;
+    if (use_tma_epi) {
+        if ((rc = make_tmap_bf16_2d(h, &to, out, M, N, ldc, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tmap_bf16_2d(h, &tr, ep.resid ? ep.resid : out, M, N, ldc, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B)))
+            return rc;
+    } else {
+        to = ta; tr = ta;   // unused
+    }
     static bool attr_set = false;
     if (!attr_set) {
         B200_CUDA(h, cudaFuncSetAttribute(b200::gemm_bf16_tcgen05_2cta_kernel,
@@ -93,7 +103,7 @@ static int launch_gemm_2cta(b200clip_handle* h, const bf16* a, int lda, const bf
     {
         ProfScope ps(h, PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
         b200::gemm_bf16_tcgen05_2cta_kernel<<<2 * clusters, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, st>>>(
-            ta, tw, out, ldc, M, N, K, ep);
+            ta, tw, to, tr, out, ldc, M, N, K, ep, use_tma_epi);
     }
     h->launches++;
     B200_CUDA(h, cudaGetLastError());

@@ -45,8 +45,10 @@ struct GemmCfg {
 
 __device__ __forceinline__ float apply_act(float x, int act) {
     if (act == 1) {
-        // QuickGELU: x * sigmoid(1.702 x)
-        return __fdividef(x, 1.0f + __expf(-1.702f * x));
+        // QuickGELU: x * sigmoid(1.702 x), sigmoid(y) = 0.5 + 0.5 tanh(y/2): one MUFU (tanh.approx, rel. err ~2^-11)
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+        return x * fmaf(0.5f, t, 0.5f);
     } else if (act == 2) {
         return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
     }

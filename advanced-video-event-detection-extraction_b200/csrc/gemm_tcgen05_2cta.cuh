@@ -15,11 +15,14 @@ namespace b200 {
 
 constexpr int G2_BLOCK_N = 256;
 constexpr int G2_HALF_N = 128;
-constexpr int G2_STAGES = 6;
+constexpr int G2_STAGES = 4;
 constexpr int G2_A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB: this CTA's 128 rows of A
 constexpr int G2_B_BYTES = G2_HALF_N * GEMM_BLOCK_K * 2;      // 16 KB: this CTA's half of B
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 256 + 1024;
+// epilogue staging: every epilogue warp owns two [32 rows x 64 cols] bf16 boxes (128-byte rows, SWIZZLE_128B)
+constexpr int G2_BOX_BYTES = 32 * 128;
+constexpr int G2_STAGING_BYTES = GEMM_EPI_WARPS * 2 * G2_BOX_BYTES;   // 64 KB
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_STAGING_BYTES + 512 + 1024;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster barrier address
 
 // one 32-column chunk of the epilogue (shared by the 1-CTA and 2-CTA kernels)
@@ -70,19 +73,63 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&acc)[32], int n0, int 
     }
 }
 
+// 32 accumulator columns of one row -> bf16 into a [32 rows][64 cols] SWIZZLE_128B box (row = lane).
+// chunk0 = index of the first 16-byte chunk of the row these 32 columns occupy (0 or 4).  If has_res, the box
+// already holds the residual tile (TMA-loaded) and it is added in place.
+__device__ __forceinline__ void epilogue_chunk_smem(uint32_t (&acc)[32], int n0, int N, const GemmEpilogue& ep,
+                                                    uint8_t* box, int lane, int chunk0, bool has_res) {
+    if (n0 >= N) return;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+    if (ep.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+    }
+    if (ep.act) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+    }
+    uint8_t* rowp = box + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4* slot = reinterpret_cast<uint4*>(rowp + (((chunk0 + j) ^ (lane & 7)) << 4));
+        if (has_res) {
+            const uint4 r = *slot;
+            float2 f;
+            f = unpack_bf16x2(r.x); v[j * 8] += f.x; v[j * 8 + 1] += f.y;
+            f = unpack_bf16x2(r.y); v[j * 8 + 2] += f.x; v[j * 8 + 3] += f.y;
+            f = unpack_bf16x2(r.z); v[j * 8 + 4] += f.x; v[j * 8 + 5] += f.y;
+            f = unpack_bf16x2(r.w); v[j * 8 + 6] += f.x; v[j * 8 + 7] += f.y;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[j * 8], v[j * 8 + 1]);
+        o.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+        o.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
+        o.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+        *slot = o;
+    }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                              __nv_bfloat16* out, int ldc, int M, int N, int K, GemmEpilogue ep) {
+                              const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                              __nv_bfloat16* out, int ldc, int M, int N, int K, GemmEpilogue ep, int use_tma_epi) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + G2_STAGES * G2_A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+    uint8_t* staging = smem + G2_STAGES * G2_STAGE_BYTES;   // 1024-byte aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + G2_STAGING_BYTES);
     uint64_t* full_bar = bars;                           // [STAGES]  (used in the leader)
     uint64_t* empty_bar = bars + G2_STAGES;              // [STAGES]  (both CTAs)
     uint64_t* tmem_full_bar = bars + 2 * G2_STAGES;      // [2]       (both CTAs)
     uint64_t* tmem_empty_bar = bars + 2 * G2_STAGES + 2; // [2]       (used in the leader)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4);
+    uint64_t* res_bar = bars + 2 * G2_STAGES + 4;         // [GEMM_EPI_WARPS] residual-tile loads, one per warp
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4 + GEMM_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -107,6 +154,9 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
             mbar_init(&tmem_full_bar[s], 1);
             mbar_init(&tmem_empty_bar[s], 2 * GEMM_EPI_WARPS);  // epilogue warps of both CTAs
         }
+        for (int s = 0; s < GEMM_EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
+        tma_prefetch_desc(&tmap_out);
+        tma_prefetch_desc(&tmap_res);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<2>(tmem_slot, 512);
@@ -170,6 +220,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
         constexpr int NCH = COLS_PER_WARP / 32;
         int as = 0;
         uint32_t aphase = 0;
+        uint32_t res_phase = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int m_blk = tile / n_blocks;
             const int n_blk = tile - m_blk * n_blocks;
@@ -187,20 +238,58 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
             const float* tab_ptr = ep.rowtab ? ep.rowtab + static_cast<long>(tpos) * N : nullptr;
             const int col0 = n_blk * G2_BLOCK_N + half * COLS_PER_WARP;
 
-            mbar_wait(&tmem_full_bar[as], aphase, 14);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * G2_BLOCK_N + half * COLS_PER_WARP;
-            uint32_t acc_a[32], acc_b[32];
-            tmem_ld_32x32(taddr, acc_a);
+            if (use_tma_epi) {
+                // ---- staged epilogue: TMEM -> registers -> swizzled smem box -> TMA bulk store (full 128-byte
+                // lines); the residual tile is TMA-loaded into the same box while the MMAs of this tile still run.
+                uint8_t* my_stage = staging + (warp - 2) * 2 * G2_BOX_BYTES;
+                uint64_t* my_bar = &res_bar[warp - 2];
+                const int box_row0 = m_blk * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M + q * 32;
+                if (lane == 0) tma_store_wait_read<0>();   // previous tile's stores no longer read the boxes
+                __syncwarp();
+                if (res_ptr && lane == 0) {
+                    mbar_arrive_expect_tx(my_bar, 2 * G2_BOX_BYTES);
+                    tma_load_2d(my_stage, &tmap_res, my_bar, col0, box_row0);
+                    tma_load_2d(my_stage + G2_BOX_BYTES, &tmap_res, my_bar, col0 + 64, box_row0);
+                }
+                mbar_wait(&tmem_full_bar[as], aphase, 14);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * G2_BLOCK_N + half * COLS_PER_WARP;
+                uint32_t acc_a[32], acc_b[32];
+                tmem_ld_32x32(taddr, acc_a);
+                if (res_ptr) mbar_wait(my_bar, res_phase, 15);
 #pragma unroll
-            for (int c = 0; c < NCH; c += 2) {
-                tmem_ld_wait_regs(acc_a);
-                if (c + 1 < NCH) tmem_ld_32x32(taddr + (c + 1) * 32, acc_b);
-                epilogue_chunk(acc_a, col0 + c * 32, N, row_ok, ep, out_ptr, res_ptr, tab_ptr);
-                if (c + 1 < NCH) {
+                for (int c = 0; c < NCH; c += 2) {   // one 64-column box per iteration
+                    uint8_t* box = my_stage + (c >> 1) * G2_BOX_BYTES;
+                    tmem_ld_wait_regs(acc_a);
+                    tmem_ld_32x32(taddr + (c + 1) * 32, acc_b);
+                    epilogue_chunk_smem(acc_a, col0 + c * 32, N, ep, box, lane, 0, res_ptr != nullptr);
                     tmem_ld_wait_regs(acc_b);
                     if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, acc_a);
-                    epilogue_chunk(acc_b, col0 + (c + 1) * 32, N, row_ok, ep, out_ptr, res_ptr, tab_ptr);
+                    epilogue_chunk_smem(acc_b, col0 + (c + 1) * 32, N, ep, box, lane, 4, res_ptr != nullptr);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && col0 + c * 32 < N) {
+                        tma_store_2d(&tmap_out, box, col0 + c * 32, box_row0);
+                        tma_store_commit();
+                    }
+                }
+                if (res_ptr) res_phase ^= 1;
+            } else {
+                mbar_wait(&tmem_full_bar[as], aphase, 14);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * G2_BLOCK_N + half * COLS_PER_WARP;
+                uint32_t acc_a[32], acc_b[32];
+                tmem_ld_32x32(taddr, acc_a);
+    #pragma unroll
+                for (int c = 0; c < NCH; c += 2) {
+                    tmem_ld_wait_regs(acc_a);
+                    if (c + 1 < NCH) tmem_ld_32x32(taddr + (c + 1) * 32, acc_b);
+                    epilogue_chunk(acc_a, col0 + c * 32, N, row_ok, ep, out_ptr, res_ptr, tab_ptr);
+                    if (c + 1 < NCH) {
+                        tmem_ld_wait_regs(acc_b);
+                        if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, acc_a);
+                        epilogue_chunk(acc_b, col0 + (c + 1) * 32, N, row_ok, ep, out_ptr, res_ptr, tab_ptr);
+                    }
                 }
             }
             tc_fence_before();
@@ -210,6 +299,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
         }
     }
 
+    if (warp >= 2 && lane == 0) tma_store_wait<0>();   // bulk stores of the last tile are complete
     __syncwarp();
     tc_fence_before();
     cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer may still signal / read
