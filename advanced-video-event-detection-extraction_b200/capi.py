@@ -159,7 +159,8 @@ class Handle:
     def reserve(self, max_images: int, max_texts: int = 0):
         self.call("b200clip_reserve", int(max_images), int(max_texts))
 
-    PROFILE_CLASSES = ("gemm", "attention", "layernorm", "preprocess", "head", "sim_topk", "misc")
+    PROFILE_CLASSES = ("gemm", "attention", "layernorm", "preprocess", "head", "sim_topk", "misc", "pre_area", "pre_hpass",
+                       "pre_vpass")
 
     def profile_enable(self, on: bool = True):
         self.call("b200clip_profile_enable", int(on))

@@ -79,7 +79,7 @@ struct b200clip_handle {
 };
 
 // kernel classes for the profiler
-enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_PRE = 3, PROF_HEAD = 4, PROF_SIM = 5, PROF_MISC = 6, PROF_NCLS = 7 };
+enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_PRE = 3, PROF_HEAD = 4, PROF_SIM = 5, PROF_MISC = 6, PROF_PRE_A = 7, PROF_PRE_B = 8, PROF_PRE_C = 9, PROF_NCLS = 10 };
 // RAII bracket: records an event pair around the launches made in its scope when profiling is on
 struct ProfScope {
     b200clip_handle* h; cudaStream_t st; int idx;

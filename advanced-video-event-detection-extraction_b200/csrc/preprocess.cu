@@ -136,6 +136,7 @@ struct Plan {
     bool has_a = false, has_b = false, has_c = false;
     bool a_fast = false;     // integer scale factors in both axes (OpenCV ResizeAreaFast path)
     int a_max_cx = 0;        // largest horizontal tap count of the area stage
+    int b_max_cnt = 0;       // largest tap count of the Pillow horizontal pass
     int a_fx = 1, a_fy = 1;
     int h1 = 0, w1 = 0;      // size after the area shrink
     int nw = 0, nh = 0;      // size after the Pillow resize
@@ -192,145 +193,144 @@ int py_round_half_even(double v) {  // Python round()
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------- kernels
-// A: area shrink.  One thread per output pixel (3 channels); taps accumulated in OpenCV's order with
-// unfused fp32 multiply/add.
-__global__ void area_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride,
-                            uint8_t* __restrict__ dst, int64_t dst_frame_stride, int n, int oy0, int ny, int ox0,
-                            int nx, DevTaps ax, DevTaps ay) {
-    const int64_t total = static_cast<int64_t>(n) * ny * nx;
-    for (int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; id < total;
-         id += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int x = static_cast<int>(id % nx);
-        const int64_t r = id / nx;
-        const int y = static_cast<int>(r % ny);
-        const int64_t f = r / ny;
-        const int dx = ox0 + x, dy = oy0 + y;
-        const int sx0 = ax.start[dx], cx = ax.cnt[dx];
-        const int sy0 = ay.start[dy], cy = ay.cnt[dy];
-        const float* wx = ax.wf + static_cast<int64_t>(dx) * ax.stride;
-        const float* wy = ay.wf + static_cast<int64_t>(dy) * ay.stride;
-        const uint8_t* base = src + f * frame_stride + static_cast<int64_t>(sx0) * 3;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        for (int j = 0; j < cy; ++j) {
-            const uint8_t* row = base + static_cast<int64_t>(sy0 + j) * row_stride;
-            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-            for (int i = 0; i < cx; ++i) {
-                const float a = wx[i];
-                b0 = __fadd_rn(b0, __fmul_rn(static_cast<float>(row[i * 3 + 0]), a));
-                b1 = __fadd_rn(b1, __fmul_rn(static_cast<float>(row[i * 3 + 1]), a));
-                b2 = __fadd_rn(b2, __fmul_rn(static_cast<float>(row[i * 3 + 2]), a));
-            }
-            const float beta = wy[j];
-            if (j == 0) {
-                s0 = __fmul_rn(beta, b0); s1 = __fmul_rn(beta, b1); s2 = __fmul_rn(beta, b2);
-            } else {
-                s0 = __fadd_rn(s0, __fmul_rn(beta, b0));
-                s1 = __fadd_rn(s1, __fmul_rn(beta, b1));
-                s2 = __fadd_rn(s2, __fmul_rn(beta, b2));
-            }
+// All three stages use a 2-D grid: blockIdx.y = frame, blockIdx.x * blockDim.x + threadIdx.x = work item inside the
+// frame (32-bit index math only -- 64-bit div/mod per thread used to dominate the instruction count).
+
+// Aligned-word fetch of NB contiguous bytes starting at an arbitrary address: NW+1 aligned 32-bit loads, realigned
+// with funnel shifts into u[0..NW).  Words past the last needed byte are not dereferenced (clamped).
+template <int NW>
+__device__ __forceinline__ void load_bytes_aligned(const uint8_t* p, int nbytes, uint32_t (&u)[NW]) {
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+    const uint32_t sh = static_cast<uint32_t>(addr & 3) * 8;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(addr & ~uintptr_t(3));
+    const int last = static_cast<int>(((addr & 3) + static_cast<uintptr_t>(nbytes) - 1) >> 2);
+    uint32_t w[NW + 1];
+#pragma unroll
+    for (int k = 0; k <= NW; ++k) w[k] = __ldg(wp + (k < last ? k : last));
+#pragma unroll
+    for (int k = 0; k < NW; ++k) u[k] = __funnelshift_r(w[k], w[k + 1], sh);
+}
+// byte n (compile-time) of a realigned word array as float, exactly: splice into the mantissa of 2^23, subtract 2^23
+template <int NW>
+__device__ __forceinline__ float byte_as_float(const uint32_t (&u)[NW], int n) {
+    return __fadd_rn(__uint_as_float(__byte_perm(u[n >> 2], 0x4B000000u, 0x7650u | (n & 3))), -8388608.0f);
+}
+template <int NW>
+__device__ __forceinline__ int byte_as_int(const uint32_t (&u)[NW], int n) {
+    return static_cast<int>(__byte_perm(u[n >> 2], 0u, 0x4440u | (n & 3)));
+}
+
+// A: area shrink, generic tap counts.  One thread per output pixel (3 channels); taps accumulated in OpenCV's order
+// with unfused fp32 multiply/add.
+__global__ void __launch_bounds__(256)
+area_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride, uint8_t* __restrict__ dst,
+            int64_t dst_frame_stride, int oy0, int ny, int ox0, int nx, DevTaps ax, DevTaps ay) {
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= static_cast<unsigned>(ny * nx)) return;
+    const int y = id / nx, x = id - y * nx;
+    const int64_t f = blockIdx.y;
+    const int dx = ox0 + x, dy = oy0 + y;
+    const int sx0 = ax.start[dx], cx = ax.cnt[dx];
+    const int sy0 = ay.start[dy], cy = ay.cnt[dy];
+    const float* wx = ax.wf + dx * ax.stride;
+    const float* wy = ay.wf + dy * ay.stride;
+    const uint8_t* base = src + f * frame_stride + sx0 * 3;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int j = 0; j < cy; ++j) {
+        const uint8_t* row = base + static_cast<int64_t>(sy0 + j) * row_stride;
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        for (int i = 0; i < cx; ++i) {
+            const float a = wx[i];
+            b0 = __fadd_rn(b0, __fmul_rn(static_cast<float>(row[i * 3 + 0]), a));
+            b1 = __fadd_rn(b1, __fmul_rn(static_cast<float>(row[i * 3 + 1]), a));
+            b2 = __fadd_rn(b2, __fmul_rn(static_cast<float>(row[i * 3 + 2]), a));
         }
-        uint8_t* o = dst + f * dst_frame_stride + (static_cast<int64_t>(y) * nx + x) * 3;
-        o[0] = static_cast<uint8_t>(min(max(__float2int_rn(s0), 0), 255));
-        o[1] = static_cast<uint8_t>(min(max(__float2int_rn(s1), 0), 255));
-        o[2] = static_cast<uint8_t>(min(max(__float2int_rn(s2), 0), 255));
+        const float beta = wy[j];
+        if (j == 0) {
+            s0 = __fmul_rn(beta, b0); s1 = __fmul_rn(beta, b1); s2 = __fmul_rn(beta, b2);
+        } else {
+            s0 = __fadd_rn(s0, __fmul_rn(beta, b0));
+            s1 = __fadd_rn(s1, __fmul_rn(beta, b1));
+            s2 = __fadd_rn(s2, __fmul_rn(beta, b2));
+        }
     }
+    uint8_t* o = dst + f * dst_frame_stride + (y * nx + x) * 3;
+    o[0] = static_cast<uint8_t>(min(max(__float2int_rn(s0), 0), 255));
+    o[1] = static_cast<uint8_t>(min(max(__float2int_rn(s1), 0), 255));
+    o[2] = static_cast<uint8_t>(min(max(__float2int_rn(s2), 0), 255));
 }
 
 // A, fast path for <= 5 horizontal taps (scale <= 4, e.g. 1080p/720p -> 512 wide): per source row the <= 15 source
-// bytes are fetched as five aligned 32-bit words and realigned with funnel shifts, the tap weights live in
-// registers (zero padded: adding +0.0f leaves the fp32 accumulator bit-identical), so a thread issues ~30 loads
-// instead of ~100.  Accumulation order and rounding are exactly those of area_kernel.
+// bytes come from aligned words, the tap weights live in registers (zero padded: adding +0.0f leaves the fp32
+// accumulator bit-identical).  Accumulation order and rounding are exactly those of area_kernel.
 __global__ void __launch_bounds__(256)
 area_kernel_w5(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride, uint8_t* __restrict__ dst,
-               int64_t dst_frame_stride, int n, int oy0, int ny, int ox0, int nx, DevTaps ax, DevTaps ay) {
-    const int64_t total = static_cast<int64_t>(n) * ny * nx;
-    for (int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; id < total;
-         id += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int x = static_cast<int>(id % nx);
-        const int64_t r = id / nx;
-        const int y = static_cast<int>(r % ny);
-        const int64_t f = r / ny;
-        const int dx = ox0 + x, dy = oy0 + y;
-        const int sx0 = ax.start[dx], cx = ax.cnt[dx];
-        const int sy0 = ay.start[dy], cy = ay.cnt[dy];
-        const float* wxp = ax.wf + static_cast<int64_t>(dx) * ax.stride;
-        const float* wy = ay.wf + static_cast<int64_t>(dy) * ay.stride;
-        float wx[5];
+               int64_t dst_frame_stride, int oy0, int ny, int ox0, int nx, DevTaps ax, DevTaps ay) {
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= static_cast<unsigned>(ny * nx)) return;
+    const int y = id / nx, x = id - y * nx;
+    const int64_t f = blockIdx.y;
+    const int dx = ox0 + x, dy = oy0 + y;
+    const int sx0 = ax.start[dx], cx = ax.cnt[dx];
+    const int sy0 = ay.start[dy], cy = ay.cnt[dy];
+    const float* wxp = ax.wf + dx * ax.stride;
+    const float* wy = ay.wf + dy * ay.stride;
+    float wx[5];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) wx[i] = i < cx ? wxp[i] : 0.f;
-        const uint8_t* base = src + f * frame_stride + static_cast<int64_t>(sx0) * 3;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        for (int j = 0; j < cy; ++j) {
-            const uintptr_t addr = reinterpret_cast<uintptr_t>(base + static_cast<int64_t>(sy0 + j) * row_stride);
-            const uint32_t sh = static_cast<uint32_t>(addr & 3) * 8;
-            const uint32_t* wp = reinterpret_cast<const uint32_t*>(addr & ~uintptr_t(3));
-            // last word that holds a needed byte: never read past it (bytes beyond only meet zero weights)
-            const int last = static_cast<int>(((addr & 3) + static_cast<uintptr_t>(cx) * 3 - 1) >> 2);
-            uint32_t w[5];
+    for (int i = 0; i < 5; ++i) wx[i] = i < cx ? wxp[i] : 0.f;
+    const uint8_t* base = src + f * frame_stride + static_cast<int64_t>(sy0) * row_stride + sx0 * 3;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int j = 0; j < cy; ++j) {
+        uint32_t u[4];
+        load_bytes_aligned<4>(base + j * row_stride, cx * 3, u);
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
 #pragma unroll
-            for (int k = 0; k < 5; ++k) w[k] = __ldg(wp + (k < last ? k : last));
-            uint32_t u[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) u[k] = __funnelshift_r(w[k], w[k + 1], sh);
-            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const int n0 = i * 3, n1 = i * 3 + 1, n2 = i * 3 + 2;
-                // uint8 -> float without the quarter-rate I2F: splice the byte into the mantissa of 2^23 and
-                // subtract 2^23 (exact)
-                const float p0 = __fadd_rn(__uint_as_float(__byte_perm(u[n0 >> 2], 0x4B000000u, 0x7650u | (n0 & 3))), -8388608.0f);
-                const float p1 = __fadd_rn(__uint_as_float(__byte_perm(u[n1 >> 2], 0x4B000000u, 0x7650u | (n1 & 3))), -8388608.0f);
-                const float p2 = __fadd_rn(__uint_as_float(__byte_perm(u[n2 >> 2], 0x4B000000u, 0x7650u | (n2 & 3))), -8388608.0f);
-                b0 = __fadd_rn(b0, __fmul_rn(p0, wx[i]));
-                b1 = __fadd_rn(b1, __fmul_rn(p1, wx[i]));
-                b2 = __fadd_rn(b2, __fmul_rn(p2, wx[i]));
-            }
-            const float beta = wy[j];
-            if (j == 0) {
-                s0 = __fmul_rn(beta, b0); s1 = __fmul_rn(beta, b1); s2 = __fmul_rn(beta, b2);
-            } else {
-                s0 = __fadd_rn(s0, __fmul_rn(beta, b0));
-                s1 = __fadd_rn(s1, __fmul_rn(beta, b1));
-                s2 = __fadd_rn(s2, __fmul_rn(beta, b2));
-            }
+        for (int i = 0; i < 5; ++i) {
+            b0 = __fadd_rn(b0, __fmul_rn(byte_as_float<4>(u, i * 3), wx[i]));
+            b1 = __fadd_rn(b1, __fmul_rn(byte_as_float<4>(u, i * 3 + 1), wx[i]));
+            b2 = __fadd_rn(b2, __fmul_rn(byte_as_float<4>(u, i * 3 + 2), wx[i]));
         }
-        uint8_t* o = dst + f * dst_frame_stride + (static_cast<int64_t>(y) * nx + x) * 3;
-        o[0] = static_cast<uint8_t>(min(max(__float2int_rn(s0), 0), 255));
-        o[1] = static_cast<uint8_t>(min(max(__float2int_rn(s1), 0), 255));
-        o[2] = static_cast<uint8_t>(min(max(__float2int_rn(s2), 0), 255));
+        const float beta = wy[j];
+        if (j == 0) {
+            s0 = __fmul_rn(beta, b0); s1 = __fmul_rn(beta, b1); s2 = __fmul_rn(beta, b2);
+        } else {
+            s0 = __fadd_rn(s0, __fmul_rn(beta, b0));
+            s1 = __fadd_rn(s1, __fmul_rn(beta, b1));
+            s2 = __fadd_rn(s2, __fmul_rn(beta, b2));
+        }
     }
+    uint8_t* o = dst + f * dst_frame_stride + (y * nx + x) * 3;
+    o[0] = static_cast<uint8_t>(min(max(__float2int_rn(s0), 0), 255));
+    o[1] = static_cast<uint8_t>(min(max(__float2int_rn(s1), 0), 255));
+    o[2] = static_cast<uint8_t>(min(max(__float2int_rn(s2), 0), 255));
 }
 
 // A (integer scale factors): OpenCV ResizeAreaFast -- integer box sum times float(1/area), rint;
 // the 2x2 uint8 case is (a+b+c+d+2)>>2.
-__global__ void area_fast_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride,
-                                 uint8_t* __restrict__ dst, int64_t dst_frame_stride, int n, int oy0, int ny, int ox0,
-                                 int nx, int fx, int fy) {
-    const int64_t total = static_cast<int64_t>(n) * ny * nx;
+__global__ void __launch_bounds__(256)
+area_fast_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride, uint8_t* __restrict__ dst,
+                 int64_t dst_frame_stride, int oy0, int ny, int ox0, int nx, int fx, int fy) {
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= static_cast<unsigned>(ny * nx)) return;
+    const int y = id / nx, x = id - y * nx;
+    const int64_t f = blockIdx.y;
     const float inv_area = 1.0f / static_cast<float>(fx * fy);
-    for (int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; id < total;
-         id += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int x = static_cast<int>(id % nx);
-        const int64_t r = id / nx;
-        const int y = static_cast<int>(r % ny);
-        const int64_t f = r / ny;
-        const uint8_t* base = src + f * frame_stride + static_cast<int64_t>(oy0 + y) * fy * row_stride +
-                              static_cast<int64_t>(ox0 + x) * fx * 3;
-        int s0 = 0, s1 = 0, s2 = 0;
-        for (int j = 0; j < fy; ++j) {
-            const uint8_t* row = base + j * row_stride;
-            for (int i = 0; i < fx; ++i) { s0 += row[i * 3]; s1 += row[i * 3 + 1]; s2 += row[i * 3 + 2]; }
-        }
-        uint8_t* o = dst + f * dst_frame_stride + (static_cast<int64_t>(y) * nx + x) * 3;
-        if (fx == 2 && fy == 2) {
-            o[0] = static_cast<uint8_t>((s0 + 2) >> 2);
-            o[1] = static_cast<uint8_t>((s1 + 2) >> 2);
-            o[2] = static_cast<uint8_t>((s2 + 2) >> 2);
-        } else {
-            o[0] = static_cast<uint8_t>(min(max(__float2int_rn(__fmul_rn(static_cast<float>(s0), inv_area)), 0), 255));
-            o[1] = static_cast<uint8_t>(min(max(__float2int_rn(__fmul_rn(static_cast<float>(s1), inv_area)), 0), 255));
-            o[2] = static_cast<uint8_t>(min(max(__float2int_rn(__fmul_rn(static_cast<float>(s2), inv_area)), 0), 255));
-        }
+    const uint8_t* base = src + f * frame_stride + static_cast<int64_t>(oy0 + y) * fy * row_stride +
+                          static_cast<int64_t>(ox0 + x) * fx * 3;
+    int s0 = 0, s1 = 0, s2 = 0;
+    for (int j = 0; j < fy; ++j) {
+        const uint8_t* row = base + j * row_stride;
+        for (int i = 0; i < fx; ++i) { s0 += row[i * 3]; s1 += row[i * 3 + 1]; s2 += row[i * 3 + 2]; }
+    }
+    uint8_t* o = dst + f * dst_frame_stride + (y * nx + x) * 3;
+    if (fx == 2 && fy == 2) {
+        o[0] = static_cast<uint8_t>((s0 + 2) >> 2);
+        o[1] = static_cast<uint8_t>((s1 + 2) >> 2);
+        o[2] = static_cast<uint8_t>((s2 + 2) >> 2);
+    } else {
+        o[0] = static_cast<uint8_t>(min(max(__float2int_rn(__fmul_rn(static_cast<float>(s0), inv_area)), 0), 255));
+        o[1] = static_cast<uint8_t>(min(max(__float2int_rn(__fmul_rn(static_cast<float>(s1), inv_area)), 0), 255));
+        o[2] = static_cast<uint8_t>(min(max(__float2int_rn(__fmul_rn(static_cast<float>(s2), inv_area)), 0), 255));
     }
 }
 
@@ -340,109 +340,113 @@ __device__ __forceinline__ uint8_t clip8(int v) {
 }
 
 // B: Pillow horizontal pass for output columns [ocol0, ocol0+S) on rows [0, ny) of the (possibly compacted)
-// source whose column 0 is absolute column src_x0.
-__global__ void hpass_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride, int src_x0,
-                             uint8_t* __restrict__ dst, int64_t dst_frame_stride, int n, int ny, int ocol0, int S,
-                             DevTaps bx) {
-    const int64_t total = static_cast<int64_t>(n) * ny * S;
-    for (int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; id < total;
-         id += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int x = static_cast<int>(id % S);
-        const int64_t r = id / S;
-        const int y = static_cast<int>(r % ny);
-        const int64_t f = r / ny;
-        const int ox = ocol0 + x;
-        const int lo = bx.start[ox], cnt = bx.cnt[ox];
-        const int* k = bx.wi + static_cast<int64_t>(ox) * bx.stride;
-        const uint8_t* p = src + f * frame_stride + static_cast<int64_t>(y) * row_stride +
-                           static_cast<int64_t>(lo - src_x0) * 3;
-        int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+// source whose column 0 is absolute column src_x0.  FAST: at most 7 taps (21 bytes) -> aligned word loads.
+template <bool FAST>
+__global__ void __launch_bounds__(256)
+hpass_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride, int src_x0,
+             uint8_t* __restrict__ dst, int64_t dst_frame_stride, int ny, int ocol0, int S, DevTaps bx) {
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= static_cast<unsigned>(ny * S)) return;
+    const int y = id / S, x = id - y * S;
+    const int64_t f = blockIdx.y;
+    const int ox = ocol0 + x;
+    const int lo = bx.start[ox], cnt = bx.cnt[ox];
+    const int* k = bx.wi + ox * bx.stride;
+    const uint8_t* p = src + f * frame_stride + static_cast<int64_t>(y) * row_stride + (lo - src_x0) * 3;
+    int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+    if (FAST) {
+        uint32_t u[6];
+        load_bytes_aligned<6>(p, cnt * 3, u);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const int kk = i < cnt ? k[i] : 0;   // bytes past cnt may be junk: weight 0
+            a0 += kk * byte_as_int<6>(u, i * 3);
+            a1 += kk * byte_as_int<6>(u, i * 3 + 1);
+            a2 += kk * byte_as_int<6>(u, i * 3 + 2);
+        }
+    } else {
         for (int i = 0; i < cnt; ++i) {
             const int kk = k[i];
             a0 += kk * p[i * 3]; a1 += kk * p[i * 3 + 1]; a2 += kk * p[i * 3 + 2];
         }
-        uint8_t* o = dst + f * dst_frame_stride + (static_cast<int64_t>(y) * S + x) * 3;
-        o[0] = clip8(a0); o[1] = clip8(a1); o[2] = clip8(a2);
     }
+    uint8_t* o = dst + f * dst_frame_stride + (y * S + x) * 3;
+    o[0] = clip8(a0); o[1] = clip8(a1); o[2] = clip8(a2);
 }
 
 // C: vertical pass (or plain crop) + ToTensor/Normalize lookup + store.  One thread per 8 output pixels of one
-// output row (all 3 channels): 24 contiguous source bytes per tap.  Output either bf16 patch-major rows
-// (col = c*P*P + y*P + x, patch_k padded) or fp32 CHW.
-__global__ void vpass_store_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride,
-                                   int src_y0, int src_x0, int has_v, int top, DevTaps cy, int n, int S, int P,
-                                   int grid, int patch_k, const float* __restrict__ lut /*[3][256]*/,
-                                   bf16* __restrict__ patches, float* __restrict__ chw) {
+// output row (all 3 channels): 24 contiguous source bytes per tap, fetched as aligned words.  Output either bf16
+// patch-major rows (col = c*P*P + y*P + x, patch_k padded) or fp32 CHW.
+__global__ void __launch_bounds__(128)
+vpass_store_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride, int src_y0, int src_x0,
+                   int has_v, int top, DevTaps cy, int S, int P, int grid, int patch_k,
+                   const float* __restrict__ lut /*[3][256]*/, bf16* __restrict__ patches, float* __restrict__ chw) {
     __shared__ float s_lut[768];
     for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
     __syncthreads();
     const int xchunks = (S + 7) >> 3;
-    const int64_t total = static_cast<int64_t>(n) * S * xchunks;
-    for (int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; id < total;
-         id += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int xc = static_cast<int>(id % xchunks);
-        const int64_t r = id / xchunks;
-        const int oy = static_cast<int>(r % S);
-        const int64_t f = r / S;
-        const int x0 = xc << 3;
-        const int npx = min(8, S - x0);
-        uint8_t u[24];
-        const uint8_t* fbase = src + f * frame_stride + static_cast<int64_t>(x0 - src_x0) * 3;
-        if (has_v) {
-            const int o = top + oy;
-            const int lo = cy.start[o], cnt = cy.cnt[o];
-            const int* k = cy.wi + static_cast<int64_t>(o) * cy.stride;
-            int acc[24];
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= static_cast<unsigned>(S * xchunks)) return;
+    const int oy = id / xchunks, xc = id - oy * xchunks;
+    const int64_t f = blockIdx.y;
+    const int x0 = xc << 3;
+    const int npx = min(8, S - x0);
+    uint8_t u8[24];
+    const uint8_t* fbase = src + f * frame_stride + (x0 - src_x0) * 3;
+    if (has_v) {
+        const int o = top + oy;
+        const int lo = cy.start[o], cnt = cy.cnt[o];
+        const int* k = cy.wi + o * cy.stride;
+        int acc[24];
 #pragma unroll
-            for (int j = 0; j < 24; ++j) acc[j] = 1 << 21;
-            for (int i = 0; i < cnt; ++i) {
-                const uint8_t* p = fbase + static_cast<int64_t>(lo + i - src_y0) * row_stride;
-                const int kk = k[i];
+        for (int j = 0; j < 24; ++j) acc[j] = 1 << 21;
+        for (int i = 0; i < cnt; ++i) {
+            uint32_t u[6];
+            load_bytes_aligned<6>(fbase + static_cast<int64_t>(lo + i - src_y0) * row_stride, npx * 3, u);
+            const int kk = k[i];
 #pragma unroll
-                for (int j = 0; j < 24; ++j)
-                    if (j < npx * 3) acc[j] += kk * p[j];
-            }
-#pragma unroll
-            for (int j = 0; j < 24; ++j) u[j] = clip8(acc[j]);
-        } else {
-            const uint8_t* p = fbase + static_cast<int64_t>(top + oy - src_y0) * row_stride;
-#pragma unroll
-            for (int j = 0; j < 24; ++j) u[j] = (j < npx * 3) ? p[j] : 0;
+            for (int j = 0; j < 24; ++j) acc[j] += kk * byte_as_int<6>(u, j);
         }
-        if (patches) {
-            const int py = oy / P, yy = oy - py * P;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                // the 8 pixels may straddle a patch boundary when P is not a multiple of 8 -> element stores
-                const int px0 = x0 / P;
-                const bool one_patch = (npx == 8) && ((x0 + 7) / P == px0) && (((x0 - px0 * P) & 7) == 0) && ((P & 7) == 0);
-                if (one_patch) {
-                    uint4 o;
-                    o.x = pack_bf16x2(s_lut[c * 256 + u[0 * 3 + c]], s_lut[c * 256 + u[1 * 3 + c]]);
-                    o.y = pack_bf16x2(s_lut[c * 256 + u[2 * 3 + c]], s_lut[c * 256 + u[3 * 3 + c]]);
-                    o.z = pack_bf16x2(s_lut[c * 256 + u[4 * 3 + c]], s_lut[c * 256 + u[5 * 3 + c]]);
-                    o.w = pack_bf16x2(s_lut[c * 256 + u[6 * 3 + c]], s_lut[c * 256 + u[7 * 3 + c]]);
-                    const int64_t row = (f * grid + py) * grid + px0;
-                    *reinterpret_cast<uint4*>(patches + row * patch_k + c * P * P + yy * P + (x0 - px0 * P)) = o;
-                } else {
-                    for (int j = 0; j < npx; ++j) {
-                        const int x = x0 + j;
-                        const int px = x / P, xx = x - px * P;
-                        if (px < grid && py < grid) {
-                            const int64_t row = (f * grid + py) * grid + px;
-                            patches[row * patch_k + c * P * P + yy * P + xx] =
-                                __float2bfloat16(s_lut[c * 256 + u[j * 3 + c]]);
-                        }
+        for (int j = 0; j < 24; ++j) u8[j] = clip8(acc[j]);
+    } else {
+        uint32_t u[6];
+        load_bytes_aligned<6>(fbase + static_cast<int64_t>(top + oy - src_y0) * row_stride, npx * 3, u);
+#pragma unroll
+        for (int j = 0; j < 24; ++j) u8[j] = static_cast<uint8_t>(byte_as_int<6>(u, j));
+    }
+    if (patches) {
+        const int py = oy / P, yy = oy - py * P;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            // the 8 pixels may straddle a patch boundary when P is not a multiple of 8 -> element stores
+            const int px0 = x0 / P;
+            const bool one_patch = (npx == 8) && ((x0 + 7) / P == px0) && (((x0 - px0 * P) & 7) == 0) && ((P & 7) == 0);
+            if (one_patch) {
+                uint4 o;
+                o.x = pack_bf16x2(s_lut[c * 256 + u8[0 * 3 + c]], s_lut[c * 256 + u8[1 * 3 + c]]);
+                o.y = pack_bf16x2(s_lut[c * 256 + u8[2 * 3 + c]], s_lut[c * 256 + u8[3 * 3 + c]]);
+                o.z = pack_bf16x2(s_lut[c * 256 + u8[4 * 3 + c]], s_lut[c * 256 + u8[5 * 3 + c]]);
+                o.w = pack_bf16x2(s_lut[c * 256 + u8[6 * 3 + c]], s_lut[c * 256 + u8[7 * 3 + c]]);
+                const int64_t row = (f * grid + py) * grid + px0;
+                *reinterpret_cast<uint4*>(patches + row * patch_k + c * P * P + yy * P + (x0 - px0 * P)) = o;
+            } else {
+                for (int j = 0; j < npx; ++j) {
+                    const int x = x0 + j;
+                    const int px = x / P, xx = x - px * P;
+                    if (px < grid && py < grid) {
+                        const int64_t row = (f * grid + py) * grid + px;
+                        patches[row * patch_k + c * P * P + yy * P + xx] = __float2bfloat16(s_lut[c * 256 + u8[j * 3 + c]]);
                     }
                 }
             }
         }
-        if (chw) {
+    }
+    if (chw) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float* o = chw + ((f * 3 + c) * S + oy) * S + x0;
-                for (int j = 0; j < npx; ++j) o[j] = s_lut[c * 256 + u[j * 3 + c]];
-            }
+        for (int c = 0; c < 3; ++c) {
+            float* o = chw + ((f * 3 + c) * S + oy) * S + x0;
+            for (int j = 0; j < npx; ++j) o[j] = s_lut[c * 256 + u8[j * 3 + c]];
         }
     }
 }
@@ -495,6 +499,7 @@ static int build_plan(b200clip_handle* h, int H, int W, int mode, Plan& p) {
     if (p.has_b) {
         bx = pillow_taps(w1, p.nw, bicubic);
         taps_range(bx, p.left, p.left + S, p.rx0, p.rx1);
+        for (int c : bx.cnt) p.b_max_cnt = c > p.b_max_cnt ? c : p.b_max_cnt;
     } else {
         p.rx0 = p.left; p.rx1 = p.left + S;
     }
@@ -596,18 +601,20 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
     const uint8_t* cur = frames;
     int64_t cur_fs = frame_stride, cur_rs = row_stride;
     int cur_x0 = 0, cur_y0 = 0;  // absolute (stage-coordinate) position of cur's element (0,0)
+    if (n > 65535) return b200_fail(h, B200CLIP_E_SHAPE, "preprocess: at most 65535 frames per call (got %d)", n);
     if (p.has_a) {
         const int ny = p.ry1 - p.ry0, nx = p.rx1 - p.rx0;
-        const int64_t total = static_cast<int64_t>(n) * ny * nx;
+        dim3 grid((static_cast<unsigned>(ny) * nx + 255) / 256, n);
+        ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(H) * (p.rx1 - p.rx0) * W / p.w1 * 3.0 + ny * nx * 3.0), st);
         if (p.a_fast)
-            area_fast_kernel<<<grid_for(h, total, 256), 256, 0, st>>>(cur, cur_fs, cur_rs, mid1, p.mid1_per_frame, n,
-                                                                      p.ry0, ny, p.rx0, nx, p.a_fx, p.a_fy);
+            area_fast_kernel<<<grid, 256, 0, st>>>(cur, cur_fs, cur_rs, mid1, p.mid1_per_frame, p.ry0, ny, p.rx0, nx,
+                                                   p.a_fx, p.a_fy);
         else if (p.a_max_cx <= 5)
-            area_kernel_w5<<<grid_for(h, total, 256), 256, 0, st>>>(cur, cur_fs, cur_rs, mid1, p.mid1_per_frame, n,
-                                                                    p.ry0, ny, p.rx0, nx, p.ax, p.ay);
+            area_kernel_w5<<<grid, 256, 0, st>>>(cur, cur_fs, cur_rs, mid1, p.mid1_per_frame, p.ry0, ny, p.rx0, nx, p.ax,
+                                                 p.ay);
         else
-            area_kernel<<<grid_for(h, total, 256), 256, 0, st>>>(cur, cur_fs, cur_rs, mid1, p.mid1_per_frame, n, p.ry0,
-                                                                 ny, p.rx0, nx, p.ax, p.ay);
+            area_kernel<<<grid, 256, 0, st>>>(cur, cur_fs, cur_rs, mid1, p.mid1_per_frame, p.ry0, ny, p.rx0, nx, p.ax,
+                                              p.ay);
         h->launches++;
         cur = mid1; cur_fs = p.mid1_per_frame; cur_rs = static_cast<int64_t>(nx) * 3;
         cur_x0 = p.rx0; cur_y0 = p.ry0;
@@ -616,9 +623,14 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         const int ny = p.ry1 - p.ry0;
         // rows [ry0, ry1) of cur: shift the base pointer so that row 0 of the kernel == row ry0
         const uint8_t* base = cur + static_cast<int64_t>(p.ry0 - cur_y0) * cur_rs;
-        const int64_t total = static_cast<int64_t>(n) * ny * S;
-        hpass_kernel<<<grid_for(h, total, 256), 256, 0, st>>>(base, cur_fs, cur_rs, cur_x0, mid2, p.mid2_per_frame, n,
-                                                              ny, p.left, S, p.bx);
+        dim3 grid((static_cast<unsigned>(ny) * S + 255) / 256, n);
+        ProfScope psb(h, PROF_PRE_B, static_cast<double>(n) * ny * (p.rx1 - p.rx0 + S) * 3.0, st);
+        if (p.b_max_cnt <= 7)
+            hpass_kernel<true><<<grid, 256, 0, st>>>(base, cur_fs, cur_rs, cur_x0, mid2, p.mid2_per_frame, ny, p.left, S,
+                                                     p.bx);
+        else
+            hpass_kernel<false><<<grid, 256, 0, st>>>(base, cur_fs, cur_rs, cur_x0, mid2, p.mid2_per_frame, ny, p.left,
+                                                      S, p.bx);
         h->launches++;
         cur = mid2; cur_fs = p.mid2_per_frame; cur_rs = static_cast<int64_t>(S) * 3;
         cur_x0 = 0 /* column 0 of mid2 is output column `left`, handled below */; cur_y0 = p.ry0;
@@ -626,10 +638,10 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
     {
         // stage C reads output-column x0 at cur column (x0 + xoff - cur_x0): after B the crop is already applied
         const int src_x0 = p.has_b ? 0 : cur_x0 - p.left;  // so that (x0 - src_x0) = x0 + left - cur_x0
-        const int64_t total = static_cast<int64_t>(n) * S * ((S + 7) >> 3);
-        vpass_store_kernel<<<grid_for(h, total, 128), 128, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, src_x0, p.has_c ? 1 : 0,
-                                                                    p.top, p.cy, n, S, P, h->grid, h->patch_k, lut,
-                                                                    patches, chw);
+        dim3 grid((static_cast<unsigned>(S) * ((S + 7) >> 3) + 127) / 128, n);
+        ProfScope psc(h, PROF_PRE_C, static_cast<double>(n) * ((p.ry1 - p.ry0) * S * 3.0 + (patches ? static_cast<double>(h->grid) * h->grid * h->patch_k * 2.0 : 3.0 * S * S * 4.0)), st);
+        vpass_store_kernel<<<grid, 128, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, src_x0, p.has_c ? 1 : 0, p.top, p.cy, S, P,
+                                                 h->grid, h->patch_k, lut, patches, chw);
         h->launches++;
     }
     if (patches && h->patch_k != 3 * P * P) {

@@ -326,6 +326,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         kernels = {}
         for name, r in prof.items():
             if r["launches"]:
+                # pre_* are sub-ranges of "preprocess" (not additive with it)
                 kernels[name] = {"ms_per_step": r["ms"] / args.steps, "launches_per_step": r["launches"] / args.steps,
                                  "share": r["ms"] / total_ms,
                                  ("tflops" if name == "gemm" else "gbs"): (r["work"] / (r["ms"] / 1e3) / (1e12 if name == "gemm" else 1e9))}

@@ -168,7 +168,8 @@ int b200clip_attention_bf16(b200clip_handle* h, const void* qkv_dev, void* out_d
 /* Opt-in per-kernel-class device timing: while enabled, every launch is bracketed by a CUDA event pair on the
  * launching stream.  profile_read synchronises the device and returns, for one class, the summed elapsed ms, the
  * summed algorithmic work (FLOP for class 0 = GEMM; bytes for 1 = attention, 2 = LayerNorm, 3 = K1 preprocess chain,
- * 4 = head, 5 = K4 similarity/top-k, 6 = misc) and the number of timed launches. */
+ * 4 = head, 5 = K4 similarity/top-k, 6 = misc, 7/8/9 = the K1 stages area / horizontal / vertical, which are also
+ * inside 3) and the number of timed launches. */
 int b200clip_profile_enable(b200clip_handle* h, int on);
 int b200clip_profile_read(b200clip_handle* h, int kernel_class, double* ms_out, double* work_out,
                           int64_t* launches_out, int reset);
