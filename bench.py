@@ -140,7 +140,7 @@ def run_reference(args, rank: int):
     value = args.steps * len(frames) / dt
     sample = (f"{len(frames)} of {args.frames} frames ({args.height}x{args.width} uint8) per step: cv2 INTER_AREA shrink + "
               f"PIL/torchvision transform + fp32 PyTorch ViT-B/32 (batch 32) + np.dot/argsort, {cores} threads")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -148,7 +148,7 @@ def run_reference(args, rank: int):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
 
 
 def workload_config(args, world: int) -> dict:
@@ -346,13 +346,31 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             "model_flop_per_frame": cfg.flops_per_image(),
             "model_tflops": value * cfg.flops_per_image() / 1e12 / world,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else any library prints to fd 1 (e.g. NCCL's version
+    banner) has been redirected to stderr so that it cannot pollute it."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
