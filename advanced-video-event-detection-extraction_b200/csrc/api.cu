@@ -149,6 +149,13 @@ extern "C" int b200clip_destroy(b200clip_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_qkv); cudaFree(h->ws_h); cudaFree(h->ws_patches);
     cudaFree(h->ws_emb); cudaFree(h->ws_pre); cudaFree(h->ws_topk); cudaFree(h->ws_eot); cudaFree(h->ws_tokens);
+    cudaFree(h->ws_patches2); cudaFree(h->ws_stats);
+    if (h->pre_stream) cudaStreamDestroy(h->pre_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
+        if (h->ev_tower[i]) cudaEventDestroy(h->ev_tower[i]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->ws_stage_dev[i]);
         if (h->ws_stage_host[i]) cudaFreeHost(h->ws_stage_host[i]);
@@ -205,16 +212,17 @@ static int set_block_weight(b200clip_handle* h, b200clip_handle::Tower& tw, cons
     b200clip_handle::Block& b = tw.blocks[li];
     const std::string p(end + 1);
     const int64_t W = tw.width, F = tw.mlp;
-    if (p == "ln_1.weight") { WANT_SHAPE(W); return upload_f32(h, data, W, &b.ln1_g); }
-    if (p == "ln_1.bias") { WANT_SHAPE(W); return upload_f32(h, data, W, &b.ln1_b); }
-    if (p == "ln_2.weight") { WANT_SHAPE(W); return upload_f32(h, data, W, &b.ln2_g); }
-    if (p == "ln_2.bias") { WANT_SHAPE(W); return upload_f32(h, data, W, &b.ln2_b); }
-    if (p == "attn.in_proj_weight") { WANT_SHAPE(3 * W, W); return upload_bf16(h, data, 3 * W, W, W, &b.w_qkv); }
-    if (p == "attn.in_proj_bias") { WANT_SHAPE(3 * W); return upload_f32(h, data, 3 * W, &b.b_qkv); }
+    // LayerNorm parameters and the matrices they fold into are kept on the host until finalize
+    if (p == "ln_1.weight") { WANT_SHAPE(W); b.h_ln1_g.assign(data, data + W); return 0; }
+    if (p == "ln_1.bias") { WANT_SHAPE(W); b.h_ln1_b.assign(data, data + W); return 0; }
+    if (p == "ln_2.weight") { WANT_SHAPE(W); b.h_ln2_g.assign(data, data + W); return 0; }
+    if (p == "ln_2.bias") { WANT_SHAPE(W); b.h_ln2_b.assign(data, data + W); return 0; }
+    if (p == "attn.in_proj_weight") { WANT_SHAPE(3 * W, W); b.h_w_qkv.assign(data, data + 3 * W * W); return 0; }
+    if (p == "attn.in_proj_bias") { WANT_SHAPE(3 * W); b.h_b_qkv.assign(data, data + 3 * W); return 0; }
     if (p == "attn.out_proj.weight") { WANT_SHAPE(W, W); return upload_bf16(h, data, W, W, W, &b.w_out); }
     if (p == "attn.out_proj.bias") { WANT_SHAPE(W); return upload_f32(h, data, W, &b.b_out); }
-    if (p == "mlp.c_fc.weight") { WANT_SHAPE(F, W); return upload_bf16(h, data, F, W, W, &b.w_fc); }
-    if (p == "mlp.c_fc.bias") { WANT_SHAPE(F); return upload_f32(h, data, F, &b.b_fc); }
+    if (p == "mlp.c_fc.weight") { WANT_SHAPE(F, W); b.h_w_fc.assign(data, data + F * W); return 0; }
+    if (p == "mlp.c_fc.bias") { WANT_SHAPE(F); b.h_b_fc.assign(data, data + F); return 0; }
     if (p == "mlp.c_proj.weight") { WANT_SHAPE(W, F); return upload_bf16(h, data, W, F, F, &b.w_proj); }
     if (p == "mlp.c_proj.bias") { WANT_SHAPE(W); return upload_f32(h, data, W, &b.b_proj); }
     return b200_fail(h, B200CLIP_E_ARG, "set_weight(%s): unknown block parameter", name);
@@ -262,6 +270,41 @@ extern "C" int b200clip_set_weight(b200clip_handle* h, const char* name, const f
     return rc;
 }
 
+// LN(x) W^T + b = rstd * (x (W.diag(g))^T - mean * c1) + c2,  c1[n] = sum_k bf16(W[n,k] g[k]),  c2[n] = sum_k beta[k] W[n,k] + b[n]
+static int fold_layernorm(b200clip_handle* h, std::vector<float>& w, const std::vector<float>& bias,
+                          const std::vector<float>& g, const std::vector<float>& beta, size_t rows, size_t cols,
+                          bf16** w_dev, float** c1_dev, float** c2_dev) {
+    std::vector<float> c1(rows), c2(rows);
+    for (size_t n = 0; n < rows; ++n) {
+        double s1 = 0.0, s2 = 0.0;
+        float* wr = &w[n * cols];
+        for (size_t k = 0; k < cols; ++k) {
+            s2 += static_cast<double>(beta[k]) * wr[k];
+            const float folded = __bfloat162float(__float2bfloat16(wr[k] * g[k]));
+            wr[k] = folded;
+            s1 += folded;
+        }
+        c1[n] = static_cast<float>(s1);
+        c2[n] = static_cast<float>(s2 + bias[n]);
+    }
+    int rc = upload_bf16(h, w.data(), rows, cols, cols, w_dev);
+    if (rc) return rc;
+    if ((rc = upload_f32(h, c1.data(), rows, c1_dev))) return rc;
+    return upload_f32(h, c2.data(), rows, c2_dev);
+}
+
+static int fold_tower(b200clip_handle* h, b200clip_handle::Tower& tw) {
+    const size_t W = tw.width, F = tw.mlp;
+    for (auto& b : tw.blocks) {
+        int rc = fold_layernorm(h, b.h_w_qkv, b.h_b_qkv, b.h_ln1_g, b.h_ln1_b, 3 * W, W, &b.w_qkv, &b.c1_qkv, &b.c2_qkv);
+        if (rc) return rc;
+        if ((rc = fold_layernorm(h, b.h_w_fc, b.h_b_fc, b.h_ln2_g, b.h_ln2_b, F, W, &b.w_fc, &b.c1_fc, &b.c2_fc))) return rc;
+        for (auto* v : {&b.h_ln1_g, &b.h_ln1_b, &b.h_ln2_g, &b.h_ln2_b, &b.h_w_qkv, &b.h_b_qkv, &b.h_w_fc, &b.h_b_fc})
+            std::vector<float>().swap(*v);
+    }
+    return 0;
+}
+
 extern "C" int b200clip_finalize(b200clip_handle* h) {
     if (!h) return b200_fail(h, B200CLIP_E_ARG, "finalize: null handle");
     B200_CUDA(h, cudaSetDevice(h->device));
@@ -282,6 +325,10 @@ extern "C" int b200clip_finalize(b200clip_handle* h) {
     for (int i = 0; i < h->cfg.width; ++i) cp[i] = h->host_cls[i] + h->host_pos0[i];
     int rc = upload_f32(h, cp.data(), cp.size(), &h->cls_pos0);
     if (rc) return rc;
+    if (!h->finalized) {
+        if ((rc = fold_tower(h, h->vis))) return rc;
+        if ((rc = fold_tower(h, h->txt))) return rc;
+    }
     h->finalized = true;
     return 0;
 }
@@ -300,8 +347,10 @@ static int ensure_workspace(b200clip_handle* h, int images, int texts, cudaStrea
     const size_t h_el = mx(mv * c.mlp_dim, mt * c.text_mlp_dim);
     const size_t p_el = static_cast<size_t>(ni) * h->grid * h->grid * h->patch_k;
     cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_qkv); cudaFree(h->ws_h); cudaFree(h->ws_patches);
+    cudaFree(h->ws_patches2); cudaFree(h->ws_stats);
     cudaFree(h->ws_eot); cudaFree(h->ws_tokens);
-    h->ws_x = h->ws_y = h->ws_qkv = h->ws_h = h->ws_patches = nullptr;
+    h->ws_stats = nullptr;
+    h->ws_x = h->ws_y = h->ws_qkv = h->ws_h = h->ws_patches = h->ws_patches2 = nullptr;
     h->ws_eot = nullptr; h->ws_tokens = nullptr;
     h->ws_images = h->ws_texts = 0;
     B200_CUDA(h, cudaMalloc(&h->ws_x, mx(x_el, 8) * 2));
@@ -309,6 +358,8 @@ static int ensure_workspace(b200clip_handle* h, int images, int texts, cudaStrea
     B200_CUDA(h, cudaMalloc(&h->ws_qkv, mx(qkv_el, 8) * 2));
     B200_CUDA(h, cudaMalloc(&h->ws_h, mx(h_el, 8) * 2));
     B200_CUDA(h, cudaMalloc(&h->ws_patches, mx(p_el, 8) * 2));
+    B200_CUDA(h, cudaMalloc(&h->ws_patches2, mx(p_el, 8) * 2));
+    B200_CUDA(h, cudaMalloc(&h->ws_stats, mx(mx(mv, mt), 1) * 16 * sizeof(float)));
     B200_CUDA(h, cudaMalloc(&h->ws_eot, mx(nt, 1) * sizeof(int32_t)));
     B200_CUDA(h, cudaMalloc(&h->ws_tokens, mx(mt, 1) * sizeof(int64_t)));
     h->ws_images = ni;
@@ -325,25 +376,26 @@ extern "C" int b200clip_reserve(b200clip_handle* h, int max_images, int max_text
 }
 
 // ------------------------------------------------------------------------------------------- towers
+// Residual blocks.  ws_x holds the residual stream and ws_stats the (sum, sum of squares) partials of its rows
+// (written by ln_pre / the text embedding, then by every residual GEMM); ln_1 / ln_2 never run as kernels: they
+// are folded into the QKV / fc GEMM epilogues.
 static int run_blocks(b200clip_handle* h, b200clip_handle::Tower& tw, int n_seq, int T, int causal, cudaStream_t st) {
     const int M = n_seq * T;
     const int W = tw.width, F = tw.mlp;
     const int act = h->cfg.act == 0 ? 1 : 2;
-    const float eps = h->cfg.ln_eps;
     int rc;
     for (int l = 0; l < tw.layers; ++l) {
         const b200clip_handle::Block& b = tw.blocks[l];
         b200::GemmEpilogue ep{};
-        if ((rc = launch_layernorm(h, h->ws_x, b.ln1_g, b.ln1_b, h->ws_y, M, W, eps, 0, nullptr, st))) return rc;
-        ep = {}; ep.bias = b.b_qkv;
-        if ((rc = launch_gemm(h, h->ws_y, W, b.w_qkv, W, h->ws_qkv, 3 * W, M, 3 * W, W, ep, st))) return rc;
+        ep.bias = b.c2_qkv; ep.ln_stats = h->ws_stats; ep.ln_c1 = b.c1_qkv; ep.ln_eps = h->cfg.ln_eps; ep.ln_width = W;
+        if ((rc = launch_gemm(h, h->ws_x, W, b.w_qkv, W, h->ws_qkv, 3 * W, M, 3 * W, W, ep, st))) return rc;
         if ((rc = launch_attention(h, h->ws_qkv, h->ws_y, n_seq, T, tw.heads, causal, st))) return rc;
-        ep = {}; ep.bias = b.b_out; ep.resid = h->ws_x;
+        ep = {}; ep.bias = b.b_out; ep.resid = h->ws_x; ep.stats_out = h->ws_stats;
         if ((rc = launch_gemm(h, h->ws_y, W, b.w_out, W, h->ws_x, W, M, W, W, ep, st))) return rc;
-        if ((rc = launch_layernorm(h, h->ws_x, b.ln2_g, b.ln2_b, h->ws_y, M, W, eps, 0, nullptr, st))) return rc;
-        ep = {}; ep.bias = b.b_fc; ep.act = act;
-        if ((rc = launch_gemm(h, h->ws_y, W, b.w_fc, W, h->ws_h, F, M, F, W, ep, st))) return rc;
-        ep = {}; ep.bias = b.b_proj; ep.resid = h->ws_x;
+        ep = {}; ep.bias = b.c2_fc; ep.ln_stats = h->ws_stats; ep.ln_c1 = b.c1_fc; ep.ln_eps = h->cfg.ln_eps;
+        ep.ln_width = W; ep.act = act;
+        if ((rc = launch_gemm(h, h->ws_x, W, b.w_fc, W, h->ws_h, F, M, F, W, ep, st))) return rc;
+        ep = {}; ep.bias = b.b_proj; ep.resid = h->ws_x; ep.stats_out = h->ws_stats;
         if ((rc = launch_gemm(h, h->ws_h, F, b.w_proj, F, h->ws_x, W, M, W, F, ep, st))) return rc;
     }
     return 0;
@@ -360,8 +412,9 @@ static int encode_patches_chunk(b200clip_handle* h, const bf16* patches, int n, 
     if ((rc = launch_gemm(h, patches, h->patch_k, h->w_patch, h->patch_k, h->ws_y, c.width, n * g2, c.width, h->patch_k,
                           ep, st)))
         return rc;
+    B200_CUDA(h, cudaMemsetAsync(h->ws_stats, 0, static_cast<size_t>(n) * h->tokens * 16 * sizeof(float), st));
     if ((rc = launch_layernorm(h, h->ws_y, h->ln_pre_g, h->ln_pre_b, h->ws_x, static_cast<int64_t>(n) * h->tokens,
-                               c.width, c.ln_eps, h->tokens, h->cls_pos0, st)))
+                               c.width, c.ln_eps, h->tokens, h->cls_pos0, h->ws_stats, st)))
         return rc;
     if ((rc = run_blocks(h, h->vis, n, h->tokens, 0, st))) return rc;
     return launch_head(h, h->ws_x, static_cast<int64_t>(h->tokens) * c.width, nullptr, h->ln_post_g, h->ln_post_b,
@@ -443,6 +496,22 @@ extern "C" int b200clip_preprocess_u8_chw(b200clip_handle* h, const uint8_t* fra
                              chw_out_dev, static_cast<cudaStream_t>(stream));
 }
 
+// Device frames -> embeddings in `parts` pipelined chunks: K1 of chunk i+1 runs on a second, lower-priority stream
+// while the tower of chunk i runs on the caller's stream (the GEMM kernels keep one register- and smem-heavy CTA per
+// SM whose issue slots are mostly idle; the register-light K1 kernels co-reside with it).
+static int ensure_pipeline(b200clip_handle* h) {
+    if (h->pre_stream) return 0;
+    int lo = 0, hi = 0;
+    B200_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    B200_CUDA(h, cudaStreamCreateWithPriority(&h->pre_stream, cudaStreamNonBlocking, lo));
+    for (int i = 0; i < 2; ++i) {
+        B200_CUDA(h, cudaEventCreateWithFlags(&h->ev_pre[i], cudaEventDisableTiming));
+        B200_CUDA(h, cudaEventCreateWithFlags(&h->ev_tower[i], cudaEventDisableTiming));
+    }
+    B200_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    return 0;
+}
+
 extern "C" int b200clip_encode_frames_u8(b200clip_handle* h, const uint8_t* frames_dev, int n, int height, int width,
                                          int64_t frame_stride, int64_t row_stride, int resize_mode, void* emb_out_dev,
                                          int out_dtype, int l2norm, void* stream) {
@@ -450,20 +519,57 @@ extern "C" int b200clip_encode_frames_u8(b200clip_handle* h, const uint8_t* fram
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!frames_dev || !emb_out_dev))) return b200_fail(h, B200CLIP_E_ARG, "encode_frames_u8: bad argument");
     if (out_dtype != B200CLIP_F32 && out_dtype != B200CLIP_BF16) return b200_fail(h, B200CLIP_E_ARG, "bad out_dtype");
+    if (n == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int chunk = chunk_images(h, n);
-    if (n > 0 && (rc = ensure_workspace(h, chunk, 0, st))) return rc;
-    for (int i = 0; i < n; i += chunk) {
-        const int nc = (n - i) < chunk ? (n - i) : chunk;
-        if ((rc = launch_preprocess(h, frames_dev + static_cast<int64_t>(i) * frame_stride, nc, height, width,
-                                    frame_stride, row_stride, resize_mode, h->ws_patches, nullptr, st)))
-            return rc;
-        rc = encode_patches_chunk(h, h->ws_patches, nc,
-                                  static_cast<uint8_t*>(emb_out_dev) + static_cast<size_t>(i) * h->cfg.embed_dim * out_elem(out_dtype),
-                                  out_dtype, l2norm, st);
-        if (rc) return rc;
+    int chunk = chunk_images(h, n);
+    // large batches: at least 4 pipelined chunks so that only the first K1 pass is exposed
+    static const bool no_overlap = getenv("B200CLIP_OVERLAP") == nullptr;
+    const bool pipelined = !no_overlap && n >= 256;  // measured slower on B200 (K1 blocks crowd out the tower): opt-in
+    if (pipelined) {
+        int parts = (n + chunk - 1) / chunk;
+        if (parts < 4) parts = 4;
+        chunk = (n + parts - 1) / parts;
     }
-    return 0;
+    if ((rc = ensure_workspace(h, chunk, 0, st))) return rc;
+    auto emb_at = [&](int i) {
+        return static_cast<uint8_t*>(emb_out_dev) + static_cast<size_t>(i) * h->cfg.embed_dim * out_elem(out_dtype);
+    };
+    if (!pipelined) {
+        for (int i = 0; i < n; i += chunk) {
+            const int nc = (n - i) < chunk ? (n - i) : chunk;
+            if ((rc = launch_preprocess(h, frames_dev + static_cast<int64_t>(i) * frame_stride, nc, height, width,
+                                        frame_stride, row_stride, resize_mode, h->ws_patches, nullptr, st)))
+                return rc;
+            if ((rc = encode_patches_chunk(h, h->ws_patches, nc, emb_at(i), out_dtype, l2norm, st))) return rc;
+        }
+        return 0;
+    }
+    if ((rc = ensure_pipeline(h))) return rc;
+    bf16* pbuf[2] = {h->ws_patches, h->ws_patches2};
+    const int nchunks = (n + chunk - 1) / chunk;
+    // fork: K1 may not start before the work already queued on the caller's stream (it produced the frames)
+    B200_CUDA(h, cudaEventRecord(h->ev_fork, st));
+    B200_CUDA(h, cudaStreamWaitEvent(h->pre_stream, h->ev_fork, 0));
+    auto issue_pre = [&](int ci) -> int {
+        const int b = ci & 1, i0 = ci * chunk;
+        const int nc = (n - i0) < chunk ? (n - i0) : chunk;
+        if (ci >= 2) B200_CUDA(h, cudaStreamWaitEvent(h->pre_stream, h->ev_tower[b], 0));  // patch buffer b is free
+        int r = launch_preprocess(h, frames_dev + static_cast<int64_t>(i0) * frame_stride, nc, height, width,
+                                  frame_stride, row_stride, resize_mode, pbuf[b], nullptr, h->pre_stream);
+        if (r) return r;
+        B200_CUDA(h, cudaEventRecord(h->ev_pre[b], h->pre_stream));
+        return 0;
+    };
+    if ((rc = issue_pre(0))) return rc;
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int b = ci & 1, i0 = ci * chunk;
+        const int nc = (n - i0) < chunk ? (n - i0) : chunk;
+        if (ci + 1 < nchunks && (rc = issue_pre(ci + 1))) return rc;
+        B200_CUDA(h, cudaStreamWaitEvent(st, h->ev_pre[b], 0));
+        if ((rc = encode_patches_chunk(h, pbuf[b], nc, emb_at(i0), out_dtype, l2norm, st))) return rc;
+        B200_CUDA(h, cudaEventRecord(h->ev_tower[b], st));
+    }
+    return 0;   // the caller's stream has joined every K1 pass through ev_pre
 }
 
 // HOST frames -> HOST embeddings.  Device staging is double buffered: the copy stream uploads chunk i+1 while the
@@ -570,7 +676,9 @@ static int encode_text_dev(b200clip_handle* h, const int64_t* tokens_dev, int q,
     if ((rc = ensure_workspace(h, 0, chunk, st))) return rc;
     for (int i = 0; i < q; i += chunk) {
         const int nc = (q - i) < chunk ? (q - i) : chunk;
-        if ((rc = launch_text_embed(h, tokens_dev + static_cast<size_t>(i) * c.text_ctx, nc, h->ws_x, h->ws_eot, st)))
+        B200_CUDA(h, cudaMemsetAsync(h->ws_stats, 0, static_cast<size_t>(nc) * c.text_ctx * 16 * sizeof(float), st));
+        if ((rc = launch_text_embed(h, tokens_dev + static_cast<size_t>(i) * c.text_ctx, nc, h->ws_x, h->ws_eot,
+                                    h->ws_stats, st)))
             return rc;
         if ((rc = run_blocks(h, h->txt, nc, c.text_ctx, 1, st))) return rc;
         if ((rc = launch_head(h, h->ws_x, c.text_width, h->ws_eot, h->ln_final_g, h->ln_final_b, h->txt_proj, nc,
@@ -675,7 +783,7 @@ extern "C" int b200clip_layernorm_bf16(b200clip_handle* h, const void* x_dev, co
     if (!h || !x_dev || !gamma_dev || !beta_dev || !y_dev) return b200_fail(h, B200CLIP_E_ARG, "layernorm: null argument");
     B200_CUDA(h, cudaSetDevice(h->device));
     return launch_layernorm(h, static_cast<const bf16*>(x_dev), gamma_dev, beta_dev, static_cast<bf16*>(y_dev), rows,
-                            width, eps, 0, nullptr, static_cast<cudaStream_t>(stream));
+                            width, eps, 0, nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int b200clip_attention_bf16(b200clip_handle* h, const void* qkv_dev, void* out_dev, int n_seq, int t,

@@ -24,7 +24,17 @@ struct GemmEpilogue {
     const float* rowtab;        // [t_out, N] fp32 row table added by token position, or nullptr
     int act;                    // 0 none, 1 QuickGELU x*sigmoid(1.702x), 2 GELU(erf)
     int t_in, t_out, row_off;   // out_row = (r / t_in) * t_out + r % t_in + row_off   (t_in == 0: identity)
+    // LayerNorm folded into this GEMM:  LN(x) W^T + b  ==  rstd * (x (W.gamma)^T - mean * c1) + c2  with
+    // c1[n] = sum_k (W.gamma)[n,k], c2[n] = sum_k beta[k] W[n,k] + b[n] (passed as `bias`).  The per-row sums
+    // (sum x, sum x^2) come from `ln_stats` [rows, LN_SLOTS, 2], written by whoever produced x.
+    const float* ln_stats;      // nullptr: no fold
+    const float* ln_c1;         // [N]
+    float ln_eps;
+    int ln_width;               // row length of x (= K)
+    // this GEMM produces the residual stream: emit (sum, sum of squares) of each output row segment
+    float* stats_out;           // [rows, LN_SLOTS, 2] or nullptr
 };
+constexpr int LN_SLOTS = 8;     // row segments (128 or 64 columns wide) whose partial sums are kept separately
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
@@ -53,6 +63,91 @@ __device__ __forceinline__ float apply_act(float x, int act) {
         return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
     }
     return x;
+}
+
+// per-row LayerNorm statistics from the partial sums
+__device__ __forceinline__ void ln_row_stats(const GemmEpilogue& ep, long row, bool row_ok, float& mean, float& rstd) {
+    mean = 0.f; rstd = 1.f;
+    if (!ep.ln_stats || !row_ok) return;
+    const float4* p = reinterpret_cast<const float4*>(ep.ln_stats + row * (LN_SLOTS * 2));
+    float s = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_SLOTS / 2; ++i) {
+        const float4 v = __ldg(p + i);
+        s += v.x + v.z; s2 += v.y + v.w;
+    }
+    const float inv = 1.0f / static_cast<float>(ep.ln_width);
+    mean = s * inv;
+    const float var = fmaxf(s2 * inv - mean * mean, 0.f);
+    rstd = rsqrtf(var + ep.ln_eps);
+}
+
+// bias / LN-fold / row table / activation on 32 accumulator columns (everything before the residual add)
+__device__ __forceinline__ void epilogue_math(float (&v)[32], int n0, const GemmEpilogue& ep, const float* tab_ptr,
+                                              float mean, float rstd) {
+    if (ep.ln_stats) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 c1 = __ldg(reinterpret_cast<const float4*>(ep.ln_c1 + n0 + j));
+            const float4 c2 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+            v[j] = fmaf(rstd, fmaf(-mean, c1.x, v[j]), c2.x);
+            v[j + 1] = fmaf(rstd, fmaf(-mean, c1.y, v[j + 1]), c2.y);
+            v[j + 2] = fmaf(rstd, fmaf(-mean, c1.z, v[j + 2]), c2.z);
+            v[j + 3] = fmaf(rstd, fmaf(-mean, c1.w, v[j + 3]), c2.w);
+        }
+    } else if (ep.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+    }
+    if (tab_ptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(tab_ptr + n0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+    }
+    if (ep.act) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+    }
+}
+
+// one 32-column chunk, direct global stores (row-remapped outputs, small problems)
+__device__ __forceinline__ void epilogue_chunk(uint32_t (&acc)[32], int n0, int N, bool row_ok, const GemmEpilogue& ep,
+                                               __nv_bfloat16* out_ptr, const __nv_bfloat16* res_ptr,
+                                               const float* tab_ptr, float mean, float rstd, float& ssum, float& ssq) {
+    if (!row_ok || n0 >= N) return;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+    epilogue_math(v, n0, ep, tab_ptr, mean, rstd);
+    if (res_ptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            const uint4 r = *reinterpret_cast<const uint4*>(res_ptr + n0 + j);
+            float2 f;
+            f = unpack_bf16x2(r.x); v[j] += f.x; v[j + 1] += f.y;
+            f = unpack_bf16x2(r.y); v[j + 2] += f.x; v[j + 3] += f.y;
+            f = unpack_bf16x2(r.z); v[j + 4] += f.x; v[j + 5] += f.y;
+            f = unpack_bf16x2(r.w); v[j + 6] += f.x; v[j + 7] += f.y;
+        }
+    }
+    if (ep.stats_out) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { ssum += v[j]; ssq = fmaf(v[j], v[j], ssq); }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        uint4 o;
+        o.x = pack_bf16x2(v[j], v[j + 1]);
+        o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+        o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(out_ptr + n0 + j) = o;
+    }
 }
 
 template <int BLOCK_N>
@@ -176,50 +271,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const float* tab_ptr = ep.rowtab ? ep.rowtab + static_cast<long>(tpos) * N : nullptr;
             const int col0 = n_blk * BLOCK_N + half * COLS_PER_WARP;
 
-            auto process = [&](uint32_t (&acc)[32], int n0) {
-                if (!row_ok || n0 >= N) return;
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-                if (ep.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
-                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                    }
-                }
-                if (tab_ptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(tab_ptr + n0 + j));
-                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                    }
-                }
-                if (ep.act) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-                }
-                if (res_ptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        const uint4 r = *reinterpret_cast<const uint4*>(res_ptr + n0 + j);
-                        float2 f;
-                        f = unpack_bf16x2(r.x); v[j] += f.x; v[j + 1] += f.y;
-                        f = unpack_bf16x2(r.y); v[j + 2] += f.x; v[j + 3] += f.y;
-                        f = unpack_bf16x2(r.z); v[j + 4] += f.x; v[j + 5] += f.y;
-                        f = unpack_bf16x2(r.w); v[j + 6] += f.x; v[j + 7] += f.y;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    uint4 o;
-                    o.x = pack_bf16x2(v[j], v[j + 1]);
-                    o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                    o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                    o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                    *reinterpret_cast<uint4*>(out_ptr + n0 + j) = o;
-                }
-            };
+            float mean, rstd, ssum = 0.f, ssq = 0.f;
+            ln_row_stats(ep, out_row, row_ok, mean, rstd);
 
             mbar_wait(&tmem_full_bar[as], aphase, 4);
             tc_fence_after();
@@ -231,12 +284,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             for (int c = 0; c < NCH; c += 2) {
                 tmem_ld_wait_regs(acc_a);
                 if (c + 1 < NCH) tmem_ld_32x32(taddr + (c + 1) * 32, acc_b);
-                process(acc_a, col0 + c * 32);
+                epilogue_chunk(acc_a, col0 + c * 32, N, row_ok, ep, out_ptr, res_ptr, tab_ptr, mean, rstd, ssum, ssq);
                 if (c + 1 < NCH) {
                     tmem_ld_wait_regs(acc_b);
                     if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, acc_a);
-                    process(acc_b, col0 + (c + 1) * 32);
+                    epilogue_chunk(acc_b, col0 + (c + 1) * 32, N, row_ok, ep, out_ptr, res_ptr, tab_ptr, mean, rstd, ssum, ssq);
                 }
+            }
+            if (ep.stats_out && row_ok && col0 < N) {
+                const int seg = col0 / COLS_PER_WARP;
+                if (seg < LN_SLOTS)
+                    *reinterpret_cast<float2*>(ep.stats_out + (out_row * LN_SLOTS + seg) * 2) = make_float2(ssum, ssq);
             }
             // this warp is done reading the accumulator stage
             tc_fence_before();

@@ -25,74 +25,17 @@ constexpr int G2_STAGING_BYTES = GEMM_EPI_WARPS * 2 * G2_BOX_BYTES;   // 64 KB
 constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_STAGING_BYTES + 512 + 1024;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster barrier address
 
-// one 32-column chunk of the epilogue (shared by the 1-CTA and 2-CTA kernels)
-__device__ __forceinline__ void epilogue_chunk(uint32_t (&acc)[32], int n0, int N, bool row_ok, const GemmEpilogue& ep,
-                                               __nv_bfloat16* out_ptr, const __nv_bfloat16* res_ptr,
-                                               const float* tab_ptr) {
-    if (!row_ok || n0 >= N) return;
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-    if (ep.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-        }
-    }
-    if (tab_ptr) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(tab_ptr + n0 + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-        }
-    }
-    if (ep.act) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-    }
-    if (res_ptr) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-            const uint4 r = *reinterpret_cast<const uint4*>(res_ptr + n0 + j);
-            float2 f;
-            f = unpack_bf16x2(r.x); v[j] += f.x; v[j + 1] += f.y;
-            f = unpack_bf16x2(r.y); v[j + 2] += f.x; v[j + 3] += f.y;
-            f = unpack_bf16x2(r.z); v[j + 4] += f.x; v[j + 5] += f.y;
-            f = unpack_bf16x2(r.w); v[j + 6] += f.x; v[j + 7] += f.y;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-        uint4 o;
-        o.x = pack_bf16x2(v[j], v[j + 1]);
-        o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-        o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-        o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(out_ptr + n0 + j) = o;
-    }
-}
-
 // 32 accumulator columns of one row -> bf16 into a [32 rows][64 cols] SWIZZLE_128B box (row = lane).
 // chunk0 = index of the first 16-byte chunk of the row these 32 columns occupy (0 or 4).  If has_res, the box
 // already holds the residual tile (TMA-loaded) and it is added in place.
 __device__ __forceinline__ void epilogue_chunk_smem(uint32_t (&acc)[32], int n0, int N, const GemmEpilogue& ep,
-                                                    uint8_t* box, int lane, int chunk0, bool has_res) {
+                                                    uint8_t* box, int lane, int chunk0, bool has_res, float mean,
+                                                    float rstd, float& ssum, float& ssq) {
     if (n0 >= N) return;
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-    if (ep.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-        }
-    }
-    if (ep.act) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-    }
+    epilogue_math(v, n0, ep, nullptr, mean, rstd);
     uint8_t* rowp = box + lane * 128;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -104,6 +47,10 @@ __device__ __forceinline__ void epilogue_chunk_smem(uint32_t (&acc)[32], int n0,
             f = unpack_bf16x2(r.y); v[j * 8 + 2] += f.x; v[j * 8 + 3] += f.y;
             f = unpack_bf16x2(r.z); v[j * 8 + 4] += f.x; v[j * 8 + 5] += f.y;
             f = unpack_bf16x2(r.w); v[j * 8 + 6] += f.x; v[j * 8 + 7] += f.y;
+        }
+        if (ep.stats_out) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { ssum += v[j * 8 + e]; ssq = fmaf(v[j * 8 + e], v[j * 8 + e], ssq); }
         }
         uint4 o;
         o.x = pack_bf16x2(v[j * 8], v[j * 8 + 1]);
@@ -237,6 +184,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
             const __nv_bfloat16* res_ptr = ep.resid ? ep.resid + out_row * ldc : nullptr;
             const float* tab_ptr = ep.rowtab ? ep.rowtab + static_cast<long>(tpos) * N : nullptr;
             const int col0 = n_blk * G2_BLOCK_N + half * COLS_PER_WARP;
+            float mean, rstd, ssum = 0.f, ssq = 0.f;
+            ln_row_stats(ep, out_row, row_ok, mean, rstd);
 
             if (use_tma_epi) {
                 // ---- staged epilogue: TMEM -> registers -> swizzled smem box -> TMA bulk store (full 128-byte
@@ -262,10 +211,10 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
                     uint8_t* box = my_stage + (c >> 1) * G2_BOX_BYTES;
                     tmem_ld_wait_regs(acc_a);
                     tmem_ld_32x32(taddr + (c + 1) * 32, acc_b);
-                    epilogue_chunk_smem(acc_a, col0 + c * 32, N, ep, box, lane, 0, res_ptr != nullptr);
+                    epilogue_chunk_smem(acc_a, col0 + c * 32, N, ep, box, lane, 0, res_ptr != nullptr, mean, rstd, ssum, ssq);
                     tmem_ld_wait_regs(acc_b);
                     if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, acc_a);
-                    epilogue_chunk_smem(acc_b, col0 + (c + 1) * 32, N, ep, box, lane, 4, res_ptr != nullptr);
+                    epilogue_chunk_smem(acc_b, col0 + (c + 1) * 32, N, ep, box, lane, 4, res_ptr != nullptr, mean, rstd, ssum, ssq);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0 && col0 + c * 32 < N) {
@@ -284,13 +233,18 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
                 for (int c = 0; c < NCH; c += 2) {
                     tmem_ld_wait_regs(acc_a);
                     if (c + 1 < NCH) tmem_ld_32x32(taddr + (c + 1) * 32, acc_b);
-                    epilogue_chunk(acc_a, col0 + c * 32, N, row_ok, ep, out_ptr, res_ptr, tab_ptr);
+                    epilogue_chunk(acc_a, col0 + c * 32, N, row_ok, ep, out_ptr, res_ptr, tab_ptr, mean, rstd, ssum, ssq);
                     if (c + 1 < NCH) {
                         tmem_ld_wait_regs(acc_b);
                         if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, acc_a);
-                        epilogue_chunk(acc_b, col0 + (c + 1) * 32, N, row_ok, ep, out_ptr, res_ptr, tab_ptr);
+                        epilogue_chunk(acc_b, col0 + (c + 1) * 32, N, row_ok, ep, out_ptr, res_ptr, tab_ptr, mean, rstd, ssum, ssq);
                     }
                 }
+            }
+            if (ep.stats_out && row_ok && col0 < N) {
+                const int seg = col0 / COLS_PER_WARP;   // 128-column segments
+                if (seg < LN_SLOTS)
+                    *reinterpret_cast<float2*>(ep.stats_out + (out_row * LN_SLOTS + seg) * 2) = make_float2(ssum, ssq);
             }
             tc_fence_before();
             __syncwarp();

@@ -29,9 +29,13 @@ struct b200clip_handle {
 
     // ---- packed weights (device) ----
     struct Block {
-        float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+        // ln_1 / ln_2 are folded into the QKV / fc GEMMs at finalize: w_qkv = W.diag(gamma1) (bf16),
+        // c1 = row sums of the folded weights, c2 = W.beta + bias (see GemmEpilogue)
         bf16 *w_qkv = nullptr, *w_out = nullptr, *w_fc = nullptr, *w_proj = nullptr;
-        float *b_qkv = nullptr, *b_out = nullptr, *b_fc = nullptr, *b_proj = nullptr;
+        float *c1_qkv = nullptr, *c2_qkv = nullptr, *c1_fc = nullptr, *c2_fc = nullptr;
+        float *b_out = nullptr, *b_proj = nullptr;
+        // host copies kept between set_weight and finalize
+        std::vector<float> h_ln1_g, h_ln1_b, h_ln2_g, h_ln2_b, h_w_qkv, h_b_qkv, h_w_fc, h_b_fc;
     };
     struct Tower {
         int width = 0, layers = 0, heads = 0, mlp = 0;
@@ -64,6 +68,7 @@ struct b200clip_handle {
     uint8_t* ws_stage_dev[2] = {nullptr, nullptr};   // device staging for host-frame calls
     uint8_t* ws_stage_host[2] = {nullptr, nullptr};  // pinned
     size_t ws_stage_bytes = 0;
+    float* ws_stats = nullptr;     // [rows, LN_SLOTS, 2] per-row (sum, sum of squares) partials of the residual stream
     int32_t* ws_eot = nullptr;     // [ws_texts] row of the EOT token per text
     int64_t* ws_tokens = nullptr;  // [ws_texts * ctx]
     float* ws_emb = nullptr;       // device scratch for host-output calls
@@ -74,6 +79,9 @@ struct b200clip_handle {
     size_t ws_pre_bytes = 0;
     void* ws_topk = nullptr;       // sim/top-k partial candidates
     size_t ws_topk_bytes = 0;
+    bf16* ws_patches2 = nullptr;   // second patch buffer: K1 of chunk i+1 overlaps the tower of chunk i
+    cudaStream_t pre_stream = nullptr;
+    cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_tower[2] = {nullptr, nullptr}, ev_fork = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
@@ -104,14 +112,15 @@ struct GemmEpilogue;
 int launch_gemm(b200clip_handle* h, const bf16* a, int lda, const bf16* w, int ldw, bf16* out, int ldc, int M, int N,
                 int K, const b200::GemmEpilogue& ep, cudaStream_t st);
 int launch_layernorm(b200clip_handle* h, const bf16* x, const float* g, const float* b, bf16* y, int64_t rows,
-                     int width, float eps, int t_per_img, const float* cls_row, cudaStream_t st);
+                     int width, float eps, int t_per_img, const float* cls_row, float* stats_out, cudaStream_t st);
 int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, int t, int heads, int causal,
                      cudaStream_t st);
 int launch_head(b200clip_handle* h, const bf16* x, int64_t row_stride, const int32_t* row_index, const float* g,
                 const float* b, const bf16* proj, int n, int width, int embed, float eps, void* out, int out_dtype,
                 int l2norm, cudaStream_t st);
 int launch_patchify_chw(b200clip_handle* h, const float* chw, int n, bf16* patches, cudaStream_t st);
-int launch_text_embed(b200clip_handle* h, const int64_t* tokens, int q, bf16* x, int32_t* eot_rows, cudaStream_t st);
+int launch_text_embed(b200clip_handle* h, const int64_t* tokens, int q, bf16* x, int32_t* eot_rows, float* stats_out,
+                      cudaStream_t st);
 int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
                       int64_t row_stride, int mode, bf16* patches, float* chw, cudaStream_t st);
 int launch_sim_topk(b200clip_handle* h, const void* img, int dtype, int64_t n, int e, const float* txt, int q, int k,

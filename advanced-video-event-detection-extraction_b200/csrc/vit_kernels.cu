@@ -18,7 +18,7 @@ constexpr int LN_MAXV = 4;  // uint4 (8 bf16) per lane
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  bf16* __restrict__ y, int64_t rows, int width, float eps, int t_per_img,
-                 const float* __restrict__ cls_row) {
+                 const float* __restrict__ cls_row, float* __restrict__ stats_out) {
     const int lane = threadIdx.x & 31;
     const int64_t row = static_cast<int64_t>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -66,6 +66,7 @@ layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, co
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = rsqrtf(sq / width + eps);
     uint4* yr = reinterpret_cast<uint4*>(y + row * width);
+    float osum = 0.f, osq = 0.f;
 #pragma unroll
     for (int i = 0; i < LN_MAXV; ++i) {
         const int idx = lane + i * 32;
@@ -74,18 +75,34 @@ layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, co
             const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + idx * 2 + 1);
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + idx * 2);
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + idx * 2 + 1);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float o8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                o8[j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
+                osum += o8[j];
+                osq = fmaf(o8[j], o8[j], osq);
+            }
             uint4 o;
-            o.x = pack_bf16x2((v[i][0] - mean) * rstd * g0.x + b0.x, (v[i][1] - mean) * rstd * g0.y + b0.y);
-            o.y = pack_bf16x2((v[i][2] - mean) * rstd * g0.z + b0.z, (v[i][3] - mean) * rstd * g0.w + b0.w);
-            o.z = pack_bf16x2((v[i][4] - mean) * rstd * g1.x + b1.x, (v[i][5] - mean) * rstd * g1.y + b1.y);
-            o.w = pack_bf16x2((v[i][6] - mean) * rstd * g1.z + b1.z, (v[i][7] - mean) * rstd * g1.w + b1.w);
+            o.x = pack_bf16x2(o8[0], o8[1]); o.y = pack_bf16x2(o8[2], o8[3]);
+            o.z = pack_bf16x2(o8[4], o8[5]); o.w = pack_bf16x2(o8[6], o8[7]);
             yr[idx] = o;
         }
+    }
+    if (stats_out) {
+        // (sum, sum of squares) of the OUTPUT row: slot 0 of the row's LN_SLOTS partials (the others stay zero)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            osum += __shfl_xor_sync(0xffffffffu, osum, o);
+            osq += __shfl_xor_sync(0xffffffffu, osq, o);
+        }
+        if (lane == 0) *reinterpret_cast<float2*>(stats_out + row * 16) = make_float2(osum, osq);
     }
 }
 
 int launch_layernorm(b200clip_handle* h, const bf16* x, const float* g, const float* b, bf16* y, int64_t rows,
-                     int width, float eps, int t_per_img, const float* cls_row, cudaStream_t st) {
+                     int width, float eps, int t_per_img, const float* cls_row, float* stats_out, cudaStream_t st) {
     if (rows <= 0) return 0;
     if (width % 8 != 0 || width > LN_MAXV * 256)
         return b200_fail(h, B200CLIP_E_SHAPE, "layernorm: width %d must be a multiple of 8 and <= %d", width,
@@ -93,7 +110,7 @@ int launch_layernorm(b200clip_handle* h, const bf16* x, const float* g, const fl
     const int64_t blocks = (rows + LN_WARPS - 1) / LN_WARPS;
     ProfScope ps(h, PROF_LN, static_cast<double>(rows) * width * 4.0, st);
     layernorm_kernel<<<static_cast<unsigned>(blocks), LN_WARPS * 32, 0, st>>>(x, g, b, y, rows, width, eps, t_per_img,
-                                                                             cls_row);
+                                                                             cls_row, stats_out);
     h->launches++;
     B200_CUDA(h, cudaGetLastError());
     return 0;
@@ -497,15 +514,33 @@ int launch_patchify_chw(b200clip_handle* h, const float* chw, int n, bf16* patch
 // (first maximum, as torch.argmax).
 __global__ void text_embed_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ tok_emb,
                                   const float* __restrict__ pos, bf16* __restrict__ x, int32_t* __restrict__ eot_rows,
-                                  int q, int ctx, int width, int vocab) {
+                                  float* __restrict__ stats_out, int q, int ctx, int width, int vocab) {
     const int row = blockIdx.x;  // q*ctx + t
     const int qi = row / ctx, t = row - qi * ctx;
     int64_t id = tokens[row];
     if (id < 0) id = 0;
     if (id >= vocab) id = vocab - 1;
     const float* e = tok_emb + id * width;
-    for (int i = threadIdx.x; i < width; i += blockDim.x)
-        x[static_cast<int64_t>(row) * width + i] = __float2bfloat16(e[i] + pos[t * width + i]);
+    float ssum = 0.f, ssq = 0.f;
+    for (int i = threadIdx.x; i < width; i += blockDim.x) {
+        const float v = e[i] + pos[t * width + i];
+        x[static_cast<int64_t>(row) * width + i] = __float2bfloat16(v);
+        ssum += v;
+        ssq = fmaf(v, v, ssq);
+    }
+    if (stats_out) {
+        __shared__ float red[2][4];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+            ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+        }
+        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ssum; red[1][threadIdx.x >> 5] = ssq; }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            *reinterpret_cast<float2*>(stats_out + static_cast<int64_t>(row) * 16) =
+                make_float2(red[0][0] + red[0][1] + red[0][2] + red[0][3], red[1][0] + red[1][1] + red[1][2] + red[1][3]);
+    }
     if (t == 0 && threadIdx.x == 0) {
         int best = 0;
         int64_t bv = tokens[static_cast<int64_t>(qi) * ctx];
@@ -517,10 +552,11 @@ __global__ void text_embed_kernel(const int64_t* __restrict__ tokens, const floa
     }
 }
 
-int launch_text_embed(b200clip_handle* h, const int64_t* tokens, int q, bf16* x, int32_t* eot_rows, cudaStream_t st) {
+int launch_text_embed(b200clip_handle* h, const int64_t* tokens, int q, bf16* x, int32_t* eot_rows, float* stats_out,
+                      cudaStream_t st) {
     if (q <= 0) return 0;
     ProfScope ps(h, PROF_MISC, static_cast<double>(q) * h->cfg.text_ctx * h->cfg.text_width * 10.0, st);
-    text_embed_kernel<<<q * h->cfg.text_ctx, 128, 0, st>>>(tokens, h->tok_emb, h->txt_pos, x, eot_rows, q,
+    text_embed_kernel<<<q * h->cfg.text_ctx, 128, 0, st>>>(tokens, h->tok_emb, h->txt_pos, x, eot_rows, stats_out, q,
                                                           h->cfg.text_ctx, h->cfg.text_width, h->cfg.text_vocab);
     h->launches++;
     B200_CUDA(h, cudaGetLastError());
