@@ -215,12 +215,16 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
                     tmem_ld_wait_regs(acc_b);
                     if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, acc_a);
                     epilogue_chunk_smem(acc_b, col0 + (c + 1) * 32, N, ep, box, lane, 4, res_ptr != nullptr, mean, rstd, ssum, ssq);
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0 && col0 + c * 32 < N) {
-                        tma_store_2d(&tmap_out, box, col0 + c * 32, box_row0);
-                        tma_store_commit();
+                }
+                // one generic->async proxy fence for both boxes, then the bulk stores
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int bx = 0; bx < NCH / 2; ++bx) {
+                        if (col0 + bx * 64 < N) tma_store_2d(&tmap_out, my_stage + bx * G2_BOX_BYTES, col0 + bx * 64, box_row0);
                     }
+                    tma_store_commit();
                 }
                 if (res_ptr) res_phase ^= 1;
             } else {

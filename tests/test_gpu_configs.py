@@ -1,0 +1,106 @@
+"""Parity for the other BASELINE.json configurations (they are parity-test cases, not bench lines):
+  config 3  ViT-L/14 (patch 14 -> K padded 588->640, T = 257, width 1024, 24 layers; text width 768)
+  config 4  multi-query batch: 256 queries x cached embeddings (bf16 and fp32 cache), fused top-k
+  config 5  image x image scoring: CLIP embedding of crops vs a reference-image embedding, top_k = 10
+            (ImageMatcher._compute_clip_similarity / _single_stage_matching, src/services/image_matcher.py:254-272,980-1018)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from parity import COS_MIN, SCORE_TOL, cosine_rows
+from synth import QUERIES, structured_frames
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model_l14():
+    from b200clip import open_clip as oc
+    from oracle import clip_ref
+
+    sd = clip_ref.init_state_dict(clip_ref.CONFIGS["ViT-L-14"], seed=0, gain=1.0)
+    model, _, _ = oc.create_model_and_transforms("ViT-L-14", state_dict=sd, device="cuda:0", max_images=64, max_texts=4)
+    yield model
+    model.handle.close()
+
+
+def test_vitl14_matches_golden_reference_wrapper(model_l14, golden_dir):
+    """tests/golden/vitl14.npz = the reference's OpenCLIPModel.encode_images / encode_text with OPENCLIP_MODEL=ViT-L-14."""
+    from b200clip import capi
+    from oracle.clip_ref import synthetic_tokenize
+
+    g = np.load(os.path.join(golden_dir, "vitl14.npz"))
+    frames = structured_frames(6, 224, 224, seed=555)
+    emb = model_l14.encode_frames_u8_host(frames, capi.RESIZE_BICUBIC, normalize=True)
+    txt = model_l14.encode_text(synthetic_tokenize(list(QUERIES)).cuda(), normalize=True).cpu().numpy()
+    cos, tcos = cosine_rows(emb, g["emb"]), cosine_rows(txt, g["txt"])
+    ds = np.abs(emb @ txt.T - g["emb"] @ g["txt"].T).max()
+    print(f"\n[parity] ViT-L/14 image cosine min {cos.min():.6f}; text cosine min {tcos.min():.6f}; max |dscore| {ds:.5f}")
+    assert emb.shape == (6, 768) and cos.min() >= COS_MIN and tcos.min() >= COS_MIN and ds <= SCORE_TOL
+
+
+def test_vitl14_batching_and_1080p(model_l14):
+    """More frames than the reserved workspace (64) and the full 1080p chain, vs the fp32 oracle on a subset."""
+    from b200clip import capi
+    from oracle import clip_ref
+    from oracle import preprocess_ref as P
+
+    frames = structured_frames(70, 224, 224, seed=9)
+    dev = torch.from_numpy(frames).cuda()
+    full = model_l14.encode_frames_u8(dev, capi.RESIZE_REFERENCE).cpu().numpy()
+    part = model_l14.encode_frames_u8(dev[60:70], capi.RESIZE_REFERENCE).cpu().numpy()
+    assert np.array_equal(full[60:70], part)
+    hd = structured_frames(2, 1080, 1920, seed=3)
+    got = model_l14.encode_frames_u8_host(hd, capi.RESIZE_REFERENCE, normalize=True)
+    sd = clip_ref.init_state_dict(clip_ref.CONFIGS["ViT-L-14"], seed=0, gain=1.0)
+    ref = clip_ref.CLIPRef(clip_ref.CONFIGS["ViT-L-14"], sd)
+    x = torch.from_numpy(np.stack([P.to_chw_normalized(P.reference_preprocess_u8(f)) for f in hd]))
+    want = ref.encode_image(x)
+    want = (want / want.norm(dim=-1, keepdim=True)).numpy()
+    assert cosine_rows(got, want).min() >= COS_MIN
+
+
+def test_config4_256_queries_cached_embeddings(model_b32):
+    """256 text queries x a cached embedding matrix: K4 in bf16-cache and fp32-cache form == numpy argsort on the
+    same scores (bit-exact order), and the bf16 cache changes scores by < 1e-2."""
+    rng = np.random.default_rng(4)
+    n, q, k = 30000, 256, 5
+    img = rng.standard_normal((n, 512)).astype(np.float32)
+    img /= np.linalg.norm(img, axis=1, keepdims=True)
+    txt = rng.standard_normal((q, 512)).astype(np.float32)
+    txt /= np.linalg.norm(txt, axis=1, keepdims=True)
+    img_t, txt_t = torch.from_numpy(img).cuda(), torch.from_numpy(txt).cuda()
+    ts = torch.arange(n, dtype=torch.float64)
+    for cache in (img_t, img_t.bfloat16()):
+        s, i, iv, c = model_b32.sim_topk(cache, txt_t, k, 0.1, ts, 0, 30.0, float(n))
+        dense = model_b32.similarity(cache, txt_t).cpu().numpy()
+        want = np.stack([np.lexsort((np.arange(n), dense[:, j]))[::-1][:k] for j in range(q)])
+        assert np.array_equal(i.cpu().numpy(), want)
+        assert np.array_equal(c.cpu().numpy(), (np.take_along_axis(dense.T, want, 1) >= 0.1).sum(1))
+        assert np.abs(dense - img @ txt.T).max() < (1e-2 if cache.dtype == torch.bfloat16 else 2e-5)
+
+
+def test_config5_image_query_top10(model_b32, oracle_sd_b32):
+    """Reference-image embedding as the query over crop embeddings (image x image cosine), top_k = 10, threshold 0.7."""
+    from b200clip import capi
+    from oracle import clip_ref
+    from oracle import preprocess_ref as P
+
+    crops = structured_frames(96, 224, 224, seed=21)
+    crops[40] = crops[3]                       # an exact duplicate of the reference image further down the list
+    ref_img = crops[3:4]
+    emb = model_b32.encode_frames_u8(torch.from_numpy(crops).cuda(), capi.RESIZE_BICUBIC, normalize=True)
+    qemb = model_b32.encode_frames_u8(torch.from_numpy(ref_img).cuda(), capi.RESIZE_BICUBIC, normalize=True)
+    s, i, _, c = model_b32.sim_topk(emb, qemb, 10, 0.7)
+    i, s = i.cpu().numpy()[0], s.cpu().numpy()[0]
+    assert list(i[:2]) == [40, 3] and abs(s[0] - 1.0) < 1e-3 and s[0] == s[1]      # duplicates tie -> higher index first
+    oracle = clip_ref.CLIPRef(clip_ref.CONFIGS["ViT-B-32"], oracle_sd_b32)
+    x = torch.from_numpy(np.stack([P.to_chw_normalized(P.clip_transform_u8(f)) for f in crops]))
+    e = oracle.encode_image(x)
+    e = (e / e.norm(dim=-1, keepdim=True)).numpy()
+    ref_scores = e @ e[3]
+    assert np.abs(model_b32.similarity(emb, qemb)[:, 0].cpu().numpy() - ref_scores).max() <= SCORE_TOL
+    assert int(c[0]) == int((np.sort(model_b32.similarity(emb, qemb)[:, 0].cpu().numpy())[::-1][:10] >= 0.7).sum())
