@@ -61,6 +61,8 @@ SIGNATURES = {
     "b200clip_encode_text_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "b200clip_sim_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int, c_float, c_void_p,
                                   c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200clip_sim_topk_dense": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int, c_float, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200clip_similarity": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "b200clip_topk_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_double,
                                     c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -739,7 +739,17 @@ extern "C" int b200clip_sim_topk(b200clip_handle* h, const void* img_emb_dev, in
     if (!h) return b200_fail(h, B200CLIP_E_ARG, "sim_topk: null handle");
     B200_CUDA(h, cudaSetDevice(h->device));
     return launch_sim_topk(h, img_emb_dev, emb_dtype, n, e, txt_emb_dev, q, k, threshold, timestamps_dev, index_base,
-                           clip_duration, video_duration, top_scores_dev, top_idx_dev, intervals_dev, counts_dev,
+                           clip_duration, video_duration, top_scores_dev, top_idx_dev, intervals_dev, counts_dev, nullptr,
+                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200clip_sim_topk_dense(b200clip_handle* h, const void* img_emb_dev, int emb_dtype, int64_t n, int e,
+                                       const float* txt_emb_dev, int q, int k, float threshold, float* top_scores_dev,
+                                       int64_t* top_idx_dev, int32_t* counts_dev, float* dense_scores_dev, void* stream) {
+    if (!h || !dense_scores_dev) return b200_fail(h, B200CLIP_E_ARG, "sim_topk_dense: null argument");
+    B200_CUDA(h, cudaSetDevice(h->device));
+    return launch_sim_topk(h, img_emb_dev, emb_dtype, n, e, txt_emb_dev, q, k, threshold, nullptr, 0, 30.0, 0.0,
+                           top_scores_dev, top_idx_dev, nullptr, counts_dev, dense_scores_dev,
                            static_cast<cudaStream_t>(stream));
 }
 

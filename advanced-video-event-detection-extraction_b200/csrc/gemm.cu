@@ -91,7 +91,7 @@ static int launch_gemm_2cta(b200clip_handle* h, const bf16* a, int lda, const bf
     }
     static bool attr_set = false;
     if (!attr_set) {
-        B200_CUDA(h, cudaFuncSetAttribute(b200::gemm_bf16_tcgen05_2cta_kernel,
+        B200_CUDA(h, cudaFuncSetAttribute(b200::gemm_bf16_tcgen05_2cta_kernel<0>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, b200::G2_SMEM_BYTES));
         attr_set = true;
     }
@@ -102,7 +102,7 @@ static int launch_gemm_2cta(b200clip_handle* h, const bf16* a, int lda, const bf
     if (tiles < clusters) clusters = tiles;
     {
         ProfScope ps(h, PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
-        b200::gemm_bf16_tcgen05_2cta_kernel<<<2 * clusters, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, st>>>(
+        b200::gemm_bf16_tcgen05_2cta_kernel<0><<<2 * clusters, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, st>>>(
             ta, tw, to, tr, out, ldc, M, N, K, ep, use_tma_epi);
     }
     h->launches++;

@@ -61,6 +61,7 @@ __device__ __forceinline__ void epilogue_chunk_smem(uint32_t (&acc)[32], int n0,
     }
 }
 
+template <int kUnused>   // a template only so that the header can be included from several translation units
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,

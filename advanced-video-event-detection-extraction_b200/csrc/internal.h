@@ -125,7 +125,8 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
                       int64_t row_stride, int mode, bf16* patches, float* chw, cudaStream_t st);
 int launch_sim_topk(b200clip_handle* h, const void* img, int dtype, int64_t n, int e, const float* txt, int q, int k,
                     float thr, const double* ts, int64_t index_base, double clip_dur, double vid_dur,
-                    float* top_scores, int64_t* top_idx, double* intervals, int32_t* counts, cudaStream_t st);
+                    float* top_scores, int64_t* top_idx, double* intervals, int32_t* counts, float* dense,
+                    cudaStream_t st);
 int launch_similarity(b200clip_handle* h, const void* img, int dtype, int64_t n, int e, const float* txt, int q,
                       float* scores, cudaStream_t st);
 int launch_topk_merge(b200clip_handle* h, const float* cs, const int64_t* ci, int g, int q, int k, float thr,

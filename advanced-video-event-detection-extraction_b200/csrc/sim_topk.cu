@@ -12,8 +12,11 @@
 // The same final kernel merges candidate lists gathered from other ranks (multi-GPU path).
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "internal.h"
 #include "ptx.cuh"
+#include "sim_topk_tc.cuh"
 
 using namespace b200;
 
@@ -282,11 +285,79 @@ int launch_similarity(b200clip_handle* h, const void* img, int dtype, int64_t n,
     return run_stream(h, img, dtype, n, e, txt, q, 0, scores, nullptr, nullptr, sim_grid(h, n), st);
 }
 
+int make_tmap_bf16_2d(b200clip_handle* h, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                      uint64_t ld, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz);
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        dst[i] = __float2bfloat16(src[i]);
+}
+
+static int ensure_topk_ws(b200clip_handle* h, size_t need, cudaStream_t st) {
+    if (need <= h->ws_topk_bytes) return 0;
+    B200_CUDA(h, cudaStreamSynchronize(st));
+    if (h->ws_topk) cudaFree(h->ws_topk);
+    h->ws_topk = nullptr; h->ws_topk_bytes = 0;
+    B200_CUDA(h, cudaMalloc(&h->ws_topk, need));
+    h->ws_topk_bytes = need;
+    return 0;
+}
+
+// Tensor-core path (sim_topk_tc.cuh): bf16 cache, many queries, small k.
+static int launch_sim_topk_tc(b200clip_handle* h, const void* img, int64_t n, int e, const float* txt, int q, int k,
+                              float thr, const double* ts, int64_t index_base, double clip_dur, double vid_dur,
+                              float* top_scores, int64_t* top_idx, double* intervals, int32_t* counts, float* dense,
+                              cudaStream_t st) {
+    const int tiles = static_cast<int>((n + 2 * b200::GEMM_BLOCK_M - 1) / (2 * b200::GEMM_BLOCK_M));
+    int clusters = h->num_sms / 2;
+    if (tiles < clusters) clusters = tiles;
+    const int g = clusters * 2 * 4;
+    const size_t txt_bytes = (static_cast<size_t>(q) * e * 2 + 255) & ~size_t(255);
+    const size_t need = txt_bytes + static_cast<size_t>(g) * q * k * 8;
+    int rc = ensure_topk_ws(h, need, st);
+    if (rc) return rc;
+    bf16* txt16 = static_cast<bf16*>(h->ws_topk);
+    float* part_s = reinterpret_cast<float*>(static_cast<uint8_t*>(h->ws_topk) + txt_bytes);
+    int* part_i = reinterpret_cast<int*>(part_s + static_cast<size_t>(g) * q * k);
+    ProfScope ps(h, PROF_SIM, static_cast<double>(n) * e * 2.0 + static_cast<double>(q) * (e * 4.0 + k * 12.0), st);
+    f32_to_bf16_kernel<<<(static_cast<int64_t>(q) * e + 255) / 256, 256, 0, st>>>(txt, txt16, static_cast<int64_t>(q) * e);
+    h->launches++;
+    CUtensorMap ta, tw;
+    if ((rc = make_tmap_bf16_2d(h, &ta, img, n, e, e, b200::GEMM_BLOCK_M, b200::GEMM_BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    if ((rc = make_tmap_bf16_2d(h, &tw, txt16, q, e, e, b200::G2_HALF_N, b200::GEMM_BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200_CUDA(h, cudaFuncSetAttribute(b200::sim_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          b200::G2_SMEM_BYTES));
+        attr_set = true;
+    }
+    for (int q0 = 0; q0 < q; q0 += b200::G2_BLOCK_N) {
+        b200::sim_topk_tc_kernel<<<2 * clusters, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, st>>>(
+            ta, tw, static_cast<int>(n), q, q0, q, e, k, dense, part_s, part_i);
+        h->launches++;
+    }
+    topk_final_kernel<false><<<q, SIM_WARPS * 32, 0, st>>>(part_s, part_i, g, q, k, thr, ts, index_base, clip_dur, vid_dur,
+                                                          top_scores, top_idx, intervals, counts);
+    h->launches++;
+    B200_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
 int launch_sim_topk(b200clip_handle* h, const void* img, int dtype, int64_t n, int e, const float* txt, int q, int k,
                     float thr, const double* ts, int64_t index_base, double clip_dur, double vid_dur,
-                    float* top_scores, int64_t* top_idx, double* intervals, int32_t* counts, cudaStream_t st) {
+                    float* top_scores, int64_t* top_idx, double* intervals, int32_t* counts, float* dense,
+                    cudaStream_t st) {
     int rc = check_sim_args(h, img, dtype, n, e, txt, q);
     if (rc) return rc;
+    // many queries over a large bf16 cache: tensor-core similarity with the top-k fused into the epilogue
+    static const bool force_simt = getenv("B200CLIP_SIM_SIMT") != nullptr;
+    if (!force_simt && dtype == B200CLIP_BF16 && e % 64 == 0 && k >= 1 && k <= b200::STC_MAXK && q >= 8 && n >= 4096 &&
+        (reinterpret_cast<uintptr_t>(img) & 15) == 0 && top_scores && top_idx)
+        return launch_sim_topk_tc(h, img, n, e, txt, q, k, thr, ts, index_base, clip_dur, vid_dur, top_scores, top_idx,
+                                  intervals, counts, dense, st);
     if (k <= 0 || k > SIM_MAXK) return b200_fail(h, B200CLIP_E_SHAPE, "sim_topk: k must be in [1, %d]", SIM_MAXK);
     if (!top_scores || !top_idx) return b200_fail(h, B200CLIP_E_ARG, "sim_topk: null output");
     const int grid = sim_grid(h, n > 0 ? n : 1);
@@ -308,7 +379,7 @@ int launch_sim_topk(b200clip_handle* h, const void* img, int dtype, int64_t n, i
         B200_CUDA(h, cudaMemsetAsync(part_s, 0, static_cast<size_t>(q) * k * 4, st));
         g = 1;
     } else {
-        rc = run_stream(h, img, dtype, n, e, txt, q, k, nullptr, part_s, part_i, grid, st);
+        rc = run_stream(h, img, dtype, n, e, txt, q, k, dense, part_s, part_i, grid, st);
         if (rc) return rc;
     }
     topk_final_kernel<false><<<q, SIM_WARPS * 32, 0, st>>>(part_s, part_i, g, q, k, thr, ts, index_base, clip_dur,

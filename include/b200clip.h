@@ -138,11 +138,20 @@ int b200clip_encode_text_host(b200clip_handle* h, const int64_t* tokens_host, in
  *      Outputs (device): top_scores fp32 [q,k] and top_idx int64 [q,k] = the k best rows in descending
  *      order BEFORE thresholding (-1 marks an empty slot when n < k); counts int32 [q] = length of the
  *      prefix with score >= threshold (the reference's result list); intervals float64 [q,k,2]
- *      (start,end seconds) for every non-empty slot.  intervals_dev / counts_dev may be NULL. */
+ *      (start,end seconds) for every non-empty slot.  intervals_dev / counts_dev may be NULL.
+ *      Kernel selection: a bf16 cache with q >= 8, k <= 8, n >= 4096 and e % 64 == 0 runs the tcgen05 similarity GEMM
+ *      with the top-k fused into its epilogue (text embedding rounded to bf16); everything else runs the HBM-streaming
+ *      kernel (fp32 text embedding). */
 int b200clip_sim_topk(b200clip_handle* h, const void* img_emb_dev, int emb_dtype, int64_t n, int e,
                       const float* txt_emb_dev, int q, int k, float threshold, const double* timestamps_dev,
                       int64_t index_base, double clip_duration, double video_duration, float* top_scores_dev,
                       int64_t* top_idx_dev, double* intervals_dev, int32_t* counts_dev, void* stream);
+/* Test / debugging form of b200clip_sim_topk: additionally writes the fp32 score matrix [n,q] exactly as the selected
+ * kernel computed it (the tensor-core path rounds the text embedding to bf16), so that the top-k order can be checked
+ * bit-exactly against an argsort of the same scores. */
+int b200clip_sim_topk_dense(b200clip_handle* h, const void* img_emb_dev, int emb_dtype, int64_t n, int e,
+                            const float* txt_emb_dev, int q, int k, float threshold, float* top_scores_dev,
+                            int64_t* top_idx_dev, int32_t* counts_dev, float* dense_scores_dev, void* stream);
 /* Dense scores fp32 [n,q] (compute_similarity itself). */
 int b200clip_similarity(b200clip_handle* h, const void* img_emb_dev, int emb_dtype, int64_t n, int e,
                         const float* txt_emb_dev, int q, float* scores_out_dev, void* stream);

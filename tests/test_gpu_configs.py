@@ -74,13 +74,25 @@ def test_config4_256_queries_cached_embeddings(model_b32):
     txt /= np.linalg.norm(txt, axis=1, keepdims=True)
     img_t, txt_t = torch.from_numpy(img).cuda(), torch.from_numpy(txt).cuda()
     ts = torch.arange(n, dtype=torch.float64)
+    from b200clip import capi
+
     for cache in (img_t, img_t.bfloat16()):
-        s, i, iv, c = model_b32.sim_topk(cache, txt_t, k, 0.1, ts, 0, 30.0, float(n))
-        dense = model_b32.similarity(cache, txt_t).cpu().numpy()
+        # dense = the scores exactly as the selected kernel computed them (fp32 cache: HBM-streaming kernel, fp32 text;
+        # bf16 cache at this size: tcgen05 kernel, text rounded to bf16)
+        s = torch.empty(q, k, device="cuda")
+        i = torch.empty(q, k, device="cuda", dtype=torch.int64)
+        c = torch.empty(q, device="cuda", dtype=torch.int32)
+        dense_t = torch.empty(n, q, device="cuda")
+        dt = capi.BF16 if cache.dtype == torch.bfloat16 else capi.F32
+        model_b32.handle.call("b200clip_sim_topk_dense", capi._p(cache), dt, n, 512, capi._p(txt_t), q, k, 0.1, capi._p(s),
+                              capi._p(i), capi._p(c), capi._p(dense_t), model_b32._stream())
+        dense = dense_t.cpu().numpy()
         want = np.stack([np.lexsort((np.arange(n), dense[:, j]))[::-1][:k] for j in range(q)])
         assert np.array_equal(i.cpu().numpy(), want)
         assert np.array_equal(c.cpu().numpy(), (np.take_along_axis(dense.T, want, 1) >= 0.1).sum(1))
         assert np.abs(dense - img @ txt.T).max() < (1e-2 if cache.dtype == torch.bfloat16 else 2e-5)
+        s2, i2, _, c2 = model_b32.sim_topk(cache, txt_t, k, 0.1, ts, 0, 30.0, float(n))
+        assert torch.equal(i2, i) and torch.equal(c2, c)
 
 
 def test_config5_image_query_top10(model_b32, oracle_sd_b32):

@@ -116,3 +116,35 @@ def test_multi_shard_merge_equals_global(model_b32):
     for qq in range(q):
         o_s, o_i = R.merge_topk_lists(torch.stack(cs)[:, qq].cpu().numpy(), torch.stack(ci)[:, qq].cpu().numpy(), k)
         assert np.array_equal(o_i, mi[qq].cpu().numpy())
+
+
+@pytest.mark.parametrize("n,q,k,e", [(20000, 256, 5, 512), (9000, 40, 8, 768), (4096, 8, 1, 512), (70001, 300, 5, 512)])
+def test_tensor_core_path_order_is_exact(model_b32, n, q, k, e):
+    """bf16 cache + many queries -> sim_topk_tc_kernel (tcgen05 similarity, top-k fused in the epilogue).  The order
+    must equal an argsort (ties -> higher index) of the scores that very kernel computed, and those scores must be
+    within 1e-2 of the fp32 product."""
+    from b200clip import capi
+
+    rng = np.random.default_rng(n + q)
+    img = _unit(rng.standard_normal((n, e)).astype(np.float32))
+    img[n // 2: n // 2 + 3] = img[11]                       # exact ties across tiles
+    txt = _unit(rng.standard_normal((q, e)).astype(np.float32))
+    img_t = torch.from_numpy(img).cuda().bfloat16()
+    txt_t = torch.from_numpy(txt).cuda()
+    s = torch.empty(q, k, device="cuda")
+    i = torch.empty(q, k, device="cuda", dtype=torch.int64)
+    c = torch.empty(q, device="cuda", dtype=torch.int32)
+    dense = torch.full((n, q), float("nan"), device="cuda")
+    model_b32.handle.call("b200clip_sim_topk_dense", capi._p(img_t), capi.BF16, n, e, capi._p(txt_t), q, k, 0.05,
+                          capi._p(s), capi._p(i), capi._p(c), capi._p(dense), model_b32._stream())
+    d = dense.cpu().numpy()
+    assert not np.isnan(d).any()
+    ref = img_t.float().cpu().numpy() @ txt.T
+    assert np.abs(d - ref).max() < 1e-2
+    want = np.stack([np.lexsort((np.arange(n), d[:, j]))[::-1][:k] for j in range(q)])
+    assert np.array_equal(i.cpu().numpy(), want)
+    assert np.array_equal(s.cpu().numpy(), np.take_along_axis(d.T, want, 1))
+    assert np.array_equal(c.cpu().numpy(), (np.take_along_axis(d.T, want, 1) >= 0.05).sum(1))
+    # the public entry (same dispatch) returns the same thing
+    s2, i2, iv2, c2 = model_b32.sim_topk(img_t, txt_t, k, 0.05, torch.arange(n, dtype=torch.float64), 0, 30.0, float(n))
+    assert torch.equal(i2, i) and torch.equal(s2, s) and torch.equal(c2, c)
