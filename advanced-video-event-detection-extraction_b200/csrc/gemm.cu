@@ -118,8 +118,16 @@ int launch_gemm(b200clip_handle* h, const bf16* a, int lda, const bf16* w, int l
                          K, ldc);
     // large-M problems: CTA pairs (256x256 tiles, half the B traffic per CTA); B200CLIP_GEMM_1CTA=1 forces the
     // single-CTA kernel (used by the parity tests to cover both)
+    // Row statistics are emitted per (row, column segment of BLOCK_N/2); only LN_SLOTS segments are kept.
+    auto stats_fit = [&](int block_n) { return !ep.stats_out || (N + block_n / 2 - 1) / (block_n / 2) <= b200::LN_SLOTS; };
     static const bool force_1cta = getenv("B200CLIP_GEMM_1CTA") != nullptr;
-    if (!force_1cta && N % 256 == 0 && M >= 2048) return launch_gemm_2cta(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
-    if (N % 256 == 0 || N > 1024) return launch_gemm_bn<256>(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
+    if (!force_1cta && N % 256 == 0 && M >= 2048 && stats_fit(256)) return launch_gemm_2cta(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
+    // tiny M (text tower: 77 rows per query): narrow tiles so that more CTAs share the latency-bound problem
+    if (M <= 256 && N % 64 == 0 && stats_fit(64)) return launch_gemm_bn<64>(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
+    if (N % 256 == 0 || N > 1024) {
+        if (!stats_fit(256)) return b200_fail(h, B200CLIP_E_SHAPE, "gemm: width %d too large for the LayerNorm statistics slots", N);
+        return launch_gemm_bn<256>(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
+    }
+    if (!stats_fit(128)) return launch_gemm_bn<256>(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
     return launch_gemm_bn<128>(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
 }

@@ -15,7 +15,7 @@ namespace b200 {
 
 constexpr int G2_BLOCK_N = 256;
 constexpr int G2_HALF_N = 128;
-constexpr int G2_STAGES = 4;
+constexpr int G2_STAGES = 5;
 constexpr int G2_A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB: this CTA's 128 rows of A
 constexpr int G2_B_BYTES = G2_HALF_N * GEMM_BLOCK_K * 2;      // 16 KB: this CTA's half of B
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
@@ -30,11 +30,11 @@ constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a 
 // already holds the residual tile (TMA-loaded) and it is added in place.
 __device__ __forceinline__ void epilogue_chunk_smem(uint32_t (&acc)[32], int n0, int N, const GemmEpilogue& ep,
                                                     uint8_t* box, int lane, int chunk0, bool has_res, float mean,
-                                                    float rstd, float& ssum, float& ssq) {
+                                                    float rstd, f32x2_t& ssum, f32x2_t& ssq) {
     if (n0 >= N) return;
-    float v[32];
+    f32x2_t v[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+    for (int j = 0; j < 16; ++j) v[j] = f2_pack(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
     epilogue_math(v, n0, ep, nullptr, mean, rstd);
     uint8_t* rowp = box + lane * 128;
 #pragma unroll
@@ -42,21 +42,20 @@ __device__ __forceinline__ void epilogue_chunk_smem(uint32_t (&acc)[32], int n0,
         uint4* slot = reinterpret_cast<uint4*>(rowp + (((chunk0 + j) ^ (lane & 7)) << 4));
         if (has_res) {
             const uint4 r = *slot;
-            float2 f;
-            f = unpack_bf16x2(r.x); v[j * 8] += f.x; v[j * 8 + 1] += f.y;
-            f = unpack_bf16x2(r.y); v[j * 8 + 2] += f.x; v[j * 8 + 3] += f.y;
-            f = unpack_bf16x2(r.z); v[j * 8 + 4] += f.x; v[j * 8 + 5] += f.y;
-            f = unpack_bf16x2(r.w); v[j * 8 + 6] += f.x; v[j * 8 + 7] += f.y;
+            v[j * 4] = f2_add(v[j * 4], bf16x2_to_f2(r.x));
+            v[j * 4 + 1] = f2_add(v[j * 4 + 1], bf16x2_to_f2(r.y));
+            v[j * 4 + 2] = f2_add(v[j * 4 + 2], bf16x2_to_f2(r.z));
+            v[j * 4 + 3] = f2_add(v[j * 4 + 3], bf16x2_to_f2(r.w));
         }
         if (ep.stats_out) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { ssum += v[j * 8 + e]; ssq = fmaf(v[j * 8 + e], v[j * 8 + e], ssq); }
+            for (int e = 0; e < 4; ++e) { ssum = f2_add(ssum, v[j * 4 + e]); ssq = f2_fma(v[j * 4 + e], v[j * 4 + e], ssq); }
         }
         uint4 o;
-        o.x = pack_bf16x2(v[j * 8], v[j * 8 + 1]);
-        o.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
-        o.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
-        o.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+        o.x = f2_to_bf16x2(v[j * 4]);
+        o.y = f2_to_bf16x2(v[j * 4 + 1]);
+        o.z = f2_to_bf16x2(v[j * 4 + 2]);
+        o.w = f2_to_bf16x2(v[j * 4 + 3]);
         *slot = o;
     }
 }
@@ -185,7 +184,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
             const __nv_bfloat16* res_ptr = ep.resid ? ep.resid + out_row * ldc : nullptr;
             const float* tab_ptr = ep.rowtab ? ep.rowtab + static_cast<long>(tpos) * N : nullptr;
             const int col0 = n_blk * G2_BLOCK_N + half * COLS_PER_WARP;
-            float mean, rstd, ssum = 0.f, ssq = 0.f;
+            float mean, rstd;
+            f32x2_t ssum = f2_pack(0.f, 0.f), ssq = f2_pack(0.f, 0.f);
             ln_row_stats(ep, out_row, row_ok, mean, rstd);
 
             if (use_tma_epi) {
@@ -246,11 +246,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
                     }
                 }
             }
-            if (ep.stats_out && row_ok && col0 < N) {
-                const int seg = col0 / COLS_PER_WARP;   // 128-column segments
-                if (seg < LN_SLOTS)
-                    *reinterpret_cast<float2*>(ep.stats_out + (out_row * LN_SLOTS + seg) * 2) = make_float2(ssum, ssq);
-            }
+            if (ep.stats_out && row_ok && col0 < N) store_row_stats(ep, out_row, col0 / COLS_PER_WARP, ssum, ssq);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);  // the leader's barrier

@@ -278,17 +278,37 @@ area_kernel_w5(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t ro
     float wx[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) wx[i] = i < cx ? wxp[i] : 0.f;
+    // Packed fp32x2 arithmetic (FADD2/FMUL2: two independent round-to-nearest ops per instruction, bit-identical to
+    // the scalar sequence): channels 0/1 of a tap travel as one pair, channel 2 of taps (0,1) and (2,3) as pairs.
+    const f32x2_t kMagic = f2_pack(-8388608.0f, -8388608.0f);
+    f32x2_t w01[5], w2[2];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) w01[i] = f2_pack(wx[i], wx[i]);
+    w2[0] = f2_pack(wx[0], wx[1]);
+    w2[1] = f2_pack(wx[2], wx[3]);
     const uint8_t* base = src + f * frame_stride + static_cast<int64_t>(sy0) * row_stride + sx0 * 3;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    auto magic = [](const uint32_t (&u)[4], int n) {   // byte n spliced into the mantissa of 2^23
+        return __uint_as_float(__byte_perm(u[n >> 2], 0x4B000000u, 0x7650u | (n & 3)));
+    };
     for (int j = 0; j < cy; ++j) {
         uint32_t u[4];
         load_bytes_aligned<4>(base + j * row_stride, cx * 3, u);
+        // conversions and products run packed (two per instruction); the ACCUMULATION stays scalar: ptxas contracts a
+        // packed mul.rn + add.rn pair into FFMA2 (single rounding) even with -fmad=false, which would break parity
+        float pr[15];
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+            f2_unpack(f2_mul(f2_add(f2_pack(magic(u, i * 3), magic(u, i * 3 + 1)), kMagic), w01[i]), pr[i * 3], pr[i * 3 + 1]);
+        f2_unpack(f2_mul(f2_add(f2_pack(magic(u, 2), magic(u, 5)), kMagic), w2[0]), pr[2], pr[5]);
+        f2_unpack(f2_mul(f2_add(f2_pack(magic(u, 8), magic(u, 11)), kMagic), w2[1]), pr[8], pr[11]);
+        pr[14] = __fmul_rn(__fadd_rn(magic(u, 14), -8388608.0f), wx[4]);
         float b0 = 0.f, b1 = 0.f, b2 = 0.f;
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            b0 = __fadd_rn(b0, __fmul_rn(byte_as_float<4>(u, i * 3), wx[i]));
-            b1 = __fadd_rn(b1, __fmul_rn(byte_as_float<4>(u, i * 3 + 1), wx[i]));
-            b2 = __fadd_rn(b2, __fmul_rn(byte_as_float<4>(u, i * 3 + 2), wx[i]));
+            b0 = __fadd_rn(b0, pr[i * 3]);
+            b1 = __fadd_rn(b1, pr[i * 3 + 1]);
+            b2 = __fadd_rn(b2, pr[i * 3 + 2]);
         }
         const float beta = wy[j];
         if (j == 0) {

@@ -36,7 +36,7 @@ QUERY = "a person walking across street"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=3600, help="frames per GPU per step")
@@ -67,7 +67,11 @@ class ClockSampler:
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.first = index, None, [], 0
+
+    def mark(self):
+        """Start of the timed region: samples taken before this (nvidia-smi needs ~1 s to start) are dropped."""
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -88,7 +92,8 @@ class ClockSampler:
         time.sleep(0.06)
         self.proc.terminate()
         sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        lines = self.lines[self.first:] or self.lines[-3:]
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -217,16 +222,20 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         out = step()
     barrier()
     h.reset_launches()
     h.profile_read(reset=True)
     h.profile_enable(True)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if rank == 0:
+        time.sleep(1.2 if not sampler.lines else 0.0)   # let nvidia-smi deliver its first sample before timing
+        sampler.mark()
     barrier()
     e0.record()
     for _ in range(args.steps):
@@ -322,7 +331,10 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            # ncu dram__bytes_read.sum + dram__bytes_write.sum of the GEMM launches (profiles/r01j_gemm_ncu_summary.txt),
+            # kept as bytes per FLOP and scaled to this run's average launch
+            tj = json.load(open(tp))
+            traffic = tj["dram_bytes_per_flop"] * gemm["work"] / max(gemm["launches"], 1)
         kernels = {}
         for name, r in prof.items():
             if r["launches"]:
