@@ -75,6 +75,7 @@ SIGNATURES = {
     "b200clip_profile_read": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_double), POINTER(c_int64), c_int]),
     "b200clip_launch_count": (c_int64, [c_void_p]),
     "b200clip_reset_launch_count": (None, [c_void_p]),
+    "b200clip_transfer_bytes": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
 }
 
 _lib = None
@@ -183,3 +184,9 @@ class Handle:
 
     def reset_launches(self):
         self.lib.b200clip_reset_launch_count(self._h)
+
+    def transfer_bytes(self, reset: bool = True) -> tuple:
+        """(host->device, device->host) bytes moved by the *_host entry points since the last reset."""
+        a, b = c_int64(), c_int64()
+        self.call("b200clip_transfer_bytes", byref(a), byref(b), int(reset))
+        return a.value, b.value

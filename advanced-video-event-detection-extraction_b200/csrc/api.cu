@@ -38,6 +38,13 @@ extern "C" int64_t b200clip_launch_count(const b200clip_handle* h) { return h ? 
 extern "C" void b200clip_reset_launch_count(b200clip_handle* h) {
     if (h) h->launches = 0;
 }
+extern "C" int b200clip_transfer_bytes(b200clip_handle* h, int64_t* h2d_out, int64_t* d2h_out, int reset) {
+    if (!h) return b200_fail(h, B200CLIP_E_ARG, "transfer_bytes: null handle");
+    if (h2d_out) *h2d_out = h->h2d_bytes;
+    if (d2h_out) *d2h_out = h->d2h_bytes;
+    if (reset) { h->h2d_bytes = 0; h->d2h_bytes = 0; }
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------- profiler
 static cudaEvent_t prof_get_event(b200clip_handle* h) {
@@ -476,11 +483,22 @@ extern "C" int b200clip_encode_image_chw(b200clip_handle* h, const float* chw_de
     return 0;
 }
 
+// public device-frame entry points take whole frames: strides must cover them (the internal host-upload path hands
+// K1 a compacted window instead and is checked against that window in launch_preprocess)
+static int check_frame_strides(b200clip_handle* h, int n, int height, int width, int64_t frame_stride, int64_t row_stride) {
+    if (n > 0 && (height <= 0 || width <= 0 || row_stride < static_cast<int64_t>(width) * 3 ||
+                  frame_stride < row_stride * height))
+        return b200_fail(h, B200CLIP_E_ARG, "bad frame geometry %dx%d strides %lld/%lld", width, height,
+                         (long long)row_stride, (long long)frame_stride);
+    return 0;
+}
+
 extern "C" int b200clip_preprocess_u8(b200clip_handle* h, const uint8_t* frames_dev, int n, int height, int width,
                                       int64_t frame_stride, int64_t row_stride, int resize_mode, void* patches_out_dev,
                                       void* stream) {
     if (!h) return b200_fail(h, B200CLIP_E_ARG, "preprocess: null handle");
     if (n < 0 || (n > 0 && (!frames_dev || !patches_out_dev))) return b200_fail(h, B200CLIP_E_ARG, "preprocess: bad argument");
+    if (int rc = check_frame_strides(h, n, height, width, frame_stride, row_stride)) return rc;
     B200_CUDA(h, cudaSetDevice(h->device));
     return launch_preprocess(h, frames_dev, n, height, width, frame_stride, row_stride, resize_mode,
                              static_cast<bf16*>(patches_out_dev), nullptr, static_cast<cudaStream_t>(stream));
@@ -491,6 +509,7 @@ extern "C" int b200clip_preprocess_u8_chw(b200clip_handle* h, const uint8_t* fra
                                           float* chw_out_dev, void* stream) {
     if (!h) return b200_fail(h, B200CLIP_E_ARG, "preprocess: null handle");
     if (n < 0 || (n > 0 && (!frames_dev || !chw_out_dev))) return b200_fail(h, B200CLIP_E_ARG, "preprocess: bad argument");
+    if (int rc = check_frame_strides(h, n, height, width, frame_stride, row_stride)) return rc;
     B200_CUDA(h, cudaSetDevice(h->device));
     return launch_preprocess(h, frames_dev, n, height, width, frame_stride, row_stride, resize_mode, nullptr,
                              chw_out_dev, static_cast<cudaStream_t>(stream));
@@ -518,6 +537,7 @@ extern "C" int b200clip_encode_frames_u8(b200clip_handle* h, const uint8_t* fram
     int rc = check_ready(h, "encode_frames_u8");
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!frames_dev || !emb_out_dev))) return b200_fail(h, B200CLIP_E_ARG, "encode_frames_u8: bad argument");
+    if ((rc = check_frame_strides(h, n, height, width, frame_stride, row_stride))) return rc;
     if (out_dtype != B200CLIP_F32 && out_dtype != B200CLIP_BF16) return b200_fail(h, B200CLIP_E_ARG, "bad out_dtype");
     if (n == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -585,28 +605,45 @@ extern "C" int b200clip_encode_frames_u8_host(b200clip_handle* h, const uint8_t*
     if (height <= 0 || width <= 0) return b200_fail(h, B200CLIP_E_ARG, "encode_frames_u8_host: bad frame size");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t fbytes = static_cast<size_t>(height) * width * 3;
+    // Only the window of each frame that survives the transform's centre crop is uploaded (for 1080p: 1104 of the 1920
+    // columns): a strided 3-D copy packs rows [wy0, wy1) x columns [wx0, wx1) of every frame into the staging buffer,
+    // and K1 is pointed at a virtual frame origin in front of it.
+    int wx0, wx1, wy0, wy1;
+    if ((rc = preprocess_source_window(h, height, width, resize_mode, &wx0, &wx1, &wy0, &wy1))) return rc;
+    static const bool full_upload = getenv("B200CLIP_FULL_UPLOAD") != nullptr;
+    if (full_upload) { wx0 = 0; wx1 = width; wy0 = 0; wy1 = height; }
+    wx0 &= ~15;                                                     // 48-byte aligned window start
+    const int wrows = wy1 - wy0;
+    const size_t wbytes = static_cast<size_t>(wx1 - wx0) * 3;       // bytes copied per row
+    const size_t pitch = (wbytes + 63) & ~size_t(63);               // staging row pitch
+    const size_t fpitch = pitch * wrows;                            // staging frame pitch
+    const size_t lead = 64;                                         // K1 may read the aligned word in front of a row
     int chunk = chunk_images(h, n);
     const size_t budget = size_t(1) << 30;  // ~1 GiB of frames per staging buffer
-    if (static_cast<size_t>(chunk) * fbytes > budget) chunk = static_cast<int>(budget / fbytes);
+    if (static_cast<size_t>(chunk) * fpitch > budget) chunk = static_cast<int>(budget / fpitch);
     if (chunk < 1) chunk = 1;
     if ((rc = ensure_workspace(h, chunk, 0, st))) return rc;
     cudaPointerAttributes attr{};
     bool pinned = cudaPointerGetAttributes(&attr, frames_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    const size_t sbytes = static_cast<size_t>(chunk) * fbytes;
-    if (sbytes > h->ws_stage_bytes || (!pinned && !h->ws_stage_host[0])) {
+    const size_t sbytes = static_cast<size_t>(chunk) * fpitch + 2 * lead;
+    const size_t hbytes = static_cast<size_t>(chunk) * fbytes;      // pageable input: whole frames bounce through pinned memory
+    if (sbytes > h->ws_stage_bytes || (!pinned && (!h->ws_stage_host[0] || hbytes > h->ws_stage_host_bytes))) {
         B200_CUDA(h, cudaStreamSynchronize(st));
+        if (h->copy_stream) B200_CUDA(h, cudaStreamSynchronize(h->copy_stream));
         for (int i = 0; i < 2; ++i) {
             cudaFree(h->ws_stage_dev[i]); h->ws_stage_dev[i] = nullptr;
             if (h->ws_stage_host[i]) { cudaFreeHost(h->ws_stage_host[i]); h->ws_stage_host[i] = nullptr; }
         }
         const size_t nb = sbytes > h->ws_stage_bytes ? sbytes : h->ws_stage_bytes;
-        h->ws_stage_bytes = 0;
+        const size_t nh = hbytes > h->ws_stage_host_bytes ? hbytes : h->ws_stage_host_bytes;
+        h->ws_stage_bytes = 0; h->ws_stage_host_bytes = 0;
         for (int i = 0; i < 2; ++i) {
             B200_CUDA(h, cudaMalloc(&h->ws_stage_dev[i], nb));
-            if (!pinned) B200_CUDA(h, cudaMallocHost(&h->ws_stage_host[i], nb));
+            if (!pinned) B200_CUDA(h, cudaMallocHost(&h->ws_stage_host[i], nh));
         }
         h->ws_stage_bytes = nb;
+        if (!pinned) h->ws_stage_host_bytes = nh;
     }
     if (!h->copy_stream) {
         B200_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -645,12 +682,21 @@ extern "C" int b200clip_encode_frames_u8_host(b200clip_handle* h, const uint8_t*
             memcpy(h->ws_stage_host[b], src, static_cast<size_t>(nc) * fbytes);
             src = h->ws_stage_host[b];
         }
-        B200_CUDA(h, cudaMemcpyAsync(h->ws_stage_dev[b], src, static_cast<size_t>(nc) * fbytes, cudaMemcpyHostToDevice,
-                                     h->copy_stream));
+        uint8_t* stage = h->ws_stage_dev[b] + lead;
+        cudaMemcpy3DParms cp{};
+        cp.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(src) + static_cast<size_t>(wy0) * width * 3 + static_cast<size_t>(wx0) * 3,
+                                        static_cast<size_t>(width) * 3, static_cast<size_t>(width) * 3, height);
+        cp.dstPtr = make_cudaPitchedPtr(stage, pitch, pitch, wrows);
+        cp.extent = make_cudaExtent(wbytes, wrows, nc);
+        cp.kind = cudaMemcpyHostToDevice;
+        B200_CUDA(h, cudaMemcpy3DAsync(&cp, h->copy_stream));
+        h->h2d_bytes += static_cast<int64_t>(wbytes) * wrows * nc;
         B200_CUDA(h, cudaEventRecord(h->ev_h2d[b], h->copy_stream));
         B200_CUDA(h, cudaStreamWaitEvent(st, h->ev_h2d[b], 0));
-        if ((rc = launch_preprocess(h, h->ws_stage_dev[b], nc, height, width, static_cast<int64_t>(fbytes),
-                                    static_cast<int64_t>(width) * 3, resize_mode, h->ws_patches, nullptr, st)))
+        // virtual origin: staging (row 0, byte 0) is source (row wy0, column wx0)
+        const uint8_t* origin = stage - static_cast<int64_t>(wy0) * static_cast<int64_t>(pitch) - static_cast<int64_t>(wx0) * 3;
+        if ((rc = launch_preprocess(h, origin, nc, height, width, static_cast<int64_t>(fpitch),
+                                    static_cast<int64_t>(pitch), resize_mode, h->ws_patches, nullptr, st)))
             return rc;
         if ((rc = encode_patches_chunk(h, h->ws_patches, nc, emb_dev + static_cast<size_t>(i0) * h->cfg.embed_dim,
                                        B200CLIP_F32, l2norm, st)))
@@ -663,6 +709,7 @@ extern "C" int b200clip_encode_frames_u8_host(b200clip_handle* h, const uint8_t*
         return 0;
     }
     B200_CUDA(h, cudaMemcpyAsync(emb_out_host, h->ws_emb, emb_el * sizeof(float), cudaMemcpyDeviceToHost, st));
+    h->d2h_bytes += static_cast<int64_t>(emb_el * sizeof(float));
     B200_CUDA(h, cudaStreamSynchronize(st));
     return 0;
 }
@@ -715,6 +762,8 @@ extern "C" int b200clip_encode_text_host(b200clip_handle* h, const int64_t* toke
     }
     cudaError_t e = cudaMemcpyAsync(tok_dev, tokens_host, static_cast<size_t>(q) * c.text_ctx * sizeof(int64_t),
                                     cudaMemcpyHostToDevice, st);
+    h->h2d_bytes += static_cast<int64_t>(q) * c.text_ctx * sizeof(int64_t);
+    h->d2h_bytes += static_cast<int64_t>(q) * c.embed_dim * sizeof(float);
     if (e == cudaSuccess) {
         rc = encode_text_dev(h, tok_dev, q, emb_dev, l2norm, st);
         if (rc == 0)

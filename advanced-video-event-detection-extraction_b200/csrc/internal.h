@@ -67,7 +67,7 @@ struct b200clip_handle {
     bf16 *ws_x = nullptr, *ws_y = nullptr, *ws_qkv = nullptr, *ws_h = nullptr, *ws_patches = nullptr;
     uint8_t* ws_stage_dev[2] = {nullptr, nullptr};   // device staging for host-frame calls
     uint8_t* ws_stage_host[2] = {nullptr, nullptr};  // pinned
-    size_t ws_stage_bytes = 0;
+    size_t ws_stage_bytes = 0, ws_stage_host_bytes = 0;
     float* ws_stats = nullptr;     // [rows, LN_SLOTS, 2] per-row (sum, sum of squares) partials of the residual stream
     int32_t* ws_eot = nullptr;     // [ws_texts] row of the EOT token per text
     int64_t* ws_tokens = nullptr;  // [ws_texts * ctx]
@@ -84,6 +84,8 @@ struct b200clip_handle {
     cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_tower[2] = {nullptr, nullptr}, ev_fork = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    int64_t h2d_bytes = 0;         // bytes uploaded by the host-buffer entry points (b200clip_transfer_bytes)
+    int64_t d2h_bytes = 0;
 };
 
 // kernel classes for the profiler
@@ -133,3 +135,4 @@ int launch_topk_merge(b200clip_handle* h, const float* cs, const int64_t* ci, in
                       const double* ts, double clip_dur, double vid_dur, float* top_scores, int64_t* top_idx,
                       double* intervals, int32_t* counts, cudaStream_t st);
 void preprocess_free_plans(b200clip_handle* h);
+int preprocess_source_window(b200clip_handle* h, int H, int W, int mode, int* x0, int* x1, int* y0, int* y1);

@@ -135,6 +135,7 @@ struct Plan {
     int H = 0, W = 0, mode = 0;
     bool has_a = false, has_b = false, has_c = false;
     bool a_fast = false;     // integer scale factors in both axes (OpenCV ResizeAreaFast path)
+    bool a_seq = false;      // vertical area taps visit the source rows in sequence (strip walker usable)
     int a_max_cx = 0;        // largest horizontal tap count of the area stage
     int b_max_cnt = 0;       // largest tap count of the Pillow horizontal pass
     int a_fx = 1, a_fy = 1;
@@ -143,6 +144,7 @@ struct Plan {
     int left = 0, top = 0;   // centre crop
     int ry0 = 0, ry1 = 0;    // rows of the stage-B input/outputs that stage C needs
     int rx0 = 0, rx1 = 0;    // columns of the stage-A output that stage B needs
+    int sx0 = 0, sx1 = 0, sy0 = 0, sy1 = 0;   // window of the SOURCE frame that the first stage reads
     DevTaps ax{}, ay{}, bx{}, cy{};
     size_t mid1_per_frame = 0, mid2_per_frame = 0;
     std::vector<void*> dev;  // device allocations holding the tables
@@ -323,6 +325,105 @@ area_kernel_w5(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t ro
     o[0] = static_cast<uint8_t>(min(max(__float2int_rn(s0), 0), 255));
     o[1] = static_cast<uint8_t>(min(max(__float2int_rn(s1), 0), 255));
     o[2] = static_cast<uint8_t>(min(max(__float2int_rn(s2), 0), 255));
+}
+
+// A, strip walker for <= 5 horizontal taps and word-aligned rows (the 1080p/720p -> 512 case of the bench).  One
+// thread owns one output column over a strip of output rows and walks DOWN the source rows once, exactly like
+// OpenCV's ResizeArea_Invoker: each source row is reduced horizontally once (buf) and feeds the output row(s) it
+// overlaps, so a boundary row shared by two output rows is converted and multiplied once instead of twice.
+// Arithmetic (bit-identical to the scalar mul.rn/add.rn sequence of area_kernel):
+//   * byte -> fp32 -> times alpha in ONE fma: the byte is spliced into the mantissa of 2^23 (m = 2^23 + b, exact) and
+//     fma(m, alpha, -(2^23 * alpha)) rounds the exact value b*alpha once, which is mul.rn(float(b), alpha);
+//   * products that must not be contracted with the following add are written fma(x, y, negzero) with negzero = -0.0f
+//     passed as a kernel ARGUMENT: ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (single rounding) even with
+//     -fmad=false, but it cannot fold an fma whose addend it does not know;  x*y + (-0) == x*y in round-to-nearest;
+//   * channels 0/1 travel as one packed f32x2 pair (FFMA2/FADD2), channel 2 is scalar.
+// The next source row is prefetched while the current one is reduced.
+template <int DEPTH>   // source rows in flight ahead of the one being reduced
+__global__ void __launch_bounds__(128)
+area_strip_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int row_words, uint8_t* __restrict__ dst,
+                  int64_t dst_frame_stride, int oy0, int ny, int ox0, int nx, int rows_per_strip, int nstrips, int row_max,
+                  DevTaps ax, DevTaps ay, float negzero) {
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= static_cast<unsigned>(nstrips * nx)) return;
+    const int strip = id / nx, x = id - strip * nx;
+    const int64_t f = blockIdx.y;
+    const int dx = ox0 + x;
+    const int sx0 = ax.start[dx], cx = ax.cnt[dx];
+    const float* wxp = ax.wf + dx * ax.stride;
+    float wx[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) wx[i] = i < cx ? __ldg(wxp + i) : 0.f;
+    // weight pairs and their -(2^23 * w) addends: channels (0,1) of tap i; channel 2 of taps (0,1), (2,3), 4
+    f32x2_t w01[5], c01[5], w2[2], c2[2];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        w01[i] = f2_pack(wx[i], wx[i]);
+        c01[i] = f2_pack(-8388608.0f * wx[i], -8388608.0f * wx[i]);
+    }
+    w2[0] = f2_pack(wx[0], wx[1]); c2[0] = f2_pack(-8388608.0f * wx[0], -8388608.0f * wx[1]);
+    w2[1] = f2_pack(wx[2], wx[3]); c2[1] = f2_pack(-8388608.0f * wx[2], -8388608.0f * wx[3]);
+    const float w24 = wx[4], c24 = -8388608.0f * wx[4];
+    const f32x2_t nz2 = f2_pack(negzero, negzero);
+
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(src + f * frame_stride + sx0 * 3);
+    const uint32_t sh = static_cast<uint32_t>(addr & 3) * 8;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(addr & ~uintptr_t(3));
+    const int last = static_cast<int>(((addr & 3) + static_cast<uintptr_t>(cx * 3) - 1) >> 2);   // last word needed
+    const int o1 = min(1, last), o2 = min(2, last), o3 = min(3, last), o4 = min(4, last);
+    auto load_row = [&](int row, uint32_t (&w)[5]) {
+        const uint32_t* p = wp + static_cast<int64_t>(row) * row_words;
+        w[0] = __ldg(p); w[1] = __ldg(p + o1); w[2] = __ldg(p + o2); w[3] = __ldg(p + o3); w[4] = __ldg(p + o4);
+    };
+    auto magic = [](const uint32_t (&u)[4], int n) {   // 2^23 + byte n
+        return __uint_as_float(__byte_perm(u[n >> 2], 0x4B000000u, 0x7650u | (n & 3)));
+    };
+
+    const int dy_a = oy0 + strip * rows_per_strip;
+    const int dy_b = min(dy_a + rows_per_strip, oy0 + ny);
+    uint32_t nxt[DEPTH][5];
+    int have = __ldg(ay.start + dy_a) - 1;          // row held in (b01, b2); rows are visited in sequence
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) load_row(min(have + 1 + d, row_max), nxt[d]);
+    f32x2_t b01 = 0;
+    float b2 = 0.f;
+    uint8_t* o = dst + f * dst_frame_stride + (static_cast<int64_t>(dy_a - oy0) * nx + x) * 3;
+    for (int dy = dy_a; dy < dy_b; ++dy, o += nx * 3) {
+        const int sy0 = __ldg(ay.start + dy), cy = __ldg(ay.cnt + dy);
+        const float* wy = ay.wf + dy * ay.stride;
+        f32x2_t s01 = 0;     // 0 + beta*buf == beta*buf exactly (all terms are >= +0)
+        float s2 = 0.f;
+        for (int j = 0; j < cy; ++j) {
+            if (sy0 + j != have) {
+                have = sy0 + j;
+                uint32_t u[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) u[k] = __funnelshift_r(nxt[0][k], nxt[0][k + 1], sh);
+#pragma unroll
+                for (int d = 0; d + 1 < DEPTH; ++d)
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) nxt[d][k] = nxt[d + 1][k];
+                load_row(min(have + DEPTH, row_max), nxt[DEPTH - 1]);
+                b01 = f2_fma(f2_pack(magic(u, 0), magic(u, 1)), w01[0], c01[0]);
+#pragma unroll
+                for (int i = 1; i < 5; ++i)
+                    b01 = f2_add(b01, f2_fma(f2_pack(magic(u, i * 3), magic(u, i * 3 + 1)), w01[i], c01[i]));
+                float p0, p1, p2, p3;
+                f2_unpack(f2_fma(f2_pack(magic(u, 2), magic(u, 5)), w2[0], c2[0]), p0, p1);
+                f2_unpack(f2_fma(f2_pack(magic(u, 8), magic(u, 11)), w2[1], c2[1]), p2, p3);
+                const float p4 = __fmaf_rn(magic(u, 14), w24, c24);
+                b2 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(p0, p1), p2), p3), p4);
+            }
+            const float beta = __ldg(wy + j);
+            s01 = f2_add(s01, f2_fma(f2_pack(beta, beta), b01, nz2));
+            s2 = __fadd_rn(s2, __fmaf_rn(beta, b2, negzero));
+        }
+        float s0, s1;
+        f2_unpack(s01, s0, s1);
+        o[0] = static_cast<uint8_t>(min(max(__float2int_rn(s0), 0), 255));
+        o[1] = static_cast<uint8_t>(min(max(__float2int_rn(s1), 0), 255));
+        o[2] = static_cast<uint8_t>(min(max(__float2int_rn(s2), 0), 255));
+    }
 }
 
 // A (integer scale factors): OpenCV ResizeAreaFast -- integer box sum times float(1/area), rint;
@@ -532,6 +633,22 @@ static int build_plan(b200clip_handle* h, int H, int W, int mode, Plan& p) {
             ax = area_taps(W, w1);
             ay = area_taps(H, h1);
             for (int c : ax.cnt) p.a_max_cx = c > p.a_max_cx ? c : p.a_max_cx;
+            p.a_seq = true;
+            for (int dy = 0; dy + 1 < h1; ++dy) {
+                const int end = ay.start[dy] + ay.cnt[dy];
+                if (ay.cnt[dy] < 1 || (ay.start[dy + 1] != end && ay.start[dy + 1] != end - 1)) p.a_seq = false;
+            }
+            if (ay.cnt[h1 - 1] < 1) p.a_seq = false;
+        }
+    }
+    // source window read by the first stage
+    p.sx0 = p.rx0; p.sx1 = p.rx1; p.sy0 = p.ry0; p.sy1 = p.ry1;
+    if (p.has_a) {
+        if (p.a_fast) {
+            p.sx0 = p.rx0 * p.a_fx; p.sx1 = p.rx1 * p.a_fx; p.sy0 = p.ry0 * p.a_fy; p.sy1 = p.ry1 * p.a_fy;
+        } else {
+            taps_range(ax, p.rx0, p.rx1, p.sx0, p.sx1);
+            taps_range(ay, p.ry0, p.ry1, p.sy0, p.sy1);
         }
     }
     p.ax = upload_taps(h, p, ax, rc);
@@ -581,15 +698,11 @@ static unsigned grid_for(b200clip_handle* h, int64_t total, int threads) {
     return static_cast<unsigned>(b);
 }
 
-int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
-                      int64_t row_stride, int mode, bf16* patches, float* chw, cudaStream_t st) {
-    if (n <= 0) return 0;
+static int get_plan(b200clip_handle* h, int H, int W, int mode, const Plan** out) {
     if (mode != B200CLIP_RESIZE_REFERENCE && mode != B200CLIP_RESIZE_BILINEAR_AA && mode != B200CLIP_RESIZE_BICUBIC)
         return b200_fail(h, B200CLIP_E_ARG, "preprocess: unknown resize mode %d", mode);
-    if (H <= 0 || W <= 0 || row_stride < static_cast<int64_t>(W) * 3 || frame_stride < row_stride * H)
-        return b200_fail(h, B200CLIP_E_ARG, "preprocess: bad frame geometry %dx%d strides %lld/%lld", W, H,
-                         (long long)row_stride, (long long)frame_stride);
-    const int S = h->cfg.image_size, P = h->cfg.patch;
+    if (H <= 0 || W <= 0 || H >= (1 << 28) || W >= (1 << 28))
+        return b200_fail(h, B200CLIP_E_ARG, "preprocess: bad frame size %dx%d", W, H);
     const uint64_t key = (static_cast<uint64_t>(H) << 34) | (static_cast<uint64_t>(W) << 4) | static_cast<uint64_t>(mode);
     auto& pl = plans(h);
     auto it = pl.find(key);
@@ -599,7 +712,32 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         if (rc) return rc;
         it = pl.emplace(key, std::move(p)).first;
     }
-    const Plan& p = it->second;
+    *out = &it->second;
+    return 0;
+}
+
+// The rectangle of the source frame that K1 reads for this geometry (everything outside it is cropped away by the
+// transform): the host-frame path uploads only this window.
+int preprocess_source_window(b200clip_handle* h, int H, int W, int mode, int* x0, int* x1, int* y0, int* y1) {
+    const Plan* pp = nullptr;
+    int rc = get_plan(h, H, W, mode, &pp);
+    if (rc) return rc;
+    *x0 = pp->sx0; *x1 = pp->sx1; *y0 = pp->sy0; *y1 = pp->sy1;
+    return 0;
+}
+
+int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
+                      int64_t row_stride, int mode, bf16* patches, float* chw, cudaStream_t st) {
+    if (n <= 0) return 0;
+    const Plan* pp = nullptr;
+    int prc = get_plan(h, H, W, mode, &pp);
+    if (prc) return prc;
+    const Plan& p = *pp;
+    // strides are checked against the window K1 reads, so that a compacted upload of that window is a valid input
+    if (row_stride < static_cast<int64_t>(p.sx1 - p.sx0) * 3 || frame_stride < row_stride * (p.sy1 - p.sy0))
+        return b200_fail(h, B200CLIP_E_ARG, "preprocess: bad frame geometry %dx%d strides %lld/%lld", W, H,
+                         (long long)row_stride, (long long)frame_stride);
+    const int S = h->cfg.image_size, P = h->cfg.patch;
     float* lut = get_lut(h);
     if (!lut) return b200_fail(h, B200CLIP_E_NOMEM, "preprocess: LUT allocation failed");
     // intermediates
@@ -626,10 +764,22 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         const int ny = p.ry1 - p.ry0, nx = p.rx1 - p.rx0;
         dim3 grid((static_cast<unsigned>(ny) * nx + 255) / 256, n);
         ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(H) * (p.rx1 - p.rx0) * W / p.w1 * 3.0 + ny * nx * 3.0), st);
+        static const bool no_strip = getenv("B200CLIP_AREA_NOSTRIP") != nullptr;   // parity tests cover both paths
         if (p.a_fast)
             area_fast_kernel<<<grid, 256, 0, st>>>(cur, cur_fs, cur_rs, mid1, p.mid1_per_frame, p.ry0, ny, p.rx0, nx,
                                                    p.a_fx, p.a_fy);
-        else if (p.a_max_cx <= 5)
+        else if (p.a_max_cx <= 5 && p.a_seq && (cur_rs & 3) == 0 && !no_strip) {
+            // strips of output rows: long enough that the re-read boundary row is noise, short enough to fill the GPU
+            int rows = 12;
+            while (rows > 3 && static_cast<int64_t>(n) * nx * ((ny + rows - 1) / rows) < static_cast<int64_t>(h->num_sms) * 4096)
+                rows = (rows + 1) / 2;
+            const int nstrips = (ny + rows - 1) / rows;
+            dim3 sgrid((static_cast<unsigned>(nstrips) * nx + 127) / 128, n);
+            static const int depth = getenv("B200CLIP_AREA_DEPTH") ? atoi(getenv("B200CLIP_AREA_DEPTH")) : 2;
+            auto kern = depth <= 1 ? area_strip_kernel<1> : depth == 2 ? area_strip_kernel<2> : depth == 3 ? area_strip_kernel<3> : area_strip_kernel<4>;
+            kern<<<sgrid, 128, 0, st>>>(cur, cur_fs, static_cast<int>(cur_rs >> 2), mid1, p.mid1_per_frame,
+                                        p.ry0, ny, p.rx0, nx, rows, nstrips, p.sy1 - 1, p.ax, p.ay, -0.0f);
+        } else if (p.a_max_cx <= 5)
             area_kernel_w5<<<grid, 256, 0, st>>>(cur, cur_fs, cur_rs, mid1, p.mid1_per_frame, p.ry0, ny, p.rx0, nx, p.ax,
                                                  p.ay);
         else

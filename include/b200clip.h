@@ -187,6 +187,12 @@ int b200clip_profile_read(b200clip_handle* h, int kernel_class, double* ms_out, 
 int64_t b200clip_launch_count(const b200clip_handle* h);
 void b200clip_reset_launch_count(b200clip_handle* h);
 
+/* Bytes moved over PCIe by the *_host entry points since the last reset (bench.py's e2e h2d/d2h_bytes_per_step).
+ * b200clip_encode_frames_u8_host uploads only the window of each frame that the transform's centre crop keeps
+ * (reference: the whole frame travels through PIL, src/models/openclip_model.py:165-174), so this is less than
+ * n*H*W*3. */
+int b200clip_transfer_bytes(b200clip_handle* h, int64_t* h2d_out, int64_t* d2h_out, int reset);
+
 #ifdef __cplusplus
 }
 #endif

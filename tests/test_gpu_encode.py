@@ -143,3 +143,26 @@ def test_errors_are_loud(model_b32):
         model_b32.handle.call("b200clip_preprocess_u8_chw", capi._p(1), 1, 224, 224, 10, 10, 0, capi._p(1), None)
     with pytest.raises(capi.B200ClipError):
         model_b32.preprocess_u8(torch.zeros(1, 224, 224, 3, dtype=torch.uint8, device="cuda"), resize_mode=9)
+
+
+@pytest.mark.parametrize("w,h", [(1920, 1080), (1280, 720), (288, 512), (640, 480), (1024, 1024), (224, 224), (700, 1000)])
+@pytest.mark.parametrize("mode", ["REFERENCE", "BICUBIC", "BILINEAR_AA"])
+def test_host_upload_window_equals_device_path(model_b32, w, h, mode):
+    """b200clip_encode_frames_u8_host uploads only the source window that survives the centre crop (strided 3-D
+    copy into a compacted staging buffer); the embeddings must be bit-identical to the whole-frame device path, for
+    pinned and pageable host memory."""
+    from b200clip import capi
+
+    rm = getattr(capi, "RESIZE_" + mode)
+    frames = noise_frames(3, h, w, seed=w + 7 * h)
+    dev = model_b32.encode_frames_u8(torch.from_numpy(frames).cuda(), rm, normalize=True).cpu().numpy()
+    model_b32.handle.transfer_bytes(reset=True)
+    pageable = model_b32.encode_frames_u8_host(frames, rm, normalize=True)
+    h2d, d2h = model_b32.handle.transfer_bytes(reset=True)
+    assert np.array_equal(pageable, dev)
+    pinned_in = torch.from_numpy(frames).pin_memory()
+    pinned = model_b32.encode_frames_u8_host(pinned_in, rm, normalize=True)
+    assert np.array_equal(np.asarray(pinned), dev)
+    assert 0 < h2d <= frames.nbytes and d2h == dev.nbytes
+    if (w, h) == (1920, 1080):
+        assert h2d < 0.6 * frames.nbytes      # 1104 of 1920 columns

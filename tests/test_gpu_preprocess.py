@@ -104,3 +104,23 @@ def test_strided_frames_and_empty(model_b32):
         assert np.array_equal(out[i].cpu().numpy(), want)
     model_b32.handle.call("b200clip_preprocess_u8_chw", capi._p(None), 0, 240, 320, 0, 0, capi.RESIZE_REFERENCE,
                           capi._p(None), model_b32._stream())
+
+
+@pytest.mark.parametrize("pad_w,x_off", [(4, 1), (4, 2), (3, 1), (1, 0)])
+def test_1080p_window_alignments(model_b32, pad_w, x_off):
+    """The 1080p area stage has two code paths: the strip walker (row stride a multiple of 4 bytes, any start
+    alignment) and the per-pixel kernel (everything else).  Both must reproduce cv2 bit for bit."""
+    from b200clip import capi
+    from oracle import preprocess_ref as P
+
+    Wb = 1920 + pad_w
+    big = noise_frames(2, 1083, Wb, seed=31 + pad_w)
+    view = big[:, 2:1082, x_off:x_off + 1920]
+    dev = torch.from_numpy(big).cuda()
+    out = torch.empty(2, 3, 224, 224, device="cuda")
+    base = dev.data_ptr() + (2 * Wb + x_off) * 3
+    model_b32.handle.call("b200clip_preprocess_u8_chw", capi._p(base), 2, 1080, 1920, 1083 * Wb * 3, Wb * 3,
+                          capi.RESIZE_REFERENCE, capi._p(out), model_b32._stream())
+    for i in range(2):
+        want = P.to_chw_normalized(P.reference_preprocess_u8(np.ascontiguousarray(view[i])))
+        assert np.array_equal(out[i].cpu().numpy().view(np.uint32), want.view(np.uint32))
