@@ -460,6 +460,201 @@ __device__ __forceinline__ uint8_t clip8(int v) {
     return static_cast<uint8_t>(min(max(v, 0), 255));
 }
 
+// A+B fused, bulk-copy fed (the 1080p/720p bench path).  One CTA per (strip of area-output rows, frame):
+//   * a producer warp streams the strip's source rows -- only the [xb0, xb0+seg) byte window the crop needs -- into a
+//     shared-memory ring with 1-D bulk async copies (cp.async.bulk, mbarrier complete_tx), NSTAGE rows in flight per
+//     CTA without holding registers;
+//   * consumer thread x walks down the rows for area-output column ox0+x exactly like area_strip_kernel (same
+//     arithmetic, bit-identical), reading its <= 15 bytes per row from the ring;
+//   * each finished area row (uint8) is parked in shared memory and consumer threads t < S immediately apply Pillow's
+//     horizontal fixed-point pass to it and store row y of mid2 -- the area image never travels through HBM.
+constexpr int AH_NSTAGE = 8;
+struct AhRowInfo {      // how one source row of the strip feeds the vertical accumulation
+    float beta_cur;     // weight into the output row being accumulated
+    float beta_next;    // weight into the NEXT output row when the row straddles two (else 0)
+    int finish;         // 1: this row is the last tap of the output row being accumulated
+    int pad;
+};
+// bounded spin on an mbarrier phase without the timer bookkeeping of mbar_wait (this loop runs once per source row)
+__device__ __forceinline__ void mbar_wait_fast(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > (1u << 24)) __trap();
+}
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+area_hpass_bulk_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride,
+                       uint8_t* __restrict__ mid2, int64_t mid2_frame_stride, int oy0, int ny, int ox0, int nx,
+                       int rows_per_strip, int max_rows, int xb0, int seg_bytes, int stage_bytes, int arow_pitch,
+                       int left, int S, DevTaps ax, DevTaps ay, DevTaps bx, float negzero) {
+    extern __shared__ __align__(128) uint8_t ah_smem[];
+    const int ncons = blockDim.x - 32;                 // consumer threads; the last warp is the producer
+    const int tid = threadIdx.x;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ah_smem);
+    uint64_t* empty_bar = full_bar + AH_NSTAGE;
+    uint8_t* ring = ah_smem + 2 * AH_NSTAGE * sizeof(uint64_t);
+    uint8_t* arow = ring + AH_NSTAGE * stage_bytes;
+    AhRowInfo* rinfo = reinterpret_cast<AhRowInfo*>(arow + 2 * arow_pitch);
+
+    const int strip = blockIdx.x;
+    const int64_t f = blockIdx.y;
+    const int dy_a = oy0 + strip * rows_per_strip;
+    const int dy_b = min(dy_a + rows_per_strip, oy0 + ny);
+    const int r_lo = __ldg(ay.start + dy_a);
+    const int nrows = __ldg(ay.start + dy_b - 1) + __ldg(ay.cnt + dy_b - 1) - r_lo;
+    const uint8_t* gbase = src + f * frame_stride + xb0;
+    const int delta = static_cast<int>(reinterpret_cast<uintptr_t>(gbase) & 15);
+
+    if (tid == 0) {
+        for (int s = 0; s < AH_NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ncons >> 5); }
+        fence_mbar_init();
+    }
+    // row program of the strip: one thread per output row fills the entries of the rows it taps (a row shared by two
+    // output rows gets beta_cur/finish from the upper one and beta_next from the lower one: disjoint fields)
+    for (int i = tid; i < nrows; i += blockDim.x) rinfo[i].beta_next = 0.f, rinfo[i].finish = 0;
+    __syncthreads();
+    for (int d = tid; d < dy_b - dy_a; d += blockDim.x) {
+        const int dy = dy_a + d;
+        const int sy0 = __ldg(ay.start + dy), cy = __ldg(ay.cnt + dy);
+        const bool shared_first = d > 0 && sy0 == __ldg(ay.start + dy - 1) + __ldg(ay.cnt + dy - 1) - 1;
+        for (int j = 0; j < cy; ++j) {
+            const float beta = __ldg(ay.wf + dy * ay.stride + j);
+            AhRowInfo& ri = rinfo[sy0 + j - r_lo];
+            if (j == 0 && shared_first) ri.beta_next = beta; else ri.beta_cur = beta;
+            if (j == cy - 1) ri.finish = 1;
+        }
+    }
+    __syncthreads();
+
+    if (tid >= ncons) {
+        // ------------------------------------------------------------------ producer warp
+        if (tid == ncons) {
+            const uint8_t* g = gbase - delta + static_cast<int64_t>(r_lo) * row_stride;
+            for (int i = 0; i < nrows; ++i, g += row_stride) {
+                const int s = i % AH_NSTAGE;
+                if (i >= AH_NSTAGE) mbar_wait(&empty_bar[s], ((i / AH_NSTAGE) - 1) & 1, 11);
+                mbar_arrive_expect_tx(&full_bar[s], seg_bytes);
+                bulk_load_1d(ring + s * stage_bytes, g, seg_bytes, &full_bar[s]);
+            }
+        }
+        return;
+    }
+    // ---------------------------------------------------------------------- consumers
+    const int x = min(tid, nx - 1);
+    const bool a_active = tid < nx;
+    const int dx = ox0 + x;
+    const int cx = __ldg(ax.cnt + dx);
+    const float* wxp = ax.wf + dx * ax.stride;
+    float wx[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) wx[i] = i < cx ? __ldg(wxp + i) : 0.f;
+    f32x2_t w01[5], c01[5], w2[2], c2[2];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        w01[i] = f2_pack(wx[i], wx[i]);
+        c01[i] = f2_pack(-8388608.0f * wx[i], -8388608.0f * wx[i]);
+    }
+    w2[0] = f2_pack(wx[0], wx[1]); c2[0] = f2_pack(-8388608.0f * wx[0], -8388608.0f * wx[1]);
+    w2[1] = f2_pack(wx[2], wx[3]); c2[1] = f2_pack(-8388608.0f * wx[2], -8388608.0f * wx[3]);
+    const float w24 = wx[4], c24 = -8388608.0f * wx[4];
+    const f32x2_t nz2 = f2_pack(negzero, negzero);
+    const int boff = __ldg(ax.start + dx) * 3 - xb0 + delta;      // this thread's first byte inside a ring stage
+    const uint32_t sh = static_cast<uint32_t>(boff & 3) * 8;
+    const uint32_t my_ring = smem_u32(ring) + (boff & ~3);
+    auto magic = [](const uint32_t (&u)[4], int n) {   // 2^23 + byte n
+        return __uint_as_float(__byte_perm(u[n >> 2], 0x4B000000u, 0x7650u | (n & 3)));
+    };
+    // horizontal Pillow pass: thread t < S owns output column left + t (at most 7 taps)
+    const int t = min(tid, S - 1);
+    const bool b_active = tid < S;
+    const int ox = left + t;
+    const int blo = __ldg(bx.start + ox), bcnt = __ldg(bx.cnt + ox);
+    int bk[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) bk[i] = i < bcnt ? __ldg(bx.wi + ox * bx.stride + i) : 0;
+    const int aoff = (blo - ox0) * 3;                              // first byte inside a parked area row
+    const uint32_t bsh = static_cast<uint32_t>(aoff & 3) * 8;
+    const int aword = aoff & ~3;
+
+    const int lane = tid & 31;
+    f32x2_t s01 = 0;     // 0 + beta*buf == beta*buf exactly (all terms are >= +0)
+    float s2 = 0.f;
+    int par = 0;         // parity of the parked-row double buffer
+    uint8_t* out_row = mid2 + f * mid2_frame_stride + (static_cast<int64_t>(dy_a - oy0) * S + t) * 3;
+    // running shared-memory addresses (32-bit) of the stage being consumed: no per-row multiplies or cvta
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), rinfo0 = smem_u32(rinfo);
+    uint32_t a = my_ring, fb = full0, eb = empty0, phase = 0, ria = rinfo0;
+    int s = 0;
+    for (int i = 0; i < nrows; ++i) {
+        {
+            uint32_t ok, spins = 0;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                             "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(fb), "r"(phase) : "memory");
+                if (!ok && ++spins > (1u << 24)) __trap();
+            } while (!ok);
+        }
+        uint32_t w[5], u[4];
+        asm volatile("ld.shared.u32 %0, [%5];\n\tld.shared.u32 %1, [%5+4];\n\tld.shared.u32 %2, [%5+8];\n\t"
+                     "ld.shared.u32 %3, [%5+12];\n\tld.shared.u32 %4, [%5+16];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]) : "r"(a));
+        float4 ri;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ri.x), "=f"(ri.y), "=f"(ri.z), "=f"(ri.w) : "r"(ria));
+        ria += 16;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __funnelshift_r(w[k], w[k + 1], sh);
+        __syncwarp();
+        if (lane == 0)                                // this warp holds its bytes in registers now
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(eb) : "memory");
+        a += stage_bytes; fb += 8; eb += 8;
+        if (++s == AH_NSTAGE) { s = 0; a = my_ring; fb = full0; eb = empty0; phase ^= 1; }
+        f32x2_t b01 = f2_fma(f2_pack(magic(u, 0), magic(u, 1)), w01[0], c01[0]);
+#pragma unroll
+        for (int q = 1; q < 5; ++q)
+            b01 = f2_add(b01, f2_fma(f2_pack(magic(u, q * 3), magic(u, q * 3 + 1)), w01[q], c01[q]));
+        float p0, p1, p2, p3;
+        f2_unpack(f2_fma(f2_pack(magic(u, 2), magic(u, 5)), w2[0], c2[0]), p0, p1);
+        f2_unpack(f2_fma(f2_pack(magic(u, 8), magic(u, 11)), w2[1], c2[1]), p2, p3);
+        const float p4 = __fmaf_rn(magic(u, 14), w24, c24);
+        const float b2 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(p0, p1), p2), p3), p4);
+        s01 = f2_add(s01, f2_fma(f2_pack(ri.x, ri.x), b01, nz2));
+        s2 = __fadd_rn(s2, __fmaf_rn(ri.x, b2, negzero));
+        if (__float_as_int(ri.z) != 0) {              // uniform over the CTA: an area-output row is complete
+            uint8_t* ar = arow + par * arow_pitch;
+            par ^= 1;
+            if (a_active) {
+                float s0, s1;
+                f2_unpack(s01, s0, s1);
+                ar[x * 3 + 0] = static_cast<uint8_t>(min(max(__float2int_rn(s0), 0), 255));
+                ar[x * 3 + 1] = static_cast<uint8_t>(min(max(__float2int_rn(s1), 0), 255));
+                ar[x * 3 + 2] = static_cast<uint8_t>(min(max(__float2int_rn(s2), 0), 255));
+            }
+            // the straddling row opens the next output row (beta_next is 0 when there is none: 0*b = +0)
+            s01 = f2_fma(f2_pack(ri.y, ri.y), b01, nz2);
+            s2 = __fmaf_rn(ri.y, b2, negzero);
+            named_bar_sync(1, ncons);            // parked row complete (double buffered: one barrier per row)
+            if (b_active) {
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(ar + aword);
+                uint32_t bw[7], bu[6];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) bw[k] = wp[k];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) bu[k] = __funnelshift_r(bw[k], bw[k + 1], bsh);
+                int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+#pragma unroll
+                for (int q = 0; q < 7; ++q) {
+                    a0 += bk[q] * byte_as_int<6>(bu, q * 3);
+                    a1 += bk[q] * byte_as_int<6>(bu, q * 3 + 1);
+                    a2 += bk[q] * byte_as_int<6>(bu, q * 3 + 2);
+                }
+                out_row[0] = clip8(a0); out_row[1] = clip8(a1); out_row[2] = clip8(a2);
+            }
+            out_row += S * 3;
+        }
+    }
+    (void)max_rows;
+}
+
 // B: Pillow horizontal pass for output columns [ocol0, ocol0+S) on rows [0, ny) of the (possibly compacted)
 // source whose column 0 is absolute column src_x0.  FAST: at most 7 taps (21 bytes) -> aligned word loads.
 template <bool FAST>
@@ -636,9 +831,9 @@ static int build_plan(b200clip_handle* h, int H, int W, int mode, Plan& p) {
             p.a_seq = true;
             for (int dy = 0; dy + 1 < h1; ++dy) {
                 const int end = ay.start[dy] + ay.cnt[dy];
-                if (ay.cnt[dy] < 1 || (ay.start[dy + 1] != end && ay.start[dy + 1] != end - 1)) p.a_seq = false;
+                if (ay.cnt[dy] < 2 || (ay.start[dy + 1] != end && ay.start[dy + 1] != end - 1)) p.a_seq = false;
             }
-            if (ay.cnt[h1 - 1] < 1) p.a_seq = false;
+            if (ay.cnt[h1 - 1] < 2) p.a_seq = false;
         }
     }
     // source window read by the first stage
@@ -760,7 +955,39 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
     int64_t cur_fs = frame_stride, cur_rs = row_stride;
     int cur_x0 = 0, cur_y0 = 0;  // absolute (stage-coordinate) position of cur's element (0,0)
     if (n > 65535) return b200_fail(h, B200CLIP_E_SHAPE, "preprocess: at most 65535 frames per call (got %d)", n);
-    if (p.has_a) {
+    bool fused_ab = false;
+    if (p.has_a && p.has_b && !p.a_fast && p.a_seq && p.a_max_cx <= 5 && p.b_max_cnt <= 7 && (row_stride & 15) == 0 &&
+        (frame_stride & 15) == 0 && getenv("B200CLIP_K1_UNFUSED") == nullptr) {
+        // A+B fused and bulk-copy fed: needs 16-byte aligned row segments that stay inside the row
+        const int ny = p.ry1 - p.ry0, nx = p.rx1 - p.rx0;
+        const int xb0 = p.sx0 * 3;
+        const int delta = static_cast<int>((reinterpret_cast<uintptr_t>(frames) + xb0) & 15);
+        const int seg = (delta + (p.sx1 - p.sx0) * 3 + 15) & ~15;
+        const int ncons = (max(nx, S) + 31) & ~31;
+        if (xb0 - delta >= 0 && xb0 - delta + seg <= W * 3 && ncons + 32 <= 576) {
+            int rows = 24;
+            while (rows > 4 && static_cast<int64_t>(n) * ((ny + rows - 1) / rows) < static_cast<int64_t>(h->num_sms) * 6)
+                rows = (rows + 1) / 2;
+            const int stage_bytes = seg + 16, arow_pitch = (nx * 3 + 32 + 15) & ~15;
+            const int max_rows = rows * p.ay.stride;     // upper bound on the source rows of one strip
+            const size_t smem = 2 * AH_NSTAGE * sizeof(uint64_t) + static_cast<size_t>(AH_NSTAGE) * stage_bytes +
+                                2 * static_cast<size_t>(arow_pitch) + static_cast<size_t>(max_rows) * sizeof(AhRowInfo);
+            if (smem <= 200 * 1024) {
+                auto kern = ncons + 32 <= 352 ? area_hpass_bulk_kernel<352, 3> : area_hpass_bulk_kernel<576, 2>;
+                if (smem > 48 * 1024)
+                    B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(p.sy1 - p.sy0) * (p.sx1 - p.sx0) * 3.0 + ny * S * 3.0), st);
+                dim3 fgrid((ny + rows - 1) / rows, n);
+                kern<<<fgrid, ncons + 32, smem, st>>>(cur, cur_fs, cur_rs, mid2, p.mid2_per_frame, p.ry0, ny, p.rx0, nx, rows,
+                                                     max_rows, xb0, seg, stage_bytes, arow_pitch, p.left, S, p.ax, p.ay, p.bx, -0.0f);
+                h->launches++;
+                fused_ab = true;
+                cur = mid2; cur_fs = p.mid2_per_frame; cur_rs = static_cast<int64_t>(S) * 3;
+                cur_x0 = 0; cur_y0 = p.ry0;
+            }
+        }
+    }
+    if (p.has_a && !fused_ab) {
         const int ny = p.ry1 - p.ry0, nx = p.rx1 - p.rx0;
         dim3 grid((static_cast<unsigned>(ny) * nx + 255) / 256, n);
         ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(H) * (p.rx1 - p.rx0) * W / p.w1 * 3.0 + ny * nx * 3.0), st);
@@ -789,7 +1016,7 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         cur = mid1; cur_fs = p.mid1_per_frame; cur_rs = static_cast<int64_t>(nx) * 3;
         cur_x0 = p.rx0; cur_y0 = p.ry0;
     }
-    if (p.has_b) {
+    if (p.has_b && !fused_ab) {
         const int ny = p.ry1 - p.ry0;
         // rows [ry0, ry1) of cur: shift the base pointer so that row 0 of the kernel == row ry0
         const uint8_t* base = cur + static_cast<int64_t>(p.ry0 - cur_y0) * cur_rs;
