@@ -136,6 +136,9 @@ struct Plan {
     bool has_a = false, has_b = false, has_c = false;
     bool a_fast = false;     // integer scale factors in both axes (OpenCV ResizeAreaFast path)
     bool a_seq = false;      // vertical area taps visit the source rows in sequence (strip walker usable)
+    bool a_int = false;      // integer-exact area arithmetic proven equal to the fp32 evaluation (see AhIntParams)
+    int a_dx = 0, a_dy = 0, a_div_shift = 0;
+    uint32_t a_div_mul = 0;
     int a_max_cx = 0;        // largest horizontal tap count of the area stage
     int b_max_cnt = 0;       // largest tap count of the Pillow horizontal pass
     int a_fx = 1, a_fy = 1;
@@ -475,18 +478,24 @@ struct AhRowInfo {      // how one source row of the strip feeds the vertical ac
     int finish;         // 1: this row is the last tap of the output row being accumulated
     int pad;
 };
-// bounded spin on an mbarrier phase without the timer bookkeeping of mbar_wait (this loop runs once per source row)
-__device__ __forceinline__ void mbar_wait_fast(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity))
-        if (++spins > (1u << 24)) __trap();
-}
-template <int MAXT, int MINB>
+// INTX: integer-exact area arithmetic.  When every area weight is a multiple of 1/Dx (1/Dy) -- 1080p and 720p -> 512
+// wide give Dx = Dy = 15 and 5 -- the exact value of an output sample is N / (Dx*Dy) with N an integer; for odd Dx*Dy
+// it is never closer than 1/(2*Dx*Dy) to a rounding tie, while OpenCV's fp32 evaluation is within
+// (taps_x + taps_y + 6) * 255 * 2^-24 of it.  The host enables INTX only when that bound (with a 2x margin) is below
+// the tie distance, so rint(fp32 result) == floor((2N + D) / 2D) for every input: the horizontal taps then run as
+// byte dot products (IDP.4A, 4 bytes per instruction, no byte->float conversions).  Verified bit-exact against cv2
+// in tests/test_gpu_preprocess.py like the fp32 path.
+// PX: area-output columns per consumer thread (tid, tid + ncons): the per-row pipeline bookkeeping (barrier wait,
+// release, address updates) is paid once for PX columns.  The horizontal Pillow pass likewise owns up to PX output
+// columns per thread.
+struct AhIntParams { int dx, dy, d, div_shift; uint32_t div_mul; };
+template <int MAXT, int MINB, bool INTX, int PX>
 __global__ void __launch_bounds__(MAXT, MINB)
 area_hpass_bulk_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride,
                        uint8_t* __restrict__ mid2, int64_t mid2_frame_stride, int oy0, int ny, int ox0, int nx,
                        int rows_per_strip, int max_rows, int xb0, int seg_bytes, int stage_bytes, int arow_pitch,
-                       int left, int S, DevTaps ax, DevTaps ay, DevTaps bx, float negzero) {
+                       int left, int S, DevTaps ax, DevTaps ay, DevTaps bx, float negzero, AhIntParams ip) {
+    static_assert(PX == 1 || INTX, "two columns per thread only with the integer-exact arithmetic (registers)");
     extern __shared__ __align__(128) uint8_t ah_smem[];
     const int ncons = blockDim.x - 32;                 // consumer threads; the last warp is the producer
     const int tid = threadIdx.x;
@@ -511,7 +520,7 @@ area_hpass_bulk_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, in
     }
     // row program of the strip: one thread per output row fills the entries of the rows it taps (a row shared by two
     // output rows gets beta_cur/finish from the upper one and beta_next from the lower one: disjoint fields)
-    for (int i = tid; i < nrows; i += blockDim.x) rinfo[i].beta_next = 0.f, rinfo[i].finish = 0;
+    for (int i = tid; i < nrows; i += blockDim.x) rinfo[i].beta_next = 0.f, rinfo[i].finish = 0, rinfo[i].pad = 0;
     __syncthreads();
     for (int d = tid; d < dy_b - dy_a; d += blockDim.x) {
         const int dy = dy_a + d;
@@ -520,7 +529,11 @@ area_hpass_bulk_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, in
         for (int j = 0; j < cy; ++j) {
             const float beta = __ldg(ay.wf + dy * ay.stride + j);
             AhRowInfo& ri = rinfo[sy0 + j - r_lo];
-            if (j == 0 && shared_first) ri.beta_next = beta; else ri.beta_cur = beta;
+            // pad: integer weights (INTX) -- low half into the current output row, high half into the next one; the two
+            // writers of a straddled row touch different halves, hence the atomic OR
+            const int ib = INTX ? __float2int_rn(beta * static_cast<float>(ip.dy)) : 0;
+            if (j == 0 && shared_first) { ri.beta_next = beta; if (INTX) atomicOr(&ri.pad, ib << 16); }
+            else { ri.beta_cur = beta; if (INTX) atomicOr(&ri.pad, ib); }
             if (j == cy - 1) ri.finish = 1;
         }
     }
@@ -540,14 +553,42 @@ area_hpass_bulk_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, in
         return;
     }
     // ---------------------------------------------------------------------- consumers
-    const int x = min(tid, nx - 1);
-    const bool a_active = tid < nx;
-    const int dx = ox0 + x;
-    const int cx = __ldg(ax.cnt + dx);
-    const float* wxp = ax.wf + dx * ax.stride;
-    float wx[5];
+    bool a_active[PX];
+    int xcol[PX];
+    uint32_t sh[PX], my_ring[PX];
+    uint32_t qw[PX][3][4];          // INTX: per channel c and realigned word k, the four byte weights
+    float wx[5];                    // fp32 path (PX == 1)
 #pragma unroll
-    for (int i = 0; i < 5; ++i) wx[i] = i < cx ? __ldg(wxp + i) : 0.f;
+    for (int p = 0; p < PX; ++p) {
+        a_active[p] = tid + p * ncons < nx;
+        xcol[p] = min(tid + p * ncons, nx - 1);
+        const int dx = ox0 + xcol[p];
+        const int cx = __ldg(ax.cnt + dx);
+        const float* wxp = ax.wf + dx * ax.stride;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) wx[i] = i < cx ? __ldg(wxp + i) : 0.f;
+        if (INTX) {
+            int ixw[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) ixw[i] = __float2int_rn(wx[i] * static_cast<float>(ip.dx));
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t q = 0;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const int n = 4 * k + m;   // byte n of the row window is tap n/3, channel n%3
+                        if (n < 15 && n % 3 == c) q |= static_cast<uint32_t>(ixw[n / 3]) << (8 * m);
+                    }
+                    qw[p][c][k] = q;
+                }
+        }
+        const int boff = __ldg(ax.start + dx) * 3 - xb0 + delta;      // first byte of this column inside a ring stage
+        sh[p] = static_cast<uint32_t>(boff & 3) * 8;
+        my_ring[p] = smem_u32(ring) + (boff & ~3);
+    }
+    // fp32 path constants (PX == 1: wx[] holds column 0)
     f32x2_t w01[5], c01[5], w2[2], c2[2];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -558,96 +599,146 @@ area_hpass_bulk_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, in
     w2[1] = f2_pack(wx[2], wx[3]); c2[1] = f2_pack(-8388608.0f * wx[2], -8388608.0f * wx[3]);
     const float w24 = wx[4], c24 = -8388608.0f * wx[4];
     const f32x2_t nz2 = f2_pack(negzero, negzero);
-    const int boff = __ldg(ax.start + dx) * 3 - xb0 + delta;      // this thread's first byte inside a ring stage
-    const uint32_t sh = static_cast<uint32_t>(boff & 3) * 8;
-    const uint32_t my_ring = smem_u32(ring) + (boff & ~3);
     auto magic = [](const uint32_t (&u)[4], int n) {   // 2^23 + byte n
         return __uint_as_float(__byte_perm(u[n >> 2], 0x4B000000u, 0x7650u | (n & 3)));
     };
-    // horizontal Pillow pass: thread t < S owns output column left + t (at most 7 taps)
-    const int t = min(tid, S - 1);
-    const bool b_active = tid < S;
-    const int ox = left + t;
-    const int blo = __ldg(bx.start + ox), bcnt = __ldg(bx.cnt + ox);
-    int bk[7];
+    // horizontal Pillow pass: output columns left + tid (+ ncons), at most 7 taps each
+    bool b_active[PX];
+    int bk[PX][7], aword[PX], tcol[PX];
+    uint32_t bsh[PX];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) bk[i] = i < bcnt ? __ldg(bx.wi + ox * bx.stride + i) : 0;
-    const int aoff = (blo - ox0) * 3;                              // first byte inside a parked area row
-    const uint32_t bsh = static_cast<uint32_t>(aoff & 3) * 8;
-    const int aword = aoff & ~3;
+    for (int p = 0; p < PX; ++p) {
+        b_active[p] = tid + p * ncons < S;
+        tcol[p] = min(tid + p * ncons, S - 1);
+        const int ox = left + tcol[p];
+        const int blo = __ldg(bx.start + ox), bcnt = __ldg(bx.cnt + ox);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) bk[p][i] = i < bcnt ? __ldg(bx.wi + ox * bx.stride + i) : 0;
+        const int aoff = (blo - ox0) * 3;                              // first byte inside a parked area row
+        bsh[p] = static_cast<uint32_t>(aoff & 3) * 8;
+        aword[p] = aoff & ~3;
+    }
 
     const int lane = tid & 31;
-    f32x2_t s01 = 0;     // 0 + beta*buf == beta*buf exactly (all terms are >= +0)
+    f32x2_t s01 = 0;     // fp32: 0 + beta*buf == beta*buf exactly (all terms are >= +0)
     float s2 = 0.f;
+    int nacc[PX][3];     // INTX vertical accumulators
+#pragma unroll
+    for (int p = 0; p < PX; ++p) nacc[p][0] = nacc[p][1] = nacc[p][2] = 0;
     int par = 0;         // parity of the parked-row double buffer
-    uint8_t* out_row = mid2 + f * mid2_frame_stride + (static_cast<int64_t>(dy_a - oy0) * S + t) * 3;
+    uint8_t* out_row = mid2 + f * mid2_frame_stride + static_cast<int64_t>(dy_a - oy0) * S * 3;
     // running shared-memory addresses (32-bit) of the stage being consumed: no per-row multiplies or cvta
-    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), rinfo0 = smem_u32(rinfo);
-    uint32_t a = my_ring, fb = full0, eb = empty0, phase = 0, ria = rinfo0;
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    uint32_t soff = 0, fb = full0, eb = empty0, phase = 0, ria = smem_u32(rinfo);
     int s = 0;
     for (int i = 0; i < nrows; ++i) {
         {
-            uint32_t ok, spins = 0;
-            do {
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                             "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(fb), "r"(phase) : "memory");
-                if (!ok && ++spins > (1u << 24)) __trap();
-            } while (!ok);
+            uint32_t ok;
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(fb), "r"(phase) : "memory");
+            if (!ok) {                                 // slow path: bounded spin (a protocol bug must trap, not hang)
+                uint32_t spins = 0;
+                do {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(fb), "r"(phase) : "memory");
+                    if (!ok && ++spins > (1u << 24)) __trap();
+                } while (!ok);
+            }
         }
-        uint32_t w[5], u[4];
-        asm volatile("ld.shared.u32 %0, [%5];\n\tld.shared.u32 %1, [%5+4];\n\tld.shared.u32 %2, [%5+8];\n\t"
-                     "ld.shared.u32 %3, [%5+12];\n\tld.shared.u32 %4, [%5+16];"
-                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]) : "r"(a));
+        uint32_t u[PX][4];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            uint32_t w[5];
+            asm volatile("ld.shared.u32 %0, [%5];\n\tld.shared.u32 %1, [%5+4];\n\tld.shared.u32 %2, [%5+8];\n\t"
+                         "ld.shared.u32 %3, [%5+12];\n\tld.shared.u32 %4, [%5+16];"
+                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]) : "r"(my_ring[p] + soff));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[p][k] = __funnelshift_r(w[k], w[k + 1], sh[p]);
+        }
         float4 ri;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ri.x), "=f"(ri.y), "=f"(ri.z), "=f"(ri.w) : "r"(ria));
         ria += 16;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) u[k] = __funnelshift_r(w[k], w[k + 1], sh);
         __syncwarp();
         if (lane == 0)                                // this warp holds its bytes in registers now
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(eb) : "memory");
-        a += stage_bytes; fb += 8; eb += 8;
-        if (++s == AH_NSTAGE) { s = 0; a = my_ring; fb = full0; eb = empty0; phase ^= 1; }
-        f32x2_t b01 = f2_fma(f2_pack(magic(u, 0), magic(u, 1)), w01[0], c01[0]);
+        soff += stage_bytes; fb += 8; eb += 8;
+        if (++s == AH_NSTAGE) { s = 0; soff = 0; fb = full0; eb = empty0; phase ^= 1; }
+        f32x2_t b01 = 0;
+        float b2 = 0.f;
+        int hsum[PX][3];
+        if (INTX) {
+            const int iyc = __float_as_int(ri.w) & 0xffff;
 #pragma unroll
-        for (int q = 1; q < 5; ++q)
-            b01 = f2_add(b01, f2_fma(f2_pack(magic(u, q * 3), magic(u, q * 3 + 1)), w01[q], c01[q]));
-        float p0, p1, p2, p3;
-        f2_unpack(f2_fma(f2_pack(magic(u, 2), magic(u, 5)), w2[0], c2[0]), p0, p1);
-        f2_unpack(f2_fma(f2_pack(magic(u, 8), magic(u, 11)), w2[1], c2[1]), p2, p3);
-        const float p4 = __fmaf_rn(magic(u, 14), w24, c24);
-        const float b2 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(p0, p1), p2), p3), p4);
-        s01 = f2_add(s01, f2_fma(f2_pack(ri.x, ri.x), b01, nz2));
-        s2 = __fadd_rn(s2, __fmaf_rn(ri.x, b2, negzero));
+            for (int p = 0; p < PX; ++p) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    uint32_t hh = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) hh = __dp4a(u[p][k], qw[p][c][k], hh);
+                    hsum[p][c] = static_cast<int>(hh);
+                    nacc[p][c] += iyc * hsum[p][c];
+                }
+            }
+        } else {
+            b01 = f2_fma(f2_pack(magic(u[0], 0), magic(u[0], 1)), w01[0], c01[0]);
+#pragma unroll
+            for (int q = 1; q < 5; ++q)
+                b01 = f2_add(b01, f2_fma(f2_pack(magic(u[0], q * 3), magic(u[0], q * 3 + 1)), w01[q], c01[q]));
+            float p0, p1, p2, p3;
+            f2_unpack(f2_fma(f2_pack(magic(u[0], 2), magic(u[0], 5)), w2[0], c2[0]), p0, p1);
+            f2_unpack(f2_fma(f2_pack(magic(u[0], 8), magic(u[0], 11)), w2[1], c2[1]), p2, p3);
+            const float p4 = __fmaf_rn(magic(u[0], 14), w24, c24);
+            b2 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(p0, p1), p2), p3), p4);
+            s01 = f2_add(s01, f2_fma(f2_pack(ri.x, ri.x), b01, nz2));
+            s2 = __fadd_rn(s2, __fmaf_rn(ri.x, b2, negzero));
+        }
         if (__float_as_int(ri.z) != 0) {              // uniform over the CTA: an area-output row is complete
             uint8_t* ar = arow + par * arow_pitch;
             par ^= 1;
-            if (a_active) {
-                float s0, s1;
-                f2_unpack(s01, s0, s1);
-                ar[x * 3 + 0] = static_cast<uint8_t>(min(max(__float2int_rn(s0), 0), 255));
-                ar[x * 3 + 1] = static_cast<uint8_t>(min(max(__float2int_rn(s1), 0), 255));
-                ar[x * 3 + 2] = static_cast<uint8_t>(min(max(__float2int_rn(s2), 0), 255));
-            }
-            // the straddling row opens the next output row (beta_next is 0 when there is none: 0*b = +0)
-            s01 = f2_fma(f2_pack(ri.y, ri.y), b01, nz2);
-            s2 = __fmaf_rn(ri.y, b2, negzero);
-            named_bar_sync(1, ncons);            // parked row complete (double buffered: one barrier per row)
-            if (b_active) {
-                const uint32_t* wp = reinterpret_cast<const uint32_t*>(ar + aword);
-                uint32_t bw[7], bu[6];
+            if (INTX) {
+                const int iyn = __float_as_int(ri.w) >> 16;
 #pragma unroll
-                for (int k = 0; k < 7; ++k) bw[k] = wp[k];
+                for (int p = 0; p < PX; ++p) {
+                    if (a_active[p]) {               // rint(N / D) == floor((2N + D) / 2D): no ties for odd D
 #pragma unroll
-                for (int k = 0; k < 6; ++k) bu[k] = __funnelshift_r(bw[k], bw[k + 1], bsh);
-                int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+                        for (int c = 0; c < 3; ++c)
+                            ar[xcol[p] * 3 + c] = static_cast<uint8_t>(__umulhi(2u * nacc[p][c] + ip.d, ip.div_mul) >> ip.div_shift);
+                    }
 #pragma unroll
-                for (int q = 0; q < 7; ++q) {
-                    a0 += bk[q] * byte_as_int<6>(bu, q * 3);
-                    a1 += bk[q] * byte_as_int<6>(bu, q * 3 + 1);
-                    a2 += bk[q] * byte_as_int<6>(bu, q * 3 + 2);
+                    for (int c = 0; c < 3; ++c) nacc[p][c] = iyn * hsum[p][c];
                 }
-                out_row[0] = clip8(a0); out_row[1] = clip8(a1); out_row[2] = clip8(a2);
+            } else {
+                if (a_active[0]) {
+                    float s0, s1;
+                    f2_unpack(s01, s0, s1);
+                    ar[xcol[0] * 3 + 0] = static_cast<uint8_t>(min(max(__float2int_rn(s0), 0), 255));
+                    ar[xcol[0] * 3 + 1] = static_cast<uint8_t>(min(max(__float2int_rn(s1), 0), 255));
+                    ar[xcol[0] * 3 + 2] = static_cast<uint8_t>(min(max(__float2int_rn(s2), 0), 255));
+                }
+                // the straddling row opens the next output row (beta_next is 0 when there is none: 0*b = +0)
+                s01 = f2_fma(f2_pack(ri.y, ri.y), b01, nz2);
+                s2 = __fmaf_rn(ri.y, b2, negzero);
+            }
+            named_bar_sync(1, ncons);            // parked row complete (double buffered: one barrier per row)
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+                if (b_active[p]) {
+                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(ar + aword[p]);
+                    uint32_t bw[7], bu[6];
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) bw[k] = wp[k];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) bu[k] = __funnelshift_r(bw[k], bw[k + 1], bsh[p]);
+                    int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+#pragma unroll
+                    for (int q = 0; q < 7; ++q) {
+                        a0 += bk[p][q] * byte_as_int<6>(bu, q * 3);
+                        a1 += bk[p][q] * byte_as_int<6>(bu, q * 3 + 1);
+                        a2 += bk[p][q] * byte_as_int<6>(bu, q * 3 + 2);
+                    }
+                    uint8_t* o = out_row + tcol[p] * 3;
+                    o[0] = clip8(a0); o[1] = clip8(a1); o[2] = clip8(a2);
+                }
             }
             out_row += S * 3;
         }
@@ -779,6 +870,26 @@ __global__ void zero_pad_kernel(bf16* __restrict__ patches, int64_t rows, int kk
 }
 
 // ---------------------------------------------------------------------------------------------- host
+// Smallest d <= 255 such that every weight of outputs [o0, o1) is an integer multiple of 1/d (and each output's
+// weights sum to exactly d); 0 if there is none.
+static int common_denominator(const AxisTaps& t, int o0, int o1) {
+    for (int d = 1; d <= 255; ++d) {
+        bool ok = true;
+        for (int o = o0; o < o1 && ok; ++o) {
+            int sum = 0;
+            for (int i = 0; i < t.cnt[o] && ok; ++i) {
+                const double v = static_cast<double>(t.wf[static_cast<size_t>(o) * t.stride + i]) * d;
+                const double r = nearbyint(v);
+                if (fabs(v - r) > 1e-4 || r < 0 || r > 255) ok = false;
+                sum += static_cast<int>(r);
+            }
+            if (sum != d) ok = false;
+        }
+        if (ok) return d;
+    }
+    return 0;
+}
+
 static int build_plan(b200clip_handle* h, int H, int W, int mode, Plan& p) {
     const int S = h->cfg.image_size;
     p.H = H; p.W = W; p.mode = mode;
@@ -834,6 +945,26 @@ static int build_plan(b200clip_handle* h, int H, int W, int mode, Plan& p) {
                 if (ay.cnt[dy] < 2 || (ay.start[dy + 1] != end && ay.start[dy + 1] != end - 1)) p.a_seq = false;
             }
             if (ay.cnt[h1 - 1] < 2) p.a_seq = false;
+            // integer-exact evaluation: weights on a 1/(dx*dy) lattice with odd dx*dy (no rounding ties), and the fp32
+            // evaluation error bound (2x margin) below the distance 1/(2*dx*dy) to the nearest tie
+            int max_cy = 0;
+            for (int dy = p.ry0; dy < p.ry1; ++dy) max_cy = ay.cnt[dy] > max_cy ? ay.cnt[dy] : max_cy;
+            const int ddx = common_denominator(ax, p.rx0, p.rx1), ddy = common_denominator(ay, p.ry0, p.ry1);
+            if (ddx > 0 && ddy > 0 && ((ddx * ddy) & 1)) {
+                const double D = static_cast<double>(ddx) * ddy;
+                const double err = 2.0 * (p.a_max_cx + max_cy + 6) * 255.0 * ldexp(1.0, -24);
+                const uint32_t d2 = 2u * ddx * ddy, vmax = 2u * 255u * ddx * ddy + ddx * ddy;
+                if (err < 1.0 / (2.0 * D)) {
+                    for (int sft = 0; sft <= 16 && !p.a_int; ++sft) {     // magic divide by 2D, checked exhaustively
+                        const uint64_t m = ((uint64_t(1) << (32 + sft)) + d2 - 1) / d2;
+                        if (m >> 32) break;
+                        bool ok = true;
+                        for (uint32_t v = 0; v <= vmax && ok; ++v)
+                            ok = static_cast<uint32_t>((static_cast<uint64_t>(v) * m) >> (32 + sft)) == v / d2;
+                        if (ok) { p.a_int = true; p.a_dx = ddx; p.a_dy = ddy; p.a_div_shift = sft; p.a_div_mul = static_cast<uint32_t>(m); }
+                    }
+                }
+            }
         }
     }
     // source window read by the first stage
@@ -963,7 +1094,12 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         const int xb0 = p.sx0 * 3;
         const int delta = static_cast<int>((reinterpret_cast<uintptr_t>(frames) + xb0) & 15);
         const int seg = (delta + (p.sx1 - p.sx0) * 3 + 15) & ~15;
-        const int ncons = (max(nx, S) + 31) & ~31;
+        static const bool no_int = getenv("B200CLIP_AREA_FP32") != nullptr;    // parity tests cover every variant
+        static const bool no_px2 = getenv("B200CLIP_AREA_PX1") != nullptr;
+        const bool intx = p.a_int && !no_int;
+        // two columns per thread when that still fits a 160-thread consumer group
+        const int px = (intx && !no_px2 && (max(nx, S) + 1) / 2 <= 160) ? 2 : 1;
+        const int ncons = ((max(nx, S) + px - 1) / px + 31) & ~31;
         if (xb0 - delta >= 0 && xb0 - delta + seg <= W * 3 && ncons + 32 <= 576) {
             int rows = 24;
             while (rows > 4 && static_cast<int64_t>(n) * ((ny + rows - 1) / rows) < static_cast<int64_t>(h->num_sms) * 6)
@@ -973,13 +1109,16 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
             const size_t smem = 2 * AH_NSTAGE * sizeof(uint64_t) + static_cast<size_t>(AH_NSTAGE) * stage_bytes +
                                 2 * static_cast<size_t>(arow_pitch) + static_cast<size_t>(max_rows) * sizeof(AhRowInfo);
             if (smem <= 200 * 1024) {
-                auto kern = ncons + 32 <= 352 ? area_hpass_bulk_kernel<352, 3> : area_hpass_bulk_kernel<576, 2>;
+                AhIntParams ip{p.a_dx, p.a_dy, p.a_dx * p.a_dy, p.a_div_shift, p.a_div_mul};
+                auto kern = px == 2 ? area_hpass_bulk_kernel<192, 4, true, 2>
+                          : ncons + 32 <= 352 ? (intx ? area_hpass_bulk_kernel<352, 3, true, 1> : area_hpass_bulk_kernel<352, 3, false, 1>)
+                                              : (intx ? area_hpass_bulk_kernel<576, 2, true, 1> : area_hpass_bulk_kernel<576, 2, false, 1>);
                 if (smem > 48 * 1024)
                     B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
                 ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(p.sy1 - p.sy0) * (p.sx1 - p.sx0) * 3.0 + ny * S * 3.0), st);
                 dim3 fgrid((ny + rows - 1) / rows, n);
                 kern<<<fgrid, ncons + 32, smem, st>>>(cur, cur_fs, cur_rs, mid2, p.mid2_per_frame, p.ry0, ny, p.rx0, nx, rows,
-                                                     max_rows, xb0, seg, stage_bytes, arow_pitch, p.left, S, p.ax, p.ay, p.bx, -0.0f);
+                                                     max_rows, xb0, seg, stage_bytes, arow_pitch, p.left, S, p.ax, p.ay, p.bx, -0.0f, ip);
                 h->launches++;
                 fused_ab = true;
                 cur = mid2; cur_fs = p.mid2_per_frame; cur_rs = static_cast<int64_t>(S) * 3;
