@@ -2,6 +2,8 @@
 // ln_post + projection + L2-normalise head, fp32-CHW patchify and the text token embedding.
 // Semantics follow open_clip's VisionTransformer / TextTransformer as restated in oracle/clip_ref.py
 // (reference call sites: src/models/openclip_model.py:177-178,196-197,205-209).
+#include <stdlib.h>
+
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -162,7 +164,17 @@ __device__ __forceinline__ void load_tile_async(uint8_t* smem_tile, const bf16* 
     }
 }
 
-__global__ void __launch_bounds__(ATT_THREADS)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// SINGLE: the whole sequence fits one 64-key block and there is no causal mask (the ViT-B/32 image tower, T = 50):
+// plain softmax (no running max / rescale of O), key masking only on the 8-key tiles that straddle T, tiles beyond
+// T skipped altogether.
+template <bool SINGLE>
+__global__ void __launch_bounds__(ATT_THREADS, 4)
 attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int heads, int causal) {
     __shared__ __align__(128) uint8_t sQ[ATT_BQ * 128];
     __shared__ __align__(128) uint8_t sK[ATT_BK * 128];
@@ -213,10 +225,12 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
         const uint32_t kb = smem_u32(sK);
+        const int jmax = SINGLE ? (T + 7) >> 3 : 8;    // 8-key tiles that hold at least one valid key
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
             for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-key tiles
+                if (SINGLE && jp * 2 >= jmax) continue;
                 uint32_t b0, b1, b2, b3;
                 const int r = jp * 16 + (lane & 7) + ((lane >> 4) << 3);
                 const int c = ks * 2 + ((lane >> 3) & 1);
@@ -225,6 +239,41 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
                 mma_bf16_16816(s[jp * 2 + 1], qf[ks], b2, b3);
             }
         }
+        uint32_t pf[4][4];  // P as A fragments for 4 k-steps over keys
+        if (SINGLE) {
+            // ---- plain softmax over the single key block; the scale is folded into the exponent
+            float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j * 8 + 8 > T) {          // straddling (or empty) tile: mask the keys >= T
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (j * 8 + t4 * 2 + (e & 1) >= T) s[j][e] = -INFINITY;
+                }
+                mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
+                mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
+            }
+            float nm[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+                nm[r] = -mx[r] * scale_log2;          // T >= 1: at least one finite score per row
+            }
+            float rs[2] = {0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float p0 = ex2_approx(fmaf(s[j][0], scale_log2, nm[0]));
+                const float p1 = ex2_approx(fmaf(s[j][1], scale_log2, nm[0]));
+                const float p2 = ex2_approx(fmaf(s[j][2], scale_log2, nm[1]));
+                const float p3 = ex2_approx(fmaf(s[j][3], scale_log2, nm[1]));
+                rs[0] += p0 + p1;
+                rs[1] += p2 + p3;
+                pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+                pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+            }
+            l_run[0] = rs[0]; l_run[1] = rs[1];
+        } else {
         // ---- mask + online softmax (rows g and g+8 of this warp's 16)
         const int qrow0 = q0 + warp * 16 + g;
         float mx[2] = {-INFINITY, -INFINITY};
@@ -250,7 +299,6 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
             m_run[r] = m_new;
         }
         float rs[2] = {0.f, 0.f};
-        uint32_t pf[4][4];  // P as A fragments for 4 k-steps over keys
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float p0 = exp2f(s[j][0] - m_use[0]);
@@ -269,10 +317,12 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
             o_acc[j][0] *= corr[0]; o_acc[j][1] *= corr[0];
             o_acc[j][2] *= corr[1]; o_acc[j][3] *= corr[1];
         }
+        }
         // ---- O += P V
         const uint32_t vb = smem_u32(sV);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {       // 16 keys per step
+            if (SINGLE && ks * 16 >= T) continue;  // P is exactly 0 there
 #pragma unroll
             for (int jp = 0; jp < 4; ++jp) {   // pairs of 8-wide d tiles
                 uint32_t b0, b1, b2, b3;
@@ -314,6 +364,176 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
     }
 }
 
+// ---------------------------------------------------------------------------- persistent, TMA-fed variant
+// For sequences that fit one key block without a causal mask (the ViT-B/32 image tower: T = 50, 12 heads -> 43 200
+// (sequence, head) items per 3600-frame layer).  Each CTA walks items blockIdx.x, +gridDim.x, ... ; the Q, K and V
+// tiles of an item ([T rows] x [64 columns] boxes of the [tokens, 3*width] qkv matrix) arrive by TMA
+// (cp.async.bulk.tensor, 128-byte swizzle == the ldmatrix XOR pattern above) into a ring of ATP_STAGES stages, so the
+// loads of the next items are in flight while the current one runs on the tensor cores -- the one-shot kernel above
+// exposes the full load latency of every item.  Math is identical to attention_kernel<true>.
+constexpr int ATP_STAGES = 2;
+constexpr int ATP_STAGE_BYTES = 3 * ATT_BK * 128;                       // Q | K | V tiles of 64 rows x 128 B
+constexpr int ATP_SO_BYTES = 4 * 8 * 128;                                // per warp: 8 rows x 128 B, used twice per item
+constexpr int ATP_SMEM_BYTES = 1024 + ATP_STAGES * ATP_STAGE_BYTES + ATP_SO_BYTES + 64;
+
+__global__ void __launch_bounds__(ATT_THREADS, 4)
+attention_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* __restrict__ out, int T, int heads,
+                            int n_items) {
+    extern __shared__ uint8_t atp_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atp_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stages = base;                                             // 1024-byte aligned (swizzle atom)
+    uint8_t* sO = base + ATP_STAGES * ATP_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sO + ATP_SO_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int D = heads * ATT_D;
+    const uint32_t tile_bytes = static_cast<uint32_t>(T) * 128u;
+
+    // rows >= T of every tile are never written by TMA: make them finite once (P is exactly 0 there, 0 * NaN is not)
+    for (int i = threadIdx.x; i < ATP_STAGES * ATP_STAGE_BYTES / 16; i += ATT_THREADS)
+        reinterpret_cast<uint4*>(stages)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ATP_STAGES; ++s) mbar_init(&full_bar[s], 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmap_qkv);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    auto issue = [&](int item, int stage) {         // thread 0 only
+        const int seq = item / heads, head = item - seq * heads;
+        uint8_t* st = stages + stage * ATP_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], 3 * tile_bytes);
+        tma_load_2d(st, &tmap_qkv, &full_bar[stage], head * ATT_D, seq * T);
+        tma_load_2d(st + ATT_BK * 128, &tmap_qkv, &full_bar[stage], D + head * ATT_D, seq * T);
+        tma_load_2d(st + 2 * ATT_BK * 128, &tmap_qkv, &full_bar[stage], 2 * D + head * ATT_D, seq * T);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ATP_STAGES; ++s) {
+            const int item = blockIdx.x + s * gridDim.x;
+            if (item < n_items) issue(item, s);
+        }
+    }
+    const float scale_log2 = 0.125f * 1.4426950408889634f;
+    const int jmax = (T + 7) >> 3;                  // 8-key tiles that hold at least one valid key
+    int k = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+        const int stage = k % ATP_STAGES;
+        mbar_wait(&full_bar[stage], (k / ATP_STAGES) & 1, 21);
+        const uint32_t qb = smem_u32(stages + stage * ATP_STAGE_BYTES);
+        const uint32_t kb = qb + ATT_BK * 128, vb = qb + 2 * ATT_BK * 128;
+        uint32_t qf[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int r = warp * 16 + (lane & 15);
+            const int c = ks * 2 + (lane >> 4);
+            ldmatrix_x4(qb + sw_off(r, c), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+        }
+        float s[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                if (jp * 2 >= jmax) continue;
+                uint32_t b0, b1, b2, b3;
+                const int r = jp * 16 + (lane & 7) + ((lane >> 4) << 3);
+                const int c = ks * 2 + ((lane >> 3) & 1);
+                ldmatrix_x4(kb + sw_off(r, c), b0, b1, b2, b3);
+                mma_bf16_16816(s[jp * 2], qf[ks], b0, b1);
+                mma_bf16_16816(s[jp * 2 + 1], qf[ks], b2, b3);
+            }
+        }
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j * 8 + 8 > T) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (j * 8 + t4 * 2 + (e & 1) >= T) s[j][e] = -INFINITY;
+            }
+            mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
+        }
+        float nm[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            nm[r] = -mx[r] * scale_log2;
+        }
+        float rs[2] = {0.f, 0.f};
+        uint32_t pf[4][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float p0 = ex2_approx(fmaf(s[j][0], scale_log2, nm[0]));
+            const float p1 = ex2_approx(fmaf(s[j][1], scale_log2, nm[0]));
+            const float p2 = ex2_approx(fmaf(s[j][2], scale_log2, nm[1]));
+            const float p3 = ex2_approx(fmaf(s[j][3], scale_log2, nm[1]));
+            rs[0] += p0 + p1;
+            rs[1] += p2 + p3;
+            pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+            pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+        float o_acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { o_acc[j][0] = o_acc[j][1] = o_acc[j][2] = o_acc[j][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            if (ks * 16 >= T) continue;
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                uint32_t b0, b1, b2, b3;
+                const int r = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+                const int c = jp * 2 + (lane >> 4);
+                ldmatrix_x4_trans(vb + sw_off(r, c), b0, b1, b2, b3);
+                mma_bf16_16816(o_acc[jp * 2], pf[ks], b0, b1);
+                mma_bf16_16816(o_acc[jp * 2 + 1], pf[ks], b2, b3);
+            }
+        }
+        // every warp is done with this stage: refill it with the item ATP_STAGES ahead
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int nxt = item + ATP_STAGES * gridDim.x;
+            if (nxt < n_items) issue(nxt, stage);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+            rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+        }
+        const float inv0 = 1.f / rs[0], inv1 = 1.f / rs[1];     // T >= 1: the row maximum contributes exp2(0) = 1
+        // this warp's rows g (then g + 8) -> its private 8-row slice of sO -> coalesced 16-byte stores
+        const int seq = item / heads, head = item - seq * heads;
+        bf16* obase = out + static_cast<int64_t>(seq) * T * D + head * ATT_D;
+        uint8_t* so = sO + warp * (8 * 128);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const float inv = hh ? inv1 : inv0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint32_t*>(so + sw_off(g, j) + t4 * 4) =
+                    pack_bf16x2(o_acc[j][hh * 2] * inv, o_acc[j][hh * 2 + 1] * inv);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int id = lane + i * 32;      // 8 rows x 8 chunks
+                const int r = id >> 3, c = id & 7;
+                const int row = warp * 16 + hh * 8 + r;
+                if (row < T) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(so + sw_off(r, c));
+                    *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(row) * D + c * 8) = v;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+int make_tmap_bf16_2d(b200clip_handle* h, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                      uint64_t ld, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz);
+
 int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, int t, int heads, int causal,
                      cudaStream_t st) {
     if (n_seq <= 0) return 0;
@@ -322,12 +542,38 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
     // gridDim.z is limited to 65535: split long batches
     const int64_t per_seq_in = static_cast<int64_t>(t) * 3 * heads * ATT_D;
     const int64_t per_seq_out = static_cast<int64_t>(t) * heads * ATT_D;
+    static const bool no_persist = getenv("B200CLIP_ATTN_ONESHOT") != nullptr;     // parity tests cover both
+    const int64_t n_items = static_cast<int64_t>(n_seq) * heads;
+    if (!causal && t <= ATT_BK && !no_persist && n_items >= 2 * h->num_sms && n_items * t < (int64_t(1) << 31) &&
+        (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) {
+        CUtensorMap tq;
+        int rc = make_tmap_bf16_2d(h, &tq, qkv, static_cast<uint64_t>(n_seq) * t, 3ull * heads * ATT_D, 3ull * heads * ATT_D,
+                                   t, ATT_D, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        static bool attr_set = false;
+        if (!attr_set) {
+            B200_CUDA(h, cudaFuncSetAttribute(attention_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              ATP_SMEM_BYTES));
+            attr_set = true;
+        }
+        int64_t grid = 4ll * h->num_sms;
+        if (grid > n_items) grid = n_items;
+        ProfScope ps(h, PROF_ATTN, static_cast<double>(n_seq) * t * heads * ATT_D * 2.0 * 4.0, st);
+        attention_persistent_kernel<<<static_cast<unsigned>(grid), ATT_THREADS, ATP_SMEM_BYTES, st>>>(
+            tq, out, t, heads, static_cast<int>(n_items));
+        h->launches++;
+        B200_CUDA(h, cudaGetLastError());
+        return 0;
+    }
     for (int s0 = 0; s0 < n_seq; s0 += 65535) {
         const int ns = (n_seq - s0) < 65535 ? (n_seq - s0) : 65535;
         dim3 grid((t + ATT_BQ - 1) / ATT_BQ, heads, ns);
         // work = algorithmic bytes (qkv read + out write); FLOPs are 4*t*t*64 per (seq, head)
         ProfScope ps(h, PROF_ATTN, static_cast<double>(ns) * t * heads * ATT_D * 2.0 * 4.0, st);
-        attention_kernel<<<grid, ATT_THREADS, 0, st>>>(qkv + s0 * per_seq_in, out + s0 * per_seq_out, t, heads, causal);
+        if (t <= ATT_BK && !causal)
+            attention_kernel<true><<<grid, ATT_THREADS, 0, st>>>(qkv + s0 * per_seq_in, out + s0 * per_seq_out, t, heads, causal);
+        else
+            attention_kernel<false><<<grid, ATT_THREADS, 0, st>>>(qkv + s0 * per_seq_in, out + s0 * per_seq_out, t, heads, causal);
         h->launches++;
     }
     B200_CUDA(h, cudaGetLastError());

@@ -75,7 +75,10 @@ def test_layernorm_matches_torch(handle, rows, width):
 
 
 @pytest.mark.parametrize("n_seq,t,heads,causal", [(3, 50, 12, 0), (2, 77, 8, 1), (2, 257, 16, 0), (5, 5, 2, 0),
-                                                    (1, 16, 1, 1), (70, 50, 12, 0), (1, 64, 2, 1), (1, 65, 2, 0)])
+                                                    (1, 16, 1, 1), (70, 50, 12, 0), (1, 64, 2, 1), (1, 65, 2, 0),
+                                                    # >= 296 (sequence, head) items, T <= 64, no mask: persistent TMA-fed kernel
+                                                    (300, 50, 12, 0), (40, 64, 8, 0), (100, 33, 4, 0), (500, 1, 1, 0),
+                                                    (37, 7, 9, 0)])
 def test_attention_matches_torch(handle, n_seq, t, heads, causal):
     from b200clip import capi
 
