@@ -288,10 +288,13 @@ int launch_similarity(b200clip_handle* h, const void* img, int dtype, int64_t n,
 int make_tmap_bf16_2d(b200clip_handle* h, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz);
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
+// queries fp32 -> bf16 (the tensor-core operand) and the per-query global k-th-score bounds reset to -inf
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n, int* gthr, int q) {
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         dst[i] = __float2bfloat16(src[i]);
+        if (i < q) gthr[i] = b200::ord_encode(-INFINITY);
+    }
 }
 
 static int ensure_topk_ws(b200clip_handle* h, size_t need, cudaStream_t st) {
@@ -309,34 +312,41 @@ static int launch_sim_topk_tc(b200clip_handle* h, const void* img, int64_t n, in
                               float thr, const double* ts, int64_t index_base, double clip_dur, double vid_dur,
                               float* top_scores, int64_t* top_idx, double* intervals, int32_t* counts, float* dense,
                               cudaStream_t st) {
-    const int tiles = static_cast<int>((n + 2 * b200::GEMM_BLOCK_M - 1) / (2 * b200::GEMM_BLOCK_M));
+    const int tiles = static_cast<int>((n + b200::G2_BLOCK_N - 1) / b200::G2_BLOCK_N);
     int clusters = h->num_sms / 2;
     if (tiles < clusters) clusters = tiles;
-    const int g = clusters * 2 * 4;
+    const int g = clusters * 2;      // one candidate list per (cluster, column half) and query
     const size_t txt_bytes = (static_cast<size_t>(q) * e * 2 + 255) & ~size_t(255);
-    const size_t need = txt_bytes + static_cast<size_t>(g) * q * k * 8;
+    const size_t thr_bytes = (static_cast<size_t>(q) * 4 + 255) & ~size_t(255);
+    const size_t need = txt_bytes + thr_bytes + static_cast<size_t>(g) * q * k * 8;
     int rc = ensure_topk_ws(h, need, st);
     if (rc) return rc;
     bf16* txt16 = static_cast<bf16*>(h->ws_topk);
-    float* part_s = reinterpret_cast<float*>(static_cast<uint8_t*>(h->ws_topk) + txt_bytes);
+    int* gthr = reinterpret_cast<int*>(static_cast<uint8_t*>(h->ws_topk) + txt_bytes);
+    float* part_s = reinterpret_cast<float*>(static_cast<uint8_t*>(h->ws_topk) + txt_bytes + thr_bytes);
     int* part_i = reinterpret_cast<int*>(part_s + static_cast<size_t>(g) * q * k);
     ProfScope ps(h, PROF_SIM, static_cast<double>(n) * e * 2.0 + static_cast<double>(q) * (e * 4.0 + k * 12.0), st);
-    f32_to_bf16_kernel<<<(static_cast<int64_t>(q) * e + 255) / 256, 256, 0, st>>>(txt, txt16, static_cast<int64_t>(q) * e);
+    f32_to_bf16_kernel<<<(static_cast<int64_t>(q) * e + 255) / 256, 256, 0, st>>>(txt, txt16, static_cast<int64_t>(q) * e, gthr, q);
     h->launches++;
     CUtensorMap ta, tw;
-    if ((rc = make_tmap_bf16_2d(h, &ta, img, n, e, e, b200::GEMM_BLOCK_M, b200::GEMM_BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)))
+    // A (M side, 128 rows per CTA) = the queries, B (N side, 128 rows per CTA per tile) = the embedding rows
+    if ((rc = make_tmap_bf16_2d(h, &ta, txt16, q, e, e, b200::GEMM_BLOCK_M, b200::GEMM_BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)))
         return rc;
-    if ((rc = make_tmap_bf16_2d(h, &tw, txt16, q, e, e, b200::G2_HALF_N, b200::GEMM_BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)))
+    if ((rc = make_tmap_bf16_2d(h, &tw, img, n, e, e, b200::G2_HALF_N, b200::GEMM_BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)))
         return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        B200_CUDA(h, cudaFuncSetAttribute(b200::sim_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        B200_CUDA(h, cudaFuncSetAttribute(b200::sim_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          b200::G2_SMEM_BYTES));
+        B200_CUDA(h, cudaFuncSetAttribute(b200::sim_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           b200::G2_SMEM_BYTES));
         attr_set = true;
     }
+    static const bool no_ares = getenv("B200CLIP_SIM_STREAM_A") != nullptr;
+    auto kern = (e <= 512 && !no_ares) ? b200::sim_topk_tc_kernel<true> : b200::sim_topk_tc_kernel<false>;
     for (int q0 = 0; q0 < q; q0 += b200::G2_BLOCK_N) {
-        b200::sim_topk_tc_kernel<<<2 * clusters, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, st>>>(
-            ta, tw, static_cast<int>(n), q, q0, q, e, k, dense, part_s, part_i);
+        kern<<<2 * clusters, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, st>>>(
+            ta, tw, static_cast<int>(n), q, q0, q, e, k, dense, part_s, part_i, gthr);
         h->launches++;
     }
     topk_final_kernel<false><<<q, SIM_WARPS * 32, 0, st>>>(part_s, part_i, g, q, k, thr, ts, index_base, clip_dur, vid_dur,

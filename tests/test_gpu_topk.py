@@ -118,7 +118,8 @@ def test_multi_shard_merge_equals_global(model_b32):
         assert np.array_equal(o_i, mi[qq].cpu().numpy())
 
 
-@pytest.mark.parametrize("n,q,k,e", [(20000, 256, 5, 512), (9000, 40, 8, 768), (4096, 8, 1, 512), (70001, 300, 5, 512)])
+@pytest.mark.parametrize("n,q,k,e", [(20000, 256, 5, 512), (9000, 40, 8, 768), (4096, 8, 1, 512), (70001, 300, 5, 512),
+                                     (150001, 130, 3, 512), (4200, 9, 8, 64)])
 def test_tensor_core_path_order_is_exact(model_b32, n, q, k, e):
     """bf16 cache + many queries -> sim_topk_tc_kernel (tcgen05 similarity, top-k fused in the epilogue).  The order
     must equal an argsort (ties -> higher index) of the scores that very kernel computed, and those scores must be
