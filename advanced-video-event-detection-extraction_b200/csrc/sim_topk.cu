@@ -297,6 +297,19 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restri
     }
 }
 
+// fp32 -> bf16 cast of a cache slice, 8 elements per thread (two 16-byte loads, one 16-byte store); n % 8 == 0
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_x8_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, int64_t n8) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float4 a = __ldcs(src + 2 * i), b = __ldcs(src + 2 * i + 1);
+        uint4 o;
+        o.x = b200::pack_bf16x2(a.x, a.y); o.y = b200::pack_bf16x2(a.z, a.w);
+        o.z = b200::pack_bf16x2(b.x, b.y); o.w = b200::pack_bf16x2(b.z, b.w);
+        dst[i] = o;
+    }
+}
+
 static int ensure_topk_ws(b200clip_handle* h, size_t need, cudaStream_t st) {
     if (need <= h->ws_topk_bytes) return 0;
     B200_CUDA(h, cudaStreamSynchronize(st));
@@ -307,32 +320,42 @@ static int ensure_topk_ws(b200clip_handle* h, size_t need, cudaStream_t st) {
     return 0;
 }
 
-// Tensor-core path (sim_topk_tc.cuh): bf16 cache, many queries, small k.
-static int launch_sim_topk_tc(b200clip_handle* h, const void* img, int64_t n, int e, const float* txt, int q, int k,
-                              float thr, const double* ts, int64_t index_base, double clip_dur, double vid_dur,
+// Tensor-core path (sim_topk_tc.cuh): many queries, small k.  A bf16 cache is consumed in place; an fp32 cache (what
+// the reference holds) is converted to bf16 slice by slice into a scratch buffer and each slice is scored right away
+// (one extra pass over the data instead of Q/8 passes of the streaming kernel); the global k-th-score bounds carry
+// over from slice to slice, every slice appends its candidate lists and one final merge sees them all.
+constexpr int64_t STC_SLICE_ROWS = int64_t(1) << 18;
+
+static int launch_sim_topk_tc(b200clip_handle* h, const void* img, int dtype, int64_t n, int e, const float* txt, int q,
+                              int k, float thr, const double* ts, int64_t index_base, double clip_dur, double vid_dur,
                               float* top_scores, int64_t* top_idx, double* intervals, int32_t* counts, float* dense,
                               cudaStream_t st) {
-    const int tiles = static_cast<int>((n + b200::G2_BLOCK_N - 1) / b200::G2_BLOCK_N);
+    const bool f32 = dtype != B200CLIP_BF16;
+    const int64_t slice = f32 ? (n < STC_SLICE_ROWS ? n : STC_SLICE_ROWS) : n;
+    const int n_slices = static_cast<int>((n + slice - 1) / slice);
+    const int tiles = static_cast<int>((slice + b200::G2_BLOCK_N - 1) / b200::G2_BLOCK_N);
     int clusters = h->num_sms / 2;
     if (tiles < clusters) clusters = tiles;
-    const int g = clusters * 2;      // one candidate list per (cluster, column half) and query
+    const int g = clusters * 2;      // one candidate list per (cluster, column half) and query, per slice
     const size_t txt_bytes = (static_cast<size_t>(q) * e * 2 + 255) & ~size_t(255);
     const size_t thr_bytes = (static_cast<size_t>(q) * 4 + 255) & ~size_t(255);
-    const size_t need = txt_bytes + thr_bytes + static_cast<size_t>(g) * q * k * 8;
+    const size_t cast_bytes = f32 ? ((static_cast<size_t>(slice) * e * 2 + 255) & ~size_t(255)) : 0;
+    const size_t list_elems = static_cast<size_t>(g) * n_slices * q * k;
+    const size_t need = txt_bytes + thr_bytes + cast_bytes + list_elems * 8;
     int rc = ensure_topk_ws(h, need, st);
     if (rc) return rc;
-    bf16* txt16 = static_cast<bf16*>(h->ws_topk);
-    int* gthr = reinterpret_cast<int*>(static_cast<uint8_t*>(h->ws_topk) + txt_bytes);
-    float* part_s = reinterpret_cast<float*>(static_cast<uint8_t*>(h->ws_topk) + txt_bytes + thr_bytes);
-    int* part_i = reinterpret_cast<int*>(part_s + static_cast<size_t>(g) * q * k);
-    ProfScope ps(h, PROF_SIM, static_cast<double>(n) * e * 2.0 + static_cast<double>(q) * (e * 4.0 + k * 12.0), st);
+    uint8_t* wsb = static_cast<uint8_t*>(h->ws_topk);
+    bf16* txt16 = reinterpret_cast<bf16*>(wsb);
+    int* gthr = reinterpret_cast<int*>(wsb + txt_bytes);
+    bf16* cast = reinterpret_cast<bf16*>(wsb + txt_bytes + thr_bytes);
+    float* part_s = reinterpret_cast<float*>(wsb + txt_bytes + thr_bytes + cast_bytes);
+    int* part_i = reinterpret_cast<int*>(part_s + list_elems);
+    ProfScope ps(h, PROF_SIM, static_cast<double>(n) * e * (f32 ? 4.0 : 2.0) + static_cast<double>(q) * (e * 4.0 + k * 12.0), st);
     f32_to_bf16_kernel<<<(static_cast<int64_t>(q) * e + 255) / 256, 256, 0, st>>>(txt, txt16, static_cast<int64_t>(q) * e, gthr, q);
     h->launches++;
     CUtensorMap ta, tw;
     // A (M side, 128 rows per CTA) = the queries, B (N side, 128 rows per CTA per tile) = the embedding rows
     if ((rc = make_tmap_bf16_2d(h, &ta, txt16, q, e, e, b200::GEMM_BLOCK_M, b200::GEMM_BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)))
-        return rc;
-    if ((rc = make_tmap_bf16_2d(h, &tw, img, n, e, e, b200::G2_HALF_N, b200::GEMM_BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)))
         return rc;
     static bool attr_set = false;
     if (!attr_set) {
@@ -344,13 +367,30 @@ static int launch_sim_topk_tc(b200clip_handle* h, const void* img, int64_t n, in
     }
     static const bool no_ares = getenv("B200CLIP_SIM_STREAM_A") != nullptr;
     auto kern = (e <= 512 && !no_ares) ? b200::sim_topk_tc_kernel<true> : b200::sim_topk_tc_kernel<false>;
-    for (int q0 = 0; q0 < q; q0 += b200::G2_BLOCK_N) {
-        kern<<<2 * clusters, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, st>>>(
-            ta, tw, static_cast<int>(n), q, q0, q, e, k, dense, part_s, part_i, gthr);
-        h->launches++;
+    for (int si = 0; si < n_slices; ++si) {
+        const int64_t r0 = si * slice;
+        const int64_t nr = (n - r0) < slice ? (n - r0) : slice;
+        const void* rows = img;
+        if (f32) {
+            const int64_t n8 = nr * e / 8;
+            const int64_t blocks = (n8 + 255) / 256;
+            cast_f32_bf16_x8_kernel<<<static_cast<unsigned>(blocks < h->num_sms * 16 ? blocks : h->num_sms * 16), 256, 0, st>>>(
+                reinterpret_cast<const float4*>(static_cast<const float*>(img) + r0 * e), reinterpret_cast<uint4*>(cast), n8);
+            h->launches++;
+            rows = cast;
+        }
+        if ((rc = make_tmap_bf16_2d(h, &tw, rows, nr, e, e, b200::G2_HALF_N, b200::GEMM_BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)))
+            return rc;
+        const size_t loff = static_cast<size_t>(si) * g * q * k;
+        for (int q0 = 0; q0 < q; q0 += b200::G2_BLOCK_N) {
+            kern<<<2 * clusters, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, st>>>(
+                ta, tw, static_cast<int>(nr), static_cast<int>(r0), q, q0, q, e, k,
+                dense ? dense + static_cast<size_t>(r0) * q : nullptr, part_s + loff, part_i + loff, gthr);
+            h->launches++;
+        }
     }
-    topk_final_kernel<false><<<q, SIM_WARPS * 32, 0, st>>>(part_s, part_i, g, q, k, thr, ts, index_base, clip_dur, vid_dur,
-                                                          top_scores, top_idx, intervals, counts);
+    topk_final_kernel<false><<<q, SIM_WARPS * 32, 0, st>>>(part_s, part_i, g * n_slices, q, k, thr, ts, index_base, clip_dur,
+                                                          vid_dur, top_scores, top_idx, intervals, counts);
     h->launches++;
     B200_CUDA(h, cudaGetLastError());
     return 0;
@@ -364,10 +404,12 @@ int launch_sim_topk(b200clip_handle* h, const void* img, int dtype, int64_t n, i
     if (rc) return rc;
     // many queries over a large bf16 cache: tensor-core similarity with the top-k fused into the epilogue
     static const bool force_simt = getenv("B200CLIP_SIM_SIMT") != nullptr;
-    if (!force_simt && dtype == B200CLIP_BF16 && e % 64 == 0 && k >= 1 && k <= b200::STC_MAXK && q >= 8 && n >= 4096 &&
-        (reinterpret_cast<uintptr_t>(img) & 15) == 0 && top_scores && top_idx)
-        return launch_sim_topk_tc(h, img, n, e, txt, q, k, thr, ts, index_base, clip_dur, vid_dur, top_scores, top_idx,
-                                  intervals, counts, dense, st);
+    // (an fp32 cache takes this path only from 16 queries on: below that the streaming kernel reads it once anyway
+    // and keeps full fp32 scores)
+    if (!force_simt && e % 64 == 0 && k >= 1 && k <= b200::STC_MAXK && n >= 4096 && n < (int64_t(1) << 31) &&
+        (dtype == B200CLIP_BF16 ? q >= 8 : q >= 16) && (reinterpret_cast<uintptr_t>(img) & 15) == 0 && top_scores && top_idx)
+        return launch_sim_topk_tc(h, img, dtype, n, e, txt, q, k, thr, ts, index_base, clip_dur, vid_dur, top_scores,
+                                  top_idx, intervals, counts, dense, st);
     if (k <= 0 || k > SIM_MAXK) return b200_fail(h, B200CLIP_E_SHAPE, "sim_topk: k must be in [1, %d]", SIM_MAXK);
     if (!top_scores || !top_idx) return b200_fail(h, B200CLIP_E_ARG, "sim_topk: null output");
     const int grid = sim_grid(h, n > 0 ? n : 1);

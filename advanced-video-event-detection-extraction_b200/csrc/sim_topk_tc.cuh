@@ -36,7 +36,7 @@ constexpr int STC_MAX_STAGES = 6;
 template <bool ARES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int N_rows,
-                   int Q, int q0, int q_total, int K, int k, float* __restrict__ dense_out,
+                   int row_offset /* index of row 0 of this launch's slice of the cache */, int Q, int q0, int q_total, int K, int k, float* __restrict__ dense_out,
                    float* __restrict__ part_s, int* __restrict__ part_i, int* __restrict__ gthr) {
     extern __shared__ uint8_t smem_raw[];
     // pointer arithmetic on smem_raw (not an integer round trip) keeps the shared address space visible: LDS / STS
@@ -179,7 +179,7 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     // reference's tie rule (equal scores: higher index first)
                     if (s >= sc[STC_MAXK - 1]) {
                         changed = true;
-                        sc[STC_MAXK - 1] = s; id[STC_MAXK - 1] = rbase + j;
+                        sc[STC_MAXK - 1] = s; id[STC_MAXK - 1] = row_offset + rbase + j;
 #pragma unroll
                         for (int e = STC_MAXK - 1; e > 0; --e) {       // bubble up; the newcomer passes equal scores
                             const bool sw = sc[e] >= sc[e - 1];

@@ -77,8 +77,10 @@ def test_config4_256_queries_cached_embeddings(model_b32):
     from b200clip import capi
 
     for cache in (img_t, img_t.bfloat16()):
-        # dense = the scores exactly as the selected kernel computed them (fp32 cache: HBM-streaming kernel, fp32 text;
-        # bf16 cache at this size: tcgen05 kernel, text rounded to bf16)
+        # dense = the scores exactly as the selected kernel computed them.  Both caches take the tcgen05 kernel at this
+        # size (the fp32 cache is cast to bf16 slice by slice, the text is rounded to bf16): |dscore| < 1e-2, the bar
+        # BASELINE.json's north_star sets; fewer than 16 queries on an fp32 cache keep the exact fp32 streaming kernel
+        # (test_gpu_topk.py)
         s = torch.empty(q, k, device="cuda")
         i = torch.empty(q, k, device="cuda", dtype=torch.int64)
         c = torch.empty(q, device="cuda", dtype=torch.int32)
@@ -90,7 +92,7 @@ def test_config4_256_queries_cached_embeddings(model_b32):
         want = np.stack([np.lexsort((np.arange(n), dense[:, j]))[::-1][:k] for j in range(q)])
         assert np.array_equal(i.cpu().numpy(), want)
         assert np.array_equal(c.cpu().numpy(), (np.take_along_axis(dense.T, want, 1) >= 0.1).sum(1))
-        assert np.abs(dense - img @ txt.T).max() < (1e-2 if cache.dtype == torch.bfloat16 else 2e-5)
+        assert np.abs(dense - img @ txt.T).max() < 1e-2
         s2, i2, _, c2 = model_b32.sim_topk(cache, txt_t, k, 0.1, ts, 0, 30.0, float(n))
         assert torch.equal(i2, i) and torch.equal(c2, c)
 

@@ -118,6 +118,29 @@ def test_multi_shard_merge_equals_global(model_b32):
         assert np.array_equal(o_i, mi[qq].cpu().numpy())
 
 
+def test_tensor_core_path_fp32_cache_sliced(model_b32):
+    """An fp32 cache with >= 16 queries is cast to bf16 slice by slice (2^18 rows) and scored on the tensor cores; the
+    lists of all slices meet in one merge.  Planted winners (gap >> bf16 rounding) must come back exactly, in order,
+    with global indices, from every slice."""
+    n, q, k, e = (1 << 18) * 2 + 5000, 24, 5, 512
+    g = torch.Generator(device="cuda").manual_seed(3)
+    img = torch.randn(n, e, device="cuda", generator=g)
+    img = img / img.norm(dim=-1, keepdim=True)
+    txt = torch.randn(q, e, device="cuda", generator=g)
+    txt = txt / txt.norm(dim=-1, keepdim=True)
+    rows = torch.tensor([7, (1 << 18) - 100, (1 << 18) + 100, (1 << 18) + 12345, (1 << 19) + 4900], device="cuda")
+    for qq in range(q):
+        for r, row in enumerate(rows):          # winner r of query qq: cosine 0.9 - 0.05 r
+            c = 0.9 - 0.05 * r
+            noise = img[row] - (img[row] @ txt[qq]) * txt[qq]
+            img[(row + qq) % n] = c * txt[qq] + (1 - c * c) ** 0.5 * noise / noise.norm()
+    s, i, iv, cnt = model_b32.sim_topk(img, txt, k, 0.5, torch.arange(n, dtype=torch.float64), 0, 30.0, float(n))
+    want = torch.stack([(rows + qq) % n for qq in range(q)])
+    assert torch.equal(i, want)
+    assert float((s - torch.tensor([0.9 - 0.05 * r for r in range(5)], device="cuda")).abs().max()) < 1e-2
+    assert torch.equal(cnt, torch.full((q,), 5, dtype=torch.int32, device="cuda"))
+
+
 @pytest.mark.parametrize("n,q,k,e", [(20000, 256, 5, 512), (9000, 40, 8, 768), (4096, 8, 1, 512), (70001, 300, 5, 512),
                                      (150001, 130, 3, 512), (4200, 9, 8, 64)])
 def test_tensor_core_path_order_is_exact(model_b32, n, q, k, e):
