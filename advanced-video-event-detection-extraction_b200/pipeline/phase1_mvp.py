@@ -29,11 +29,49 @@ class Phase1MVP:
         self.clip_model = clip_model if clip_model is not None else OpenCLIPModel()
         self.frame_extractor = FrameExtractor()
         self.debug_mode = debug_mode
+        self._caches = {}
+        self._fp = None
 
     # -------------------------------------------------------------------------------------------
     def process_video(self, video_path: str, query: str, top_k: int = None, debug_mode: bool = None):
+        use_cache = settings.B200_EMBEDDING_CACHE and not (self.debug_mode if debug_mode is None else debug_mode)
+        if use_cache:
+            return self._process_video_cached(video_path, query, top_k)
         frames, timestamps = self.frame_extractor.extract_frames(video_path)
         return self.process_frames(frames, timestamps, query, top_k, debug_mode)
+
+    def _process_video_cached(self, video_path: str, query: str, top_k: int = None):
+        """Opt-in (settings.B200_EMBEDDING_CACHE): embed a video once into data/embeddings/*.b2emb -- the directory
+        the reference reserves but never uses (README.md:208) -- and answer this and every later query from the
+        cached window embeddings with K4 alone.  Same result dicts as the uncached path."""
+        import os
+
+        from ..services.embedding_cache import EmbeddingCache, cache_path_for
+
+        cache_dir = str(settings.DATA_DIR / "embeddings")
+        path = cache_path_for(video_path, cache_dir, settings.OPENCLIP_MODEL, self._fingerprint())
+        cache = self._caches.get(path)
+        if cache is None:
+            if os.path.exists(path):
+                cache = EmbeddingCache.load(self.clip_model, path)
+            if cache is None or len(cache) != cache.meta.get("windows", len(cache)):     # absent or interrupted build
+                frames, timestamps = self.frame_extractor.extract_frames(video_path)
+                cache = EmbeddingCache.build(self.clip_model, frames, timestamps, dtype="float32", path=path,
+                                             resume=os.path.exists(path))
+            self._caches[path] = cache
+        res = cache.query(query, top_k)
+        for r in res:           # the reference's dicts carry no interval
+            r.pop("start", None)
+            r.pop("end", None)
+        return res
+
+    def _fingerprint(self) -> str:
+        if self._fp is None:
+            from ..services.embedding_cache import weights_fingerprint
+
+            sd = getattr(self.clip_model, "_state_dict", None)
+            self._fp = weights_fingerprint(sd) if sd else f"seed{getattr(self.clip_model, '_seed', 0)}"
+        return self._fp
 
     def process_frames(self, frames: np.ndarray, timestamps: Sequence[float], query: str, top_k: int = None,
                        debug_mode: bool = None, video_duration: float = 0.0, return_device: bool = False):

@@ -39,6 +39,9 @@ class Settings:
         # b200clip additions (not in the reference): frames per pass of the tower, frame cap compatibility
         self.B200_MAX_IMAGES_PER_PASS = _env("B200_MAX_IMAGES_PER_PASS", 1024, int)
         self.MAX_SAMPLED_FRAMES = _env("MAX_SAMPLED_FRAMES", 1000, int)  # frame_extractor.py:69-74
+        # embed each video once into DATA_DIR/embeddings/*.b2emb and answer later queries from the cache (off = the
+        # reference's behaviour: decode + embed on every query)
+        self.B200_EMBEDDING_CACHE = bool(_env("B200_EMBEDDING_CACHE", 0, int))
 
 
 settings = Settings()
