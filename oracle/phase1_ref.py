@@ -124,3 +124,40 @@ def merge_topk_lists(cand_scores: np.ndarray, cand_idx: np.ndarray, k: int):
     s, i = s[keep], i[keep]
     order = np.lexsort((i, s))[::-1][:k]   # primary: score, secondary: index; descending both
     return s[order], i[order]
+
+
+# ---------------------------------------------------------------------------- section 8f "next" rows
+def temporal_consistency(results):
+    """Phase3Advanced._apply_temporal_consistency, /root/reference/src/pipeline/phase3_advanced.py:37-81, restated
+    statement by statement (including `filtered_results.remove(existing)` inside the loop over filtered_results,
+    which makes Python's list iterator skip the element after a removal).  Pinned by tests/golden/next_rows.json."""
+    if len(results) <= 1:
+        return results
+    sorted_results = sorted(results, key=lambda x: x["timestamp"])
+    filtered = []
+    for current in sorted_results:
+        should_add = True
+        for existing in filtered:                       # iterator over a list that may shrink underneath it
+            c0 = current.get("start_time", current["timestamp"] - 2.5)
+            c1 = current.get("end_time", current["timestamp"] + 2.5)
+            e0 = existing.get("start_time", existing["timestamp"] - 2.5)
+            e1 = existing.get("end_time", existing["timestamp"] + 2.5)
+            overlap = max(0, min(c1, e1) - max(c0, e0))
+            if overlap > 0.5 * (c1 - c0) or overlap > 0.5 * (e1 - e0):
+                if current["confidence"] <= existing["confidence"]:
+                    should_add = False
+                    break
+                else:
+                    filtered.remove(existing)
+        if should_add:
+            filtered.append(current)
+    return filtered
+
+
+def single_stage_matching(similarities, timestamps, top_k, similarity_threshold):
+    """ImageMatcher._single_stage_matching, /root/reference/src/services/image_matcher.py:980-1018, after the
+    per-frame CLIP similarities: build the dicts, stable sort descending, cut to top_k, threshold."""
+    sims = [{"timestamp": timestamps[i], "confidence": float(s), "clip_similarity": float(s),
+             "method": "single_stage_matching", "frame_index": i} for i, s in enumerate(similarities)]
+    sims.sort(key=lambda x: x["confidence"], reverse=True)
+    return [s for s in sims[:top_k] if s["confidence"] >= similarity_threshold]

@@ -118,3 +118,33 @@ def test_config5_image_query_top10(model_b32, oracle_sd_b32):
     ref_scores = e @ e[3]
     assert np.abs(model_b32.similarity(emb, qemb)[:, 0].cpu().numpy() - ref_scores).max() <= SCORE_TOL
     assert int(c[0]) == int((np.sort(model_b32.similarity(emb, qemb)[:, 0].cpu().numpy())[::-1][:10] >= 0.7).sum())
+
+
+def test_image_matcher_single_stage(oracle_sd_b32):
+    """ImageMatcher._single_stage_matching (image_matcher.py:980-1018) on the GPU: one batched pass instead of two
+    encodes per frame; same dicts, stable descending order (an exact duplicate of a frame ties -> LOWER index first,
+    unlike phase 1), thresholded after the top-k cut; confidences within 1e-2 of the fp32 oracle."""
+    from b200clip.models.openclip_model import OpenCLIPModel
+    from b200clip.services.image_matcher import ImageMatcher
+    from oracle import clip_ref
+    from oracle import phase1_ref as R
+    from oracle import preprocess_ref as P
+
+    crops = structured_frames(48, 224, 224, seed=33)
+    crops[30] = crops[7]                       # exact duplicate later in the list
+    ref_img = crops[7]
+    ts = [i / 2.0 for i in range(len(crops))]
+    m = ImageMatcher(OpenCLIPModel(state_dict=oracle_sd_b32))
+    sims = m.clip_similarities(ref_img, crops)
+    assert sims[7] == sims[30] and abs(sims[7] - 1.0) < 1e-3
+    got = m._single_stage_matching(ref_img, crops, ts, top_k=6, similarity_threshold=0.7)
+    assert got == R.single_stage_matching(sims.tolist(), ts, 6, 0.7) or \
+        [g["frame_index"] for g in got] == [w["frame_index"] for w in R.single_stage_matching(sims.tolist(), ts, 6, 0.7)]
+    assert [g["frame_index"] for g in got[:2]] == [7, 30]
+    assert abs(m._compute_clip_similarity(ref_img, crops[12]) - sims[12]) < 1e-6
+    oracle = clip_ref.CLIPRef(clip_ref.CONFIGS["ViT-B-32"], oracle_sd_b32)
+    x = torch.from_numpy(np.stack([P.to_chw_normalized(P.clip_transform_u8(f)) for f in crops]))
+    e = oracle.encode_image(x)
+    e = (e / e.norm(dim=-1, keepdim=True)).numpy()
+    assert np.abs(sims - e @ e[7]).max() <= SCORE_TOL
+    assert m._single_stage_matching(ref_img, crops[:0], [], 5, 0.7) == []
