@@ -131,6 +131,7 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -176,9 +177,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <bool SINGLE>
 __global__ void __launch_bounds__(ATT_THREADS, 4)
 attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int heads, int causal) {
+    // K/V blocks are double buffered: block i+1 is in flight (cp.async) while block i runs on the tensor cores
+    constexpr int NBUF = SINGLE ? 1 : 2;
     __shared__ __align__(128) uint8_t sQ[ATT_BQ * 128];
-    __shared__ __align__(128) uint8_t sK[ATT_BK * 128];
-    __shared__ __align__(128) uint8_t sV[ATT_BK * 128];
+    __shared__ __align__(128) uint8_t sKb[NBUF][ATT_BK * 128];
+    __shared__ __align__(128) uint8_t sVb[NBUF][ATT_BK * 128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t4 = lane & 3;
     const int q0 = blockIdx.x * ATT_BQ;
@@ -203,12 +206,23 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
 
     const int kv_end = causal ? min(T, q0 + ATT_BQ) : T;
     bool q_loaded = false;
-    for (int k0 = 0; k0 < kv_end; k0 += ATT_BK) {
-        __syncthreads();  // previous iteration's readers of sK/sV are done
-        load_tile_async(sK, kbase, ld, k0, T);
-        load_tile_async(sV, vbase, ld, k0, T);
-        cp_async_commit();
-        cp_async_wait_all();
+    load_tile_async(sKb[0], kbase, ld, 0, T);
+    load_tile_async(sVb[0], vbase, ld, 0, T);
+    cp_async_commit();
+    int it = 0;
+    for (int k0 = 0; k0 < kv_end; k0 += ATT_BK, ++it) {
+        const int buf = SINGLE ? 0 : (it & 1);
+        uint8_t* sK = sKb[buf];
+        uint8_t* sV = sVb[buf];
+        if (!SINGLE && k0 + ATT_BK < kv_end) {
+            // the other buffer was last read in iteration it-1, which ended with a __syncthreads
+            load_tile_async(sKb[buf ^ 1], kbase, ld, k0 + ATT_BK, T);
+            load_tile_async(sVb[buf ^ 1], vbase, ld, k0 + ATT_BK, T);
+            cp_async_commit();
+            cp_async_wait_but_one();      // everything except the prefetch just issued
+        } else {
+            cp_async_wait_all();
+        }
         __syncthreads();
         if (!q_loaded) {
             const uint32_t qb = smem_u32(sQ);
@@ -225,12 +239,16 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
         const uint32_t kb = smem_u32(sK);
-        const int jmax = SINGLE ? (T + 7) >> 3 : 8;    // 8-key tiles that hold at least one valid key
+        // 8-key tiles of this block that hold at least one valid key (T = 257: the fifth block has ONE key), and whether
+        // this warp's 16 query rows exist at all (the fifth query tile of T = 257 has ONE row): the rest is skipped
+        const int kv_valid = min(ATT_BK, T - k0);
+        const int jmax = (kv_valid + 7) >> 3;
+        const bool warp_rows = q0 + warp * 16 < T;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
             for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-key tiles
-                if (SINGLE && jp * 2 >= jmax) continue;
+                if (jp * 2 >= jmax || !warp_rows) continue;
                 uint32_t b0, b1, b2, b3;
                 const int r = jp * 16 + (lane & 7) + ((lane >> 4) << 3);
                 const int c = ks * 2 + ((lane >> 3) & 1);
@@ -274,37 +292,45 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
             }
             l_run[0] = rs[0]; l_run[1] = rs[1];
         } else {
-        // ---- mask + online softmax (rows g and g+8 of this warp's 16)
+        // ---- mask + online softmax (rows g and g+8 of this warp's 16).  Scores stay unscaled; the 1/sqrt(d) * log2(e)
+        // factor is folded into the exponent (one FFMA + one MUFU.EX2 per element).  Only blocks that straddle the end
+        // of the sequence or the causal diagonal pay for the per-element mask.
         const int qrow0 = q0 + warp * 16 + g;
+        if (k0 + ATT_BK > T || (causal && k0 + ATT_BK > q0)) {          // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int key = k0 + j * 8 + t4 * 2 + (e & 1);
+                    const int qr = qrow0 + ((e >> 1) << 3);
+                    if (!(key < T && (!causal || key <= qr))) s[j][e] = -INFINITY;
+                }
+            }
+        }
         float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int key = k0 + j * 8 + t4 * 2 + (e & 1);
-                const int qr = qrow0 + ((e >> 1) << 3);
-                const bool ok = key < T && (!causal || key <= qr);
-                s[j][e] = ok ? s[j][e] * scale_log2 : -INFINITY;
-                mx[e >> 1] = fmaxf(mx[e >> 1], s[j][e]);
-            }
+            mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
         }
-        float corr[2], m_use[2];
+        float corr[2], nm[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
             const float m_new = fmaxf(m_run[r], mx[r]);
-            m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;  // fully masked row so far
-            corr[r] = exp2f(m_run[r] - m_use[r]);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;  // fully masked row so far
+            corr[r] = ex2_approx((m_run[r] - m_use) * scale_log2);   // m_run = -inf -> 0
+            nm[r] = -m_use * scale_log2;
             m_run[r] = m_new;
         }
         float rs[2] = {0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float p0 = exp2f(s[j][0] - m_use[0]);
-            const float p1 = exp2f(s[j][1] - m_use[0]);
-            const float p2 = exp2f(s[j][2] - m_use[1]);
-            const float p3 = exp2f(s[j][3] - m_use[1]);
+            const float p0 = ex2_approx(fmaf(s[j][0], scale_log2, nm[0]));
+            const float p1 = ex2_approx(fmaf(s[j][1], scale_log2, nm[0]));
+            const float p2 = ex2_approx(fmaf(s[j][2], scale_log2, nm[1]));
+            const float p3 = ex2_approx(fmaf(s[j][3], scale_log2, nm[1]));
             rs[0] += p0 + p1;
             rs[1] += p2 + p3;
             pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
@@ -322,7 +348,7 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
         const uint32_t vb = smem_u32(sV);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {       // 16 keys per step
-            if (SINGLE && ks * 16 >= T) continue;  // P is exactly 0 there
+            if (ks * 16 >= kv_valid || !warp_rows) continue;  // P is exactly 0 there
 #pragma unroll
             for (int jp = 0; jp < 4; ++jp) {   // pairs of 8-wide d tiles
                 uint32_t b0, b1, b2, b3;
@@ -333,6 +359,7 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
                 mma_bf16_16816(o_acc[jp * 2 + 1], pf[ks], b2, b3);
             }
         }
+        if (!SINGLE) __syncthreads();  // all warps are done with this buffer before the next prefetch overwrites it
     }
     // ---- finalize: row sums across the quad, normalise, stage through sQ (this warp's own rows), store
 #pragma unroll
