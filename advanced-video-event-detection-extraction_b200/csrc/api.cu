@@ -157,6 +157,7 @@ extern "C" int b200clip_destroy(b200clip_handle* h) {
     cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_qkv); cudaFree(h->ws_h); cudaFree(h->ws_patches);
     cudaFree(h->ws_emb); cudaFree(h->ws_pre); cudaFree(h->ws_topk); cudaFree(h->ws_eot); cudaFree(h->ws_tokens);
     cudaFree(h->ws_patches2); cudaFree(h->ws_stats);
+    cudaFree(h->ws_tx); cudaFree(h->ws_ty); cudaFree(h->ws_tqkv); cudaFree(h->ws_th); cudaFree(h->ws_tstats);
     if (h->pre_stream) cudaStreamDestroy(h->pre_stream);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
@@ -349,13 +350,15 @@ static int ensure_workspace(b200clip_handle* h, int images, int texts, cudaStrea
     const b200clip_config& c = h->cfg;
     const size_t mv = static_cast<size_t>(ni) * h->tokens, mt = static_cast<size_t>(nt) * c.text_ctx;
     auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
-    const size_t x_el = mx(mv * c.width, mt * c.text_width);
+    const size_t x_el = mv * c.width, tx_el = mt * c.text_width;
     const size_t qkv_el = 3 * x_el;
-    const size_t h_el = mx(mv * c.mlp_dim, mt * c.text_mlp_dim);
+    const size_t h_el = mv * c.mlp_dim, th_el = mt * c.text_mlp_dim;
     const size_t p_el = static_cast<size_t>(ni) * h->grid * h->grid * h->patch_k;
     cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_qkv); cudaFree(h->ws_h); cudaFree(h->ws_patches);
     cudaFree(h->ws_patches2); cudaFree(h->ws_stats);
     cudaFree(h->ws_eot); cudaFree(h->ws_tokens);
+    cudaFree(h->ws_tx); cudaFree(h->ws_ty); cudaFree(h->ws_tqkv); cudaFree(h->ws_th); cudaFree(h->ws_tstats);
+    h->ws_tx = h->ws_ty = h->ws_tqkv = h->ws_th = nullptr; h->ws_tstats = nullptr;
     h->ws_stats = nullptr;
     h->ws_x = h->ws_y = h->ws_qkv = h->ws_h = h->ws_patches = h->ws_patches2 = nullptr;
     h->ws_eot = nullptr; h->ws_tokens = nullptr;
@@ -366,7 +369,12 @@ static int ensure_workspace(b200clip_handle* h, int images, int texts, cudaStrea
     B200_CUDA(h, cudaMalloc(&h->ws_h, mx(h_el, 8) * 2));
     B200_CUDA(h, cudaMalloc(&h->ws_patches, mx(p_el, 8) * 2));
     B200_CUDA(h, cudaMalloc(&h->ws_patches2, mx(p_el, 8) * 2));
-    B200_CUDA(h, cudaMalloc(&h->ws_stats, mx(mx(mv, mt), 1) * 16 * sizeof(float)));
+    B200_CUDA(h, cudaMalloc(&h->ws_stats, mx(mv, 1) * 16 * sizeof(float)));
+    B200_CUDA(h, cudaMalloc(&h->ws_tx, mx(tx_el, 8) * 2));
+    B200_CUDA(h, cudaMalloc(&h->ws_ty, mx(tx_el, 8) * 2));
+    B200_CUDA(h, cudaMalloc(&h->ws_tqkv, mx(3 * tx_el, 8) * 2));
+    B200_CUDA(h, cudaMalloc(&h->ws_th, mx(th_el, 8) * 2));
+    B200_CUDA(h, cudaMalloc(&h->ws_tstats, mx(mt, 1) * 16 * sizeof(float)));
     B200_CUDA(h, cudaMalloc(&h->ws_eot, mx(nt, 1) * sizeof(int32_t)));
     B200_CUDA(h, cudaMalloc(&h->ws_tokens, mx(mt, 1) * sizeof(int64_t)));
     h->ws_images = ni;
@@ -386,7 +394,9 @@ extern "C" int b200clip_reserve(b200clip_handle* h, int max_images, int max_text
 // Residual blocks.  ws_x holds the residual stream and ws_stats the (sum, sum of squares) partials of its rows
 // (written by ln_pre / the text embedding, then by every residual GEMM); ln_1 / ln_2 never run as kernels: they
 // are folded into the QKV / fc GEMM epilogues.
-static int run_blocks(b200clip_handle* h, b200clip_handle::Tower& tw, int n_seq, int T, int causal, cudaStream_t st) {
+struct TowerWs { bf16 *x, *y, *qkv, *hid; float* stats; };
+static int run_blocks(b200clip_handle* h, b200clip_handle::Tower& tw, const TowerWs& ws, int n_seq, int T, int causal,
+                      cudaStream_t st) {
     const int M = n_seq * T;
     const int W = tw.width, F = tw.mlp;
     const int act = h->cfg.act == 0 ? 1 : 2;
@@ -394,16 +404,16 @@ static int run_blocks(b200clip_handle* h, b200clip_handle::Tower& tw, int n_seq,
     for (int l = 0; l < tw.layers; ++l) {
         const b200clip_handle::Block& b = tw.blocks[l];
         b200::GemmEpilogue ep{};
-        ep.bias = b.c2_qkv; ep.ln_stats = h->ws_stats; ep.ln_c1 = b.c1_qkv; ep.ln_eps = h->cfg.ln_eps; ep.ln_width = W;
-        if ((rc = launch_gemm(h, h->ws_x, W, b.w_qkv, W, h->ws_qkv, 3 * W, M, 3 * W, W, ep, st))) return rc;
-        if ((rc = launch_attention(h, h->ws_qkv, h->ws_y, n_seq, T, tw.heads, causal, st))) return rc;
-        ep = {}; ep.bias = b.b_out; ep.resid = h->ws_x; ep.stats_out = h->ws_stats;
-        if ((rc = launch_gemm(h, h->ws_y, W, b.w_out, W, h->ws_x, W, M, W, W, ep, st))) return rc;
-        ep = {}; ep.bias = b.c2_fc; ep.ln_stats = h->ws_stats; ep.ln_c1 = b.c1_fc; ep.ln_eps = h->cfg.ln_eps;
+        ep.bias = b.c2_qkv; ep.ln_stats = ws.stats; ep.ln_c1 = b.c1_qkv; ep.ln_eps = h->cfg.ln_eps; ep.ln_width = W;
+        if ((rc = launch_gemm(h, ws.x, W, b.w_qkv, W, ws.qkv, 3 * W, M, 3 * W, W, ep, st))) return rc;
+        if ((rc = launch_attention(h, ws.qkv, ws.y, n_seq, T, tw.heads, causal, st))) return rc;
+        ep = {}; ep.bias = b.b_out; ep.resid = ws.x; ep.stats_out = ws.stats;
+        if ((rc = launch_gemm(h, ws.y, W, b.w_out, W, ws.x, W, M, W, W, ep, st))) return rc;
+        ep = {}; ep.bias = b.c2_fc; ep.ln_stats = ws.stats; ep.ln_c1 = b.c1_fc; ep.ln_eps = h->cfg.ln_eps;
         ep.ln_width = W; ep.act = act;
-        if ((rc = launch_gemm(h, h->ws_x, W, b.w_fc, W, h->ws_h, F, M, F, W, ep, st))) return rc;
-        ep = {}; ep.bias = b.b_proj; ep.resid = h->ws_x; ep.stats_out = h->ws_stats;
-        if ((rc = launch_gemm(h, h->ws_h, F, b.w_proj, F, h->ws_x, W, M, W, F, ep, st))) return rc;
+        if ((rc = launch_gemm(h, ws.x, W, b.w_fc, W, ws.hid, F, M, F, W, ep, st))) return rc;
+        ep = {}; ep.bias = b.b_proj; ep.resid = ws.x; ep.stats_out = ws.stats;
+        if ((rc = launch_gemm(h, ws.hid, F, b.w_proj, F, ws.x, W, M, W, F, ep, st))) return rc;
     }
     return 0;
 }
@@ -423,7 +433,8 @@ static int encode_patches_chunk(b200clip_handle* h, const bf16* patches, int n, 
     if ((rc = launch_layernorm(h, h->ws_y, h->ln_pre_g, h->ln_pre_b, h->ws_x, static_cast<int64_t>(n) * h->tokens,
                                c.width, c.ln_eps, h->tokens, h->cls_pos0, h->ws_stats, st)))
         return rc;
-    if ((rc = run_blocks(h, h->vis, n, h->tokens, 0, st))) return rc;
+    const TowerWs vws{h->ws_x, h->ws_y, h->ws_qkv, h->ws_h, h->ws_stats};
+    if ((rc = run_blocks(h, h->vis, vws, n, h->tokens, 0, st))) return rc;
     return launch_head(h, h->ws_x, static_cast<int64_t>(h->tokens) * c.width, nullptr, h->ln_post_g, h->ln_post_b,
                        h->vis_proj, n, c.width, c.embed_dim, c.ln_eps, out, out_dtype, l2norm, st);
 }
@@ -723,12 +734,13 @@ static int encode_text_dev(b200clip_handle* h, const int64_t* tokens_dev, int q,
     if ((rc = ensure_workspace(h, 0, chunk, st))) return rc;
     for (int i = 0; i < q; i += chunk) {
         const int nc = (q - i) < chunk ? (q - i) : chunk;
-        B200_CUDA(h, cudaMemsetAsync(h->ws_stats, 0, static_cast<size_t>(nc) * c.text_ctx * 16 * sizeof(float), st));
-        if ((rc = launch_text_embed(h, tokens_dev + static_cast<size_t>(i) * c.text_ctx, nc, h->ws_x, h->ws_eot,
-                                    h->ws_stats, st)))
+        B200_CUDA(h, cudaMemsetAsync(h->ws_tstats, 0, static_cast<size_t>(nc) * c.text_ctx * 16 * sizeof(float), st));
+        if ((rc = launch_text_embed(h, tokens_dev + static_cast<size_t>(i) * c.text_ctx, nc, h->ws_tx, h->ws_eot,
+                                    h->ws_tstats, st)))
             return rc;
-        if ((rc = run_blocks(h, h->txt, nc, c.text_ctx, 1, st))) return rc;
-        if ((rc = launch_head(h, h->ws_x, c.text_width, h->ws_eot, h->ln_final_g, h->ln_final_b, h->txt_proj, nc,
+        const TowerWs tws{h->ws_tx, h->ws_ty, h->ws_tqkv, h->ws_th, h->ws_tstats};
+        if ((rc = run_blocks(h, h->txt, tws, nc, c.text_ctx, 1, st))) return rc;
+        if ((rc = launch_head(h, h->ws_tx, c.text_width, h->ws_eot, h->ln_final_g, h->ln_final_b, h->txt_proj, nc,
                               c.text_width, c.embed_dim, c.ln_eps, out_dev + static_cast<size_t>(i) * c.embed_dim,
                               B200CLIP_F32, l2norm, st)))
             return rc;

@@ -65,6 +65,10 @@ struct b200clip_handle {
     // ---- persistent workspace ----
     int ws_images = 0, ws_texts = 0;
     bf16 *ws_x = nullptr, *ws_y = nullptr, *ws_qkv = nullptr, *ws_h = nullptr, *ws_patches = nullptr;
+    // the text tower has its own (small) activation buffers, so that a text call on one stream may overlap an image
+    // call on another stream of the same handle
+    bf16 *ws_tx = nullptr, *ws_ty = nullptr, *ws_tqkv = nullptr, *ws_th = nullptr;
+    float* ws_tstats = nullptr;
     uint8_t* ws_stage_dev[2] = {nullptr, nullptr};   // device staging for host-frame calls
     uint8_t* ws_stage_host[2] = {nullptr, nullptr};  // pinned
     size_t ws_stage_bytes = 0, ws_stage_host_bytes = 0;

@@ -166,3 +166,26 @@ def test_host_upload_window_equals_device_path(model_b32, w, h, mode):
     assert 0 < h2d <= frames.nbytes and d2h == dev.nbytes
     if (w, h) == (1920, 1080):
         assert h2d < 0.6 * frames.nbytes      # 1104 of 1920 columns
+
+
+def test_text_and_image_towers_overlap_on_two_streams(model_b32):
+    """The towers use disjoint workspaces of one handle: a text call on a side stream may be in flight while an image
+    call runs on the main stream.  Results must equal the serial ones bit for bit."""
+    from b200clip import capi
+    from oracle.clip_ref import synthetic_tokenize
+
+    frames = torch.from_numpy(structured_frames(200, 224, 224, seed=91)).cuda()
+    tok = synthetic_tokenize(list(QUERIES)).cuda()
+    emb0 = model_b32.encode_frames_u8(frames, capi.RESIZE_REFERENCE, normalize=True).clone()
+    txt0 = model_b32.encode_text(tok, normalize=True).clone()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    cur = torch.cuda.current_stream()
+    for _ in range(5):
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            txt = model_b32.encode_text(tok, normalize=True)
+        emb = model_b32.encode_frames_u8(frames, capi.RESIZE_REFERENCE, normalize=True)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        assert torch.equal(emb, emb0) and torch.equal(txt, txt0)
