@@ -100,10 +100,28 @@ static int launch_gemm_2cta(b200clip_handle* h, const bf16* a, int lda, const bf
     const int tiles = m_blocks * n_blocks;
     int clusters = h->num_sms / 2;
     if (tiles < clusters) clusters = tiles;
+    static const bool probe_on = getenv("B200CLIP_GEMM_PROBE") != nullptr;   // development aid, see GemmEpilogue::probe
+    b200::GemmEpilogue epp = ep;
+    long long* probe = nullptr;
+    if (probe_on) {
+        B200_CUDA(h, cudaMallocManaged(&probe, sizeof(long long) * 4 * clusters));
+        B200_CUDA(h, cudaMemset(probe, 0, sizeof(long long) * 4 * clusters));
+        epp.probe = probe;
+    }
     {
         ProfScope ps(h, PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
         b200::gemm_bf16_tcgen05_2cta_kernel<0><<<2 * clusters, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, st>>>(
-            ta, tw, to, tr, out, ldc, M, N, K, ep, use_tma_epi);
+            ta, tw, to, tr, out, ldc, M, N, K, epp, use_tma_epi);
+    }
+    if (probe) {
+        B200_CUDA(h, cudaStreamSynchronize(st));
+        double t[4] = {0, 0, 0, 0};
+        for (int c = 0; c < clusters; ++c)
+            for (int j = 0; j < 4; ++j) t[j] += static_cast<double>(probe[c * 4 + j]) / clusters;
+        fprintf(stderr, "[gemm probe] M=%d N=%d K=%d tiles/cluster=%.1f: total %.0f clk; MMA waits: TMA data %.1f%%, free accumulator "
+                        "%.1f%%; epilogue waits for accumulator %.1f%%\n", M, N, K, static_cast<double>(tiles) / clusters, t[0],
+                100.0 * t[1] / t[0], 100.0 * t[2] / t[0], 100.0 * t[3] / t[0]);
+        cudaFree(probe);
     }
     h->launches++;
     B200_CUDA(h, cudaGetLastError());
@@ -124,6 +142,8 @@ int launch_gemm(b200clip_handle* h, const bf16* a, int lda, const bf16* w, int l
     if (!force_1cta && N % 256 == 0 && M >= 2048 && stats_fit(256)) return launch_gemm_2cta(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
     // tiny M (text tower: 77 rows per query): narrow tiles so that more CTAs share the latency-bound problem
     if (M <= 256 && N % 64 == 0 && stats_fit(64)) return launch_gemm_bn<64>(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
+    // (statistics-emitting GEMMs keep the 256-wide tiles at every M: the width of the partial-sum segments is part of
+    // the numerics, and a query's embedding must not depend on how many queries share the batch)
     if (N % 256 == 0 || N > 1024) {
         if (!stats_fit(256)) return b200_fail(h, B200CLIP_E_SHAPE, "gemm: width %d too large for the LayerNorm statistics slots", N);
         return launch_gemm_bn<256>(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);

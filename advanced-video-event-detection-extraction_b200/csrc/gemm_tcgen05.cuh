@@ -33,6 +33,9 @@ struct GemmEpilogue {
     int ln_width;               // row length of x (= K)
     // this GEMM produces the residual stream: emit (sum, sum of squares) of each output row segment
     float* stats_out;           // [rows, LN_SLOTS, 2] or nullptr
+    // development probe (B200CLIP_GEMM_PROBE): per cluster {total, MMA wait on TMA data, MMA wait on a free
+    // accumulator, epilogue wait on the accumulator} in SM clocks; nullptr in production
+    long long* probe;
 };
 constexpr int LN_SLOTS = 8;     // row segments (128 or 64 columns wide) whose partial sums are kept separately
 

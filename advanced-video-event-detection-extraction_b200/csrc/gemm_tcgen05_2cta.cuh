@@ -140,12 +140,18 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
+            long long p_full = 0, p_tmem = 0;
+            const long long p_t0 = clock64();
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                long long c0 = ep.probe ? clock64() : 0;
                 mbar_wait(&tmem_empty_bar[as], aphase ^ 1, 12);
+                if (ep.probe) p_tmem += clock64() - c0;
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * G2_BLOCK_N;
                 for (int kb = 0; kb < k_blocks; ++kb) {
+                    c0 = ep.probe ? clock64() : 0;
                     mbar_wait(&full_bar[stage], phase, 13);
+                    if (ep.probe) p_full += clock64() - c0;
                     tc_fence_after();
                     const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smem_a + stage * G2_A_BYTES));
                     const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smem_b + stage * G2_B_BYTES));
@@ -158,9 +164,15 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
                 umma_commit_cg2(&tmem_full_bar[as], 0b11);      // accumulator ready in both CTAs
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
+            if (ep.probe) {
+                ep.probe[cluster_id * 4 + 0] = clock64() - p_t0;
+                ep.probe[cluster_id * 4 + 1] = p_full;
+                ep.probe[cluster_id * 4 + 2] = p_tmem;
+            }
         }
     } else {
         // ===================== epilogue warps (both CTAs, own 128 rows) =====================
+        long long p_epi = 0;
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         constexpr int COLS_PER_WARP = G2_BLOCK_N / (GEMM_EPI_WARPS / 4);
@@ -201,7 +213,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
                     tma_load_2d(my_stage, &tmap_res, my_bar, col0, box_row0);
                     tma_load_2d(my_stage + G2_BOX_BYTES, &tmap_res, my_bar, col0 + 64, box_row0);
                 }
-                mbar_wait(&tmem_full_bar[as], aphase, 14);
+                { const long long c0 = ep.probe ? clock64() : 0; mbar_wait(&tmem_full_bar[as], aphase, 14); if (ep.probe) p_epi += clock64() - c0; }
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * G2_BLOCK_N + half * COLS_PER_WARP;
                 uint32_t acc_a[32], acc_b[32];
@@ -229,7 +241,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
                 }
                 if (res_ptr) res_phase ^= 1;
             } else {
-                mbar_wait(&tmem_full_bar[as], aphase, 14);
+                { const long long c0 = ep.probe ? clock64() : 0; mbar_wait(&tmem_full_bar[as], aphase, 14); if (ep.probe) p_epi += clock64() - c0; }
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * G2_BLOCK_N + half * COLS_PER_WARP;
                 uint32_t acc_a[32], acc_b[32];
@@ -252,6 +264,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
             if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);  // the leader's barrier
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        if (ep.probe && leader && warp == 2 && lane == 0) ep.probe[cluster_id * 4 + 3] = p_epi;
     }
 
     if (warp >= 2 && lane == 0) tma_store_wait<0>();   // bulk stores of the last tile are complete
