@@ -44,8 +44,10 @@ __device__ __forceinline__ void warp_insert(float* ls, int* li, int k, float s, 
     __syncwarp();
 }
 
-template <bool BF16>
-__global__ void __launch_bounds__(SIM_WARPS * 32)
+// MAXC: 16-byte chunks of a row per lane (ceil(e / VEC / 32)); a template parameter so that the row registers are
+// sized for the actual embedding width (E = 512: 2 for bf16, 4 for fp32) and two CTAs fit an SM
+template <bool BF16, int MAXC>
+__global__ void __launch_bounds__(SIM_WARPS * 32, 2)
 sim_stream_kernel(const void* __restrict__ img, int64_t n, int e, const float* __restrict__ txt, int q0, int qn,
                   int q_total, int k, float* __restrict__ scores_out, float* __restrict__ part_s,
                   int* __restrict__ part_i) {
@@ -64,23 +66,27 @@ sim_stream_kernel(const void* __restrict__ img, int64_t n, int e, const float* _
     const int chunks = e / VEC;                  // 16-byte chunks per row
     const int64_t warps_total = static_cast<int64_t>(gridDim.x) * SIM_WARPS;
     const int64_t wid = static_cast<int64_t>(blockIdx.x) * SIM_WARPS + warp;
-    constexpr int MAXC = BF16 ? 4 : 8;           // e <= 1024
-    for (int64_t row = wid * 2; row < n; row += warps_total * 2) {
-        // two rows in flight per warp
-        uint4 d0[MAXC], d1[MAXC];
-        const bool has1 = row + 1 < n;
-        const uint4* r0 = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(img) +
-                                                         row * static_cast<int64_t>(e) * (BF16 ? 2 : 4));
-        const uint4* r1 = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(img) +
-                                                         (row + (has1 ? 1 : 0)) * static_cast<int64_t>(e) * (BF16 ? 2 : 4));
+    // rows in flight per warp: as many as 64 data registers hold (E = 512: 8 bf16 rows = 8 KB, 2 fp32 rows = 4 KB).
+    // With two rows the bf16 stream was latency bound at 48 % of the HBM peak while fp32 reached 84 %.
+    constexpr int ROWS = MAXC <= 1 ? 8 : (BF16 ? (MAXC <= 2 ? 8 : 4) : (MAXC <= 2 ? 4 : 2));   // <= 64 data registers
+    for (int64_t row = wid * ROWS; row < n; row += warps_total * ROWS) {
+        uint4 d[ROWS][MAXC];
 #pragma unroll
-        for (int j = 0; j < MAXC; ++j) {
-            const int c = lane + j * 32;
-            if (c < chunks) { d0[j] = __ldg(r0 + c); d1[j] = __ldg(r1 + c); }
+        for (int r = 0; r < ROWS; ++r) {
+            const int64_t rr = row + r < n ? row + r : row;      // tail: re-read row 0 of the group, result unused
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(img) +
+                                                             rr * static_cast<int64_t>(e) * (BF16 ? 2 : 4));
+#pragma unroll
+            for (int j = 0; j < MAXC; ++j) {
+                const int c = lane + j * 32;
+                if (c < chunks) d[r][j] = __ldg(rp + c);
+            }
         }
         for (int qi = 0; qi < qn; ++qi) {
             const float* qv = sq + static_cast<size_t>(qi) * e;
-            float a0 = 0.f, a1 = 0.f;
+            float acc[ROWS];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
 #pragma unroll
             for (int j = 0; j < MAXC; ++j) {
                 const int c = lane + j * 32;
@@ -88,39 +94,42 @@ sim_stream_kernel(const void* __restrict__ img, int64_t n, int e, const float* _
                     const float4 t0 = *reinterpret_cast<const float4*>(qv + c * VEC);
                     if (BF16) {
                         const float4 t1 = *reinterpret_cast<const float4*>(qv + c * VEC + 4);
-                        float2 f;
-                        f = unpack_bf16x2(d0[j].x); a0 = fmaf(f.x, t0.x, a0); a0 = fmaf(f.y, t0.y, a0);
-                        f = unpack_bf16x2(d0[j].y); a0 = fmaf(f.x, t0.z, a0); a0 = fmaf(f.y, t0.w, a0);
-                        f = unpack_bf16x2(d0[j].z); a0 = fmaf(f.x, t1.x, a0); a0 = fmaf(f.y, t1.y, a0);
-                        f = unpack_bf16x2(d0[j].w); a0 = fmaf(f.x, t1.z, a0); a0 = fmaf(f.y, t1.w, a0);
-                        f = unpack_bf16x2(d1[j].x); a1 = fmaf(f.x, t0.x, a1); a1 = fmaf(f.y, t0.y, a1);
-                        f = unpack_bf16x2(d1[j].y); a1 = fmaf(f.x, t0.z, a1); a1 = fmaf(f.y, t0.w, a1);
-                        f = unpack_bf16x2(d1[j].z); a1 = fmaf(f.x, t1.x, a1); a1 = fmaf(f.y, t1.y, a1);
-                        f = unpack_bf16x2(d1[j].w); a1 = fmaf(f.x, t1.z, a1); a1 = fmaf(f.y, t1.w, a1);
+#pragma unroll
+                        for (int r = 0; r < ROWS; ++r) {
+                            float2 f;
+                            float a0 = acc[r];
+                            f = unpack_bf16x2(d[r][j].x); a0 = fmaf(f.x, t0.x, a0); a0 = fmaf(f.y, t0.y, a0);
+                            f = unpack_bf16x2(d[r][j].y); a0 = fmaf(f.x, t0.z, a0); a0 = fmaf(f.y, t0.w, a0);
+                            f = unpack_bf16x2(d[r][j].z); a0 = fmaf(f.x, t1.x, a0); a0 = fmaf(f.y, t1.y, a0);
+                            f = unpack_bf16x2(d[r][j].w); a0 = fmaf(f.x, t1.z, a0); a0 = fmaf(f.y, t1.w, a0);
+                            acc[r] = a0;
+                        }
                     } else {
-                        a0 = fmaf(__uint_as_float(d0[j].x), t0.x, a0); a0 = fmaf(__uint_as_float(d0[j].y), t0.y, a0);
-                        a0 = fmaf(__uint_as_float(d0[j].z), t0.z, a0); a0 = fmaf(__uint_as_float(d0[j].w), t0.w, a0);
-                        a1 = fmaf(__uint_as_float(d1[j].x), t0.x, a1); a1 = fmaf(__uint_as_float(d1[j].y), t0.y, a1);
-                        a1 = fmaf(__uint_as_float(d1[j].z), t0.z, a1); a1 = fmaf(__uint_as_float(d1[j].w), t0.w, a1);
+#pragma unroll
+                        for (int r = 0; r < ROWS; ++r) {
+                            float a0 = acc[r];
+                            a0 = fmaf(__uint_as_float(d[r][j].x), t0.x, a0); a0 = fmaf(__uint_as_float(d[r][j].y), t0.y, a0);
+                            a0 = fmaf(__uint_as_float(d[r][j].z), t0.z, a0); a0 = fmaf(__uint_as_float(d[r][j].w), t0.w, a0);
+                            acc[r] = a0;
+                        }
                     }
                 }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
             }
-            if (scores_out && lane == 0) {
-                scores_out[row * q_total + q0 + qi] = a0;
-                if (has1) scores_out[(row + 1) * q_total + q0 + qi] = a1;
-            }
-            if (k > 0) {
-                float* l_s = wls + qi * k;
-                int* l_i = wli + qi * k;
-                if (beats(a0, static_cast<int>(row), l_s[k - 1], l_i[k - 1]))
-                    warp_insert(l_s, l_i, k, a0, static_cast<int>(row), lane);
-                if (has1 && beats(a1, static_cast<int>(row + 1), l_s[k - 1], l_i[k - 1]))
-                    warp_insert(l_s, l_i, k, a1, static_cast<int>(row + 1), lane);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                if (row + r >= n) break;                         // warp-uniform
+                if (scores_out && lane == 0) scores_out[(row + r) * q_total + q0 + qi] = acc[r];
+                if (k > 0) {
+                    float* l_s = wls + qi * k;
+                    int* l_i = wli + qi * k;
+                    if (beats(acc[r], static_cast<int>(row + r), l_s[k - 1], l_i[k - 1]))
+                        warp_insert(l_s, l_i, k, acc[r], static_cast<int>(row + r), lane);
+                }
             }
         }
     }
@@ -244,23 +253,13 @@ static int run_stream(b200clip_handle* h, const void* img, int dtype, int64_t n,
     for (int q0 = 0; q0 < q; q0 += SIM_QTILE) {
         const int qn = (q - q0) < SIM_QTILE ? (q - q0) : SIM_QTILE;
         const size_t smem = static_cast<size_t>(qn) * e * 4 + static_cast<size_t>(SIM_WARPS) * qn * (k > 0 ? k : 0) * 8;
-        if (dtype == B200CLIP_BF16) {
-            static bool set = false;
-            if (!set) {
-                B200_CUDA(h, cudaFuncSetAttribute(sim_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  160 * 1024));
-                set = true;
-            }
-            sim_stream_kernel<true><<<grid, SIM_WARPS * 32, smem, st>>>(img, n, e, txt, q0, qn, q, k, scores, part_s, part_i);
-        } else {
-            static bool set = false;
-            if (!set) {
-                B200_CUDA(h, cudaFuncSetAttribute(sim_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  160 * 1024));
-                set = true;
-            }
-            sim_stream_kernel<false><<<grid, SIM_WARPS * 32, smem, st>>>(img, n, e, txt, q0, qn, q, k, scores, part_s, part_i);
-        }
+        const int vec = dtype == B200CLIP_BF16 ? 8 : 4;
+        const int cpl = (e / vec + 31) / 32;                     // chunks per lane
+        void (*kern)(const void*, int64_t, int, const float*, int, int, int, int, float*, float*, int*) = nullptr;
+        if (dtype == B200CLIP_BF16) kern = cpl <= 1 ? sim_stream_kernel<true, 1> : cpl <= 2 ? sim_stream_kernel<true, 2> : sim_stream_kernel<true, 4>;
+        else kern = cpl <= 2 ? sim_stream_kernel<false, 2> : cpl <= 4 ? sim_stream_kernel<false, 4> : sim_stream_kernel<false, 8>;
+        if (smem > 48 * 1024) B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        kern<<<grid, SIM_WARPS * 32, smem, st>>>(img, n, e, txt, q0, qn, q, k, scores, part_s, part_i);
         h->launches++;
     }
     B200_CUDA(h, cudaGetLastError());
