@@ -102,6 +102,10 @@ static int launch_gemm_2cta(b200clip_handle* h, const bf16* a, int lda, const bf
     if (tiles < clusters) clusters = tiles;
     static const bool probe_on = getenv("B200CLIP_GEMM_PROBE") != nullptr;   // development aid, see GemmEpilogue::probe
     b200::GemmEpilogue epp = ep;
+    // epilogue warps sleep between polls of the accumulator barrier (A/B on one box: 0.5-1 % faster steps under the
+    // power cap); B200CLIP_GEMM_SPIN_WAIT=1 restores the tight spin
+    static const int relaxed = getenv("B200CLIP_GEMM_SPIN_WAIT") ? 0 : 1;
+    epp.relaxed_wait = relaxed;
     long long* probe = nullptr;
     if (probe_on) {
         B200_CUDA(h, cudaMallocManaged(&probe, sizeof(long long) * 4 * clusters));

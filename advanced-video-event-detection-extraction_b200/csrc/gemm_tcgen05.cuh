@@ -36,6 +36,7 @@ struct GemmEpilogue {
     // development probe (B200CLIP_GEMM_PROBE): per cluster {total, MMA wait on TMA data, MMA wait on a free
     // accumulator, epilogue wait on the accumulator} in SM clocks; nullptr in production
     long long* probe;
+    int relaxed_wait;           // nanosleep back-off in the epilogue's accumulator wait (set by the launcher)
 };
 constexpr int LN_SLOTS = 8;     // row segments (128 or 64 columns wide) whose partial sums are kept separately
 

@@ -213,7 +213,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
                     tma_load_2d(my_stage, &tmap_res, my_bar, col0, box_row0);
                     tma_load_2d(my_stage + G2_BOX_BYTES, &tmap_res, my_bar, col0 + 64, box_row0);
                 }
-                { const long long c0 = ep.probe ? clock64() : 0; mbar_wait(&tmem_full_bar[as], aphase, 14); if (ep.probe) p_epi += clock64() - c0; }
+                { const long long c0 = ep.probe ? clock64() : 0; if (ep.relaxed_wait) mbar_wait_relaxed(&tmem_full_bar[as], aphase, 14); else mbar_wait(&tmem_full_bar[as], aphase, 14); if (ep.probe) p_epi += clock64() - c0; }
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * G2_BLOCK_N + half * COLS_PER_WARP;
                 uint32_t acc_a[32], acc_b[32];
@@ -241,7 +241,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
                 }
                 if (res_ptr) res_phase ^= 1;
             } else {
-                { const long long c0 = ep.probe ? clock64() : 0; mbar_wait(&tmem_full_bar[as], aphase, 14); if (ep.probe) p_epi += clock64() - c0; }
+                { const long long c0 = ep.probe ? clock64() : 0; if (ep.relaxed_wait) mbar_wait_relaxed(&tmem_full_bar[as], aphase, 14); else mbar_wait(&tmem_full_bar[as], aphase, 14); if (ep.probe) p_epi += clock64() - c0; }
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * G2_BLOCK_N + half * COLS_PER_WARP;
                 uint32_t acc_a[32], acc_b[32];

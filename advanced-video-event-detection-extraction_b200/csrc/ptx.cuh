@@ -70,6 +70,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
     }
 }
 
+// Waiting with back-off: for warps that are expected to wait LONG (the GEMM epilogue warps idle 30-80 % of the time
+// behind the mainloop).  A tight try_wait spin keeps the issue slots and the scheduler busy -- under the board power cap
+// that is clock frequency taken away from the tensor cores; sleeping between polls gives it back.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int tag = 0) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(64);
+        if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+            printf("b200clip: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
+                   (int)threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
