@@ -612,6 +612,9 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
 // HEAD_IMGS rows per CTA share one pass over the projection matrix.
 constexpr int HEAD_IMGS = 8, HEAD_THREADS = 256, HEAD_MAXCOL = 4;  // embed <= 1024
 
+// MAXCOL = ceil(embed / HEAD_THREADS): output columns per thread (2 for E = 512), so that no zero-weight columns
+// are multiplied; the normalised rows are read from shared memory four features at a time.
+template <int MAXCOL>
 __global__ void __launch_bounds__(HEAD_THREADS)
 head_kernel(const bf16* __restrict__ x, int64_t row_stride, const int32_t* __restrict__ row_index,
             const float* __restrict__ gamma, const float* __restrict__ beta, const bf16* __restrict__ proj, int n,
@@ -651,25 +654,32 @@ head_kernel(const bf16* __restrict__ x, int64_t row_stride, const int32_t* __res
         }
     }
     __syncthreads();
-    // (2) projection: thread owns columns threadIdx.x + c*HEAD_THREADS
-    float acc[HEAD_MAXCOL][HEAD_IMGS];
+    // (2) projection: thread owns columns threadIdx.x + c*HEAD_THREADS; accumulation runs over d in order (the
+    // vectorised shared-memory reads do not change the summation order)
+    float acc[MAXCOL][HEAD_IMGS];
 #pragma unroll
-    for (int c = 0; c < HEAD_MAXCOL; ++c)
+    for (int c = 0; c < MAXCOL; ++c)
 #pragma unroll
         for (int i = 0; i < HEAD_IMGS; ++i) acc[c][i] = 0.f;
-#pragma unroll 8
-    for (int d = 0; d < width; ++d) {
-        float w[HEAD_MAXCOL];
+    for (int d0 = 0; d0 < width; d0 += 4) {      // width % 4 == 0 (checked by the launcher)
+        float w[4][MAXCOL];
 #pragma unroll
-        for (int c = 0; c < HEAD_MAXCOL; ++c) {
-            const int col = threadIdx.x + c * HEAD_THREADS;
-            w[c] = col < embed ? __bfloat162float(proj[static_cast<int64_t>(d) * embed + col]) : 0.f;
-        }
+        for (int dd = 0; dd < 4; ++dd)
+#pragma unroll
+            for (int c = 0; c < MAXCOL; ++c) {
+                const int col = threadIdx.x + c * HEAD_THREADS;
+                w[dd][c] = col < embed ? __bfloat162float(proj[static_cast<int64_t>(d0 + dd) * embed + col]) : 0.f;
+            }
 #pragma unroll
         for (int i = 0; i < HEAD_IMGS; ++i) {
-            const float xv = xs[i * width + d];
+            const float4 xv = *reinterpret_cast<const float4*>(xs + i * width + d0);
 #pragma unroll
-            for (int c = 0; c < HEAD_MAXCOL; ++c) acc[c][i] = fmaf(xv, w[c], acc[c][i]);
+            for (int c = 0; c < MAXCOL; ++c) {
+                float a = acc[c][i];
+                a = fmaf(xv.x, w[0][c], a); a = fmaf(xv.y, w[1][c], a);
+                a = fmaf(xv.z, w[2][c], a); a = fmaf(xv.w, w[3][c], a);
+                acc[c][i] = a;
+            }
         }
     }
     // (3) L2 norm per image
@@ -679,7 +689,7 @@ head_kernel(const bf16* __restrict__ x, int64_t row_stride, const int32_t* __res
         for (int i = 0; i < HEAD_IMGS; ++i) {
             float sq = 0.f;
 #pragma unroll
-            for (int c = 0; c < HEAD_MAXCOL; ++c) sq += acc[c][i] * acc[c][i];
+            for (int c = 0; c < MAXCOL; ++c) sq += acc[c][i] * acc[c][i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
             if (lane == 0) red[i * (HEAD_THREADS / 32) + warp] = sq;
@@ -701,7 +711,7 @@ head_kernel(const bf16* __restrict__ x, int64_t row_stride, const int32_t* __res
         const int img = img0 + i;
         if (img >= n) break;
 #pragma unroll
-        for (int c = 0; c < HEAD_MAXCOL; ++c) {
+        for (int c = 0; c < MAXCOL; ++c) {
             const int col = threadIdx.x + c * HEAD_THREADS;
             if (col < embed) {
                 const float v = acc[c][i] * inv[i];
@@ -719,16 +729,16 @@ int launch_head(b200clip_handle* h, const bf16* x, int64_t row_stride, const int
                 int l2norm, cudaStream_t st) {
     if (n <= 0) return 0;
     if (embed > HEAD_MAXCOL * HEAD_THREADS) return b200_fail(h, B200CLIP_E_SHAPE, "head: embed_dim %d too large", embed);
+    if (width % 4 != 0) return b200_fail(h, B200CLIP_E_SHAPE, "head: width %d must be a multiple of 4", width);
     const size_t smem = (static_cast<size_t>(HEAD_IMGS) * width + HEAD_IMGS * (HEAD_THREADS / 32)) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
-        B200_CUDA(h, cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set = true;
-    }
+    const int maxcol = (embed + HEAD_THREADS - 1) / HEAD_THREADS;
+    auto kern = maxcol <= 1 ? head_kernel<1> : maxcol == 2 ? head_kernel<2> : maxcol == 3 ? head_kernel<3> : head_kernel<4>;
+    if (smem > 48 * 1024)
+        B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     const int blocks = (n + HEAD_IMGS - 1) / HEAD_IMGS;
     ProfScope ps(h, PROF_HEAD, static_cast<double>(n) * (width * 2.0 + embed * 4.0) + static_cast<double>(width) * embed * 2.0, st);
-    head_kernel<<<blocks, HEAD_THREADS, smem, st>>>(x, row_stride, row_index, g, b, proj, n, width, embed, eps, out,
-                                                    out_dtype, l2norm);
+    kern<<<blocks, HEAD_THREADS, smem, st>>>(x, row_stride, row_index, g, b, proj, n, width, embed, eps, out, out_dtype,
+                                             l2norm);
     h->launches++;
     B200_CUDA(h, cudaGetLastError());
     return 0;
