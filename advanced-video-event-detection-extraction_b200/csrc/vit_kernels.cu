@@ -558,6 +558,175 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* 
     }
 }
 
+// ---------------------------------------------------------------------------- K/V-resident variant
+// Mid-length sequences without a mask (ViT-L/14: T = 257, 16 heads).  One CTA per (sequence, head): ALL keys and
+// values of the head (ceil(T/64) TMA boxes each, 128-byte swizzle) are loaded ONCE and stay in shared memory, and each
+// of the 6 warps walks its 16-row query tiles (tile = warp, warp + 6, warp + 12 ...) over the resident key blocks with
+// an online softmax -- no block-wide barrier inside the key loop and no re-read of K/V per query tile (the tiled
+// kernel above re-loads them for each of its 5 query tiles and synchronises the CTA twice per key block).
+constexpr int ATS_WARPS = 6, ATS_THREADS = ATS_WARPS * 32, ATS_MAX_BLOCKS = 5;      // T <= 320
+__global__ void __launch_bounds__(ATS_THREADS, 2)
+attention_seq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* __restrict__ qkv,
+                     bf16* __restrict__ out, int T, int heads) {
+    extern __shared__ uint8_t ats_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ats_raw) + 1023) & ~uintptr_t(1023));
+    const int nb = (T + ATT_BK - 1) / ATT_BK;
+    uint8_t* sK = base;                                   // [nb][64 rows x 128 B]
+    uint8_t* sV = base + nb * ATT_BK * 128;
+    uint8_t* sW = sV + nb * ATT_BK * 128;                 // per warp: 16 rows x 128 B (Q tile in, O tile out)
+    uint64_t* kv_bar = reinterpret_cast<uint64_t*>(sW + ATS_WARPS * 16 * 128);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int head = blockIdx.x;
+    const int64_t seq = blockIdx.y;
+    const int D = heads * ATT_D;
+    const int64_t ld = 3 * static_cast<int64_t>(D);
+
+    if (threadIdx.x == 0) {
+        mbar_init(kv_bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(kv_bar, 2u * nb * ATT_BK * 128u);
+        for (int b = 0; b < nb; ++b) {
+            tma_load_2d(sK + b * ATT_BK * 128, &tmap_qkv, kv_bar, D + head * ATT_D, static_cast<int>(seq) * T + b * ATT_BK);
+            tma_load_2d(sV + b * ATT_BK * 128, &tmap_qkv, kv_bar, 2 * D + head * ATT_D, static_cast<int>(seq) * T + b * ATT_BK);
+        }
+    }
+    const float scale_log2 = 0.125f * 1.4426950408889634f;
+    const bf16* qbase = qkv + seq * T * ld + head * ATT_D;
+    bf16* obase = out + seq * T * static_cast<int64_t>(D) + head * ATT_D;
+    uint8_t* sq = sW + warp * 16 * 128;
+    const uint32_t sqa = smem_u32(sq);
+    bool kv_ready = false;
+    for (int q0 = warp * 16; q0 < T; q0 += ATS_WARPS * 16) {
+        // ---- this warp's 16 query rows -> its staging tile (rows >= T zero filled) -> A fragments
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int id = lane + i * 32;
+            const int r = id >> 3, c = id & 7;
+            const bool ok = q0 + r < T;
+            cp_async_16(sqa + sw_off(r, c), qbase + static_cast<int64_t>(ok ? q0 + r : 0) * ld + c * 8, ok);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncwarp();
+        uint32_t qf[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            ldmatrix_x4(sqa + sw_off(lane & 15, ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+        if (!kv_ready) { mbar_wait(kv_bar, 0, 31); kv_ready = true; }
+        float o_acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { o_acc[j][0] = o_acc[j][1] = o_acc[j][2] = o_acc[j][3] = 0.f; }
+        float m_run[2] = {-INFINITY, -INFINITY};
+        float l_run[2] = {0.f, 0.f};
+        for (int b = 0; b < nb; ++b) {
+            const int k0 = b * ATT_BK;
+            const int kv_valid = min(ATT_BK, T - k0);
+            const int jmax = (kv_valid + 7) >> 3;
+            const uint32_t kb = smem_u32(sK + b * ATT_BK * 128), vb = smem_u32(sV + b * ATT_BK * 128);
+            float s[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                for (int jp = 0; jp < 4; ++jp) {
+                    if (jp * 2 >= jmax) continue;
+                    uint32_t b0, b1, b2, b3;
+                    const int r = jp * 16 + (lane & 7) + ((lane >> 4) << 3);
+                    const int c = ks * 2 + ((lane >> 3) & 1);
+                    ldmatrix_x4(kb + sw_off(r, c), b0, b1, b2, b3);
+                    mma_bf16_16816(s[jp * 2], qf[ks], b0, b1);
+                    mma_bf16_16816(s[jp * 2 + 1], qf[ks], b2, b3);
+                }
+            }
+            if (kv_valid < ATT_BK) {                    // the block that straddles the end of the sequence
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (j * 8 + t4 * 2 + (e & 1) >= kv_valid) s[j][e] = -INFINITY;
+            }
+            float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
+                mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
+            }
+            float corr[2], nm[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+                const float m_new = fmaxf(m_run[r], mx[r]);         // finite: every block holds >= 1 valid key
+                corr[r] = ex2_approx((m_run[r] - m_new) * scale_log2);
+                nm[r] = -m_new * scale_log2;
+                m_run[r] = m_new;
+            }
+            float rs[2] = {0.f, 0.f};
+            uint32_t pf[4][4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float p0 = ex2_approx(fmaf(s[j][0], scale_log2, nm[0]));
+                const float p1 = ex2_approx(fmaf(s[j][1], scale_log2, nm[0]));
+                const float p2 = ex2_approx(fmaf(s[j][2], scale_log2, nm[1]));
+                const float p3 = ex2_approx(fmaf(s[j][3], scale_log2, nm[1]));
+                rs[0] += p0 + p1;
+                rs[1] += p2 + p3;
+                pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+                pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                o_acc[j][0] *= corr[0]; o_acc[j][1] *= corr[0];
+                o_acc[j][2] *= corr[1]; o_acc[j][3] *= corr[1];
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                if (ks * 16 >= kv_valid) continue;      // P is exactly 0 there
+#pragma unroll
+                for (int jp = 0; jp < 4; ++jp) {
+                    uint32_t b0, b1, b2, b3;
+                    const int r = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+                    const int c = jp * 2 + (lane >> 4);
+                    ldmatrix_x4_trans(vb + sw_off(r, c), b0, b1, b2, b3);
+                    mma_bf16_16816(o_acc[jp * 2], pf[ks], b0, b1);
+                    mma_bf16_16816(o_acc[jp * 2 + 1], pf[ks], b2, b3);
+                }
+            }
+        }
+        // ---- normalise, stage through this warp's tile, coalesced 16-byte stores
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+            l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+        }
+        const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            *reinterpret_cast<uint32_t*>(sq + sw_off(g, j) + t4 * 4) = pack_bf16x2(o_acc[j][0] * inv0, o_acc[j][1] * inv0);
+            *reinterpret_cast<uint32_t*>(sq + sw_off(g + 8, j) + t4 * 4) = pack_bf16x2(o_acc[j][2] * inv1, o_acc[j][3] * inv1);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int id = lane + i * 32;
+            const int r = id >> 3, c = id & 7;
+            if (q0 + r < T) {
+                const uint4 v = *reinterpret_cast<const uint4*>(sq + sw_off(r, c));
+                *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(q0 + r) * D + c * 8) = v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 int make_tmap_bf16_2d(b200clip_handle* h, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz);
 
@@ -588,6 +757,22 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
         ProfScope ps(h, PROF_ATTN, static_cast<double>(n_seq) * t * heads * ATT_D * 2.0 * 4.0, st);
         attention_persistent_kernel<<<static_cast<unsigned>(grid), ATT_THREADS, ATP_SMEM_BYTES, st>>>(
             tq, out, t, heads, static_cast<int>(n_items));
+        h->launches++;
+        B200_CUDA(h, cudaGetLastError());
+        return 0;
+    }
+    static const bool no_seq = getenv("B200CLIP_ATTN_TILED") != nullptr;            // parity tests cover both
+    if (!causal && t > ATT_BK && t <= ATS_MAX_BLOCKS * ATT_BK && !no_seq && n_seq <= 65535 &&
+        static_cast<int64_t>(n_seq) * t < (int64_t(1) << 31) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) {
+        CUtensorMap tq;
+        int rc = make_tmap_bf16_2d(h, &tq, qkv, static_cast<uint64_t>(n_seq) * t, 3ull * heads * ATT_D, 3ull * heads * ATT_D,
+                                   ATT_BK, ATT_D, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        const int nb = (t + ATT_BK - 1) / ATT_BK;
+        const int smem = 1024 + 2 * nb * ATT_BK * 128 + ATS_WARPS * 16 * 128 + 64;
+        B200_CUDA(h, cudaFuncSetAttribute(attention_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ProfScope ps(h, PROF_ATTN, static_cast<double>(n_seq) * t * heads * ATT_D * 2.0 * 4.0, st);
+        attention_seq_kernel<<<dim3(heads, n_seq), ATS_THREADS, smem, st>>>(tq, qkv, out, t, heads);
         h->launches++;
         B200_CUDA(h, cudaGetLastError());
         return 0;

@@ -78,7 +78,11 @@ def test_layernorm_matches_torch(handle, rows, width):
                                                     (1, 16, 1, 1), (70, 50, 12, 0), (1, 64, 2, 1), (1, 65, 2, 0),
                                                     # >= 296 (sequence, head) items, T <= 64, no mask: persistent TMA-fed kernel
                                                     (300, 50, 12, 0), (40, 64, 8, 0), (100, 33, 4, 0), (500, 1, 1, 0),
-                                                    (37, 7, 9, 0)])
+                                                    (37, 7, 9, 0),
+                                                    # 64 < T <= 320, no mask: K/V-resident kernel (one CTA per sequence and head)
+                                                    (3, 257, 16, 0), (5, 100, 4, 0), (2, 320, 2, 0), (1, 129, 1, 0), (4, 96, 3, 0),
+                                                    # beyond it / causal: the tiled kernel
+                                                    (1, 321, 2, 0), (2, 200, 4, 1)])
 def test_attention_matches_torch(handle, n_seq, t, heads, causal):
     from b200clip import capi
 
