@@ -727,6 +727,247 @@ attention_seq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* _
     }
 }
 
+// ---------------------------------------------------------------------------- tcgen05 variant
+// Attention on the 5th-generation tensor cores for mid-length sequences without a mask (ViT-L/14: T = 257).
+// One CTA per (sequence, head); K and V of the head are TMA-loaded once and stay resident, Q streams tile by tile.
+//   S  = Q_tile[128 x 64] . K_b[64 keys x 64]^T   tcgen05.mma M=128, N=64 (N=16 for the last, partial block), both
+//                                                  operands K-major; S lives in TMEM (two 64-column buffers)
+//   P  = exp2(scale*S - max)                       4 softmax warps, one query row per thread: tcgen05.ld S -> registers,
+//                                                  online softmax, P (bf16) -> shared memory in the K-major swizzle
+//   PV = P[128 x 64 keys] . V_b[64 keys x 64]      tcgen05.mma M=128, N=64 with V consumed as an MN-MAJOR B operand
+//                                                  (a TMA box of V rows is exactly that layout; SBO = 1024 B, 2048 B
+//                                                  per 16-key step -- pinned by tools/probes/umma_mn_probe.cu)
+//   O  = O*corr + PV                               in registers (64 fp32 per thread), normalised and stored per tile
+// A single thread issues all MMAs and runs one step ahead of the softmax warps (S is double buffered), so the tensor
+// core works on block b+1 while block b is exponentiated.  192 threads, ~100 KB of shared memory, 256 TMEM columns:
+// two CTAs per SM overlap each other's load and drain phases.
+constexpr int ATC_BM = 128, ATC_BN = 64, ATC_THREADS = 192, ATC_MAX_KB = 5;          // T <= 320
+struct AtcLayout {           // byte offsets inside the 1024-byte aligned dynamic shared memory
+    int q, k, v, p, bars, total;
+};
+__host__ __device__ inline AtcLayout atc_layout(int T) {
+    const int nk = (T + ATC_BN - 1) / ATC_BN;
+    const int last = T - (nk - 1) * ATC_BN;                       // keys in the last block
+    const int last_rows = last <= 16 ? 16 : ATC_BN;               // its TMA box
+    const int kv_bytes = ((nk - 1) * ATC_BN + last_rows) * 128;
+    AtcLayout l;
+    l.q = 0;
+    l.k = ATC_BM * 128;
+    l.v = l.k + ((kv_bytes + 1023) & ~1023);
+    l.p = l.v + ((kv_bytes + 1023) & ~1023);
+    l.bars = l.p + ATC_BM * 128;
+    l.total = l.bars + 128;
+    return l;
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constant__ CUtensorMap tmap_kv64,
+                    const __grid_constant__ CUtensorMap tmap_kv16, bf16* __restrict__ out, int T, int heads) {
+    extern __shared__ uint8_t atc_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atc_raw) + 1023) & ~uintptr_t(1023));
+    const AtcLayout L = atc_layout(T);
+    uint8_t* sQ = base + L.q;
+    uint8_t* sK = base + L.k;
+    uint8_t* sV = base + L.v;
+    uint8_t* sP = base + L.p;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + L.bars);
+    uint64_t* kv_bar = bars;            // K and V resident
+    uint64_t* q_bar = bars + 1;         // Q tile t loaded                  (phase t & 1)
+    uint64_t* q_free = bars + 2;        // last S-MMA of tile t committed    (phase t & 1)
+    uint64_t* s_full = bars + 3;        // [2] S buffer written              (phase (i >> 1) & 1)
+    uint64_t* s_free = bars + 5;        // [2] S buffer read by the softmax warps
+    uint64_t* p_full = bars + 7;        // P of step i in shared memory      (phase i & 1)
+    uint64_t* pv_full = bars + 8;       // PV of step i in TMEM, P consumed  (phase i & 1)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = blockIdx.x;
+    const int seq = blockIdx.y;
+    const int D = heads * ATT_D;
+    const int nq = (T + ATC_BM - 1) / ATC_BM;
+    const int nk = (T + ATC_BN - 1) / ATC_BN;
+    const int last_keys = T - (nk - 1) * ATC_BN;
+    const bool last_small = last_keys <= 16;
+    const int nsteps = nq * nk;
+
+    if (threadIdx.x == 0) {
+        mbar_init(kv_bar, 1); mbar_init(q_bar, 1); mbar_init(q_free, 1);
+        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+        mbar_init(&s_free[0], 4); mbar_init(&s_free[1], 4);
+        mbar_init(p_full, 4); mbar_init(pv_full, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmap_q128); tma_prefetch_desc(&tmap_kv64); tma_prefetch_desc(&tmap_kv16);
+    }
+    if (warp == 5) tmem_alloc<1>(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;          // columns: S0 [0,64)  S1 [64,128)  PV [128,192)
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const int row0 = seq * T;
+            const uint32_t kv_tx = 2u * static_cast<uint32_t>(((nk - 1) * ATC_BN + (last_small ? 16 : ATC_BN)) * 128);
+            mbar_arrive_expect_tx(kv_bar, kv_tx);
+            for (int b = 0; b < nk; ++b) {
+                const CUtensorMap* m = (b == nk - 1 && last_small) ? &tmap_kv16 : &tmap_kv64;
+                tma_load_2d(sK + b * ATC_BN * 128, m, kv_bar, D + head * ATT_D, row0 + b * ATC_BN);
+                tma_load_2d(sV + b * ATC_BN * 128, m, kv_bar, 2 * D + head * ATT_D, row0 + b * ATC_BN);
+            }
+            for (int t = 0; t < nq; ++t) {
+                if (t > 0) mbar_wait(q_free, (t - 1) & 1, 41);       // the S-MMAs of tile t-1 no longer read sQ
+                mbar_arrive_expect_tx(q_bar, ATC_BM * 128);
+                tma_load_2d(sQ, &tmap_q128, q_bar, head * ATT_D, row0 + t * ATC_BM);
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc_pv = make_idesc_bf16(ATC_BM, ATT_D) | (1u << 16);   // B (= V) MN-major
+            auto issue_s = [&](int i) {
+                const int t = i / nk, b = i - t * nk;
+                if (b == 0) { mbar_wait(q_bar, t & 1, 42); }
+                if (i >= 2) mbar_wait(&s_free[i & 1], ((i >> 1) - 1) & 1, 43);
+                tc_fence_after();
+                const int n_cols = (b == nk - 1) ? ((last_keys + 15) & ~15) : ATC_BN;
+                const uint32_t idesc = make_idesc_bf16(ATC_BM, n_cols);
+                const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(sQ));
+                const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sK + b * ATC_BN * 128));
+#pragma unroll
+                for (int k = 0; k < ATT_D / 16; ++k)
+                    umma_bf16<1>(tmem + (i & 1) * ATC_BN, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0);
+                umma_commit(&s_full[i & 1]);
+                if (b == nk - 1) umma_commit(q_free);
+            };
+            mbar_wait(kv_bar, 0, 44);
+            issue_s(0);
+            for (int i = 0; i < nsteps; ++i) {
+                if (i + 1 < nsteps) issue_s(i + 1);
+                const int b = i % nk;
+                const int kv_valid = (b == nk - 1) ? last_keys : ATC_BN;
+                mbar_wait(p_full, i & 1, 45);
+                tc_fence_after();
+                const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(sP));
+                uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sV + b * ATC_BN * 128));   // SBO = 1024: MN-major too
+                const int ksteps = (kv_valid + 15) >> 4;
+                for (int k = 0; k < ksteps; ++k)
+                    umma_bf16<1>(tmem + 2 * ATC_BN, adesc + 2 * k, bdesc + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv,
+                                 k != 0);
+                umma_commit(pv_full);
+            }
+        }
+    } else {
+        // ===================== softmax warps: one query row per thread =====================
+        const int row_in_tile = warp * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+        const float scale_log2 = 0.125f * 1.4426950408889634f;
+        float o[ATT_D];
+#pragma unroll
+        for (int j = 0; j < ATT_D; ++j) o[j] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;
+        uint8_t* prow = sP + row_in_tile * 128;
+        auto add_pv = [&]() {      // o += PV (TMEM columns [128, 192)), 32 columns at a time
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t pr[32];
+                tmem_ld_32x32(tmem + lane_addr + 2 * ATC_BN + hh * 32, pr);
+                tmem_ld_wait_regs(pr);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[hh * 32 + j] += __uint_as_float(pr[j]);
+            }
+        };
+        for (int i = 0; i < nsteps; ++i) {
+            const int t = i / nk, b = i - t * nk;
+            const int kv_valid = (b == nk - 1) ? last_keys : ATC_BN;
+            const bool warp_rows = t * ATC_BM + warp * 32 < T;          // warp-uniform
+            // (1) the PV of the previous block of this tile joins O (still relative to the previous maximum); waiting
+            //     for it also guarantees that the tensor core has finished reading the previous P from shared memory
+            if (i > 0) {
+                mbar_wait(pv_full, (i - 1) & 1, 47);
+                if (b > 0) { tc_fence_after(); add_pv(); }
+            }
+            // (2) S of this block -> registers, buffer handed back to the MMA issuer
+            uint32_t sa[32], sb[32];
+            mbar_wait(&s_full[i & 1], (i >> 1) & 1, 46);
+            tc_fence_after();
+            tmem_ld_32x32(tmem + lane_addr + (i & 1) * ATC_BN, sa);
+            if (kv_valid > 32) tmem_ld_32x32(tmem + lane_addr + (i & 1) * ATC_BN + 32, sb);
+            tmem_ld_wait_regs(sa);
+            if (kv_valid > 32) tmem_ld_wait_regs(sb);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[i & 1]);
+            // (3) online softmax on the row
+            if (kv_valid < ATC_BN) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (j >= kv_valid) sa[j] = 0xff800000u;          // -inf
+                    if (32 + j >= kv_valid) sb[j] = 0xff800000u;
+                }
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(sa[j]), __uint_as_float(sb[j])));
+            const float m_new = fmaxf(m_run, mx);                        // finite: every block has >= 1 valid key
+            const float corr = ex2_approx((m_run - m_new) * scale_log2);
+            const float nm = -m_new * scale_log2;
+            float rs = 0.f;
+            if (warp_rows) {
+#pragma unroll
+                for (int j = 0; j < ATT_D; ++j) o[j] *= corr;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float pv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int j = c * 8 + e;
+                        pv[e] = ex2_approx(fmaf(__uint_as_float(j < 32 ? sa[j] : sb[j - 32]), scale_log2, nm));
+                        rs += pv[e];
+                    }
+                    uint4 w;
+                    w.x = pack_bf16x2(pv[0], pv[1]); w.y = pack_bf16x2(pv[2], pv[3]);
+                    w.z = pack_bf16x2(pv[4], pv[5]); w.w = pack_bf16x2(pv[6], pv[7]);
+                    *reinterpret_cast<uint4*>(prow + ((c ^ (row_in_tile & 7)) << 4)) = w;
+                }
+            }
+            l_run = l_run * corr + rs;
+            m_run = m_new;
+            // (4) P (generic proxy writes) -> visible to the tensor core (async proxy), then hand it over
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+            if (b == nk - 1) {
+                // (5) end of the tile: last PV, normalise, store this thread's row, reset the running state
+                mbar_wait(pv_full, i & 1, 48);
+                tc_fence_after();
+                add_pv();
+                const int row = t * ATC_BM + row_in_tile;
+                if (row < T) {
+                    const float inv = 1.f / l_run;
+                    bf16* orow = out + (static_cast<int64_t>(seq) * T + row) * D + head * ATT_D;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint4 w;
+                        w.x = pack_bf16x2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv);
+                        w.y = pack_bf16x2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
+                        w.z = pack_bf16x2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv);
+                        w.w = pack_bf16x2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
+                        *reinterpret_cast<uint4*>(orow + c * 8) = w;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < ATT_D; ++j) o[j] = 0.f;
+                m_run = -INFINITY; l_run = 0.f;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) { tc_fence_after(); tmem_dealloc<1>(tmem, 256); }
+}
+
 int make_tmap_bf16_2d(b200clip_handle* h, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz);
 
@@ -757,6 +998,25 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
         ProfScope ps(h, PROF_ATTN, static_cast<double>(n_seq) * t * heads * ATT_D * 2.0 * 4.0, st);
         attention_persistent_kernel<<<static_cast<unsigned>(grid), ATT_THREADS, ATP_SMEM_BYTES, st>>>(
             tq, out, t, heads, static_cast<int>(n_items));
+        h->launches++;
+        B200_CUDA(h, cudaGetLastError());
+        return 0;
+    }
+    // opt-in while it is slower than the mma.sync K/V-resident kernel (24.5 vs 18.7 ms per 512 L/14 frames: four softmax
+    // warps per CTA cannot keep up with the tensor core)
+    static const bool no_tc = getenv("B200CLIP_ATTN_TC") == nullptr;
+    if (!causal && t > ATT_BK && t <= ATC_MAX_KB * ATC_BN && !no_tc && n_seq <= 65535 &&
+        static_cast<int64_t>(n_seq) * t < (int64_t(1) << 31) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) {
+        CUtensorMap tq, t64, t16;
+        const uint64_t rows = static_cast<uint64_t>(n_seq) * t, cols = 3ull * heads * ATT_D;
+        int rc;
+        if ((rc = make_tmap_bf16_2d(h, &tq, qkv, rows, cols, cols, ATC_BM, ATT_D, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tmap_bf16_2d(h, &t64, qkv, rows, cols, cols, ATC_BN, ATT_D, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tmap_bf16_2d(h, &t16, qkv, rows, cols, cols, 16, ATT_D, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        const int smem = atc_layout(t).total + 1024;
+        B200_CUDA(h, cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ProfScope ps(h, PROF_ATTN, static_cast<double>(n_seq) * t * heads * ATT_D * 2.0 * 4.0, st);
+        attention_tc_kernel<<<dim3(heads, n_seq), ATC_THREADS, smem, st>>>(tq, t64, t16, out, t, heads);
         h->launches++;
         B200_CUDA(h, cudaGetLastError());
         return 0;

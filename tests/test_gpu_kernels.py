@@ -100,3 +100,38 @@ def test_attention_matches_torch(handle, n_seq, t, heads, causal):
     assert not torch.isnan(out.float()).any()
     # P is rounded to bf16 before the PV product and the output is bf16
     assert float((out.float() - ref).abs().max()) <= 0.03
+
+
+def test_attention_kernel_variants_in_subprocess():
+    """The attention kernel for 64 < T <= 320 is chosen once per process: default = mma.sync with resident K/V,
+    B200CLIP_ATTN_TC=1 = tcgen05 (S and PV on the 5th-generation tensor cores, V as an MN-major operand),
+    B200CLIP_ATTN_TILED=1 = the tiled fallback.  All three must match torch on the ViT-L/14 shape and friends."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import ctypes, sys, torch
+sys.path.insert(0, %r)
+from b200clip import capi
+from b200clip.model_configs import MODEL_CONFIGS, to_capi_config
+h = capi.Handle(to_capi_config(MODEL_CONFIGS["ViT-B-32"]), 0)
+st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+for n_seq, t, heads in [(3, 257, 16), (5, 100, 4), (2, 320, 2), (1, 129, 1), (4, 96, 3), (2, 65, 2), (7, 145, 5)]:
+    torch.manual_seed(t * heads)
+    d = heads * 64
+    qkv = (torch.randn(n_seq * t, 3 * d, device="cuda") * 1.5).bfloat16()
+    out = torch.full((n_seq * t, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    h.call("b200clip_attention_bf16", capi._p(qkv), capi._p(out), n_seq, t, heads, 0, st)
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(n_seq, t, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax((q @ k.transpose(-1, -2)) * 0.125, -1) @ v).permute(0, 2, 1, 3).reshape(n_seq * t, d)
+    err = float((out.float() - ref).abs().max())
+    assert not torch.isnan(out.float()).any() and err <= 0.03, (n_seq, t, heads, err)
+print("variant ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for env in ({}, {"B200CLIP_ATTN_TC": "1"}, {"B200CLIP_ATTN_TILED": "1"}):
+        e = {k: v for k, v in os.environ.items() if not k.startswith("B200CLIP_ATTN")}
+        e.update(env)
+        r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "variant ok" in r.stdout, (env, r.stdout[-1500:], r.stderr[-1500:])
