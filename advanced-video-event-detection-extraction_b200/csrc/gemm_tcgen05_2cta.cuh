@@ -66,7 +66,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
                               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                               __nv_bfloat16* out, int ldc, int M, int N, int K, GemmEpilogue ep, int use_tma_epi) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)   /* pointer arithmetic keeps the shared address space: LDS/STS, not generic LD/ST */;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + G2_STAGES * G2_A_BYTES;
     uint8_t* staging = smem + G2_STAGES * G2_STAGE_BYTES;   // 1024-byte aligned

@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 4)
 attention_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* __restrict__ out, int T, int heads,
                             int n_items) {
     extern __shared__ uint8_t atp_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atp_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* base = atp_raw + ((1024u - (smem_u32(atp_raw) & 1023u)) & 1023u)   /* pointer arithmetic keeps the shared address space: LDS/STS, not generic LD/ST */;
     uint8_t* stages = base;                                             // 1024-byte aligned (swizzle atom)
     uint8_t* sO = base + ATP_STAGES * ATP_STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sO + ATP_SO_BYTES);
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(ATS_THREADS, 2)
 attention_seq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* __restrict__ qkv,
                      bf16* __restrict__ out, int T, int heads) {
     extern __shared__ uint8_t ats_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ats_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* base = ats_raw + ((1024u - (smem_u32(ats_raw) & 1023u)) & 1023u)   /* pointer arithmetic keeps the shared address space: LDS/STS, not generic LD/ST */;
     const int nb = (T + ATT_BK - 1) / ATT_BK;
     uint8_t* sK = base;                                   // [nb][64 rows x 128 B]
     uint8_t* sV = base + nb * ATT_BK * 128;
@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constant__ CUtensorMap tmap_kv64,
                     const __grid_constant__ CUtensorMap tmap_kv16, bf16* __restrict__ out, int T, int heads) {
     extern __shared__ uint8_t atc_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atc_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* base = atc_raw + ((1024u - (smem_u32(atc_raw) & 1023u)) & 1023u)   /* pointer arithmetic keeps the shared address space: LDS/STS, not generic LD/ST */;
     const AtcLayout L = atc_layout(T);
     uint8_t* sQ = base + L.q;
     uint8_t* sK = base + L.k;

@@ -117,7 +117,8 @@ from b200clip import capi
 from b200clip.model_configs import MODEL_CONFIGS, to_capi_config
 h = capi.Handle(to_capi_config(MODEL_CONFIGS["ViT-B-32"]), 0)
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-for n_seq, t, heads in [(3, 257, 16), (5, 100, 4), (2, 320, 2), (1, 129, 1), (4, 96, 3), (2, 65, 2), (7, 145, 5)]:
+for n_seq, t, heads in [(3, 257, 16), (5, 100, 4), (2, 320, 2), (1, 129, 1), (4, 96, 3), (2, 65, 2), (7, 145, 5), (2, 130, 2),
+                          (2, 196, 3), (1, 258, 1), (3, 197, 12), (2, 260, 2), (1, 68, 1)]:
     torch.manual_seed(t * heads)
     d = heads * 64
     qkv = (torch.randn(n_seq * t, 3 * d, device="cuda") * 1.5).bfloat16()
