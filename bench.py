@@ -259,7 +259,9 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     emb_dev_ref, txt_ref, s_ref, i_ref = out[0], out[1], out[2], out[3]
     host_frames = None
     if not args.no_e2e:
-        n_host = n if world == 1 else min(n, 900)
+        # pinned host frames per rank: the whole batch on one GPU, smaller slices (re-used `calls` times per step) when
+        # several ranks share the host's pinned-memory budget (8 ranks x 450 frames x 6.2 MB = 22 GB)
+        n_host = n if world == 1 else min(n, 900 if world <= 2 else 450)
         calls = -(-n // n_host)
         host_frames = torch.empty(n_host, H, W, 3, dtype=torch.uint8, pin_memory=True)
         host_frames.copy_(frames[:n_host])
