@@ -570,7 +570,12 @@ attention_seq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* _
                      bf16* __restrict__ out, int T, int heads) {
     extern __shared__ uint8_t ats_raw[];
     uint8_t* base = ats_raw + ((1024u - (smem_u32(ats_raw) & 1023u)) & 1023u)   /* pointer arithmetic keeps the shared address space: LDS/STS, not generic LD/ST */;
-    const int nb = (T + ATT_BK - 1) / ATT_BK;
+    const int nb = (T + ATT_BK - 1) / ATT_BK;             // key blocks resident in shared memory
+    // T = 257 = 4*64 + 1: a fifth block for ONE key would cost a fifth of the exponentials and MMAs.  Up to 4 such
+    // remainder keys are instead scored on the CUDA cores from the Q fragments (quad reduction), join the softmax of the
+    // last full block and add p * V[key] to O in fp32.
+    const int xk = (T > ATT_BK && T % ATT_BK >= 1 && T % ATT_BK <= 4) ? T % ATT_BK : 0;
+    const int nbr = xk ? nb - 1 : nb;                     // blocks that run on the tensor cores
     uint8_t* sK = base;                                   // [nb][64 rows x 128 B]
     uint8_t* sV = base + nb * ATT_BK * 128;
     uint8_t* sW = sV + nb * ATT_BK * 128;                 // per warp: 16 rows x 128 B (Q tile in, O tile out)
@@ -622,9 +627,9 @@ attention_seq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* _
         for (int j = 0; j < 8; ++j) { o_acc[j][0] = o_acc[j][1] = o_acc[j][2] = o_acc[j][3] = 0.f; }
         float m_run[2] = {-INFINITY, -INFINITY};
         float l_run[2] = {0.f, 0.f};
-        for (int b = 0; b < nb; ++b) {
+        for (int b = 0; b < nbr; ++b) {
             const int k0 = b * ATT_BK;
-            const int kv_valid = min(ATT_BK, T - k0);
+            const int kv_valid = min(ATT_BK, T - xk - k0);
             const int jmax = (kv_valid + 7) >> 3;
             const uint32_t kb = smem_u32(sK + b * ATT_BK * 128), vb = smem_u32(sV + b * ATT_BK * 128);
             float s[8][4];
@@ -656,6 +661,36 @@ attention_seq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* _
                 mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
                 mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
             }
+            // remainder keys (last full block only): q . k on the CUDA cores.  A-fragment layout: qf[ks][0] / [2] hold
+            // row g at columns ks*16 + t4*2 (+1) / +8 (+9), qf[ks][1] / [3] the same columns of row g + 8.
+            const bool with_x = xk && b == nbr - 1;
+            float sx[4][2];
+            if (with_x) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    sx[e][0] = sx[e][1] = -INFINITY;
+                    if (e < xk) {
+                        const int r = ATT_BK * nbr + e;              // row inside the resident K / V tiles
+                        const uint8_t* kr = sK + (r >> 6) * ATT_BK * 128 + (r & 63) * 128;
+                        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const float2 k0v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(kr + (((ks * 2) ^ (r & 7)) << 4) + t4 * 4));
+                            const float2 k1v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(kr + (((ks * 2 + 1) ^ (r & 7)) << 4) + t4 * 4));
+                            float2 q;
+                            q = unpack_bf16x2(qf[ks][0]); a0 = fmaf(q.x, k0v.x, a0); a0 = fmaf(q.y, k0v.y, a0);
+                            q = unpack_bf16x2(qf[ks][2]); a0 = fmaf(q.x, k1v.x, a0); a0 = fmaf(q.y, k1v.y, a0);
+                            q = unpack_bf16x2(qf[ks][1]); a1 = fmaf(q.x, k0v.x, a1); a1 = fmaf(q.y, k0v.y, a1);
+                            q = unpack_bf16x2(qf[ks][3]); a1 = fmaf(q.x, k1v.x, a1); a1 = fmaf(q.y, k1v.y, a1);
+                        }
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+                        sx[e][0] = a0; sx[e][1] = a1;
+                        mx[0] = fmaxf(mx[0], a0);
+                        mx[1] = fmaxf(mx[1], a1);
+                    }
+                }
+            }
             float corr[2], nm[2];
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -680,12 +715,30 @@ attention_seq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* _
                 pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
             }
 #pragma unroll
-            for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
-#pragma unroll
             for (int j = 0; j < 8; ++j) {
                 o_acc[j][0] *= corr[0]; o_acc[j][1] *= corr[0];
                 o_acc[j][2] *= corr[1]; o_acc[j][3] *= corr[1];
             }
+            if (with_x) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (e < xk) {
+                        const float p0 = ex2_approx(fmaf(sx[e][0], scale_log2, nm[0]));
+                        const float p1 = ex2_approx(fmaf(sx[e][1], scale_log2, nm[1]));
+                        if (t4 == 0) { rs[0] += p0; rs[1] += p1; }   // the row sums are reduced over the quad later
+                        const int r = ATT_BK * nbr + e;
+                        const uint8_t* vr = sV + (r >> 6) * ATT_BK * 128 + (r & 63) * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {                // o_acc[j] holds columns j*8 + t4*2 (+1)
+                            const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vr + ((j ^ (r & 7)) << 4) + t4 * 4));
+                            o_acc[j][0] = fmaf(p0, v.x, o_acc[j][0]); o_acc[j][1] = fmaf(p0, v.y, o_acc[j][1]);
+                            o_acc[j][2] = fmaf(p1, v.x, o_acc[j][2]); o_acc[j][3] = fmaf(p1, v.y, o_acc[j][3]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 if (ks * 16 >= kv_valid) continue;      // P is exactly 0 there
