@@ -141,6 +141,7 @@ struct Plan {
     uint32_t a_div_mul = 0;
     int a_max_cx = 0;        // largest horizontal tap count of the area stage
     int b_max_cnt = 0;       // largest tap count of the Pillow horizontal pass
+    int c_max_cnt = 0;       // largest tap count of the Pillow vertical pass (rows [top, top+S))
     int a_fx = 1, a_fy = 1;
     int h1 = 0, w1 = 0;      // size after the area shrink
     int nw = 0, nh = 0;      // size after the Pillow resize
@@ -858,6 +859,90 @@ vpass_store_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_
     }
 }
 
+// C, tile form (the bench path: patch-major bf16 output, P and S multiples of 8, 8-byte aligned 24-byte pixel groups,
+// at most 7 vertical taps).  A CTA owns `rows_per_block` output rows of one frame, so the LUT is staged once per
+// 32 rows instead of once per 4; thread (ry, xc) walks rows ry, ry + blockDim/xchunks, ...  All tap rows of an item
+// are fetched up front as 64-bit loads (3 per tap, up to 21 in flight per thread) before the fixed-point
+// accumulation -- the arithmetic (order, rounding, clip) is exactly vpass_store_kernel's.
+template <bool HAS_V>
+__global__ void __launch_bounds__(256)
+vpass_store_tile_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride, int src_y0,
+                        int xoff_bytes, int top, DevTaps cy, int S, int P, int grid, int patch_k, int rows_per_block,
+                        const float* __restrict__ lut /*[3][256]*/, bf16* __restrict__ patches) {
+    __shared__ float s_lut[768];
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = __ldg(lut + i);
+    __syncthreads();
+    const int xchunks = S >> 3;
+    const int rows_per_pass = blockDim.x / xchunks;
+    const int ry = threadIdx.x / xchunks, xc = threadIdx.x - ry * xchunks;
+    if (ry >= rows_per_pass) return;
+    const int64_t f = blockIdx.y;
+    const int x0 = xc << 3;
+    const int px0 = x0 / P, xx = x0 - px0 * P;
+    const uint8_t* fbase = src + f * frame_stride + xoff_bytes + x0 * 3;
+    const int oy_end = min(S, static_cast<int>(blockIdx.x + 1) * rows_per_block);
+    for (int oy = blockIdx.x * rows_per_block + ry; oy < oy_end; oy += rows_per_pass) {
+        uint32_t u8w[6];      // the 24 result bytes, packed
+        if (HAS_V) {
+            const int o = top + oy;
+            const int lo = __ldg(cy.start + o), cnt = __ldg(cy.cnt + o);
+            const int* k = cy.wi + o * cy.stride;
+            // the rows of one warp (it spans at most a few output rows) rarely need all 7 taps: taps >= the warp's
+            // largest count are skipped by a warp-uniform branch (their weight would be 0)
+            const int wcnt = __reduce_max_sync(__activemask(), cnt);
+            int kk[7];
+            uint32_t w[7][6];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                if (i < 4 || i < wcnt) {
+                    const int ii = i < cnt ? i : cnt - 1;      // rows past cnt: re-read the last one with weight 0
+                    kk[i] = i < cnt ? __ldg(k + i) : 0;
+                    const uint2* rp = reinterpret_cast<const uint2*>(fbase + static_cast<int64_t>(lo + ii - src_y0) * row_stride);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const uint2 v = __ldg(rp + q);
+                        w[i][2 * q] = v.x; w[i][2 * q + 1] = v.y;
+                    }
+                }
+            }
+            int acc[24];
+#pragma unroll
+            for (int j = 0; j < 24; ++j) acc[j] = 1 << 21;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                if (i < 4 || i < wcnt) {
+#pragma unroll
+                    for (int j = 0; j < 24; ++j) acc[j] += kk[i] * byte_as_int<6>(w[i], j);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+                u8w[q] = static_cast<uint32_t>(clip8(acc[4 * q])) | (static_cast<uint32_t>(clip8(acc[4 * q + 1])) << 8) |
+                         (static_cast<uint32_t>(clip8(acc[4 * q + 2])) << 16) | (static_cast<uint32_t>(clip8(acc[4 * q + 3])) << 24);
+        } else {
+            const uint2* rp = reinterpret_cast<const uint2*>(fbase + static_cast<int64_t>(top + oy - src_y0) * row_stride);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const uint2 v = __ldg(rp + q);
+                u8w[2 * q] = v.x; u8w[2 * q + 1] = v.y;
+            }
+        }
+        const int py = oy / P, yy = oy - py * P;
+        const int64_t row = (f * grid + py) * grid + px0;
+        bf16* orow = patches + row * patch_k + yy * P + xx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* l = s_lut + c * 256;
+            uint4 o;
+            o.x = pack_bf16x2(l[byte_as_int<6>(u8w, 0 * 3 + c)], l[byte_as_int<6>(u8w, 1 * 3 + c)]);
+            o.y = pack_bf16x2(l[byte_as_int<6>(u8w, 2 * 3 + c)], l[byte_as_int<6>(u8w, 3 * 3 + c)]);
+            o.z = pack_bf16x2(l[byte_as_int<6>(u8w, 4 * 3 + c)], l[byte_as_int<6>(u8w, 5 * 3 + c)]);
+            o.w = pack_bf16x2(l[byte_as_int<6>(u8w, 6 * 3 + c)], l[byte_as_int<6>(u8w, 7 * 3 + c)]);
+            *reinterpret_cast<uint4*>(orow + c * P * P) = o;
+        }
+    }
+}
+
 // zero the K padding columns of the patch rows (only when 3*P*P is not a multiple of 64, e.g. P = 14)
 __global__ void zero_pad_kernel(bf16* __restrict__ patches, int64_t rows, int kk, int patch_k) {
     const int pad = patch_k - kk;
@@ -920,6 +1005,7 @@ static int build_plan(b200clip_handle* h, int H, int W, int mode, Plan& p) {
     if (p.has_c) {
         cy = pillow_taps(h1, p.nh, bicubic);
         taps_range(cy, p.top, p.top + S, p.ry0, p.ry1);
+        for (int o = p.top; o < p.top + S; ++o) p.c_max_cnt = cy.cnt[o] > p.c_max_cnt ? cy.cnt[o] : p.c_max_cnt;
     } else {
         p.ry0 = p.top; p.ry1 = p.top + S;
     }
@@ -1176,8 +1262,27 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         const int src_x0 = p.has_b ? 0 : cur_x0 - p.left;  // so that (x0 - src_x0) = x0 + left - cur_x0
         dim3 grid((static_cast<unsigned>(S) * ((S + 7) >> 3) + 127) / 128, n);
         ProfScope psc(h, PROF_PRE_C, static_cast<double>(n) * ((p.ry1 - p.ry0) * S * 3.0 + (patches ? static_cast<double>(h->grid) * h->grid * h->patch_k * 2.0 : 3.0 * S * S * 4.0)), st);
-        vpass_store_kernel<<<grid, 128, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, src_x0, p.has_c ? 1 : 0, p.top, p.cy, S, P,
-                                                 h->grid, h->patch_k, lut, patches, chw);
+        // tile form: bf16 patch output, 8-pixel groups never straddle a patch, every 24-byte group 8-byte aligned
+        static const bool no_tile = getenv("B200CLIP_VPASS_GENERIC") != nullptr;   // parity tests cover both forms
+        const int xoff = -src_x0 * 3;
+        const bool tile = !no_tile && patches && !chw && (P & 7) == 0 && (S & 7) == 0 && (S >> 3) <= 256 &&
+                          (!p.has_c || p.c_max_cnt <= 7) && (cur_rs & 7) == 0 && (cur_fs & 7) == 0 &&
+                          ((reinterpret_cast<uintptr_t>(cur) + xoff) & 7) == 0;
+        if (tile) {
+            const int xchunks = S >> 3;
+            const int threads = xchunks * (256 / xchunks);
+            const int rows_per_block = 32;
+            dim3 tgrid((S + rows_per_block - 1) / rows_per_block, n);
+            if (p.has_c)
+                vpass_store_tile_kernel<true><<<tgrid, threads, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, xoff, p.top, p.cy, S, P,
+                                                                         h->grid, h->patch_k, rows_per_block, lut, patches);
+            else
+                vpass_store_tile_kernel<false><<<tgrid, threads, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, xoff, p.top, p.cy, S, P,
+                                                                          h->grid, h->patch_k, rows_per_block, lut, patches);
+        } else {
+            vpass_store_kernel<<<grid, 128, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, src_x0, p.has_c ? 1 : 0, p.top, p.cy, S, P,
+                                                     h->grid, h->patch_k, lut, patches, chw);
+        }
         h->launches++;
     }
     if (patches && h->patch_k != 3 * P * P) {

@@ -1,6 +1,7 @@
 """Helper run in a SUBPROCESS by tests/test_gpu_preprocess.py::test_k1_code_path_variants: K1 picks its code path once
 per process from environment switches (B200CLIP_AREA_FP32: fp32 area arithmetic instead of the integer-exact one;
-B200CLIP_K1_UNFUSED: separate area / horizontal kernels; B200CLIP_AREA_NOSTRIP: per-pixel area kernel), so each
+B200CLIP_K1_UNFUSED: separate area / horizontal kernels; B200CLIP_AREA_NOSTRIP: per-pixel area kernel;
+B200CLIP_VPASS_GENERIC: per-item vertical-pass kernel instead of the tile form for the bf16 patch output), so each
 variant needs its own process.  Checks 1080p and 720p frames byte for byte against the oracle (which is itself pinned
 to cv2 / Pillow / torchvision)."""
 import os
@@ -31,11 +32,16 @@ def main() -> int:
         frames[0, ::2] = 255
         frames[0, :, ::3] = 0
         chw = model.preprocess_u8(torch.from_numpy(frames).cuda(), capi.RESIZE_REFERENCE, chw=True).cpu().numpy()
+        patches = model.preprocess_u8(torch.from_numpy(frames).cuda(), capi.RESIZE_REFERENCE, chw=False).float().cpu().numpy()
         for i in range(len(frames)):
             want = P.to_chw_normalized(P.reference_preprocess_u8(frames[i]))
             n = int((chw[i].view(np.uint32) != want.view(np.uint32)).sum())
             if n:
                 print(f"{w}x{h} frame {i}: {n} of {want.size} values differ")
+                bad += 1
+            want_patches = torch.from_numpy(P.patchify(want, 32)).bfloat16().float().numpy()
+            if not np.array_equal(patches[i * 49:(i + 1) * 49], want_patches):
+                print(f"{w}x{h} frame {i}: bf16 patch rows differ")
                 bad += 1
     print("variant ok" if not bad else "variant FAILED", {k: v for k, v in os.environ.items() if k.startswith("B200CLIP_")})
     return 1 if bad else 0

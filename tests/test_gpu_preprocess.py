@@ -127,8 +127,9 @@ def test_1080p_window_alignments(model_b32, pad_w, x_off):
 
 
 @pytest.mark.parametrize("env", [{}, {"B200CLIP_AREA_PX1": "1"}, {"B200CLIP_AREA_FP32": "1"}, {"B200CLIP_K1_UNFUSED": "1"},
-                                 {"B200CLIP_K1_UNFUSED": "1", "B200CLIP_AREA_NOSTRIP": "1"}],
-                         ids=["default-int-exact-2col", "int-exact-1col", "fused-fp32", "unfused-strip", "unfused-per-pixel"])
+                                 {"B200CLIP_K1_UNFUSED": "1", "B200CLIP_AREA_NOSTRIP": "1"}, {"B200CLIP_VPASS_GENERIC": "1"}],
+                         ids=["default-int-exact-2col", "int-exact-1col", "fused-fp32", "unfused-strip", "unfused-per-pixel",
+                              "generic-vpass"])
 def test_k1_code_path_variants(env):
     """Every K1 area-stage implementation (integer-exact fused, fp32 fused, strip walker, per-pixel) must give the
     same bytes as cv2; the path is chosen once per process, so each variant runs tests/k1_variant_check.py in its own
@@ -137,7 +138,7 @@ def test_k1_code_path_variants(env):
     import sys
 
     e = dict(os.environ)
-    for k in ("B200CLIP_AREA_FP32", "B200CLIP_AREA_PX1", "B200CLIP_K1_UNFUSED", "B200CLIP_AREA_NOSTRIP"):
+    for k in ("B200CLIP_AREA_FP32", "B200CLIP_AREA_PX1", "B200CLIP_K1_UNFUSED", "B200CLIP_AREA_NOSTRIP", "B200CLIP_VPASS_GENERIC"):
         e.pop(k, None)
     e.update(env)
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "k1_variant_check.py")
