@@ -150,6 +150,7 @@ struct Plan {
     int rx0 = 0, rx1 = 0;    // columns of the stage-A output that stage B needs
     int sx0 = 0, sx1 = 0, sy0 = 0, sy1 = 0;   // window of the SOURCE frame that the first stage reads
     DevTaps ax{}, ay{}, bx{}, cy{};
+    const uint32_t* aq = nullptr;   // [w1][8] packed IDP.2A weights of the vertical-first area kernel (a_int only)
     size_t mid1_per_frame = 0, mid2_per_frame = 0;
     std::vector<void*> dev;  // device allocations holding the tables
 };
@@ -747,6 +748,301 @@ area_hpass_bulk_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, in
     (void)max_rows;
 }
 
+// A+B fused, VERTICAL-FIRST integer form (INTX geometries; the 1080p / 720p bench path).  Same CTA decomposition,
+// producer warp and bulk-copy ring as area_hpass_bulk_kernel, same integers out -- but the consumers accumulate down
+// the rows BEFORE they combine across a row:
+//   * per source row, consumer t owns the 16 bytes [16t, 16t+16) of the ring stage: one LDS.128, the even and the odd
+//     bytes split into 16-bit lanes (two masks per word) and multiplied by the row's integer weight as packed pairs
+//     (one IMAD per two bytes; a lane never exceeds 255 * Dy < 2^16).  That is 4 instructions per source word instead
+//     of the ~8.5 (byte dot products + realignment) of the horizontal-first form, and the per-row bookkeeping is paid
+//     once per 16 bytes;
+//   * when an area-output row completes, the lanes are parked in shared memory (even-byte stream L, odd-byte stream
+//     H), and thread x combines the 15 sums under area column x with IDP.2A (two 16-bit sums x two byte weights per
+//     instruction), divides exactly as the horizontal-first form and parks the uint8 area row;
+//   * Pillow's horizontal pass then runs on the PREVIOUS parked row (one CTA barrier per area row, everything double
+//     buffered).
+// N = sum_y sum_x iy*ix*byte is the same integer in either order, so the result is bit-identical by construction.
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// VW: 16-byte slices of a stage row per consumer; PA / PB: area / Pillow output columns per consumer (thread t owns
+// slices t + v*ncons, area columns t + p*ncons, Pillow columns t + p*ncons).  1080p and 720p run <2, 3, 2> with 128
+// consumers: fewer, fatter threads pay the per-row pipeline bookkeeping once per 32 bytes.
+// GW: the per-column constants of the combine (packed IDP.2A weights, Pillow coefficients) are re-read from their
+// L1-resident global tables once per area row instead of living in ~38 registers: one more CTA per SM.
+template <int MAXT, int MINB, int VW, int PA, int PB, bool GW>
+__global__ void __launch_bounds__(MAXT, MINB)
+area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride,
+                         uint8_t* __restrict__ mid2, int64_t mid2_frame_stride, int oy0, int ny, int ox0, int nx,
+                         int rows_per_strip, int xb0, int seg_bytes, int stage_bytes, int arow_pitch, int vpitch,
+                         int left, int S, DevTaps ax, DevTaps ay, DevTaps bx, AhIntParams ip,
+                         const uint32_t* __restrict__ aq /*[area columns][8] packed weights, see build_plan*/) {
+    extern __shared__ __align__(128) uint8_t ah_smem[];
+    const int ncons = blockDim.x - 32;                 // consumer threads; the last warp is the producer
+    const int tid = threadIdx.x;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ah_smem);
+    uint64_t* empty_bar = full_bar + AH_NSTAGE;
+    uint8_t* ring = ah_smem + 2 * AH_NSTAGE * sizeof(uint64_t);
+    uint8_t* vbuf = ring + AH_NSTAGE * stage_bytes;     // [2 parities][L | H] streams, vpitch bytes each
+    uint8_t* arow = vbuf + 4 * vpitch;                  // [2] parked uint8 area rows
+    AhRowInfo* rinfo = reinterpret_cast<AhRowInfo*>(arow + 2 * arow_pitch);
+
+    const int strip = blockIdx.x;
+    const int64_t f = blockIdx.y;
+    const int dy_a = oy0 + strip * rows_per_strip;
+    const int dy_b = min(dy_a + rows_per_strip, oy0 + ny);
+    const int r_lo = __ldg(ay.start + dy_a);
+    const int nrows = __ldg(ay.start + dy_b - 1) + __ldg(ay.cnt + dy_b - 1) - r_lo;
+    const uint8_t* gbase = src + f * frame_stride + xb0;
+    const int delta = static_cast<int>(reinterpret_cast<uintptr_t>(gbase) & 15);
+
+    if (tid == 0) {
+        for (int s = 0; s < AH_NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ncons >> 5); }
+        fence_mbar_init();
+    }
+    // row program of the strip (see area_hpass_bulk_kernel): pad = integer weights, low half into the output row being
+    // accumulated, high half into the next one
+    for (int i = tid; i < nrows; i += blockDim.x) rinfo[i].beta_next = 0.f, rinfo[i].finish = 0, rinfo[i].pad = 0;
+    // the slack words behind the streams are read (with weight 0, or shifted out) but never written per row
+    for (int i = tid; i < vpitch; i += blockDim.x) reinterpret_cast<uint32_t*>(vbuf)[i] = 0u;
+    __syncthreads();
+    for (int d = tid; d < dy_b - dy_a; d += blockDim.x) {
+        const int dy = dy_a + d;
+        const int sy0 = __ldg(ay.start + dy), cy = __ldg(ay.cnt + dy);
+        const bool shared_first = d > 0 && sy0 == __ldg(ay.start + dy - 1) + __ldg(ay.cnt + dy - 1) - 1;
+        for (int j = 0; j < cy; ++j) {
+            const float beta = __ldg(ay.wf + dy * ay.stride + j);
+            AhRowInfo& ri = rinfo[sy0 + j - r_lo];
+            const int ib = __float2int_rn(beta * static_cast<float>(ip.dy));
+            if (j == 0 && shared_first) { ri.beta_next = beta; atomicOr(&ri.pad, ib << 16); }
+            else { ri.beta_cur = beta; atomicOr(&ri.pad, ib); }
+            if (j == cy - 1) ri.finish = 1;
+        }
+    }
+    __syncthreads();
+
+    if (tid >= ncons) {
+        // ------------------------------------------------------------------ producer warp
+        if (tid == ncons) {
+            const uint8_t* g = gbase - delta + static_cast<int64_t>(r_lo) * row_stride;
+            for (int i = 0; i < nrows; ++i, g += row_stride) {
+                const int s = i % AH_NSTAGE;
+                if (i >= AH_NSTAGE) mbar_wait(&empty_bar[s], ((i / AH_NSTAGE) - 1) & 1, 11);
+                mbar_arrive_expect_tx(&full_bar[s], seg_bytes);
+                bulk_load_1d(ring + s * stage_bytes, g, seg_bytes, &full_bar[s]);
+            }
+        }
+        return;
+    }
+    // ---------------------------------------------------------------------- consumers
+    // slices [16 (tid + v*ncons), +16) of every stage row; a slice past the segment re-reads slice 0 and is never parked
+    bool v_active[VW];
+    uint32_t v_off[VW];
+#pragma unroll
+    for (int v = 0; v < VW; ++v) {
+        v_active[v] = (tid + v * ncons) * 16 < seg_bytes;
+        v_off[v] = v_active[v] ? 16u * static_cast<uint32_t>(tid + v * ncons) : 0u;
+    }
+    // area columns tid + p*ncons: stream addresses, realignment shifts and the packed IDP.2A weights
+    bool a_active[PA];
+    int xcol[PA];
+    uint32_t xoff[PA], yoff[PA], q[GW ? 1 : PA][8];
+#pragma unroll
+    for (int p = 0; p < PA; ++p) {
+        a_active[p] = tid + p * ncons < nx;
+        xcol[p] = min(tid + p * ncons, nx - 1);
+        const int dx = ox0 + xcol[p];
+        const int s0 = __ldg(ax.start + dx) * 3 - xb0 + delta;        // first byte of this column inside a stage row
+        const int parity = s0 & 1, ex = s0 >> 1, ey = ex + parity;    // X_i = V[s0 + 2i], Y_i = V[s0 + 1 + 2i]
+        // bit 31 = "stream starts in the high lane" (funnel shift by 16); the shift count is taken as (word >> 27)
+        xoff[p] = static_cast<uint32_t>((parity ? vpitch : 0) + 4 * (ex >> 1)) | (static_cast<uint32_t>(ex & 1) << 31);
+        yoff[p] = static_cast<uint32_t>((parity ? 0 : vpitch) + 4 * (ey >> 1)) | (static_cast<uint32_t>(ey & 1) << 31);
+        if (!GW) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) q[p][k] = __ldg(aq + dx * 8 + k);
+        }
+    }
+    // horizontal Pillow pass: output columns left + tid + p*ncons, at most 7 taps
+    bool b_active[PB];
+    int bk[GW ? 1 : PB][7], tcol[PB];
+    uint32_t bsh[PB], aword[PB];
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+        b_active[p] = tid + p * ncons < S;
+        tcol[p] = min(tid + p * ncons, S - 1);
+        const int ox = left + tcol[p];
+        const int blo = __ldg(bx.start + ox);
+        if (!GW) {
+#pragma unroll
+            for (int i = 0; i < 7; ++i) bk[p][i] = i < bx.stride ? __ldg(bx.wi + ox * bx.stride + i) : 0;   // zero padded
+        }
+        const int aoff = (blo - ox0) * 3;                              // first byte inside a parked area row
+        bsh[p] = static_cast<uint32_t>(aoff & 3) * 8;
+        aword[p] = static_cast<uint32_t>(aoff & ~3);
+    }
+    auto hpass_row = [&](const uint8_t* ar, uint8_t* orow) {
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+            if (b_active[p]) {
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(ar + aword[p]);
+                uint32_t bw[7], bu[6];
+                int kk[7];
+#pragma unroll
+                for (int t = 0; t < 7; ++t)
+                    kk[t] = GW ? (t < bx.stride ? __ldg(bx.wi + (left + tcol[p]) * bx.stride + t) : 0) : bk[GW ? 0 : p][t];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) bw[k] = wp[k];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) bu[k] = __funnelshift_r(bw[k], bw[k + 1], bsh[p]);
+                int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+#pragma unroll
+                for (int t = 0; t < 7; ++t) {
+                    a0 += kk[t] * byte_as_int<6>(bu, t * 3);
+                    a1 += kk[t] * byte_as_int<6>(bu, t * 3 + 1);
+                    a2 += kk[t] * byte_as_int<6>(bu, t * 3 + 2);
+                }
+                uint8_t* o = orow + tcol[p] * 3;
+                o[0] = clip8(a0); o[1] = clip8(a1); o[2] = clip8(a2);
+            }
+        }
+    };
+
+    const int lane = tid & 31;
+    uint32_t aL[VW][4], aH[VW][4];
+#pragma unroll
+    for (int v = 0; v < VW; ++v)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) aL[v][k] = aH[v][k] = 0u;
+    int par = 0;         // parity of the parked-row / stream double buffers
+    int nfin = 0;        // area rows finished so far
+    uint8_t* out_row = mid2 + f * mid2_frame_stride + static_cast<int64_t>(dy_a - oy0) * S * 3;
+    // 32-bit shared addresses, made opaque so that they stay in registers (ptxas otherwise re-derives them from
+    // SR_CgaCtaId in every row: an S2R round trip on the critical path of the row loop)
+    uint32_t full0 = smem_u32(full_bar), ring0 = smem_u32(ring), vb0 = smem_u32(vbuf), ria = smem_u32(rinfo);
+    uint32_t sbytes = static_cast<uint32_t>(stage_bytes);
+    asm volatile("" : "+r"(full0), "+r"(ring0), "+r"(vb0), "+r"(ria), "+r"(sbytes));
+    for (int i = 0; i < nrows; ++i) {
+        const uint32_t s = static_cast<uint32_t>(i) & (AH_NSTAGE - 1), phase = (static_cast<uint32_t>(i) / AH_NSTAGE) & 1u;
+        const uint32_t fb = full0 + 8u * s, eb = fb + 8u * AH_NSTAGE, soff = ring0 + s * sbytes;
+        {
+            uint32_t ok;
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(fb), "r"(phase) : "memory");
+            if (!ok) {                                 // slow path: bounded spin (a protocol bug must trap, not hang)
+                uint32_t spins = 0;
+                do {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(fb), "r"(phase) : "memory");
+                    if (!ok && ++spins > (1u << 24)) __trap();
+                } while (!ok);
+            }
+        }
+        uint32_t w[VW][4];
+#pragma unroll
+        for (int v = 0; v < VW; ++v)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[v][0]), "=r"(w[v][1]), "=r"(w[v][2]), "=r"(w[v][3]) : "r"(soff + v_off[v]));
+        uint32_t fin, wts;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(fin), "=r"(wts) : "r"(ria + 8));
+        ria += 16;
+        __syncwarp();
+        if (lane == 0)                                // this warp holds its bytes in registers now
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(eb) : "memory");
+        const uint32_t iyc = wts & 0xffffu;
+        uint32_t lo[VW][4], hi[VW][4];
+#pragma unroll
+        for (int v = 0; v < VW; ++v)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                lo[v][k] = __byte_perm(w[v][k], 0u, 0x4240);     // bytes 0 and 2 in 16-bit lanes
+                hi[v][k] = __byte_perm(w[v][k], 0u, 0x4341);     // bytes 1 and 3
+                aL[v][k] += iyc * lo[v][k];
+                aH[v][k] += iyc * hi[v][k];
+            }
+        if (fin != 0) {                               // uniform over the CTA: an area-output row is complete
+            const uint32_t vb = vb0 + static_cast<uint32_t>(par) * 2u * static_cast<uint32_t>(vpitch);
+#pragma unroll
+            for (int v = 0; v < VW; ++v) {
+                if (v_active[v]) {
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(vb + v_off[v]), "r"(aL[v][0]), "r"(aL[v][1]), "r"(aL[v][2]), "r"(aL[v][3]) : "memory");
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(vb + vpitch + v_off[v]), "r"(aH[v][0]), "r"(aH[v][1]), "r"(aH[v][2]), "r"(aH[v][3]) : "memory");
+                }
+            }
+            const uint32_t iyn = wts >> 16;           // a straddling row opens the next output row
+#pragma unroll
+            for (int v = 0; v < VW; ++v)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { aL[v][k] = iyn * lo[v][k]; aH[v][k] = iyn * hi[v][k]; }
+            named_bar_sync(1, ncons);            // streams of this row complete; the previous parked row complete
+            uint8_t* ar = arow + par * arow_pitch;
+#pragma unroll
+            for (int p = 0; p < PA; ++p) {
+                if (a_active[p]) {
+                    const uint32_t xa = vb + (xoff[p] & 0x7fffffffu), ya = vb + (yoff[p] & 0x7fffffffu);
+                    const uint32_t xsh = xoff[p] >> 27, ysh = yoff[p] >> 27;      // 0 or 16
+                    uint32_t xr[5], yr[5], x[4], y[4];
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(xr[k]) : "r"(xa + 4u * k));
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(yr[k]) : "r"(ya + 4u * k));
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        x[k] = __funnelshift_r(xr[k], xr[k + 1], xsh);
+                        y[k] = __funnelshift_r(yr[k], yr[k + 1], ysh);
+                    }
+                    uint32_t qq[8];
+                    if (GW) {
+                        const uint4* qp = reinterpret_cast<const uint4*>(aq + (ox0 + xcol[p]) * 8);
+                        const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
+                        qq[0] = qa.x; qq[1] = qa.y; qq[2] = qa.z; qq[3] = qa.w;
+                        qq[4] = qb.x; qq[5] = qb.y; qq[6] = qb.z; qq[7] = qb.w;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) qq[k] = q[GW ? 0 : p][k];
+                    }
+                    uint32_t n0 = dp2a_lo(x[0], qq[0], 0u);
+                    n0 = dp2a_hi(x[1], qq[0], n0);
+                    n0 = dp2a_lo(x[3], qq[1], n0);
+                    n0 = dp2a_hi(y[0], qq[1], n0);
+                    n0 = dp2a_lo(y[2], qq[2], n0);
+                    uint32_t n1 = dp2a_hi(x[1], qq[2], 0u);
+                    n1 = dp2a_lo(x[2], qq[3], n1);
+                    n1 = dp2a_hi(y[0], qq[3], n1);
+                    n1 = dp2a_lo(y[1], qq[4], n1);
+                    n1 = dp2a_hi(y[3], qq[4], n1);
+                    uint32_t n2 = dp2a_lo(x[0], qq[5], 0u);
+                    n2 = dp2a_hi(x[2], qq[5], n2);
+                    n2 = dp2a_lo(x[3], qq[6], n2);
+                    n2 = dp2a_hi(y[1], qq[6], n2);
+                    n2 = dp2a_lo(y[2], qq[7], n2);
+                    // rint(N / D) == floor((2N + D) / 2D): no ties for odd D
+                    uint8_t* o = ar + xcol[p] * 3;
+                    o[0] = static_cast<uint8_t>(__umulhi(2u * n0 + ip.d, ip.div_mul) >> ip.div_shift);
+                    o[1] = static_cast<uint8_t>(__umulhi(2u * n1 + ip.d, ip.div_mul) >> ip.div_shift);
+                    o[2] = static_cast<uint8_t>(__umulhi(2u * n2 + ip.d, ip.div_mul) >> ip.div_shift);
+                }
+            }
+            if (nfin > 0) {
+                hpass_row(arow + (par ^ 1) * arow_pitch, out_row);
+                out_row += S * 3;
+            }
+            ++nfin;
+            par ^= 1;
+        }
+    }
+    if (nfin > 0) {
+        named_bar_sync(1, ncons);                // the last parked row is complete
+        hpass_row(arow + (par ^ 1) * arow_pitch, out_row);
+    }
+}
+
 // B: Pillow horizontal pass for output columns [ocol0, ocol0+S) on rows [0, ny) of the (possibly compacted)
 // source whose column 0 is absolute column src_x0.  FAST: at most 7 taps (21 bytes) -> aligned word loads.
 template <bool FAST>
@@ -1067,6 +1363,27 @@ static int build_plan(b200clip_handle* h, int H, int W, int mode, Plan& p) {
     p.ay = upload_taps(h, p, ay, rc);
     p.bx = upload_taps(h, p, bx, rc);
     p.cy = upload_taps(h, p, cy, rc);
+    if (p.a_int && p.a_max_cx <= 5 && p.a_dx <= 255) {
+        // area_hpass_vfirst_kernel: per area column, the byte pairs (weight of the low 16-bit lane, weight of the high
+        // lane) in the order its combine consumes them, two pairs per word (.lo / .hi form of IDP.2A)
+        std::vector<uint32_t> aq(static_cast<size_t>(w1) * 8, 0u);
+        auto pr = [](uint32_t lo, uint32_t hi) { return lo | (hi << 8); };
+        for (int dx = 0; dx < w1; ++dx) {
+            uint32_t iw[5] = {0, 0, 0, 0, 0};
+            for (int i = 0; i < ax.cnt[dx] && i < 5; ++i)
+                iw[i] = static_cast<uint32_t>(lrintf(ax.wf[static_cast<size_t>(dx) * ax.stride + i] * static_cast<float>(p.a_dx)));
+            uint32_t* q = &aq[static_cast<size_t>(dx) * 8];
+            q[0] = pr(iw[0], 0) | (pr(0, iw[2]) << 16);     // channel 0: x0, x1
+            q[1] = pr(iw[4], 0) | (pr(0, iw[1]) << 16);     //            x3, y0
+            q[2] = pr(iw[3], 0) | (pr(iw[1], 0) << 16);     //            y2 | channel 1: x1
+            q[3] = pr(0, iw[3]) | (pr(iw[0], 0) << 16);     //            x2, y0
+            q[4] = pr(0, iw[2]) | (pr(iw[4], 0) << 16);     //            y1, y3
+            q[5] = pr(0, iw[0]) | (pr(iw[2], 0) << 16);     // channel 2: x0, x2
+            q[6] = pr(0, iw[4]) | (pr(iw[1], 0) << 16);     //            x3, y1
+            q[7] = pr(0, iw[3]);                            //            y2
+        }
+        p.aq = upload(h, p, aq, rc);
+    }
     if (rc) return b200_fail(h, rc, "preprocess: uploading resize tables failed");
     p.mid1_per_frame = p.has_a ? static_cast<size_t>(p.ry1 - p.ry0) * (p.rx1 - p.rx0) * 3 : 0;
     p.mid2_per_frame = p.has_b ? static_cast<size_t>(p.ry1 - p.ry0) * S * 3 : 0;
@@ -1186,7 +1503,45 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         // two columns per thread when that still fits a 160-thread consumer group
         const int px = (intx && !no_px2 && (max(nx, S) + 1) / 2 <= 160) ? 2 : 1;
         const int ncons = ((max(nx, S) + px - 1) / px + 31) & ~31;
-        if (xb0 - delta >= 0 && xb0 - delta + seg <= W * 3 && ncons + 32 <= 576) {
+        // vertical-first integer form: one consumer per 16 bytes of the row window, two area columns per consumer
+        static const bool no_vfirst = getenv("B200CLIP_AREA_HFIRST") != nullptr;
+        // <2, 3, 2> on 128 consumers: 32 bytes of the row window, three area columns and two Pillow columns per thread
+        const int ncv = 128;
+        const bool vfirst = intx && !no_vfirst && p.aq != nullptr && (seg >> 4) <= 2 * ncv && nx <= 3 * ncv && S <= 2 * ncv &&
+                            p.a_dy * 255 < 65536 && p.a_dx <= 255 && xb0 - delta >= 0 && xb0 - delta + seg <= W * 3;
+        if (vfirst) {
+            // strip length: 24, 48, 96 and 288 rows measured within noise of each other on B200 (the per-CTA prologue
+            // is ~10 % of the stall samples at 24 rows, but longer strips lose as much to the tail) -> keep 24
+            static const int rows0 = getenv("B200CLIP_AREA_ROWS") ? atoi(getenv("B200CLIP_AREA_ROWS")) : 24;
+            int rows = rows0 > 4 ? rows0 : 24;
+            while (rows > 4 && static_cast<int64_t>(n) * ((ny + rows - 1) / rows) < static_cast<int64_t>(h->num_sms) * 6)
+                rows = (rows + 1) / 2;
+            const int stage_bytes = seg + 16, arow_pitch = (nx * 3 + 32 + 15) & ~15, vpitch = seg + 32;
+            const int max_rows = rows * p.ay.stride;
+            const size_t smem = 2 * AH_NSTAGE * sizeof(uint64_t) + static_cast<size_t>(AH_NSTAGE) * stage_bytes +
+                                4 * static_cast<size_t>(vpitch) + 2 * static_cast<size_t>(arow_pitch) +
+                                static_cast<size_t>(max_rows) * sizeof(AhRowInfo);
+            if (smem <= 200 * 1024) {
+                AhIntParams ip{p.a_dx, p.a_dy, p.a_dx * p.a_dy, p.a_div_shift, p.a_div_mul};
+                static const int vsel = getenv("B200CLIP_AREA_V") ? atoi(getenv("B200CLIP_AREA_V")) : 3;
+                auto kern = vsel == 3 ? area_hpass_vfirst_kernel<160, 3, 2, 3, 2, false>      // constants in registers
+                          : vsel == 5 ? area_hpass_vfirst_kernel<160, 5, 2, 3, 2, true>
+                                      : area_hpass_vfirst_kernel<160, 4, 2, 3, 2, true>;
+                if (smem > 48 * 1024)
+                    B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                // ~45 KB per CTA: without the maximum carve-out the driver's default split allows only 3 CTAs per SM
+                B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(p.sy1 - p.sy0) * (p.sx1 - p.sx0) * 3.0 + ny * S * 3.0), st);
+                dim3 fgrid((ny + rows - 1) / rows, n);
+                kern<<<fgrid, ncv + 32, smem, st>>>(cur, cur_fs, cur_rs, mid2, p.mid2_per_frame, p.ry0, ny, p.rx0, nx, rows, xb0,
+                                                   seg, stage_bytes, arow_pitch, vpitch, p.left, S, p.ax, p.ay, p.bx, ip, p.aq);
+                h->launches++;
+                fused_ab = true;
+                cur = mid2; cur_fs = p.mid2_per_frame; cur_rs = static_cast<int64_t>(S) * 3;
+                cur_x0 = 0; cur_y0 = p.ry0;
+            }
+        }
+        if (!fused_ab && xb0 - delta >= 0 && xb0 - delta + seg <= W * 3 && ncons + 32 <= 576) {
             int rows = 24;
             while (rows > 4 && static_cast<int64_t>(n) * ((ny + rows - 1) / rows) < static_cast<int64_t>(h->num_sms) * 6)
                 rows = (rows + 1) / 2;

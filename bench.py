@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--top-k", type=int, default=5)
     ap.add_argument("--cpu-frames", type=int, default=256, help="frames in the cpu_baseline sample")
     ap.add_argument("--ref-frames", type=int, default=64, help="frames per step of the --impl reference arm")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per pass of the tower (0 = all frames of the step at once)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -186,7 +187,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     cfg = MODEL_CONFIGS["ViT-B-32"]
     sd = random_state_dict(cfg, 0)
     n, H, W = args.frames, args.height, args.width
-    model, _, _ = oc.create_model_and_transforms("ViT-B-32", state_dict=sd, device=dev, max_images=n, max_texts=1)
+    model, _, _ = oc.create_model_and_transforms("ViT-B-32", state_dict=sd, device=dev,
+                                                 max_images=(args.chunk if 0 < args.chunk < n else n), max_texts=1)
     h = model.handle
 
     # ---- synthetic decoded frames resident in HBM (stand-in for NVDEC output): per-frame solid colour + blocks + noise
