@@ -775,9 +775,9 @@ __device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) 
 // VW: 16-byte slices of a stage row per consumer; PA / PB: area / Pillow output columns per consumer (thread t owns
 // slices t + v*ncons, area columns t + p*ncons, Pillow columns t + p*ncons).  1080p and 720p run <2, 3, 2> with 128
 // consumers: fewer, fatter threads pay the per-row pipeline bookkeeping once per 32 bytes.
-// GW: the per-column constants of the combine (packed IDP.2A weights, Pillow coefficients) are re-read from their
-// L1-resident global tables once per area row instead of living in ~38 registers: one more CTA per SM.
-template <int MAXT, int MINB, int VW, int PA, int PB, bool GW>
+// (Re-reading the per-column constants -- packed IDP.2A weights, Pillow coefficients -- from their L1-resident tables
+// once per area row instead of holding them in ~38 registers buys a fourth CTA per SM but measured 15 % slower.)
+template <int MAXT, int MINB, int VW, int PA, int PB>
 __global__ void __launch_bounds__(MAXT, MINB)
 area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride,
                          uint8_t* __restrict__ mid2, int64_t mid2_frame_stride, int oy0, int ny, int ox0, int nx,
@@ -853,7 +853,7 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
     // area columns tid + p*ncons: stream addresses, realignment shifts and the packed IDP.2A weights
     bool a_active[PA];
     int xcol[PA];
-    uint32_t xoff[PA], yoff[PA], q[GW ? 1 : PA][8];
+    uint32_t xoff[PA], yoff[PA], q[PA][8];
 #pragma unroll
     for (int p = 0; p < PA; ++p) {
         a_active[p] = tid + p * ncons < nx;
@@ -864,14 +864,12 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
         // bit 31 = "stream starts in the high lane" (funnel shift by 16); the shift count is taken as (word >> 27)
         xoff[p] = static_cast<uint32_t>((parity ? vpitch : 0) + 4 * (ex >> 1)) | (static_cast<uint32_t>(ex & 1) << 31);
         yoff[p] = static_cast<uint32_t>((parity ? 0 : vpitch) + 4 * (ey >> 1)) | (static_cast<uint32_t>(ey & 1) << 31);
-        if (!GW) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) q[p][k] = __ldg(aq + dx * 8 + k);
-        }
+        for (int k = 0; k < 8; ++k) q[p][k] = __ldg(aq + dx * 8 + k);
     }
     // horizontal Pillow pass: output columns left + tid + p*ncons, at most 7 taps
     bool b_active[PB];
-    int bk[GW ? 1 : PB][7], tcol[PB];
+    int bk[PB][7], tcol[PB];
     uint32_t bsh[PB], aword[PB];
 #pragma unroll
     for (int p = 0; p < PB; ++p) {
@@ -879,10 +877,8 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
         tcol[p] = min(tid + p * ncons, S - 1);
         const int ox = left + tcol[p];
         const int blo = __ldg(bx.start + ox);
-        if (!GW) {
 #pragma unroll
-            for (int i = 0; i < 7; ++i) bk[p][i] = i < bx.stride ? __ldg(bx.wi + ox * bx.stride + i) : 0;   // zero padded
-        }
+        for (int i = 0; i < 7; ++i) bk[p][i] = i < bx.stride ? __ldg(bx.wi + ox * bx.stride + i) : 0;   // zero padded
         const int aoff = (blo - ox0) * 3;                              // first byte inside a parked area row
         bsh[p] = static_cast<uint32_t>(aoff & 3) * 8;
         aword[p] = static_cast<uint32_t>(aoff & ~3);
@@ -893,10 +889,6 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
             if (b_active[p]) {
                 const uint32_t* wp = reinterpret_cast<const uint32_t*>(ar + aword[p]);
                 uint32_t bw[7], bu[6];
-                int kk[7];
-#pragma unroll
-                for (int t = 0; t < 7; ++t)
-                    kk[t] = GW ? (t < bx.stride ? __ldg(bx.wi + (left + tcol[p]) * bx.stride + t) : 0) : bk[GW ? 0 : p][t];
 #pragma unroll
                 for (int k = 0; k < 7; ++k) bw[k] = wp[k];
 #pragma unroll
@@ -904,9 +896,9 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
                 int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
 #pragma unroll
                 for (int t = 0; t < 7; ++t) {
-                    a0 += kk[t] * byte_as_int<6>(bu, t * 3);
-                    a1 += kk[t] * byte_as_int<6>(bu, t * 3 + 1);
-                    a2 += kk[t] * byte_as_int<6>(bu, t * 3 + 2);
+                    a0 += bk[p][t] * byte_as_int<6>(bu, t * 3);
+                    a1 += bk[p][t] * byte_as_int<6>(bu, t * 3 + 1);
+                    a2 += bk[p][t] * byte_as_int<6>(bu, t * 3 + 2);
                 }
                 uint8_t* o = orow + tcol[p] * 3;
                 o[0] = clip8(a0); o[1] = clip8(a1); o[2] = clip8(a2);
@@ -997,16 +989,7 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
                         x[k] = __funnelshift_r(xr[k], xr[k + 1], xsh);
                         y[k] = __funnelshift_r(yr[k], yr[k + 1], ysh);
                     }
-                    uint32_t qq[8];
-                    if (GW) {
-                        const uint4* qp = reinterpret_cast<const uint4*>(aq + (ox0 + xcol[p]) * 8);
-                        const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
-                        qq[0] = qa.x; qq[1] = qa.y; qq[2] = qa.z; qq[3] = qa.w;
-                        qq[4] = qb.x; qq[5] = qb.y; qq[6] = qb.z; qq[7] = qb.w;
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) qq[k] = q[GW ? 0 : p][k];
-                    }
+                    const uint32_t (&qq)[8] = q[p];
                     uint32_t n0 = dp2a_lo(x[0], qq[0], 0u);
                     n0 = dp2a_hi(x[1], qq[0], n0);
                     n0 = dp2a_lo(x[3], qq[1], n0);
@@ -1523,10 +1506,7 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
                                 static_cast<size_t>(max_rows) * sizeof(AhRowInfo);
             if (smem <= 200 * 1024) {
                 AhIntParams ip{p.a_dx, p.a_dy, p.a_dx * p.a_dy, p.a_div_shift, p.a_div_mul};
-                static const int vsel = getenv("B200CLIP_AREA_V") ? atoi(getenv("B200CLIP_AREA_V")) : 3;
-                auto kern = vsel == 3 ? area_hpass_vfirst_kernel<160, 3, 2, 3, 2, false>      // constants in registers
-                          : vsel == 5 ? area_hpass_vfirst_kernel<160, 5, 2, 3, 2, true>
-                                      : area_hpass_vfirst_kernel<160, 4, 2, 3, 2, true>;
+                auto kern = area_hpass_vfirst_kernel<160, 3, 2, 3, 2>;
                 if (smem > 48 * 1024)
                     B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
                 // ~45 KB per CTA: without the maximum carve-out the driver's default split allows only 3 CTAs per SM
