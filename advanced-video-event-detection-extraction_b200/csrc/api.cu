@@ -171,6 +171,9 @@ extern "C" int b200clip_destroy(b200clip_handle* h) {
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->gemm_side) cudaStreamDestroy(h->gemm_side);
+    if (h->ev_gemm_fork) cudaEventDestroy(h->ev_gemm_fork);
+    if (h->ev_gemm_join) cudaEventDestroy(h->ev_gemm_join);
     delete h;
     return 0;
 }

@@ -69,67 +69,147 @@ static int launch_gemm_bn(b200clip_handle* h, const bf16* a, int lda, const bf16
     return 0;
 }
 
-static int launch_gemm_2cta(b200clip_handle* h, const bf16* a, int lda, const bf16* w, int ldw, bf16* out, int ldc,
-                            int M, int N, int K, const b200::GemmEpilogue& ep, cudaStream_t st) {
+// co-resident clusters of 2*pairs CTAs of the 2-CTA kernel (B200: GPCs of 16/18/20 SMs -> 74 / 33 / 15)
+static int g2_max_clusters(b200clip_handle* h, int pairs) {
+    static bool init = false;
+    static int maxc[5] = {0, 0, 0, 0, 0};
+    if (!init) {
+        cudaFuncSetAttribute(b200::gemm_bf16_tcgen05_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b200::G2_SMEM_BYTES);
+        cudaFuncSetAttribute(b200::gemm_bf16_tcgen05_2cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b200::G2_SMEM_BYTES);
+        cudaFuncSetAttribute(b200::gemm_bf16_tcgen05_2cta_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b200::G2_SMEM_BYTES);
+        maxc[1] = h->num_sms / 2;
+        for (int pr = 2; pr <= 4; pr += 2) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * pr * (h->num_sms / (2 * pr)));
+            cfg.blockDim = dim3(b200::GEMM_THREADS);
+            cfg.dynamicSmemBytes = b200::G2_SMEM_BYTES;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2 * pr; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaError_t e = pr == 2 ? cudaOccupancyMaxActiveClusters(&maxc[pr], b200::gemm_bf16_tcgen05_2cta_kernel<2>, &cfg)
+                                    : cudaOccupancyMaxActiveClusters(&maxc[pr], b200::gemm_bf16_tcgen05_2cta_kernel<4>, &cfg);
+            if (e != cudaSuccess || maxc[pr] <= 0) {
+                cudaGetLastError();
+                maxc[pr] = h->num_sms / (2 * pr) - (pr == 2 ? 4 : 3);
+            }
+        }
+        if (getenv("B200CLIP_GEMM_PAIRS") || getenv("B200CLIP_GEMM_HYBRID"))
+            fprintf(stderr, "[gemm] co-resident clusters: 4-CTA %d, 8-CTA %d\n", maxc[2], maxc[4]);
+        init = true;
+    }
+    return maxc[pairs];
+}
+
+// rows [r0, r0 + rows) of the problem on `pairs` CTA pairs per cluster, at most max_cl clusters, on stream s
+static int launch_gemm_2cta_range(b200clip_handle* h, const bf16* a, int lda, const bf16* w, int ldw, bf16* out, int ldc,
+                                  int r0, int rows, int N, int K, const b200::GemmEpilogue& ep, int pairs, int max_cl,
+                                  bool with_probe, cudaStream_t s) {
     CUtensorMap ta, tw;
     int rc;
-    if ((rc = make_tmap_bf16_2d(h, &ta, a, M, K, lda, b200::GEMM_BLOCK_M, b200::GEMM_BLOCK_K,
+    const int64_t o = r0;
+    if ((rc = make_tmap_bf16_2d(h, &ta, a + o * lda, rows, K, lda, b200::GEMM_BLOCK_M, b200::GEMM_BLOCK_K,
                                 CU_TENSOR_MAP_SWIZZLE_128B)))
         return rc;
-    if ((rc = make_tmap_bf16_2d(h, &tw, w, N, K, ldw, b200::G2_HALF_N, b200::GEMM_BLOCK_K,
+    if ((rc = make_tmap_bf16_2d(h, &tw, w, N, K, ldw, b200::G2_HALF_N / pairs, b200::GEMM_BLOCK_K,
                                 CU_TENSOR_MAP_SWIZZLE_128B)))
         return rc;
+    b200::GemmEpilogue epp = ep;
+    if (r0) {   // only affine epilogues are split (checked by the caller): every per-row pointer moves with the rows
+        if (epp.resid) epp.resid += o * ldc;
+        if (epp.ln_stats) epp.ln_stats += o * (b200::LN_SLOTS * 2);
+        if (epp.stats_out) epp.stats_out += o * (b200::LN_SLOTS * 2);
+    }
+    bf16* outp = out + o * ldc;
     // staged (TMA store) epilogue whenever the output rows are an affine image of the accumulator rows
     const int use_tma_epi = ep.t_in == 0 && ep.rowtab == nullptr && (ldc % 8 == 0) ? 1 : 0;
     CUtensorMap to, tr;
     if (use_tma_epi) {
-        if ((rc = make_tmap_bf16_2d(h, &to, out, M, N, ldc, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-        if ((rc = make_tmap_bf16_2d(h, &tr, ep.resid ? ep.resid : out, M, N, ldc, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B)))
+        if ((rc = make_tmap_bf16_2d(h, &to, outp, rows, N, ldc, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tmap_bf16_2d(h, &tr, epp.resid ? epp.resid : outp, rows, N, ldc, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B)))
             return rc;
     } else {
         to = ta; tr = ta;   // unused
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        B200_CUDA(h, cudaFuncSetAttribute(b200::gemm_bf16_tcgen05_2cta_kernel<0>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, b200::G2_SMEM_BYTES));
-        attr_set = true;
-    }
-    const int m_blocks = (M + 2 * b200::GEMM_BLOCK_M - 1) / (2 * b200::GEMM_BLOCK_M);
+    const int m_blocks = (rows + 2 * pairs * b200::GEMM_BLOCK_M - 1) / (2 * pairs * b200::GEMM_BLOCK_M);
     const int n_blocks = (N + b200::G2_BLOCK_N - 1) / b200::G2_BLOCK_N;
     const int tiles = m_blocks * n_blocks;
-    int clusters = h->num_sms / 2;
+    int clusters = max_cl;
     if (tiles < clusters) clusters = tiles;
-    static const bool probe_on = getenv("B200CLIP_GEMM_PROBE") != nullptr;   // development aid, see GemmEpilogue::probe
-    b200::GemmEpilogue epp = ep;
     // epilogue warps sleep between polls of the accumulator barrier (A/B on one box: 0.5-1 % faster steps under the
     // power cap); B200CLIP_GEMM_SPIN_WAIT=1 restores the tight spin
     static const int relaxed = getenv("B200CLIP_GEMM_SPIN_WAIT") ? 0 : 1;
     epp.relaxed_wait = relaxed;
     long long* probe = nullptr;
-    if (probe_on) {
+    if (with_probe) {
         B200_CUDA(h, cudaMallocManaged(&probe, sizeof(long long) * 4 * clusters));
         B200_CUDA(h, cudaMemset(probe, 0, sizeof(long long) * 4 * clusters));
         epp.probe = probe;
     }
-    {
-        ProfScope ps(h, PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
-        b200::gemm_bf16_tcgen05_2cta_kernel<0><<<2 * clusters, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, st>>>(
-            ta, tw, to, tr, out, ldc, M, N, K, epp, use_tma_epi);
-    }
+    const unsigned grid = 2u * pairs * clusters;
+    if (pairs == 4)
+        b200::gemm_bf16_tcgen05_2cta_kernel<4><<<grid, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, s>>>(
+            ta, tw, to, tr, outp, ldc, rows, N, K, epp, use_tma_epi);
+    else if (pairs == 2)
+        b200::gemm_bf16_tcgen05_2cta_kernel<2><<<grid, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, s>>>(
+            ta, tw, to, tr, outp, ldc, rows, N, K, epp, use_tma_epi);
+    else
+        b200::gemm_bf16_tcgen05_2cta_kernel<1><<<grid, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, s>>>(
+            ta, tw, to, tr, outp, ldc, rows, N, K, epp, use_tma_epi);
     if (probe) {
-        B200_CUDA(h, cudaStreamSynchronize(st));
+        B200_CUDA(h, cudaStreamSynchronize(s));
         double t[4] = {0, 0, 0, 0};
         for (int c = 0; c < clusters; ++c)
             for (int j = 0; j < 4; ++j) t[j] += static_cast<double>(probe[c * 4 + j]) / clusters;
         fprintf(stderr, "[gemm probe] M=%d N=%d K=%d tiles/cluster=%.1f: total %.0f clk; MMA waits: TMA data %.1f%%, free accumulator "
-                        "%.1f%%; epilogue waits for accumulator %.1f%%\n", M, N, K, static_cast<double>(tiles) / clusters, t[0],
+                        "%.1f%%; epilogue waits for accumulator %.1f%%\n", rows, N, K, static_cast<double>(tiles) / clusters, t[0],
                 100.0 * t[1] / t[0], 100.0 * t[2] / t[0], 100.0 * t[3] / t[0]);
         cudaFree(probe);
     }
     h->launches++;
     B200_CUDA(h, cudaGetLastError());
     return 0;
+}
+
+static int launch_gemm_2cta(b200clip_handle* h, const bf16* a, int lda, const bf16* w, int ldw, bf16* out, int ldc,
+                            int M, int N, int K, const b200::GemmEpilogue& ep, cudaStream_t st) {
+    // B200CLIP_GEMM_PAIRS=2|4: clusters of two / four CTA pairs that share their B tile by TMA multicast (see the
+    // kernel header).  Per SM that is 4 % / 11-14 % faster, but 4- / 8-CTA clusters only fit 132 / 120 of the 148 SMs.
+    static const int pairs_env = getenv("B200CLIP_GEMM_PAIRS") ? atoi(getenv("B200CLIP_GEMM_PAIRS")) : 1;
+    // B200CLIP_GEMM_HYBRID=<per mille of the rows>: 8-CTA multicast clusters take that share of the rows and, on a
+    // second low-priority stream, plain CTA pairs work on the rest on the SMs the big clusters cannot use.
+    static const int hybrid = getenv("B200CLIP_GEMM_HYBRID") ? atoi(getenv("B200CLIP_GEMM_HYBRID")) : 0;
+    static const bool probe_on = getenv("B200CLIP_GEMM_PROBE") != nullptr;   // development aid, see GemmEpilogue::probe
+    const bool affine = ep.t_in == 0 && ep.rowtab == nullptr;
+    int rc;
+    if (hybrid > 0 && hybrid < 1000 && affine && M >= 32768) {
+        const int big = g2_max_clusters(h, 4);
+        const int small = (h->num_sms - 8 * big) / 2;
+        int m1 = static_cast<int>(static_cast<int64_t>(M) * hybrid / 1000) / 1024 * 1024;
+        if (small > 0 && m1 > 0 && m1 < M) {
+            if (!h->gemm_side) {
+                int lo = 0, hi = 0;
+                B200_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                B200_CUDA(h, cudaStreamCreateWithPriority(&h->gemm_side, cudaStreamNonBlocking, lo));
+                B200_CUDA(h, cudaEventCreateWithFlags(&h->ev_gemm_fork, cudaEventDisableTiming));
+                B200_CUDA(h, cudaEventCreateWithFlags(&h->ev_gemm_join, cudaEventDisableTiming));
+            }
+            ProfScope ps(h, PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
+            B200_CUDA(h, cudaEventRecord(h->ev_gemm_fork, st));
+            static const int only = getenv("B200CLIP_GEMM_HYBRID_ONLY") ? atoi(getenv("B200CLIP_GEMM_HYBRID_ONLY")) : 0;  // probe: 1 main, 2 side
+            if (only != 2 && (rc = launch_gemm_2cta_range(h, a, lda, w, ldw, out, ldc, 0, m1, N, K, ep, 4, big, false, st))) return rc;
+            B200_CUDA(h, cudaStreamWaitEvent(h->gemm_side, h->ev_gemm_fork, 0));
+            if (only != 1 && (rc = launch_gemm_2cta_range(h, a, lda, w, ldw, out, ldc, m1, M - m1, N, K, ep, 1, small, false, h->gemm_side)))
+                return rc;
+            B200_CUDA(h, cudaEventRecord(h->ev_gemm_join, h->gemm_side));
+            B200_CUDA(h, cudaStreamWaitEvent(st, h->ev_gemm_join, 0));
+            h->launches--;   // one logical GEMM
+            return 0;
+        }
+    }
+    const int pairs = (pairs_env == 2 || pairs_env == 4) && M >= 2 * pairs_env * b200::GEMM_BLOCK_M * 8 ? pairs_env : 1;
+    ProfScope ps(h, PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
+    return launch_gemm_2cta_range(h, a, lda, w, ldw, out, ldc, 0, M, N, K, ep, pairs, g2_max_clusters(h, pairs), probe_on, st);
 }
 
 int launch_gemm(b200clip_handle* h, const bf16* a, int lda, const bf16* w, int ldw, bf16* out, int ldc, int M, int N,

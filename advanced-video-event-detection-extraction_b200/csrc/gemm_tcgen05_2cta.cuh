@@ -60,8 +60,15 @@ __device__ __forceinline__ void epilogue_chunk_smem(uint32_t (&acc)[32], int n0,
     }
 }
 
-template <int kUnused>   // a template only so that the header can be included from several translation units
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+// PAIRS = 1: a cluster is one CTA pair (the kernel described above).
+// PAIRS = 2 / 4: a cluster is two / four pairs working on M-adjacent 256 x 256 tiles that share their B tile.  Each
+// CTA loads its own 128 rows of A and only 1/PAIRS of its B half (64 / 32 weight rows), TMA-multicast to the CTA
+// holding the same B half in every pair: 24 / 20 KB instead of 32 KB of L2 reads per CTA and k-block.  Extra plumbing:
+// a stage is written by PAIRS CTAs, so empty[s] collects the MMA commits of ALL pairs (multicast to every CTA);
+// tmem_full / tmem_empty stay inside a pair.  Multicast completions land on the full barrier of each destination
+// pair's leader (cta_group::2 address with the peer bit cleared, as in CUTLASS' SM100_TMA_2SM_LOAD_MULTICAST).
+template <int PAIRS>
+__global__ void __cluster_dims__(2 * PAIRS, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                               __nv_bfloat16* out, int ldc, int M, int N, int K, GemmEpilogue ep, int use_tma_epi) {
@@ -80,12 +87,15 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t rank = crank & 1u;             // position inside the CTA pair
+    const uint32_t pair = crank >> 1;             // which pair of the cluster (0 when PAIRS == 1)
     const bool leader = rank == 0;
-    const int cluster_id = blockIdx.x >> 1;
-    const int num_clusters = gridDim.x >> 1;
+    const int cluster_id = blockIdx.x / (2 * PAIRS);
+    const int num_clusters = gridDim.x / (2 * PAIRS);
 
-    const int m_blocks = (M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
+    // a cluster walks "super tiles" of PAIRS M-adjacent 256-row blocks x one 256-column block
+    const int m_blocks = (M + 2 * PAIRS * GEMM_BLOCK_M - 1) / (2 * PAIRS * GEMM_BLOCK_M);
     const int n_blocks = (N + G2_BLOCK_N - 1) / G2_BLOCK_N;
     const int num_tiles = m_blocks * n_blocks;
     const int k_blocks = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
@@ -95,7 +105,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
         tma_prefetch_desc(&tmap_w);
         for (int s = 0; s < G2_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], PAIRS);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
@@ -118,8 +128,9 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int m_blk = tile / n_blocks;
-                const int n_blk = tile - m_blk * n_blocks;
+                const int m_sup = tile / n_blocks;
+                const int n_blk = tile - m_sup * n_blocks;
+                const int m_blk = m_sup * PAIRS + static_cast<int>(pair);
                 const int m0 = m_blk * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M;
                 const int n0 = n_blk * G2_BLOCK_N + static_cast<int>(rank) * G2_HALF_N;
                 for (int kb = 0; kb < k_blocks; ++kb) {
@@ -127,6 +138,14 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
                     const uint32_t bar = smem_u32(&full_bar[stage]) & kPeerBitMask;  // always the leader's barrier
                     tma_load_2d_cg2(smem_a + stage * G2_A_BYTES, &tmap_a, bar, kb * GEMM_BLOCK_K, m0);
+                    if (PAIRS > 1) {
+                        // this CTA's 1/PAIRS of the shared B half (64 or 32 weight rows), delivered to the CTA holding
+                        // the same half in every pair of the cluster
+                        constexpr uint32_t kAllPairs = PAIRS == 2 ? 0x5u : 0x55u;    // rank 0 of every pair
+                        tma_load_2d_cg2_mc(smem_b + stage * G2_B_BYTES + pair * (G2_B_BYTES / PAIRS), &tmap_w, bar,
+                                           kb * GEMM_BLOCK_K, n0 + static_cast<int>(pair) * (G2_HALF_N / PAIRS),
+                                           static_cast<uint16_t>(kAllPairs << rank));
+                    } else
                     tma_load_2d_cg2(smem_b + stage * G2_B_BYTES, &tmap_w, bar, kb * GEMM_BLOCK_K, n0);
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -158,13 +177,13 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
 #pragma unroll
                     for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k)
                         umma_bf16<2>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit_cg2(&empty_bar[stage], 0b11);   // frees the stage in both CTAs
+                    umma_commit_cg2(&empty_bar[stage], static_cast<uint16_t>((1u << (2 * PAIRS)) - 1u));   // frees the stage in every CTA that feeds it
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_cg2(&tmem_full_bar[as], 0b11);      // accumulator ready in both CTAs
+                umma_commit_cg2(&tmem_full_bar[as], static_cast<uint16_t>(0b11u << (2 * pair)));   // accumulator ready in both CTAs of the pair
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
-            if (ep.probe) {
+            if (ep.probe && pair == 0) {
                 ep.probe[cluster_id * 4 + 0] = clock64() - p_t0;
                 ep.probe[cluster_id * 4 + 1] = p_full;
                 ep.probe[cluster_id * 4 + 2] = p_tmem;
@@ -181,8 +200,9 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
         uint32_t aphase = 0;
         uint32_t res_phase = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-            const int m_blk = tile / n_blocks;
-            const int n_blk = tile - m_blk * n_blocks;
+            const int m_sup = tile / n_blocks;
+            const int n_blk = tile - m_sup * n_blocks;
+            const int m_blk = m_sup * PAIRS + static_cast<int>(pair);
             const int row = m_blk * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M + q * 32 + lane;
             const bool row_ok = row < M;
             long out_row = row;
@@ -261,10 +281,10 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
             if (ep.stats_out && row_ok && col0 < N) store_row_stats(ep, out_row, col0 / COLS_PER_WARP, ssum, ssq);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);  // the leader's barrier
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], crank & ~1u);  // the pair leader's barrier
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
-        if (ep.probe && leader && warp == 2 && lane == 0) ep.probe[cluster_id * 4 + 3] = p_epi;
+        if (ep.probe && leader && pair == 0 && warp == 2 && lane == 0) ep.probe[cluster_id * 4 + 3] = p_epi;
     }
 
     if (warp >= 2 && lane == 0) tma_store_wait<0>();   // bulk stores of the last tile are complete

@@ -87,6 +87,8 @@ struct b200clip_handle {
     cudaStream_t pre_stream = nullptr;
     cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_tower[2] = {nullptr, nullptr}, ev_fork = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t gemm_side = nullptr;            // hybrid GEMM: plain CTA pairs on the SMs the 8-CTA clusters leave idle
+    cudaEvent_t ev_gemm_fork = nullptr, ev_gemm_join = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     int64_t h2d_bytes = 0;         // bytes uploaded by the host-buffer entry points (b200clip_transfer_bytes)
     int64_t d2h_bytes = 0;
