@@ -783,7 +783,8 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
                          uint8_t* __restrict__ mid2, int64_t mid2_frame_stride, int oy0, int ny, int ox0, int nx,
                          int rows_per_strip, int xb0, int seg_bytes, int stage_bytes, int arow_pitch, int vpitch,
                          int left, int S, DevTaps ax, DevTaps ay, DevTaps bx, AhIntParams ip,
-                         const uint32_t* __restrict__ aq /*[area columns][8] packed weights, see build_plan*/) {
+                         const uint32_t* __restrict__ aq /*[area columns][8] packed weights, see build_plan*/,
+                         int null_consumers /*probe: consumers only drain the ring (times the load path alone)*/) {
     extern __shared__ __align__(128) uint8_t ah_smem[];
     const int ncons = blockDim.x - 32;                 // consumer threads; the last warp is the producer
     const int tid = threadIdx.x;
@@ -946,6 +947,7 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
         __syncwarp();
         if (lane == 0)                                // this warp holds its bytes in registers now
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(eb) : "memory");
+        if (null_consumers) { aL[0][0] ^= w[0][0] ^ w[VW - 1][3]; continue; }
         const uint32_t iyc = wts & 0xffffu;
         uint32_t lo[VW][4], hi[VW][4];
 #pragma unroll
@@ -1020,6 +1022,7 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
             par ^= 1;
         }
     }
+    if (null_consumers && aL[0][0] == 0x12345678u) mid2[0] = 1;   // keeps the probe's loads alive
     if (nfin > 0) {
         named_bar_sync(1, ncons);                // the last parked row is complete
         hpass_row(arow + (par ^ 1) * arow_pitch, out_row);
@@ -1514,7 +1517,8 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
                 ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(p.sy1 - p.sy0) * (p.sx1 - p.sx0) * 3.0 + ny * S * 3.0), st);
                 dim3 fgrid((ny + rows - 1) / rows, n);
                 kern<<<fgrid, ncv + 32, smem, st>>>(cur, cur_fs, cur_rs, mid2, p.mid2_per_frame, p.ry0, ny, p.rx0, nx, rows, xb0,
-                                                   seg, stage_bytes, arow_pitch, vpitch, p.left, S, p.ax, p.ay, p.bx, ip, p.aq);
+                                                   seg, stage_bytes, arow_pitch, vpitch, p.left, S, p.ax, p.ay, p.bx, ip, p.aq,
+                                                   getenv("B200CLIP_AREA_NULL") ? 1 : 0);
                 h->launches++;
                 fused_ab = true;
                 cur = mid2; cur_fs = p.mid2_per_frame; cur_rs = static_cast<int64_t>(S) * 3;
