@@ -777,7 +777,8 @@ __device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) 
 // consumers: fewer, fatter threads pay the per-row pipeline bookkeeping once per 32 bytes.
 // (Re-reading the per-column constants -- packed IDP.2A weights, Pillow coefficients -- from their L1-resident tables
 // once per area row instead of holding them in ~38 registers buys a fourth CTA per SM but measured 15 % slower.)
-template <int MAXT, int MINB, int VW, int PA, int PB>
+// NST: stages (source rows) of the bulk-copy ring, a power of two.
+template <int MAXT, int MINB, int VW, int PA, int PB, int NST>
 __global__ void __launch_bounds__(MAXT, MINB)
 area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride,
                          uint8_t* __restrict__ mid2, int64_t mid2_frame_stride, int oy0, int ny, int ox0, int nx,
@@ -789,9 +790,9 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
     const int ncons = blockDim.x - 32;                 // consumer threads; the last warp is the producer
     const int tid = threadIdx.x;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ah_smem);
-    uint64_t* empty_bar = full_bar + AH_NSTAGE;
-    uint8_t* ring = ah_smem + 2 * AH_NSTAGE * sizeof(uint64_t);
-    uint8_t* vbuf = ring + AH_NSTAGE * stage_bytes;     // [2 parities][L | H] streams, vpitch bytes each
+    uint64_t* empty_bar = full_bar + NST;
+    uint8_t* ring = ah_smem + 2 * NST * sizeof(uint64_t);
+    uint8_t* vbuf = ring + NST * stage_bytes;     // [2 parities][L | H] streams, vpitch bytes each
     uint8_t* arow = vbuf + 4 * vpitch;                  // [2] parked uint8 area rows
     AhRowInfo* rinfo = reinterpret_cast<AhRowInfo*>(arow + 2 * arow_pitch);
 
@@ -805,7 +806,7 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
     const int delta = static_cast<int>(reinterpret_cast<uintptr_t>(gbase) & 15);
 
     if (tid == 0) {
-        for (int s = 0; s < AH_NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ncons >> 5); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ncons >> 5); }
         fence_mbar_init();
     }
     // row program of the strip (see area_hpass_bulk_kernel): pad = integer weights, low half into the output row being
@@ -834,8 +835,8 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
         if (tid == ncons) {
             const uint8_t* g = gbase - delta + static_cast<int64_t>(r_lo) * row_stride;
             for (int i = 0; i < nrows; ++i, g += row_stride) {
-                const int s = i % AH_NSTAGE;
-                if (i >= AH_NSTAGE) mbar_wait(&empty_bar[s], ((i / AH_NSTAGE) - 1) & 1, 11);
+                const int s = i % NST;
+                if (i >= NST) mbar_wait(&empty_bar[s], ((i / NST) - 1) & 1, 11);
                 mbar_arrive_expect_tx(&full_bar[s], seg_bytes);
                 bulk_load_1d(ring + s * stage_bytes, g, seg_bytes, &full_bar[s]);
             }
@@ -922,8 +923,8 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
     uint32_t sbytes = static_cast<uint32_t>(stage_bytes);
     asm volatile("" : "+r"(full0), "+r"(ring0), "+r"(vb0), "+r"(ria), "+r"(sbytes));
     for (int i = 0; i < nrows; ++i) {
-        const uint32_t s = static_cast<uint32_t>(i) & (AH_NSTAGE - 1), phase = (static_cast<uint32_t>(i) / AH_NSTAGE) & 1u;
-        const uint32_t fb = full0 + 8u * s, eb = fb + 8u * AH_NSTAGE, soff = ring0 + s * sbytes;
+        const uint32_t s = static_cast<uint32_t>(i) & (NST - 1), phase = (static_cast<uint32_t>(i) / NST) & 1u;
+        const uint32_t fb = full0 + 8u * s, eb = fb + 8u * NST, soff = ring0 + s * sbytes;
         {
             uint32_t ok;
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -1492,6 +1493,8 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         // vertical-first integer form: one consumer per 16 bytes of the row window, two area columns per consumer
         static const bool no_vfirst = getenv("B200CLIP_AREA_HFIRST") != nullptr;
         // <2, 3, 2> on 128 consumers: 32 bytes of the row window, three area columns and two Pillow columns per thread
+        // <2, 3, 2> on 128 consumers.  Measured alternatives, all within noise of 1.1-1.2 ms per 1024 frames: <1, 2, 1> on
+        // 224 consumers at 3 or 4 CTAs per SM, a 16-stage ring, 24-288-row strips
         const int ncv = 128;
         const bool vfirst = intx && !no_vfirst && p.aq != nullptr && (seg >> 4) <= 2 * ncv && nx <= 3 * ncv && S <= 2 * ncv &&
                             p.a_dy * 255 < 65536 && p.a_dx <= 255 && xb0 - delta >= 0 && xb0 - delta + seg <= W * 3;
@@ -1509,7 +1512,7 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
                                 static_cast<size_t>(max_rows) * sizeof(AhRowInfo);
             if (smem <= 200 * 1024) {
                 AhIntParams ip{p.a_dx, p.a_dy, p.a_dx * p.a_dy, p.a_div_shift, p.a_div_mul};
-                auto kern = area_hpass_vfirst_kernel<160, 3, 2, 3, 2>;
+                auto kern = area_hpass_vfirst_kernel<160, 3, 2, 3, 2, AH_NSTAGE>;
                 if (smem > 48 * 1024)
                     B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
                 // ~45 KB per CTA: without the maximum carve-out the driver's default split allows only 3 CTAs per SM
