@@ -785,7 +785,7 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
                          int rows_per_strip, int xb0, int seg_bytes, int stage_bytes, int arow_pitch, int vpitch,
                          int left, int S, DevTaps ax, DevTaps ay, DevTaps bx, AhIntParams ip,
                          const uint32_t* __restrict__ aq /*[area columns][8] packed weights, see build_plan*/,
-                         int null_consumers /*probe: consumers only drain the ring (times the load path alone)*/) {
+                         int null_consumers /*probe: 1 = consumers only drain the ring (load path alone), 2 = no loads (consumers alone)*/) {
     extern __shared__ __align__(128) uint8_t ah_smem[];
     const int ncons = blockDim.x - 32;                 // consumer threads; the last warp is the producer
     const int tid = threadIdx.x;
@@ -837,6 +837,7 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
             for (int i = 0; i < nrows; ++i, g += row_stride) {
                 const int s = i % NST;
                 if (i >= NST) mbar_wait(&empty_bar[s], ((i / NST) - 1) & 1, 11);
+                if (null_consumers == 2) { mbar_arrive(&full_bar[s]); continue; }   // probe: no loads, consumers at full speed
                 mbar_arrive_expect_tx(&full_bar[s], seg_bytes);
                 bulk_load_1d(ring + s * stage_bytes, g, seg_bytes, &full_bar[s]);
             }
@@ -948,7 +949,7 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
         __syncwarp();
         if (lane == 0)                                // this warp holds its bytes in registers now
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(eb) : "memory");
-        if (null_consumers) { aL[0][0] ^= w[0][0] ^ w[VW - 1][3]; continue; }
+        if (null_consumers == 1) { aL[0][0] ^= w[0][0] ^ w[VW - 1][3]; continue; }
         const uint32_t iyc = wts & 0xffffu;
         uint32_t lo[VW][4], hi[VW][4];
 #pragma unroll
@@ -1023,7 +1024,7 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
             par ^= 1;
         }
     }
-    if (null_consumers && aL[0][0] == 0x12345678u) mid2[0] = 1;   // keeps the probe's loads alive
+    if (null_consumers == 1 && aL[0][0] == 0x12345678u) mid2[0] = 1;   // keeps the probe's loads alive
     if (nfin > 0) {
         named_bar_sync(1, ncons);                // the last parked row is complete
         hpass_row(arow + (par ^ 1) * arow_pitch, out_row);
@@ -1521,7 +1522,7 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
                 dim3 fgrid((ny + rows - 1) / rows, n);
                 kern<<<fgrid, ncv + 32, smem, st>>>(cur, cur_fs, cur_rs, mid2, p.mid2_per_frame, p.ry0, ny, p.rx0, nx, rows, xb0,
                                                    seg, stage_bytes, arow_pitch, vpitch, p.left, S, p.ax, p.ay, p.bx, ip, p.aq,
-                                                   getenv("B200CLIP_AREA_NULL") ? 1 : 0);
+                                                   getenv("B200CLIP_AREA_NULL") ? atoi(getenv("B200CLIP_AREA_NULL")) : 0);
                 h->launches++;
                 fused_ab = true;
                 cur = mid2; cur_fs = p.mid2_per_frame; cur_rs = static_cast<int64_t>(S) * 3;
