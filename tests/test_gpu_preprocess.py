@@ -22,7 +22,8 @@ def _u8_from_chw(chw: np.ndarray) -> np.ndarray:
 
 
 @pytest.mark.parametrize("w,h", [(224, 224), (512, 288), (1920, 1080), (1280, 720), (640, 480), (300, 300),
-                                 (288, 512), (399, 224), (1024, 1024), (800, 600), (2048, 1024), (225, 400)])
+                                 (288, 512), (399, 224), (1024, 1024), (800, 600), (2048, 1024), (225, 400),
+                                 (960, 540), (1600, 900)])   # integer-exact geometries with Dx = Dy = 15 / 25
 def test_reference_mode_bit_exact_vs_oracle(model_b32, w, h):
     from b200clip import capi
     from oracle import preprocess_ref as P
