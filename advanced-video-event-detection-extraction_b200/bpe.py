@@ -3,15 +3,20 @@
 (not available offline in this environment: point B200CLIP_BPE_VOCAB at it).  Algorithm as published with CLIP:
 bytes -> printable unicode table, 256 + 256 '</w>' base tokens, merges[1 : 49152-256-2+1], '<|startoftext|>' /
 '<|endoftext|>' appended; text is whitespace-collapsed and lower-cased, split with CLIP's regex, each word BPE-merged
-greedily by merge rank; output = [SOT] + ids[:ctx-2] + [EOT], zero padded.  (ftfy/html clean-up of the original is
-omitted: ftfy is not installed; plain ASCII/UTF-8 text is unaffected.)  Fidelity against open_clip is UNVERIFIED
-until a vocab file is available."""
+greedily by merge rank; output = [SOT] + ids[:ctx-2] + [EOT], zero padded.  Of the original's ftfy/html clean-up, the
+html unescape and ftfy's default NFC normalisation are kept (ftfy itself is not installed: mojibake repair is
+omitted; well-formed UTF-8 text is unaffected).  The algorithm is cross-checked against an independent implementation
+(transformers.CLIPTokenizer on the Rust `tokenizers` BPE) over a synthetic merges file in
+tests/test_bpe_tokenizer.py; the REAL 49 152-entry vocabulary is not available offline, so ids for real CLIP
+checkpoints are untested."""
 from __future__ import annotations
 
 import gzip
 import html
-import re
+import unicodedata
 from functools import lru_cache
+
+import regex as re   # \p{L} / \p{N} classes, as in CLIP's simple_tokenizer.py
 
 import torch
 
@@ -47,7 +52,7 @@ class SimpleTokenizer:
         with opener(bpe_path, "rt", encoding="utf-8") as f:
             merges = f.read().split("\n")
         merges = merges[1:49152 - 256 - 2 + 1]
-        merges = [tuple(m.split()) for m in merges]
+        merges = [tuple(m.split()) for m in merges if m.strip()]
         vocab = list(self.byte_encoder.values())
         vocab = vocab + [v + "</w>" for v in vocab]
         for m in merges:
@@ -57,7 +62,7 @@ class SimpleTokenizer:
         self.bpe_ranks = dict(zip(merges, range(len(merges))))
         self.cache = {"<|startoftext|>": "<|startoftext|>", "<|endoftext|>": "<|endoftext|>"}
         self.pat = re.compile(
-            r"""<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|[a-zA-Z]+|[0-9]|[^\sa-zA-Z0-9]+""", re.IGNORECASE)
+            r"""<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|[\p{L}]+|[\p{N}]|[^\s\p{L}\p{N}]+""", re.IGNORECASE)
         self.sot = self.encoder["<|startoftext|>"]
         self.eot = self.encoder["<|endoftext|>"]
 
@@ -97,7 +102,8 @@ class SimpleTokenizer:
         return out
 
     def encode(self, text: str):
-        text = re.sub(r"\s+", " ", html.unescape(html.unescape(text))).strip().lower()
+        text = unicodedata.normalize("NFC", html.unescape(html.unescape(text)))
+        text = re.sub(r"\s+", " ", text).strip().lower()
         ids = []
         for token in re.findall(self.pat, text):
             token = "".join(self.byte_encoder[b] for b in token.encode("utf-8"))

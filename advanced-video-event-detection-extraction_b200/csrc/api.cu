@@ -27,6 +27,23 @@ int b200_fail(const b200clip_handle* h, int code, const char* fmt, ...) {
     return code;
 }
 
+const B200Knobs& b200_knobs() {
+    static const B200Knobs k = [] {
+        auto on = [](const char* name) { const char* v = getenv(name); return v != nullptr && v[0] != '\0' && v[0] != '0'; };
+        B200Knobs b{};
+        b.k1_unfused = on("B200CLIP_K1_UNFUSED"); b.area_fp32 = on("B200CLIP_AREA_FP32"); b.area_px1 = on("B200CLIP_AREA_PX1");
+        b.area_hfirst = on("B200CLIP_AREA_HFIRST"); b.area_nostrip = on("B200CLIP_AREA_NOSTRIP");
+        b.vpass_generic = on("B200CLIP_VPASS_GENERIC");
+        b.gemm_1cta = on("B200CLIP_GEMM_1CTA"); b.gemm_spin_wait = on("B200CLIP_GEMM_SPIN_WAIT");
+        b.sim_simt = on("B200CLIP_SIM_SIMT"); b.sim_stream_a = on("B200CLIP_SIM_STREAM_A");
+        b.attn_oneshot = on("B200CLIP_ATTN_ONESHOT"); b.attn_tc = on("B200CLIP_ATTN_TC"); b.attn_tiled = on("B200CLIP_ATTN_TILED");
+        b.overlap = on("B200CLIP_OVERLAP"); b.full_upload = on("B200CLIP_FULL_UPLOAD");
+        b.nv12_unfused = on("B200CLIP_NV12_UNFUSED");
+        return b;
+    }();
+    return k;
+}
+
 extern "C" const char* b200clip_version(void) { return "b200clip 0.1 (sm_100a)"; }
 
 extern "C" const char* b200clip_last_error(const b200clip_handle* h) {
@@ -345,51 +362,70 @@ extern "C" int b200clip_finalize(b200clip_handle* h) {
 }
 
 // ------------------------------------------------------------------------------------------- workspace
-static int ensure_workspace(b200clip_handle* h, int images, int texts, cudaStream_t st) {
-    if (images <= h->ws_images && texts <= h->ws_texts) return 0;
-    const int ni = images > h->ws_images ? images : h->ws_images;
-    const int nt = texts > h->ws_texts ? texts : h->ws_texts;
-    B200_CUDA(h, cudaStreamSynchronize(st));
+// The image and the text tower own disjoint buffers and grow independently (a text call on one stream may overlap an
+// image call on another stream of the same handle).  Growing is rare and frees buffers other streams of this handle
+// may still be using, so the whole device is drained first.
+static int ensure_image_ws(b200clip_handle* h, int images) {
+    if (images <= h->ws_images) return 0;
+    B200_CUDA(h, cudaDeviceSynchronize());
     const b200clip_config& c = h->cfg;
-    const size_t mv = static_cast<size_t>(ni) * h->tokens, mt = static_cast<size_t>(nt) * c.text_ctx;
+    const size_t mv = static_cast<size_t>(images) * h->tokens;
     auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
-    const size_t x_el = mv * c.width, tx_el = mt * c.text_width;
-    const size_t qkv_el = 3 * x_el;
-    const size_t h_el = mv * c.mlp_dim, th_el = mt * c.text_mlp_dim;
-    const size_t p_el = static_cast<size_t>(ni) * h->grid * h->grid * h->patch_k;
+    const size_t x_el = mv * c.width, qkv_el = 3 * x_el, h_el = mv * c.mlp_dim;
+    const size_t p_el = static_cast<size_t>(images) * h->grid * h->grid * h->patch_k;
     cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_qkv); cudaFree(h->ws_h); cudaFree(h->ws_patches);
     cudaFree(h->ws_patches2); cudaFree(h->ws_stats);
-    cudaFree(h->ws_eot); cudaFree(h->ws_tokens);
-    cudaFree(h->ws_tx); cudaFree(h->ws_ty); cudaFree(h->ws_tqkv); cudaFree(h->ws_th); cudaFree(h->ws_tstats);
-    h->ws_tx = h->ws_ty = h->ws_tqkv = h->ws_th = nullptr; h->ws_tstats = nullptr;
     h->ws_stats = nullptr;
     h->ws_x = h->ws_y = h->ws_qkv = h->ws_h = h->ws_patches = h->ws_patches2 = nullptr;
-    h->ws_eot = nullptr; h->ws_tokens = nullptr;
-    h->ws_images = h->ws_texts = 0;
+    h->ws_images = 0;
     B200_CUDA(h, cudaMalloc(&h->ws_x, mx(x_el, 8) * 2));
     B200_CUDA(h, cudaMalloc(&h->ws_y, mx(x_el, 8) * 2));
     B200_CUDA(h, cudaMalloc(&h->ws_qkv, mx(qkv_el, 8) * 2));
     B200_CUDA(h, cudaMalloc(&h->ws_h, mx(h_el, 8) * 2));
     B200_CUDA(h, cudaMalloc(&h->ws_patches, mx(p_el, 8) * 2));
-    B200_CUDA(h, cudaMalloc(&h->ws_patches2, mx(p_el, 8) * 2));
+    if (b200_knobs().overlap) B200_CUDA(h, cudaMalloc(&h->ws_patches2, mx(p_el, 8) * 2));
     B200_CUDA(h, cudaMalloc(&h->ws_stats, mx(mv, 1) * 16 * sizeof(float)));
+    h->ws_images = images;
+    return 0;
+}
+
+static int ensure_text_ws(b200clip_handle* h, int texts) {
+    if (texts <= h->ws_texts) return 0;
+    B200_CUDA(h, cudaDeviceSynchronize());
+    const b200clip_config& c = h->cfg;
+    const size_t mt = static_cast<size_t>(texts) * c.text_ctx;
+    auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
+    const size_t tx_el = mt * c.text_width, th_el = mt * c.text_mlp_dim;
+    cudaFree(h->ws_eot); cudaFree(h->ws_tokens);
+    cudaFree(h->ws_tx); cudaFree(h->ws_ty); cudaFree(h->ws_tqkv); cudaFree(h->ws_th); cudaFree(h->ws_tstats);
+    h->ws_tx = h->ws_ty = h->ws_tqkv = h->ws_th = nullptr; h->ws_tstats = nullptr;
+    h->ws_eot = nullptr; h->ws_tokens = nullptr;
+    h->ws_texts = 0;
     B200_CUDA(h, cudaMalloc(&h->ws_tx, mx(tx_el, 8) * 2));
     B200_CUDA(h, cudaMalloc(&h->ws_ty, mx(tx_el, 8) * 2));
     B200_CUDA(h, cudaMalloc(&h->ws_tqkv, mx(3 * tx_el, 8) * 2));
     B200_CUDA(h, cudaMalloc(&h->ws_th, mx(th_el, 8) * 2));
     B200_CUDA(h, cudaMalloc(&h->ws_tstats, mx(mt, 1) * 16 * sizeof(float)));
-    B200_CUDA(h, cudaMalloc(&h->ws_eot, mx(nt, 1) * sizeof(int32_t)));
+    B200_CUDA(h, cudaMalloc(&h->ws_eot, mx(texts, 1) * sizeof(int32_t)));
     B200_CUDA(h, cudaMalloc(&h->ws_tokens, mx(mt, 1) * sizeof(int64_t)));
-    h->ws_images = ni;
-    h->ws_texts = nt;
+    h->ws_texts = texts;
     return 0;
+}
+
+static int ensure_workspace(b200clip_handle* h, int images, int texts, cudaStream_t) {
+    int rc = ensure_image_ws(h, images);
+    if (rc) return rc;
+    return ensure_text_ws(h, texts);
 }
 
 static const int kDefaultChunk = 1024;  // images per pass of the tower when the caller reserved nothing
 
+// An explicit reserve fixes the images per pass of the tower (the caller sized the workspace: bench --chunk,
+// settings.B200_MAX_IMAGES_PER_PASS); without one the default chunk applies whatever earlier calls happened to need.
 extern "C" int b200clip_reserve(b200clip_handle* h, int max_images, int max_texts) {
     if (!h || max_images < 0 || max_texts < 0) return b200_fail(h, B200CLIP_E_ARG, "reserve: bad argument");
     B200_CUDA(h, cudaSetDevice(h->device));
+    if (max_images > 0) h->chunk_cap = max_images;
     return ensure_workspace(h, max_images, max_texts, nullptr);
 }
 
@@ -452,8 +488,8 @@ static int check_ready(b200clip_handle* h, const char* what) {
 static size_t out_elem(int dt) { return dt == B200CLIP_BF16 ? 2 : 4; }
 
 static int chunk_images(b200clip_handle* h, int n) {
-    if (h->ws_images > 0) return h->ws_images;
-    return n < kDefaultChunk ? n : kDefaultChunk;
+    const int cap = h->chunk_cap > 0 ? h->chunk_cap : kDefaultChunk;
+    return n < cap ? n : cap;
 }
 
 extern "C" int b200clip_encode_patches(b200clip_handle* h, const void* patches_dev, int n, void* emb_out_dev,
@@ -557,8 +593,7 @@ extern "C" int b200clip_encode_frames_u8(b200clip_handle* h, const uint8_t* fram
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int chunk = chunk_images(h, n);
     // large batches: at least 4 pipelined chunks so that only the first K1 pass is exposed
-    static const bool no_overlap = getenv("B200CLIP_OVERLAP") == nullptr;
-    const bool pipelined = !no_overlap && n >= 256;  // measured slower on B200 (K1 blocks crowd out the tower): opt-in
+    const bool pipelined = b200_knobs().overlap && n >= 256;  // measured slower on B200 (K1 blocks crowd out the tower): opt-in
     if (pipelined) {
         int parts = (n + chunk - 1) / chunk;
         if (parts < 4) parts = 4;
@@ -624,8 +659,7 @@ extern "C" int b200clip_encode_frames_u8_host(b200clip_handle* h, const uint8_t*
     // and K1 is pointed at a virtual frame origin in front of it.
     int wx0, wx1, wy0, wy1;
     if ((rc = preprocess_source_window(h, height, width, resize_mode, &wx0, &wx1, &wy0, &wy1))) return rc;
-    static const bool full_upload = getenv("B200CLIP_FULL_UPLOAD") != nullptr;
-    if (full_upload) { wx0 = 0; wx1 = width; wy0 = 0; wy1 = height; }
+    if (b200_knobs().full_upload) { wx0 = 0; wx1 = width; wy0 = 0; wy1 = height; }
     wx0 &= ~15;                                                     // 48-byte aligned window start
     const int wrows = wy1 - wy0;
     const size_t wbytes = static_cast<size_t>(wx1 - wx0) * 3;       // bytes copied per row
@@ -733,8 +767,8 @@ static int encode_text_dev(b200clip_handle* h, const int64_t* tokens_dev, int q,
                            cudaStream_t st) {
     const b200clip_config& c = h->cfg;
     int rc;
-    int chunk = h->ws_texts > 0 ? h->ws_texts : (q < 256 ? q : 256);
-    if ((rc = ensure_workspace(h, 0, chunk, st))) return rc;
+    const int chunk = q < 256 ? q : 256;      // texts per pass of the tower; the workspace grows to it
+    if ((rc = ensure_text_ws(h, chunk))) return rc;
     for (int i = 0; i < q; i += chunk) {
         const int nc = (q - i) < chunk ? (q - i) : chunk;
         B200_CUDA(h, cudaMemsetAsync(h->ws_tstats, 0, static_cast<size_t>(nc) * c.text_ctx * 16 * sizeof(float), st));

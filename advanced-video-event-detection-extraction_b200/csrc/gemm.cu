@@ -50,11 +50,11 @@ static int launch_gemm_bn(b200clip_handle* h, const bf16* a, int lda, const bf16
         return rc;
     if ((rc = make_tmap_bf16_2d(h, &tw, w, N, K, ldw, BLOCK_N, b200::GEMM_BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B)))
         return rc;
-    static bool attr_set = false;
     auto kern = b200::gemm_bf16_tcgen05_kernel<BLOCK_N>;
-    if (!attr_set) {
+    const uint32_t abit = BLOCK_N == 64 ? ATTR_GEMM64 : BLOCK_N == 128 ? ATTR_GEMM128 : ATTR_GEMM256;
+    if (!(h->attr_done & abit)) {
         B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
+        h->attr_done |= abit;
     }
     const int m_blocks = (M + b200::GEMM_BLOCK_M - 1) / b200::GEMM_BLOCK_M;
     const int n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
@@ -69,15 +69,15 @@ static int launch_gemm_bn(b200clip_handle* h, const bf16* a, int lda, const bf16
     return 0;
 }
 
-// co-resident clusters of 2*pairs CTAs of the 2-CTA kernel (B200: GPCs of 16/18/20 SMs -> 74 / 33 / 15)
+// co-resident clusters of 2*pairs CTAs of the 2-CTA kernel on this handle's device (B200: GPCs of 16/18/20 SMs ->
+// 74 / 33 / 15); also where the kernel gets its dynamic shared-memory opt-in (per device, hence per handle)
 static int g2_max_clusters(b200clip_handle* h, int pairs) {
-    static bool init = false;
-    static int maxc[5] = {0, 0, 0, 0, 0};
-    if (!init) {
+    if (!(h->attr_done & ATTR_GEMM_2CTA)) {
         cudaFuncSetAttribute(b200::gemm_bf16_tcgen05_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b200::G2_SMEM_BYTES);
+        h->g2_clusters[1] = h->num_sms / 2;
+#ifdef B200CLIP_PROBES
         cudaFuncSetAttribute(b200::gemm_bf16_tcgen05_2cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b200::G2_SMEM_BYTES);
         cudaFuncSetAttribute(b200::gemm_bf16_tcgen05_2cta_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b200::G2_SMEM_BYTES);
-        maxc[1] = h->num_sms / 2;
         for (int pr = 2; pr <= 4; pr += 2) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(2 * pr * (h->num_sms / (2 * pr)));
@@ -87,18 +87,18 @@ static int g2_max_clusters(b200clip_handle* h, int pairs) {
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = 2 * pr; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            cudaError_t e = pr == 2 ? cudaOccupancyMaxActiveClusters(&maxc[pr], b200::gemm_bf16_tcgen05_2cta_kernel<2>, &cfg)
-                                    : cudaOccupancyMaxActiveClusters(&maxc[pr], b200::gemm_bf16_tcgen05_2cta_kernel<4>, &cfg);
-            if (e != cudaSuccess || maxc[pr] <= 0) {
+            cudaError_t e = pr == 2 ? cudaOccupancyMaxActiveClusters(&h->g2_clusters[pr], b200::gemm_bf16_tcgen05_2cta_kernel<2>, &cfg)
+                                    : cudaOccupancyMaxActiveClusters(&h->g2_clusters[pr], b200::gemm_bf16_tcgen05_2cta_kernel<4>, &cfg);
+            if (e != cudaSuccess || h->g2_clusters[pr] <= 0) {
                 cudaGetLastError();
-                maxc[pr] = h->num_sms / (2 * pr) - (pr == 2 ? 4 : 3);
+                h->g2_clusters[pr] = h->num_sms / (2 * pr) - (pr == 2 ? 4 : 3);
             }
         }
-        if (getenv("B200CLIP_GEMM_PAIRS") || getenv("B200CLIP_GEMM_HYBRID"))
-            fprintf(stderr, "[gemm] co-resident clusters: 4-CTA %d, 8-CTA %d\n", maxc[2], maxc[4]);
-        init = true;
+        fprintf(stderr, "[gemm] co-resident clusters: 4-CTA %d, 8-CTA %d\n", h->g2_clusters[2], h->g2_clusters[4]);
+#endif
+        h->attr_done |= ATTR_GEMM_2CTA;
     }
-    return maxc[pairs];
+    return h->g2_clusters[pairs];
 }
 
 // rows [r0, r0 + rows) of the problem on `pairs` CTA pairs per cluster, at most max_cl clusters, on stream s
@@ -138,15 +138,19 @@ static int launch_gemm_2cta_range(b200clip_handle* h, const bf16* a, int lda, co
     if (tiles < clusters) clusters = tiles;
     // epilogue warps sleep between polls of the accumulator barrier (A/B on one box: 0.5-1 % faster steps under the
     // power cap); B200CLIP_GEMM_SPIN_WAIT=1 restores the tight spin
-    static const int relaxed = getenv("B200CLIP_GEMM_SPIN_WAIT") ? 0 : 1;
-    epp.relaxed_wait = relaxed;
+    epp.relaxed_wait = b200_knobs().gemm_spin_wait ? 0 : 1;
     long long* probe = nullptr;
+#ifdef B200CLIP_PROBES
     if (with_probe) {
         B200_CUDA(h, cudaMallocManaged(&probe, sizeof(long long) * 4 * clusters));
         B200_CUDA(h, cudaMemset(probe, 0, sizeof(long long) * 4 * clusters));
         epp.probe = probe;
     }
+#else
+    (void)with_probe;
+#endif
     const unsigned grid = 2u * pairs * clusters;
+#ifdef B200CLIP_PROBES
     if (pairs == 4)
         b200::gemm_bf16_tcgen05_2cta_kernel<4><<<grid, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, s>>>(
             ta, tw, to, tr, outp, ldc, rows, N, K, epp, use_tma_epi);
@@ -154,6 +158,7 @@ static int launch_gemm_2cta_range(b200clip_handle* h, const bf16* a, int lda, co
         b200::gemm_bf16_tcgen05_2cta_kernel<2><<<grid, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, s>>>(
             ta, tw, to, tr, outp, ldc, rows, N, K, epp, use_tma_epi);
     else
+#endif
         b200::gemm_bf16_tcgen05_2cta_kernel<1><<<grid, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, s>>>(
             ta, tw, to, tr, outp, ldc, rows, N, K, epp, use_tma_epi);
     if (probe) {
@@ -173,13 +178,18 @@ static int launch_gemm_2cta_range(b200clip_handle* h, const bf16* a, int lda, co
 
 static int launch_gemm_2cta(b200clip_handle* h, const bf16* a, int lda, const bf16* w, int ldw, bf16* out, int ldc,
                             int M, int N, int K, const b200::GemmEpilogue& ep, cudaStream_t st) {
-    // B200CLIP_GEMM_PAIRS=2|4: clusters of two / four CTA pairs that share their B tile by TMA multicast (see the
-    // kernel header).  Per SM that is 4 % / 11-14 % faster, but 4- / 8-CTA clusters only fit 132 / 120 of the 148 SMs.
+    int pairs = 1;
+    bool probe_on = false;
+#ifdef B200CLIP_PROBES
+    // Launch forms that were measured and lost inside the power-capped step (profiles/r01aw_*); probe builds only.
+    // B200CLIP_GEMM_PAIRS=2|4: clusters of two / four CTA pairs that share their B tile by TMA multicast (per SM 4 % /
+    // 11-14 % faster, but 4- / 8-CTA clusters only fit 132 / 120 of the 148 SMs).
     static const int pairs_env = getenv("B200CLIP_GEMM_PAIRS") ? atoi(getenv("B200CLIP_GEMM_PAIRS")) : 1;
     // B200CLIP_GEMM_HYBRID=<per mille of the rows>: 8-CTA multicast clusters take that share of the rows and, on a
     // second low-priority stream, plain CTA pairs work on the rest on the SMs the big clusters cannot use.
     static const int hybrid = getenv("B200CLIP_GEMM_HYBRID") ? atoi(getenv("B200CLIP_GEMM_HYBRID")) : 0;
-    static const bool probe_on = getenv("B200CLIP_GEMM_PROBE") != nullptr;   // development aid, see GemmEpilogue::probe
+    static const bool probe_env = getenv("B200CLIP_GEMM_PROBE") != nullptr;   // clock64 waits, see GemmEpilogue::probe
+    probe_on = probe_env;
     const bool affine = ep.t_in == 0 && ep.rowtab == nullptr;
     int rc;
     if (hybrid > 0 && hybrid < 1000 && affine && M >= 32768) {
@@ -207,7 +217,8 @@ static int launch_gemm_2cta(b200clip_handle* h, const bf16* a, int lda, const bf
             return 0;
         }
     }
-    const int pairs = (pairs_env == 2 || pairs_env == 4) && M >= 2 * pairs_env * b200::GEMM_BLOCK_M * 8 ? pairs_env : 1;
+    pairs = (pairs_env == 2 || pairs_env == 4) && M >= 2 * pairs_env * b200::GEMM_BLOCK_M * 8 ? pairs_env : 1;
+#endif
     ProfScope ps(h, PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
     return launch_gemm_2cta_range(h, a, lda, w, ldw, out, ldc, 0, M, N, K, ep, pairs, g2_max_clusters(h, pairs), probe_on, st);
 }
@@ -222,8 +233,7 @@ int launch_gemm(b200clip_handle* h, const bf16* a, int lda, const bf16* w, int l
     // single-CTA kernel (used by the parity tests to cover both)
     // Row statistics are emitted per (row, column segment of BLOCK_N/2); only LN_SLOTS segments are kept.
     auto stats_fit = [&](int block_n) { return !ep.stats_out || (N + block_n / 2 - 1) / (block_n / 2) <= b200::LN_SLOTS; };
-    static const bool force_1cta = getenv("B200CLIP_GEMM_1CTA") != nullptr;
-    if (!force_1cta && N % 256 == 0 && M >= 2048 && stats_fit(256)) return launch_gemm_2cta(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
+    if (!b200_knobs().gemm_1cta && N % 256 == 0 && M >= 2048 && stats_fit(256)) return launch_gemm_2cta(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
     // tiny M (text tower: 77 rows per query): narrow tiles so that more CTAs share the latency-bound problem
     if (M <= 256 && N % 64 == 0 && stats_fit(64)) return launch_gemm_bn<64>(h, a, lda, w, ldw, out, ldc, M, N, K, ep, st);
     // (statistics-emitting GEMMs keep the 256-wide tiles at every M: the width of the partial-sum segments is part of

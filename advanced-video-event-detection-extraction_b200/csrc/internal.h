@@ -92,7 +92,26 @@ struct b200clip_handle {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     int64_t h2d_bytes = 0;         // bytes uploaded by the host-buffer entry points (b200clip_transfer_bytes)
     int64_t d2h_bytes = 0;
+    int chunk_cap = 0;             // images per pass of the tower fixed by an explicit b200clip_reserve (0 = default)
+    // cudaFuncSetAttribute is per DEVICE: which kernels of this handle's device already carry their opt-in (ATTR_*)
+    uint32_t attr_done = 0;
+    int g2_clusters[5] = {0, 0, 0, 0, 0};   // co-resident clusters of the 2-CTA GEMM on this device, per pairs
 };
+enum { ATTR_GEMM64 = 1u << 0, ATTR_GEMM128 = 1u << 1, ATTR_GEMM256 = 1u << 2, ATTR_GEMM_2CTA = 1u << 3, ATTR_SIM_TC = 1u << 4,
+       ATTR_ATTN_PERSIST = 1u << 5, ATTR_SIM_STREAM = 1u << 6, ATTR_K1_VFIRST = 1u << 7, ATTR_K1_NV12 = 1u << 8 };
+
+// Environment switches, read ONCE per process (first use).  They select between code paths that are all valid and
+// parity-tested (fallback kernels that other geometries use anyway); measurement probes that invalidate results or
+// launch forms that lost their A/B exist only in builds with -DB200CLIP_PROBES (make PROBES=1).
+struct B200Knobs {
+    bool k1_unfused, area_fp32, area_px1, area_hfirst, area_nostrip, vpass_generic;   // K1 fallbacks
+    bool gemm_1cta, gemm_spin_wait;
+    bool sim_simt, sim_stream_a;
+    bool attn_oneshot, attn_tc, attn_tiled;
+    bool overlap, full_upload;
+    bool nv12_unfused;
+};
+const B200Knobs& b200_knobs();
 
 // kernel classes for the profiler
 enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_PRE = 3, PROF_HEAD = 4, PROF_SIM = 5, PROF_MISC = 6, PROF_PRE_A = 7, PROF_PRE_B = 8, PROF_PRE_C = 9, PROF_NCLS = 10 };

@@ -1407,6 +1407,17 @@ static float* get_lut(b200clip_handle* h) {
     return d;
 }
 
+// Probe builds only (-DB200CLIP_PROBES): B200CLIP_AREA_NULL=1 consumers only drain the ring (load path alone), =2 no
+// loads (consumers alone).  Results are INVALID in either mode, so a release build cannot reach them.
+static int area_null_probe() {
+#ifdef B200CLIP_PROBES
+    static const int v = getenv("B200CLIP_AREA_NULL") ? atoi(getenv("B200CLIP_AREA_NULL")) : 0;
+    return v;
+#else
+    return 0;
+#endif
+}
+
 static unsigned grid_for(b200clip_handle* h, int64_t total, int threads) {
     int64_t b = (total + threads - 1) / threads;
     const int64_t cap = static_cast<int64_t>(h->num_sms) * 16;
@@ -1479,20 +1490,20 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
     if (n > 65535) return b200_fail(h, B200CLIP_E_SHAPE, "preprocess: at most 65535 frames per call (got %d)", n);
     bool fused_ab = false;
     if (p.has_a && p.has_b && !p.a_fast && p.a_seq && p.a_max_cx <= 5 && p.b_max_cnt <= 7 && (row_stride & 15) == 0 &&
-        (frame_stride & 15) == 0 && getenv("B200CLIP_K1_UNFUSED") == nullptr) {
+        (frame_stride & 15) == 0 && !b200_knobs().k1_unfused) {
         // A+B fused and bulk-copy fed: needs 16-byte aligned row segments that stay inside the row
         const int ny = p.ry1 - p.ry0, nx = p.rx1 - p.rx0;
         const int xb0 = p.sx0 * 3;
         const int delta = static_cast<int>((reinterpret_cast<uintptr_t>(frames) + xb0) & 15);
         const int seg = (delta + (p.sx1 - p.sx0) * 3 + 15) & ~15;
-        static const bool no_int = getenv("B200CLIP_AREA_FP32") != nullptr;    // parity tests cover every variant
-        static const bool no_px2 = getenv("B200CLIP_AREA_PX1") != nullptr;
+        const bool no_int = b200_knobs().area_fp32;    // parity tests cover every variant
+        const bool no_px2 = b200_knobs().area_px1;
         const bool intx = p.a_int && !no_int;
         // two columns per thread when that still fits a 160-thread consumer group
         const int px = (intx && !no_px2 && (max(nx, S) + 1) / 2 <= 160) ? 2 : 1;
         const int ncons = ((max(nx, S) + px - 1) / px + 31) & ~31;
         // vertical-first integer form: one consumer per 16 bytes of the row window, two area columns per consumer
-        static const bool no_vfirst = getenv("B200CLIP_AREA_HFIRST") != nullptr;
+        const bool no_vfirst = b200_knobs().area_hfirst;
         // <2, 3, 2> on 128 consumers: 32 bytes of the row window, three area columns and two Pillow columns per thread
         // <2, 3, 2> on 128 consumers.  Measured alternatives, all within noise of 1.1-1.2 ms per 1024 frames: <1, 2, 1> on
         // 224 consumers at 3 or 4 CTAs per SM, a 16-stage ring, 24-288-row strips
@@ -1502,8 +1513,7 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         if (vfirst) {
             // strip length: 24, 48, 96 and 288 rows measured within noise of each other on B200 (the per-CTA prologue
             // is ~10 % of the stall samples at 24 rows, but longer strips lose as much to the tail) -> keep 24
-            static const int rows0 = getenv("B200CLIP_AREA_ROWS") ? atoi(getenv("B200CLIP_AREA_ROWS")) : 24;
-            int rows = rows0 > 4 ? rows0 : 24;
+            int rows = 24;
             while (rows > 4 && static_cast<int64_t>(n) * ((ny + rows - 1) / rows) < static_cast<int64_t>(h->num_sms) * 6)
                 rows = (rows + 1) / 2;
             const int stage_bytes = seg + 16, arow_pitch = (nx * 3 + 32 + 15) & ~15, vpitch = seg + 32;
@@ -1514,15 +1524,17 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
             if (smem <= 200 * 1024) {
                 AhIntParams ip{p.a_dx, p.a_dy, p.a_dx * p.a_dy, p.a_div_shift, p.a_div_mul};
                 auto kern = area_hpass_vfirst_kernel<160, 3, 2, 3, 2, AH_NSTAGE>;
-                if (smem > 48 * 1024)
-                    B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                // ~45 KB per CTA: without the maximum carve-out the driver's default split allows only 3 CTAs per SM
-                B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                if (!(h->attr_done & ATTR_K1_VFIRST)) {
+                    B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    // ~45 KB per CTA: without the maximum carve-out the driver's default split allows only 3 CTAs per SM
+                    B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                    h->attr_done |= ATTR_K1_VFIRST;
+                }
                 ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(p.sy1 - p.sy0) * (p.sx1 - p.sx0) * 3.0 + ny * S * 3.0), st);
                 dim3 fgrid((ny + rows - 1) / rows, n);
                 kern<<<fgrid, ncv + 32, smem, st>>>(cur, cur_fs, cur_rs, mid2, p.mid2_per_frame, p.ry0, ny, p.rx0, nx, rows, xb0,
                                                    seg, stage_bytes, arow_pitch, vpitch, p.left, S, p.ax, p.ay, p.bx, ip, p.aq,
-                                                   getenv("B200CLIP_AREA_NULL") ? atoi(getenv("B200CLIP_AREA_NULL")) : 0);
+                                                   area_null_probe());
                 h->launches++;
                 fused_ab = true;
                 cur = mid2; cur_fs = p.mid2_per_frame; cur_rs = static_cast<int64_t>(S) * 3;
@@ -1559,7 +1571,7 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         const int ny = p.ry1 - p.ry0, nx = p.rx1 - p.rx0;
         dim3 grid((static_cast<unsigned>(ny) * nx + 255) / 256, n);
         ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(H) * (p.rx1 - p.rx0) * W / p.w1 * 3.0 + ny * nx * 3.0), st);
-        static const bool no_strip = getenv("B200CLIP_AREA_NOSTRIP") != nullptr;   // parity tests cover both paths
+        const bool no_strip = b200_knobs().area_nostrip;   // parity tests cover both paths
         if (p.a_fast)
             area_fast_kernel<<<grid, 256, 0, st>>>(cur, cur_fs, cur_rs, mid1, p.mid1_per_frame, p.ry0, ny, p.rx0, nx,
                                                    p.a_fx, p.a_fy);
@@ -1570,8 +1582,7 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
                 rows = (rows + 1) / 2;
             const int nstrips = (ny + rows - 1) / rows;
             dim3 sgrid((static_cast<unsigned>(nstrips) * nx + 127) / 128, n);
-            static const int depth = getenv("B200CLIP_AREA_DEPTH") ? atoi(getenv("B200CLIP_AREA_DEPTH")) : 2;
-            auto kern = depth <= 1 ? area_strip_kernel<1> : depth == 2 ? area_strip_kernel<2> : depth == 3 ? area_strip_kernel<3> : area_strip_kernel<4>;
+            auto kern = area_strip_kernel<2>;     // source rows in flight: 1, 3 and 4 measured no better
             kern<<<sgrid, 128, 0, st>>>(cur, cur_fs, static_cast<int>(cur_rs >> 2), mid1, p.mid1_per_frame,
                                         p.ry0, ny, p.rx0, nx, rows, nstrips, p.sy1 - 1, p.ax, p.ay, -0.0f);
         } else if (p.a_max_cx <= 5)
@@ -1606,7 +1617,7 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         dim3 grid((static_cast<unsigned>(S) * ((S + 7) >> 3) + 127) / 128, n);
         ProfScope psc(h, PROF_PRE_C, static_cast<double>(n) * ((p.ry1 - p.ry0) * S * 3.0 + (patches ? static_cast<double>(h->grid) * h->grid * h->patch_k * 2.0 : 3.0 * S * S * 4.0)), st);
         // tile form: bf16 patch output, 8-pixel groups never straddle a patch, every 24-byte group 8-byte aligned
-        static const bool no_tile = getenv("B200CLIP_VPASS_GENERIC") != nullptr;   // parity tests cover both forms
+        const bool no_tile = b200_knobs().vpass_generic;   // parity tests cover both forms
         const int xoff = -src_x0 * 3;
         const bool tile = !no_tile && patches && !chw && (P & 7) == 0 && (S & 7) == 0 && (S >> 3) <= 256 &&
                           (!p.has_c || p.c_max_cnt <= 7) && (cur_rs & 7) == 0 && (cur_fs & 7) == 0 &&

@@ -1032,7 +1032,7 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
     // gridDim.z is limited to 65535: split long batches
     const int64_t per_seq_in = static_cast<int64_t>(t) * 3 * heads * ATT_D;
     const int64_t per_seq_out = static_cast<int64_t>(t) * heads * ATT_D;
-    static const bool no_persist = getenv("B200CLIP_ATTN_ONESHOT") != nullptr;     // parity tests cover both
+    const bool no_persist = b200_knobs().attn_oneshot;     // parity tests cover both
     const int64_t n_items = static_cast<int64_t>(n_seq) * heads;
     if (!causal && t <= ATT_BK && !no_persist && n_items >= 2 * h->num_sms && n_items * t < (int64_t(1) << 31) &&
         (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) {
@@ -1040,11 +1040,10 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
         int rc = make_tmap_bf16_2d(h, &tq, qkv, static_cast<uint64_t>(n_seq) * t, 3ull * heads * ATT_D, 3ull * heads * ATT_D,
                                    t, ATT_D, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!(h->attr_done & ATTR_ATTN_PERSIST)) {
             B200_CUDA(h, cudaFuncSetAttribute(attention_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               ATP_SMEM_BYTES));
-            attr_set = true;
+            h->attr_done |= ATTR_ATTN_PERSIST;
         }
         int64_t grid = 4ll * h->num_sms;
         if (grid > n_items) grid = n_items;
@@ -1057,7 +1056,7 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
     }
     // opt-in while it is slower than the mma.sync K/V-resident kernel (24.5 vs 18.7 ms per 512 L/14 frames: four softmax
     // warps per CTA cannot keep up with the tensor core)
-    static const bool no_tc = getenv("B200CLIP_ATTN_TC") == nullptr;
+    const bool no_tc = !b200_knobs().attn_tc;
     if (!causal && t > ATT_BK && t <= ATC_MAX_KB * ATC_BN && !no_tc && n_seq <= 65535 &&
         static_cast<int64_t>(n_seq) * t < (int64_t(1) << 31) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) {
         CUtensorMap tq, t64, t16;
@@ -1074,7 +1073,7 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
         B200_CUDA(h, cudaGetLastError());
         return 0;
     }
-    static const bool no_seq = getenv("B200CLIP_ATTN_TILED") != nullptr;            // parity tests cover both
+    const bool no_seq = b200_knobs().attn_tiled;            // parity tests cover both
     if (!causal && t > ATT_BK && t <= ATS_MAX_BLOCKS * ATT_BK && !no_seq && n_seq <= 65535 &&
         static_cast<int64_t>(n_seq) * t < (int64_t(1) << 31) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) {
         CUtensorMap tq;

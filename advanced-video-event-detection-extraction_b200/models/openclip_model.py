@@ -44,6 +44,13 @@ class OpenCLIPModel:
             settings.OPENCLIP_MODEL, pretrained=settings.OPENCLIP_PRETRAINED, device=self.device,
             state_dict=self._state_dict, seed=self._seed, max_images=settings.B200_MAX_IMAGES_PER_PASS)
         self.tokenizer = b200_open_clip.get_tokenizer(settings.OPENCLIP_MODEL)
+        import os
+
+        from ..tokenizer import HashTokenizer
+        if isinstance(self.tokenizer, HashTokenizer) and self._state_dict is None and \
+                isinstance(settings.OPENCLIP_PRETRAINED, str) and os.path.exists(settings.OPENCLIP_PRETRAINED):
+            raise RuntimeError("a real checkpoint needs the real BPE vocabulary: set B200CLIP_BPE_VOCAB "
+                               "(the stand-in HashTokenizer is for synthetic weights only)")
         self.model.eval()
         self.model_loaded = True
         logger.info(f"Loaded b200clip model: {settings.OPENCLIP_MODEL} on {self.device}")

@@ -205,25 +205,42 @@ def create_model_and_transforms(model_name: str, pretrained=None, device=None, s
     """open_clip.create_model_and_transforms look-alike -> (model, preprocess_train(None), preprocess_val).
 
     Weights: `state_dict` (open_clip key names) if given; else `pretrained` may be a path to a checkpoint in
-    open_clip's native layout; otherwise (no network in this environment, so "openai" cannot be downloaded)
-    a seeded random init is used and a warning is logged -- the arithmetic is identical, only the weights differ.
+    open_clip's native layout.  A tag such as "openai" cannot be downloaded here (no network): that RAISES unless
+    B200CLIP_ALLOW_SYNTHETIC=1 opts into a seeded random init (tests / bench) -- never a silent stand-in.
+
+    Activation (open_clip semantics): QuickGELU for `pretrained="openai"` and for "*-quickgelu" model names, erf GELU
+    for every other tag / checkpoint; `quick_gelu=True/False` overrides.
     """
-    key = model_name.replace("/", "-")
+    import dataclasses
+    import os
+
+    from .tokenizer import allow_synthetic
+
+    name = model_name.replace("/", "-")
+    named_quick = name.lower().endswith("-quickgelu")
+    key = name[:-len("-quickgelu")] if named_quick else name
     if key not in MODEL_CONFIGS:
         raise ValueError(f"unknown model '{model_name}'; available: {sorted(MODEL_CONFIGS)}")
     cfg = MODEL_CONFIGS[key]
+    quick = _kw.get("quick_gelu", _kw.get("force_quick_gelu"))
+    if not quick and "quick_gelu" not in _kw:
+        quick = named_quick or pretrained is None or str(pretrained).lower() == "openai"
+    if bool(quick) != cfg.quick_gelu:
+        cfg = dataclasses.replace(cfg, quick_gelu=bool(quick))
     if state_dict is None:
-        import os
-
         if isinstance(pretrained, str) and os.path.exists(pretrained):
             state_dict = load_checkpoint(pretrained)
-        else:
+        elif allow_synthetic():
             import logging
 
             logging.getLogger(__name__).warning(
-                "no checkpoint for pretrained=%r is available offline; using a seeded random init (seed=%d)",
-                pretrained, seed)
+                "no checkpoint for pretrained=%r is available offline; B200CLIP_ALLOW_SYNTHETIC=1 -> seeded random "
+                "init (seed=%d)", pretrained, seed)
             state_dict = random_state_dict(cfg, seed)
+        else:
+            raise RuntimeError(
+                f"no checkpoint for pretrained={pretrained!r}: pass a path to an open_clip state dict (or state_dict=), "
+                "or set B200CLIP_ALLOW_SYNTHETIC=1 to run seeded random weights (results are then meaningless)")
     model = B200CLIP(cfg, state_dict, device=device, max_images=max_images, max_texts=max_texts)
     pre = _Preprocess(model)
     return model, pre, pre

@@ -33,14 +33,38 @@ class Phase1MVP:
         self._fp = None
 
     # -------------------------------------------------------------------------------------------
-    def process_video(self, video_path: str, query: str, top_k: int = None, debug_mode: bool = None):
+    def process_video(self, video_path: str, query: str, top_k: int = None, debug_mode: bool = None, merge=None):
+        """`merge` (b200clip addition, default settings.B200_TEMPORAL_MERGE = off -> the reference's phase-1 result):
+        True  -> Phase3Advanced._apply_temporal_consistency + confidence sort on the hits (timestamp +- 2.5 s segments,
+                 /root/reference/src/pipeline/phase3_advanced.py:29-81);
+        "clips" -> the same filter on the K4 clip intervals (start_time/end_time = clip_extractor.py:175-183), i.e. the
+                 hits that survive are clips no two of which overlap by more than half."""
         use_cache = settings.B200_EMBEDDING_CACHE and not (self.debug_mode if debug_mode is None else debug_mode)
+        if use_cache and world_info()[1] > 1:
+            # every rank would append to the same file, and the cached path does not shard: one writer only
+            logger.warning("B200_EMBEDDING_CACHE is ignored while torch.distributed is initialised (world > 1)")
+            use_cache = False
         if use_cache:
-            return self._process_video_cached(video_path, query, top_k)
+            return self._merge(self._process_video_cached(video_path, query, top_k, keep_intervals=True), merge)
         frames, timestamps = self.frame_extractor.extract_frames(video_path)
-        return self.process_frames(frames, timestamps, query, top_k, debug_mode)
+        return self.process_frames(frames, timestamps, query, top_k, debug_mode, merge=merge)
 
-    def _process_video_cached(self, video_path: str, query: str, top_k: int = None):
+    @staticmethod
+    def _merge(results, merge):
+        """Segment merge of a hit list (see process_video); always strips the helper interval keys of unmerged hits."""
+        if merge is None:
+            merge = settings.B200_TEMPORAL_MERGE
+        if merge:
+            from .temporal import merge_hits
+
+            if merge == "clips":
+                hits = [dict(r, start_time=r["start"], end_time=r["end"]) for r in results]
+            else:
+                hits = [{k: v for k, v in r.items() if k not in ("start", "end")} for r in results]
+            return [{k: v for k, v in r.items() if k not in ("start", "end")} for r in merge_hits(hits)]
+        return [{k: v for k, v in r.items() if k not in ("start", "end")} for r in results]
+
+    def _process_video_cached(self, video_path: str, query: str, top_k: int = None, keep_intervals: bool = False):
         """Opt-in (settings.B200_EMBEDDING_CACHE): embed a video once into data/embeddings/*.b2emb -- the directory
         the reference reserves but never uses (README.md:208) -- and answer this and every later query from the
         cached window embeddings with K4 alone.  Same result dicts as the uncached path."""
@@ -49,20 +73,32 @@ class Phase1MVP:
         from ..services.embedding_cache import EmbeddingCache, cache_path_for
 
         cache_dir = str(settings.DATA_DIR / "embeddings")
-        path = cache_path_for(video_path, cache_dir, settings.OPENCLIP_MODEL, self._fingerprint())
+        expect = {"weights_fingerprint": self._fingerprint(), "window_size": settings.WINDOW_SIZE,
+                  "window_stride": settings.WINDOW_STRIDE, "frame_sample_rate": settings.FRAME_SAMPLE_RATE,
+                  "max_sampled_frames": settings.MAX_SAMPLED_FRAMES, "resize_mode": int(capi.RESIZE_REFERENCE),
+                  "model": settings.OPENCLIP_MODEL, "pretrained": settings.OPENCLIP_PRETRAINED}
+        sampling = "|".join(f"{k}={expect[k]}" for k in sorted(expect) if k != "weights_fingerprint")
+        path = cache_path_for(video_path, cache_dir, settings.OPENCLIP_MODEL, self._fingerprint(), sampling)
         cache = self._caches.get(path)
         if cache is None:
-            if os.path.exists(path):
-                cache = EmbeddingCache.load(self.clip_model, path)
+            resume = os.path.exists(path)
+            if resume:
+                try:
+                    cache = EmbeddingCache.load(self.clip_model, path, expect=expect)
+                except (ValueError, OSError, KeyError) as e:       # torn header / other settings: treat as absent
+                    logger.warning(f"embedding cache {path} is unusable ({e}); rebuilding")
+                    cache, resume = None, False
+                    os.replace(path, path + ".bad")
             if cache is None or len(cache) != cache.meta.get("windows", len(cache)):     # absent or interrupted build
                 frames, timestamps = self.frame_extractor.extract_frames(video_path)
                 cache = EmbeddingCache.build(self.clip_model, frames, timestamps, dtype="float32", path=path,
-                                             resume=os.path.exists(path))
+                                             resume=resume, fingerprint=self._fingerprint())
             self._caches[path] = cache
         res = cache.query(query, top_k)
-        for r in res:           # the reference's dicts carry no interval
-            r.pop("start", None)
-            r.pop("end", None)
+        if not keep_intervals:
+            for r in res:           # the reference's dicts carry no interval
+                r.pop("start", None)
+                r.pop("end", None)
         return res
 
     def _fingerprint(self) -> str:
@@ -74,7 +110,7 @@ class Phase1MVP:
         return self._fp
 
     def process_frames(self, frames: np.ndarray, timestamps: Sequence[float], query: str, top_k: int = None,
-                       debug_mode: bool = None, video_duration: float = 0.0, return_device: bool = False):
+                       debug_mode: bool = None, video_duration: float = 0.0, return_device: bool = False, merge=None):
         """The body of process_video after decode (phase1_mvp.py:36-163)."""
         if top_k is None:
             top_k = settings.TOP_K_RESULTS
@@ -90,7 +126,9 @@ class Phase1MVP:
         rank, world = world_info()
         m = len(mid_idx)
         lo, hi = shard_range(m, rank, world)
-        k_eff = min(int(top_k), capi_max_k())
+        k_eff = int(top_k)      # any top_k: K4 serves k > 32 in ceil(k / 32) passes (phase1_mvp.py:145 takes any value)
+        if k_eff <= 0:
+            return ([], []) if self.debug_mode else []
         ts_dev = torch.tensor(window_ts, dtype=torch.float64, device=model.device)
         if hi > lo:
             middle = np.ascontiguousarray(np.asarray(frames)[np.asarray(mid_idx[lo:hi])])
@@ -111,10 +149,12 @@ class Phase1MVP:
             return scores, idx, iv, cnt
         n_hits = int(cnt[0].item())
         s_host, i_host = scores[0, :n_hits].cpu().numpy(), idx[0, :n_hits].cpu().numpy()
+        iv_host = iv[0, :n_hits].cpu().numpy()
         results: List[Dict] = []
-        for s, i in zip(s_host, i_host):
+        for s, i, (a, b) in zip(s_host, i_host, iv_host):
             results.append({"timestamp": window_ts[int(i)], "confidence": float(s), "phase": "phase1_mvp",
-                            "window_index": int(i)})
+                            "window_index": int(i), "start": float(a), "end": float(b)})
+        results = self._merge(results, merge)
         logger.info(f"Phase 1 found {len(results)} candidate events")
         if self.debug_mode:
             sims = model.similarity(emb, text_embedding)[:, 0].cpu().numpy()
@@ -122,9 +162,48 @@ class Phase1MVP:
             debug_info = [{"window_index": lo + j, "timestamp": window_ts[lo + j], "similarity": float(sims[j]),
                            "image_embedding_norm": float(norms[j]),
                            "frame_shape": tuple(np.asarray(frames[mid_idx[lo + j]]).shape)} for j in range(hi - lo)]
+            if len(sims):
+                self._log_debug_analysis(sims, debug_info, query, settings.CONFIDENCE_THRESHOLD)
             return results, debug_info
         return results
 
+    def _log_debug_analysis(self, similarities, debug_info, query, threshold) -> Dict:
+        """phase1_mvp.py:165-212: score statistics, best / worst windows, share above the threshold and -- when nothing
+        passes -- percentile-based threshold suggestions.  Logged like the reference; also returned (and kept in
+        `self.last_debug_analysis`) so that a caller can read the numbers without parsing the log."""
+        sims = np.asarray(similarities, dtype=np.float32)
 
-def capi_max_k() -> int:
-    return 32
+        def ts_of(i):
+            return debug_info[i].get("timestamp", 0.0) if i < len(debug_info) and isinstance(debug_info[i], dict) else 0.0
+
+        top = [int(i) for i in np.argsort(sims)[::-1][:10]]
+        bottom = [int(i) for i in np.argsort(sims)[:5]]
+        above = int(np.sum(sims >= threshold))
+        out = {"query": query, "windows": int(len(sims)), "min": float(sims.min()), "max": float(sims.max()),
+               "mean": float(sims.mean()), "std": float(sims.std()), "threshold": threshold,
+               "top10": [(i, float(sims[i]), ts_of(i)) for i in top],
+               "bottom5": [(i, float(sims[i]), ts_of(i)) for i in bottom], "above_threshold": above, "suggested": []}
+        logger.info("=== DEBUG ANALYSIS ===")
+        logger.info(f"Query: '{query}'")
+        logger.info(f"Total windows processed: {len(sims)}")
+        logger.info(f"Similarity range: [{out['min']:.6f}, {out['max']:.6f}]")
+        logger.info(f"Mean similarity: {out['mean']:.6f}")
+        logger.info(f"Std similarity: {out['std']:.6f}")
+        logger.info(f"Confidence threshold: {threshold}")
+        logger.info("Top 10 similarity scores:")
+        for n, (i, s, t) in enumerate(out["top10"]):
+            logger.info(f"  {n + 1}. Window {i}: {s:.6f} at {t:.2f}s")
+        logger.info("Bottom 5 similarity scores:")
+        for n, (i, s, t) in enumerate(out["bottom5"]):
+            logger.info(f"  {n + 1}. Window {i}: {s:.6f} at {t:.2f}s")
+        logger.info(f"Windows above threshold ({threshold}): {above}/{len(sims)} ({above / len(sims) * 100:.1f}%)")
+        if above == 0:
+            logger.info("Suggested thresholds based on percentiles:")
+            for p in (95, 90, 80, 70, 50):
+                thresh = float(np.percentile(sims, p))
+                count = int(np.sum(sims >= thresh))
+                out["suggested"].append((p, thresh, count))
+                logger.info(f"  {p}th percentile ({thresh:.4f}): {count} windows")
+        logger.info("=== END DEBUG ANALYSIS ===")
+        self.last_debug_analysis = out
+        return out

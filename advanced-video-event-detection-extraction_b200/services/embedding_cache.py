@@ -37,6 +37,8 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple, Union
 import numpy as np
 
 MAGIC = b"B2EMB\x01\x00\x00"
+# settings that decide WHICH rows a cache holds: part of the cache key, of the header meta, and validated on load
+SAMPLING_KEYS = ("frame_sample_rate", "max_sampled_frames", "resize_mode", "model", "pretrained")
 DTYPE_F32, DTYPE_BF16 = 0, 1
 FLAG_UNIT_NORM = 1
 _FIXED = struct.Struct("<8sIIIIQddIIII")     # 64 bytes
@@ -121,6 +123,11 @@ class EmbeddingCacheWriter:
                 raise ValueError("resume: embed_dim / dtype differ from the existing cache")
             if meta and self.header.meta.get("weights_fingerprint") not in (None, meta.get("weights_fingerprint")):
                 raise ValueError("resume: the existing cache was written with different weights")
+            if self.header.window_size != window_size or self.header.window_stride != window_stride:
+                raise ValueError("resume: the existing cache was built with other window settings")
+            for key in SAMPLING_KEYS:       # frames sampled / resized differently are different rows
+                if meta and key in meta and key in self.header.meta and self.header.meta[key] != meta[key]:
+                    raise ValueError(f"resume: the existing cache was built with another {key}")
             self._f = open(path, "r+b")
             end = _scan_blocks(self._f, self.header)[1]
             self._f.truncate(end)            # drop a torn block behind the last commit
@@ -178,6 +185,8 @@ class EmbeddingCacheWriter:
         self.header.duration = float(duration)
         self._f.seek(32)
         self._f.write(struct.pack("<d", self.header.duration))
+        self._f.flush()
+        os.fsync(self._f.fileno())
         self._f.seek(0, os.SEEK_END)
 
     def close(self):
@@ -250,7 +259,7 @@ class EmbeddingCache:
     @classmethod
     def build(cls, clip_model, frames: np.ndarray, timestamps: Sequence[float], dtype: str = "bfloat16",
               duration: float = 0.0, path: Optional[str] = None, chunk: int = 4096, resume: bool = False,
-              resize_mode: Optional[int] = None) -> "EmbeddingCache":
+              resize_mode: Optional[int] = None, fingerprint: Optional[str] = None) -> "EmbeddingCache":
         """Embed the sliding-window middle frames of a decoded video (frame_extractor.py:237-273 semantics) in
         chunks; with `path` every chunk is appended to a .b2emb file as it completes, and `resume=True` skips the
         windows an earlier, interrupted run already committed."""
@@ -263,7 +272,12 @@ class EmbeddingCache:
         model = clip_model.model
         mid_idx, window_ts = FrameExtractor().window_middles(len(frames), list(timestamps))
         tdt = torch.bfloat16 if dtype in ("bfloat16", "bf16") else torch.float32
-        meta = {"model": settings.OPENCLIP_MODEL, "pretrained": settings.OPENCLIP_PRETRAINED, "windows": len(mid_idx)}
+        mode = capi.RESIZE_REFERENCE if resize_mode is None else resize_mode
+        meta = {"model": settings.OPENCLIP_MODEL, "pretrained": settings.OPENCLIP_PRETRAINED, "windows": len(mid_idx),
+                "frame_sample_rate": settings.FRAME_SAMPLE_RATE, "max_sampled_frames": settings.MAX_SAMPLED_FRAMES,
+                "resize_mode": int(mode)}
+        if fingerprint:
+            meta["weights_fingerprint"] = fingerprint
         writer, done, parts = None, 0, []
         if path:
             writer = EmbeddingCacheWriter(path, model.embed_dim, dtype, True, meta, duration, 0.0,
@@ -273,7 +287,6 @@ class EmbeddingCache:
                 _, _, rows = read_cache(path)
                 prev = torch.from_numpy(rows.view(np.int16) if rows.dtype == np.uint16 else rows).to(model.device)
                 parts.append(prev.view(torch.bfloat16) if rows.dtype == np.uint16 else prev)
-        mode = capi.RESIZE_REFERENCE if resize_mode is None else resize_mode
         for lo in range(done, len(mid_idx), chunk):
             hi = min(lo + chunk, len(mid_idx))
             batch = np.ascontiguousarray(np.asarray(frames)[np.asarray(mid_idx[lo:hi])])
@@ -291,12 +304,18 @@ class EmbeddingCache:
         return cls(clip_model, all_emb.to(tdt), window_ts, duration, meta)
 
     @classmethod
-    def load(cls, clip_model, path: str) -> "EmbeddingCache":
+    def load(cls, clip_model, path: str, expect: Optional[dict] = None) -> "EmbeddingCache":
+        """`expect`: {weights_fingerprint, window_size, window_stride, frame_sample_rate, ...} of the CURRENT settings;
+        a cache written under different ones raises ValueError (the caller rebuilds)."""
         import torch
 
         header, ts, rows = read_cache(path)
         if header.embed_dim != clip_model.model.embed_dim:
             raise ValueError(f"{path}: embed_dim {header.embed_dim} does not match the loaded model")
+        for key, want in (expect or {}).items():
+            have = {"window_size": header.window_size, "window_stride": header.window_stride}.get(key, header.meta.get(key))
+            if have is not None and have != want:
+                raise ValueError(f"{path}: built with {key}={have!r}, current settings say {want!r}")
         t = torch.from_numpy(rows.view(np.int16) if rows.dtype == np.uint16 else rows)
         t = t.pin_memory().to(clip_model.model.device, non_blocking=True)
         if rows.dtype == np.uint16:
@@ -321,7 +340,6 @@ class EmbeddingCache:
         (phase1_mvp.py:145-155) plus the clip interval of clip_extractor.py:175-183 ('start', 'end')."""
         import torch
 
-        from ..pipeline.phase1_mvp import capi_max_k
         from ..utils.config import settings
 
         if isinstance(queries, str):
@@ -332,7 +350,9 @@ class EmbeddingCache:
         if len(self) == 0:
             raise ValueError("No windows could be processed due to memory constraints")      # phase1_mvp.py:130-131
         txt = torch.from_numpy(self.clip_model.encode_text(list(queries))).to(self.model.device)
-        k = min(int(top_k), capi_max_k())
+        k = int(top_k)
+        if k <= 0:
+            return [[] for _ in queries]
         scores, idx, iv, cnt = self.model.sim_topk(self.embeddings, txt, k, thr, self._ts_dev, index_base=0,
                                                    clip_duration=dur, video_duration=self.duration)
         scores, idx, iv, cnt = scores.cpu().numpy(), idx.cpu().numpy(), iv.cpu().numpy(), cnt.cpu().numpy()
@@ -350,9 +370,10 @@ class EmbeddingCache:
         return self.query_batch([query], top_k, threshold)[0]
 
 
-def cache_path_for(video_path: str, cache_dir: str, model_name: str, fingerprint: str = "") -> str:
-    """data/embeddings/<stem>-<digest>.b2emb; the digest covers path, size, mtime, model and weights."""
+def cache_path_for(video_path: str, cache_dir: str, model_name: str, fingerprint: str = "", sampling: str = "") -> str:
+    """data/embeddings/<stem>-<digest>.b2emb; the digest covers path, size, mtime, model, weights and the sampling /
+    window / resize settings (`sampling`: any string that changes when they do)."""
     st = os.stat(video_path)
-    key = f"{os.path.abspath(video_path)}|{st.st_size}|{int(st.st_mtime)}|{model_name}|{fingerprint}"
+    key = f"{os.path.abspath(video_path)}|{st.st_size}|{int(st.st_mtime)}|{model_name}|{fingerprint}|{sampling}"
     stem = os.path.splitext(os.path.basename(video_path))[0]
     return os.path.join(cache_dir, f"{stem}-{hashlib.sha256(key.encode()).hexdigest()[:12]}.b2emb")

@@ -53,7 +53,8 @@ class VideoProcessor:
         return {"valid": True}
 
     def process_query(self, video_path: str, query: str, mode: str = "mvp", top_k: Optional[int] = None,
-                      threshold: Optional[float] = None, debug_mode: bool = False) -> Dict:
+                      threshold: Optional[float] = None, debug_mode: bool = False, merge=None) -> Dict:
+        """`merge`: see Phase1MVP.process_video (None = settings.B200_TEMPORAL_MERGE, default off)."""
         if top_k is None:
             top_k = settings.TOP_K_RESULTS
         if threshold is None:
@@ -69,7 +70,7 @@ class VideoProcessor:
                 raise ValueError(f"Unknown processing mode: {mode}")
             if mode != "mvp":
                 logger.warning("Phase 2 not available, falling back to MVP mode")
-            result = self.phase1.process_video(video_path, processed_query, top_k, debug_mode=debug_mode)
+            result = self.phase1.process_video(video_path, processed_query, top_k, debug_mode=debug_mode, merge=merge)
             debug_info = None
             if debug_mode and isinstance(result, tuple):
                 results, debug_info = result

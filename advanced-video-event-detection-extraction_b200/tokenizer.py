@@ -1,7 +1,9 @@
 """Tokenizer front end.  open_clip's SimpleTokenizer needs `bpe_simple_vocab_16e6.txt.gz`, which is not
-available offline; if a vocab file is supplied (env B200CLIP_BPE_VOCAB) a byte-level BPE over
-it is used, otherwise a deterministic stand-in with the same framing ([SOT] ids... [EOT], zero padded to 77, EOT
-the largest id so that argmax pooling lands on it).  String -> BPE fidelity is therefore unverified here."""
+available offline: point B200CLIP_BPE_VOCAB at it and the byte-level BPE of bpe.py is used.
+Without it get_tokenizer() RAISES -- a trained text tower fed with stand-in ids returns meaningless hits -- unless
+B200CLIP_ALLOW_SYNTHETIC=1 explicitly opts into the deterministic stand-in below (same framing: [SOT] ids... [EOT],
+zero padded to 77, EOT the largest id so that argmax pooling lands on it).  Tests, bench.py and smoke() opt in: they
+run seeded random weights, for which any fixed string -> id map is as good as another."""
 from __future__ import annotations
 
 import os
@@ -34,8 +36,19 @@ def get_tokenizer(model_name: str):
     (reference call site: src/models/openclip_model.py:82)."""
     cfg = MODEL_CONFIGS[model_name.replace("/", "-")]
     vocab_path = os.environ.get("B200CLIP_BPE_VOCAB")
-    if vocab_path and os.path.exists(vocab_path):
+    if vocab_path:
+        if not os.path.exists(vocab_path):
+            raise FileNotFoundError(f"B200CLIP_BPE_VOCAB={vocab_path} does not exist")
         from .bpe import SimpleTokenizer
 
         return SimpleTokenizer(vocab_path, cfg.text_ctx)
+    if not allow_synthetic():
+        raise RuntimeError(
+            "no BPE vocabulary: set B200CLIP_BPE_VOCAB to CLIP's bpe_simple_vocab_16e6.txt.gz, or set "
+            "B200CLIP_ALLOW_SYNTHETIC=1 to accept the stand-in HashTokenizer (only meaningful with synthetic weights)")
     return HashTokenizer(cfg.text_ctx, cfg.text_vocab)
+
+
+def allow_synthetic() -> bool:
+    """Explicit opt-in to stand-ins (hash tokenizer, seeded random weights) -- never a silent default."""
+    return os.environ.get("B200CLIP_ALLOW_SYNTHETIC", "0") not in ("", "0")

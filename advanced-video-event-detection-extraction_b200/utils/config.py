@@ -42,6 +42,10 @@ class Settings:
         # embed each video once into DATA_DIR/embeddings/*.b2emb and answer later queries from the cache (off = the
         # reference's behaviour: decode + embed on every query)
         self.B200_EMBEDDING_CACHE = bool(_env("B200_EMBEDDING_CACHE", 0, int))
+        # segment merge of the phase-1 hits (phase3_advanced.py:29-81 temporal consistency): 0 = off (reference phase-1
+        # result), 1 = on hits (timestamp +- 2.5 s), "clips" = on the clip intervals
+        _m = _env("B200_TEMPORAL_MERGE", "0", str)
+        self.B200_TEMPORAL_MERGE = "clips" if _m == "clips" else bool(_env("B200_TEMPORAL_MERGE", 0, int))
 
 
 settings = Settings()

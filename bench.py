@@ -25,6 +25,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+os.environ.setdefault("B200CLIP_ALLOW_SYNTHETIC", "1")   # synthetic weights + stand-in tokenizer: explicit opt-in
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -9,6 +9,8 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# the suite runs seeded random weights + the stand-in tokenizer: an explicit opt-in (the product refuses by default)
+os.environ.setdefault("B200CLIP_ALLOW_SYNTHETIC", "1")
 
 
 def pytest_configure(config):

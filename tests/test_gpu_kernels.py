@@ -136,26 +136,3 @@ print("variant ok")
         e.update(env)
         r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "variant ok" in r.stdout, (env, r.stdout[-1500:], r.stderr[-1500:])
-
-
-def test_gemm_multicast_cluster_variants_in_subprocess():
-    """Opt-in launch forms of the 2-CTA GEMM, each chosen once per process: B200CLIP_GEMM_PAIRS=2|4 = clusters of two /
-    four CTA pairs whose B tile arrives by TMA multicast; B200CLIP_GEMM_HYBRID=830 = 8-CTA multicast clusters on 83 % of
-    the rows plus plain CTA pairs, on a second stream, on the SMs the big clusters cannot use.  None beats one pair
-    per cluster inside the power-capped step (profiles/r01aw_*), but all must stay correct: the probe compares every
-    epilogue flavour and an M tail with an fp32 reference (first, middle and last rows)."""
-    import json
-    import os
-    import subprocess
-    import sys
-
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for env in ({"B200CLIP_GEMM_PAIRS": "2"}, {"B200CLIP_GEMM_PAIRS": "4"}, {"B200CLIP_GEMM_HYBRID": "830"}):
-        e = {k: v for k, v in os.environ.items() if not k.startswith("B200CLIP_GEMM")}
-        e.update(env)
-        r = subprocess.run([sys.executable, os.path.join(root, "tools", "probes", "gemm_pairs_probe.py"), "40300"], env=e,
-                           capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, (env, r.stdout[-1500:] + r.stderr[-1500:])
-        res = json.loads(r.stdout.strip().splitlines()[-1])
-        for name in ("qkv", "out", "fc", "proj", "tail"):
-            assert res[name]["rel_err"] <= 0.01, (env, name, res[name])

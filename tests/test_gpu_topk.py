@@ -169,6 +169,64 @@ def test_tensor_core_path_order_is_exact(model_b32, n, q, k, e):
     assert np.array_equal(i.cpu().numpy(), want)
     assert np.array_equal(s.cpu().numpy(), np.take_along_axis(d.T, want, 1))
     assert np.array_equal(c.cpu().numpy(), (np.take_along_axis(d.T, want, 1) >= 0.05).sum(1))
-    # the public entry (same dispatch) returns the same thing
+    # the public entry selects the same k rows, then RE-SCORES them with the fp32 query in the streaming kernel's exact
+    # arithmetic and re-sorts: confidences (and threshold decisions) must not depend on how many queries share a batch
     s2, i2, iv2, c2 = model_b32.sim_topk(img_t, txt_t, k, 0.05, torch.arange(n, dtype=torch.float64), 0, 30.0, float(n))
-    assert torch.equal(i2, i) and torch.equal(s2, s) and torch.equal(c2, c)
+    sd = model_b32.similarity(img_t, txt_t).cpu().numpy()            # streaming kernel, fp32 query
+    i_np, i2_np, s2_np = i.cpu().numpy(), i2.cpu().numpy(), s2.cpu().numpy()
+    for j in range(q):
+        sel = i_np[j]
+        order = np.lexsort((sel, sd[sel, j]))[::-1]
+        assert np.array_equal(i2_np[j], sel[order]), (j, i2_np[j], sel[order])
+        assert np.array_equal(s2_np[j], sd[sel[order], j])
+        for r in range(k):
+            assert tuple(iv2[j, r].cpu().numpy()) == R.clip_interval(float(i2_np[j, r]), 30.0, float(n))
+    assert np.array_equal(c2.cpu().numpy(), (s2_np >= 0.05).sum(1))
+    # ... and equal what a single-query call (streaming path) reports for the same rows
+    s1, i1, _, _ = model_b32.sim_topk(img_t, txt_t[:1], k, 0.05, torch.arange(n, dtype=torch.float64), 0, 30.0, float(n))
+    common = np.intersect1d(i1[0].cpu().numpy(), i2_np[0])
+    assert len(common) >= k - 1                                          # bf16 pre-selection may swap the k-th on a near tie
+    for row in common:
+        assert s1[0][(i1[0] == int(row))].item() == s2[0][(i2[0] == int(row))].item()
+
+
+@pytest.mark.parametrize("n,q,k", [(5000, 1, 50), (5000, 3, 100), (40, 1, 64), (100000, 2, 33), (1000, 1, 1000),
+                                   (3600, 1, 200), (70, 17, 65)])
+def test_top_k_beyond_32(model_b32, n, q, k):
+    """phase1_mvp.py:145 accepts any top_k: k > 32 is served by ceil(k / 32) passes, each admitting only rows that come
+    strictly after the last slot of the previous pass -- the concatenation must be the plain descending argsort,
+    including tie order, the -1 padding when k > n, counts and intervals."""
+    rng = np.random.default_rng(n * 7 + k)
+    img = _unit(rng.standard_normal((n, 512)).astype(np.float32))
+    img[n // 3: n // 3 + 5] = img[1]                          # ties that straddle a pass boundary somewhere
+    txt = _unit(rng.standard_normal((q, 512)).astype(np.float32))
+    _check(model_b32, img, txt, k, 0.02, ts=np.arange(n) * 0.5, vdur=n * 0.5)
+    _check(model_b32, img, txt, k, -1.0, dtype=torch.bfloat16, base=11)
+
+
+def test_all_equal_scores_across_passes(model_b32):
+    img = np.tile(_unit(np.ones((1, 512), np.float32)), (100, 1))
+    txt = _unit(np.ones((1, 512), np.float32))
+    s, i, _, c = _check(model_b32, img, txt, 70, 0.5)
+    assert list(i[0]) == list(range(99, 29, -1)) and c[0] == 70
+
+
+def test_multi_shard_merge_beyond_32(model_b32):
+    rng = np.random.default_rng(12)
+    n, q, k, g = 6001, 3, 80, 4
+    img = _unit(rng.standard_normal((n, 512)).astype(np.float32))
+    img[3000:3003] = img[10]
+    txt = _unit(rng.standard_normal((q, 512)).astype(np.float32))
+    from b200clip.distributed import shard_range
+
+    img_t, txt_t = torch.from_numpy(img).cuda(), torch.from_numpy(txt).cuda()
+    ts = torch.arange(n, dtype=torch.float64) / 24.0
+    cs, ci = [], []
+    for r in range(g):
+        lo, hi = shard_range(n, r, g)
+        s, i, _, _ = model_b32.sim_topk(img_t[lo:hi], txt_t, k, -1.0, ts, index_base=lo)
+        cs.append(s)
+        ci.append(i)
+    ms, mi, miv, mc = model_b32.topk_merge(torch.stack(cs), torch.stack(ci), 0.05, ts, 30.0, n / 24.0)
+    ws, wi, wiv, wc = model_b32.sim_topk(img_t, txt_t, k, 0.05, ts, 0, 30.0, n / 24.0)
+    assert torch.equal(mi, wi) and torch.equal(ms, ws) and torch.equal(miv, wiv) and torch.equal(mc, wc)

@@ -1,0 +1,121 @@
+"""No-GPU checks of the host logic added in round 2: loud failure instead of silent stand-ins, the activation choice
+of create_model_and_transforms, the segment-merge switch of Phase1MVP, the phase-1 debug analysis, and the embedding
+cache key / validation."""
+import os
+
+import numpy as np
+import pytest
+
+
+def test_synthetic_weights_need_an_explicit_opt_in(monkeypatch):
+    from b200clip import open_clip as oc
+
+    monkeypatch.setenv("B200CLIP_ALLOW_SYNTHETIC", "0")
+    with pytest.raises(RuntimeError, match="B200CLIP_ALLOW_SYNTHETIC"):
+        oc.create_model_and_transforms("ViT-B-32", pretrained="openai")
+    with pytest.raises(ValueError):
+        oc.create_model_and_transforms("ViT-XYZ", pretrained="openai")
+
+
+def test_activation_follows_the_pretrained_tag(monkeypatch):
+    """open_clip: QuickGELU for pretrained='openai' and '*-quickgelu' names, erf GELU otherwise.  The choice is read
+    from the config handed to the C ABI (captured by stubbing the model class: no GPU here)."""
+    from b200clip import open_clip as oc
+
+    seen = {}
+
+    class Stub:
+        def __init__(self, cfg, sd, device=None, max_images=0, max_texts=0):
+            seen["quick"] = cfg.quick_gelu
+
+    monkeypatch.setattr(oc, "B200CLIP", Stub)
+    monkeypatch.setattr(oc, "_Preprocess", lambda m: None)
+    sd = {"x": 0}
+    oc.create_model_and_transforms("ViT-B-32", pretrained="openai", state_dict=sd)
+    assert seen["quick"] is True
+    oc.create_model_and_transforms("ViT-B-32", pretrained="laion2b_s34b_b79k", state_dict=sd)
+    assert seen["quick"] is False
+    oc.create_model_and_transforms("ViT-B-32-quickgelu", pretrained="laion400m_e32", state_dict=sd)
+    assert seen["quick"] is True
+    oc.create_model_and_transforms("ViT-B-32", pretrained="laion2b_s34b_b79k", state_dict=sd, quick_gelu=True)
+    assert seen["quick"] is True
+    oc.create_model_and_transforms("ViT-B-32", pretrained="openai", state_dict=sd, quick_gelu=False)
+    assert seen["quick"] is False
+
+
+def _hits():
+    return [{"timestamp": 10.0, "confidence": 0.9, "phase": "phase1_mvp", "window_index": 5, "start": 0.0, "end": 25.0},
+            {"timestamp": 11.0, "confidence": 0.8, "phase": "phase1_mvp", "window_index": 6, "start": 0.0, "end": 26.0},
+            {"timestamp": 30.0, "confidence": 0.7, "phase": "phase1_mvp", "window_index": 9, "start": 15.0, "end": 45.0},
+            {"timestamp": 100.0, "confidence": 0.6, "phase": "phase1_mvp", "window_index": 20, "start": 85.0, "end": 115.0}]
+
+
+def test_merge_switch_default_off_and_reference_semantics(monkeypatch):
+    from b200clip.pipeline.phase1_mvp import Phase1MVP
+    from b200clip.pipeline.temporal import merge_hits
+    from b200clip.utils.config import settings
+    from oracle.phase1_ref import temporal_consistency
+
+    keys = {"timestamp", "confidence", "phase", "window_index"}
+    off = Phase1MVP._merge(_hits(), None)
+    assert [r["window_index"] for r in off] == [5, 6, 9, 20] and all(set(r) == keys for r in off)   # reference dicts
+    on = Phase1MVP._merge(_hits(), True)                     # timestamp +- 2.5 s: 10.0 and 11.0 overlap by 4 s > 2.5
+    assert [r["window_index"] for r in on] == [5, 9, 20] and all(set(r) == keys for r in on)
+    stripped = [{k: v for k, v in r.items() if k in keys} for r in _hits()]
+    want = sorted(temporal_consistency(stripped), key=lambda r: r["confidence"], reverse=True)
+    assert on == want == merge_hits(stripped)
+    clips = Phase1MVP._merge(_hits(), "clips")               # 30 s clips: the one around 30.0 overlaps [0, 25] by 10 s only
+    assert [r["window_index"] for r in clips] == [5, 9, 20]
+    monkeypatch.setattr(settings, "B200_TEMPORAL_MERGE", True)
+    assert Phase1MVP._merge(_hits(), None) == on
+    assert [r["window_index"] for r in Phase1MVP._merge(_hits(), False)] == [5, 6, 9, 20]
+
+
+def test_debug_analysis_matches_reference_numbers():
+    """phase1_mvp.py:165-212 restated with numpy on the same scores."""
+    from b200clip.pipeline.phase1_mvp import Phase1MVP
+
+    rng = np.random.default_rng(0)
+    sims = (0.2 + 0.03 * rng.standard_normal(63)).astype(np.float32)
+    info = [{"timestamp": i * 0.5} for i in range(63)]
+    p = Phase1MVP.__new__(Phase1MVP)
+    out = p._log_debug_analysis(sims, info, "red car", 0.9)
+    assert out["windows"] == 63 and out["above_threshold"] == 0
+    assert out["min"] == float(sims.min()) and out["max"] == float(sims.max())
+    assert out["mean"] == float(sims.mean()) and out["std"] == float(sims.std())
+    assert [i for i, _, _ in out["top10"]] == list(np.argsort(sims)[::-1][:10])
+    assert [i for i, _, _ in out["bottom5"]] == list(np.argsort(sims)[:5])
+    assert [(p_, c) for p_, _, c in out["suggested"]] == [(q, int(np.sum(sims >= np.percentile(sims, q)))) for q in (95, 90, 80, 70, 50)]
+    assert out["top10"][0][2] == info[out["top10"][0][0]]["timestamp"]
+    out2 = p._log_debug_analysis(sims, info, "red car", 0.2)
+    assert out2["above_threshold"] == int((sims >= 0.2).sum()) and out2["suggested"] == []
+
+
+def test_cache_key_covers_sampling_settings(tmp_path):
+    from b200clip.services.embedding_cache import CacheHeader, EmbeddingCacheWriter, cache_path_for
+
+    v = tmp_path / "a.mp4"
+    v.write_bytes(b"x" * 10)
+    a = cache_path_for(str(v), str(tmp_path), "ViT-B-32", "fp", "frame_sample_rate=1|window_size=16")
+    b = cache_path_for(str(v), str(tmp_path), "ViT-B-32", "fp", "frame_sample_rate=2|window_size=16")
+    c = cache_path_for(str(v), str(tmp_path), "ViT-B-32", "fp2", "frame_sample_rate=1|window_size=16")
+    assert len({a, b, c}) == 3
+    # resume refuses a cache written under other window / sampling settings or other weights
+    meta = {"weights_fingerprint": "fp", "frame_sample_rate": 1, "model": "ViT-B-32"}
+    path = str(tmp_path / "c.b2emb")
+    with EmbeddingCacheWriter(path, 8, "float32", True, meta, window_size=16, window_stride=8) as w:
+        w.append(np.ones((3, 8), np.float32), [0.0, 1.0, 2.0])
+        w.set_duration(12.5)
+    with open(path, "rb") as f:
+        hdr = CacheHeader.unpack(f.read(1 << 16))
+    assert hdr.meta["weights_fingerprint"] == "fp" and hdr.duration == 12.5 and hdr.rows == 3
+    with pytest.raises(ValueError, match="window"):
+        EmbeddingCacheWriter(path, 8, "float32", True, meta, window_size=8, window_stride=4, resume=True)
+    with pytest.raises(ValueError, match="frame_sample_rate"):
+        EmbeddingCacheWriter(path, 8, "float32", True, dict(meta, frame_sample_rate=2), window_size=16, window_stride=8,
+                             resume=True)
+    with pytest.raises(ValueError, match="weights"):
+        EmbeddingCacheWriter(path, 8, "float32", True, dict(meta, weights_fingerprint="other"), window_size=16,
+                             window_stride=8, resume=True)
+    with EmbeddingCacheWriter(path, 8, "float32", True, meta, window_size=16, window_stride=8, resume=True) as w:
+        assert w.rows == 3

@@ -3,6 +3,7 @@ usage: python tools/bench_model.py --model ViT-L-14 --frames 512 [--hw 224 224]"
 import argparse
 import json
 import os
+os.environ.setdefault("B200CLIP_ALLOW_SYNTHETIC", "1")
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -9,6 +9,7 @@ usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-ad
 import argparse
 import json
 import os
+os.environ.setdefault("B200CLIP_ALLOW_SYNTHETIC", "1")
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
