@@ -57,6 +57,12 @@ SIGNATURES = {
                                           c_int, c_int, c_void_p]),
     "b200clip_encode_frames_u8_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                                c_void_p]),
+    "b200clip_preprocess_nv12": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int,
+                                         c_void_p, c_void_p, c_void_p]),
+    "b200clip_encode_frames_nv12": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int64,
+                                            c_int, c_void_p, c_int, c_int, c_void_p]),
+    "b200clip_encode_frames_nv12_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                                 c_void_p]),
     "b200clip_encode_text": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "b200clip_encode_text_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "b200clip_sim_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int, c_float, c_void_p,

@@ -172,7 +172,7 @@ extern "C" int b200clip_destroy(b200clip_handle* h) {
     for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
     cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_qkv); cudaFree(h->ws_h); cudaFree(h->ws_patches);
-    cudaFree(h->ws_emb); cudaFree(h->ws_pre); cudaFree(h->ws_topk); cudaFree(h->ws_eot); cudaFree(h->ws_tokens);
+    cudaFree(h->ws_emb); cudaFree(h->ws_pre); cudaFree(h->ws_nv12); cudaFree(h->ws_topk); cudaFree(h->ws_eot); cudaFree(h->ws_tokens);
     cudaFree(h->ws_patches2); cudaFree(h->ws_stats);
     cudaFree(h->ws_tx); cudaFree(h->ws_ty); cudaFree(h->ws_tqkv); cudaFree(h->ws_th); cudaFree(h->ws_tstats);
     if (h->pre_stream) cudaStreamDestroy(h->pre_stream);
@@ -643,38 +643,45 @@ extern "C" int b200clip_encode_frames_u8(b200clip_handle* h, const uint8_t* fram
 
 // HOST frames -> HOST embeddings.  Device staging is double buffered: the copy stream uploads chunk i+1 while the
 // compute stream runs preprocess + tower on chunk i.  Pinned caller memory is copied directly; pageable memory
-// goes through pinned bounce buffers.
-extern "C" int b200clip_encode_frames_u8_host(b200clip_handle* h, const uint8_t* frames_host, int n, int height,
-                                              int width, int resize_mode, float* emb_out_host, int l2norm,
-                                              void* stream) {
-    int rc = check_ready(h, "encode_frames_u8_host");
+// goes through pinned bounce buffers.  nv12 = false: packed RGB frames (H*W*3 bytes each); nv12 = true: NV12 frames
+// (H*W*3/2 bytes each: Y plane, then the interleaved UV plane) -- half the bytes over PCIe.
+static int encode_frames_host(b200clip_handle* h, const uint8_t* frames_host, int n, int height, int width, bool nv12,
+                              int resize_mode, float* emb_out_host, int l2norm, void* stream, const char* what) {
+    int rc = check_ready(h, what);
     if (rc) return rc;
-    if (n < 0 || (n > 0 && (!frames_host || !emb_out_host))) return b200_fail(h, B200CLIP_E_ARG, "encode_frames_u8_host: bad argument");
+    if (n < 0 || (n > 0 && (!frames_host || !emb_out_host))) return b200_fail(h, B200CLIP_E_ARG, "%s: bad argument", what);
     if (n == 0) return 0;
-    if (height <= 0 || width <= 0) return b200_fail(h, B200CLIP_E_ARG, "encode_frames_u8_host: bad frame size");
+    if (height <= 0 || width <= 0) return b200_fail(h, B200CLIP_E_ARG, "%s: bad frame size", what);
+    if (nv12 && ((height | width) & 1)) return b200_fail(h, B200CLIP_E_SHAPE, "%s: NV12 needs even width and height", what);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t fbytes = static_cast<size_t>(height) * width * 3;
+    const size_t bpp = nv12 ? 1 : 3;                                // bytes per pixel of a source row
+    const size_t src_pitch = static_cast<size_t>(width) * bpp;
+    const size_t src_rows = nv12 ? static_cast<size_t>(height) * 3 / 2 : static_cast<size_t>(height);   // rows per frame
+    const size_t fbytes = src_pitch * src_rows;
     // Only the window of each frame that survives the transform's centre crop is uploaded (for 1080p: 1104 of the 1920
-    // columns): a strided 3-D copy packs rows [wy0, wy1) x columns [wx0, wx1) of every frame into the staging buffer,
-    // and K1 is pointed at a virtual frame origin in front of it.
+    // columns): strided 3-D copies pack rows [wy0, wy1) x columns [wx0, wx1) of every frame (NV12: of both planes)
+    // into the staging buffer, and K1 is pointed at a virtual frame origin in front of it.
     int wx0, wx1, wy0, wy1;
-    if ((rc = preprocess_source_window(h, height, width, resize_mode, &wx0, &wx1, &wy0, &wy1))) return rc;
+    if (nv12) rc = preprocess_source_window_nv12(h, height, width, resize_mode, &wx0, &wx1, &wy0, &wy1);
+    else rc = preprocess_source_window(h, height, width, resize_mode, &wx0, &wx1, &wy0, &wy1);
+    if (rc) return rc;
     if (b200_knobs().full_upload) { wx0 = 0; wx1 = width; wy0 = 0; wy1 = height; }
-    wx0 &= ~15;                                                     // 48-byte aligned window start
+    wx0 &= ~15;                                                     // 16-pixel (RGB: 48-byte) aligned window start
     const int wrows = wy1 - wy0;
-    const size_t wbytes = static_cast<size_t>(wx1 - wx0) * 3;       // bytes copied per row
+    const int uv0 = wy0 >> 1, uvrows = nv12 ? ((wy1 + 1) >> 1) - uv0 : 0;       // chroma rows of the window
+    const size_t wbytes = static_cast<size_t>(wx1 - wx0) * bpp;     // bytes copied per row
     const size_t pitch = (wbytes + 63) & ~size_t(63);               // staging row pitch
-    const size_t fpitch = pitch * wrows;                            // staging frame pitch
+    const size_t fpitch = pitch * wrows, uvfpitch = pitch * uvrows; // staging frame pitches of the (luma) and chroma windows
     const size_t lead = 64;                                         // K1 may read the aligned word in front of a row
     int chunk = chunk_images(h, n);
     const size_t budget = size_t(1) << 30;  // ~1 GiB of frames per staging buffer
-    if (static_cast<size_t>(chunk) * fpitch > budget) chunk = static_cast<int>(budget / fpitch);
+    if (static_cast<size_t>(chunk) * (fpitch + uvfpitch) > budget) chunk = static_cast<int>(budget / (fpitch + uvfpitch));
     if (chunk < 1) chunk = 1;
     if ((rc = ensure_workspace(h, chunk, 0, st))) return rc;
     cudaPointerAttributes attr{};
     bool pinned = cudaPointerGetAttributes(&attr, frames_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    const size_t sbytes = static_cast<size_t>(chunk) * fpitch + 2 * lead;
+    const size_t sbytes = static_cast<size_t>(chunk) * (fpitch + uvfpitch) + 2 * lead;
     const size_t hbytes = static_cast<size_t>(chunk) * fbytes;      // pageable input: whole frames bounce through pinned memory
     if (sbytes > h->ws_stage_bytes || (!pinned && (!h->ws_stage_host[0] || hbytes > h->ws_stage_host_bytes))) {
         B200_CUDA(h, cudaStreamSynchronize(st));
@@ -731,21 +738,32 @@ extern "C" int b200clip_encode_frames_u8_host(b200clip_handle* h, const uint8_t*
             src = h->ws_stage_host[b];
         }
         uint8_t* stage = h->ws_stage_dev[b] + lead;
-        cudaMemcpy3DParms cp{};
-        cp.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(src) + static_cast<size_t>(wy0) * width * 3 + static_cast<size_t>(wx0) * 3,
-                                        static_cast<size_t>(width) * 3, static_cast<size_t>(width) * 3, height);
-        cp.dstPtr = make_cudaPitchedPtr(stage, pitch, pitch, wrows);
-        cp.extent = make_cudaExtent(wbytes, wrows, nc);
-        cp.kind = cudaMemcpyHostToDevice;
-        B200_CUDA(h, cudaMemcpy3DAsync(&cp, h->copy_stream));
-        h->h2d_bytes += static_cast<int64_t>(wbytes) * wrows * nc;
+        uint8_t* stage_uv = stage + static_cast<size_t>(nc) * fpitch;       // NV12: chroma windows behind the luma windows
+        auto upload = [&](const uint8_t* from, uint8_t* to, int rows) -> int {
+            cudaMemcpy3DParms cp{};
+            cp.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(from), src_pitch, src_pitch, src_rows);
+            cp.dstPtr = make_cudaPitchedPtr(to, pitch, pitch, rows);
+            cp.extent = make_cudaExtent(wbytes, rows, nc);
+            cp.kind = cudaMemcpyHostToDevice;
+            B200_CUDA(h, cudaMemcpy3DAsync(&cp, h->copy_stream));
+            h->h2d_bytes += static_cast<int64_t>(wbytes) * rows * nc;
+            return 0;
+        };
+        if ((rc = upload(src + static_cast<size_t>(wy0) * src_pitch + static_cast<size_t>(wx0) * bpp, stage, wrows))) return rc;
+        if (nv12 && (rc = upload(src + (static_cast<size_t>(height) + uv0) * src_pitch + wx0, stage_uv, uvrows))) return rc;
         B200_CUDA(h, cudaEventRecord(h->ev_h2d[b], h->copy_stream));
         B200_CUDA(h, cudaStreamWaitEvent(st, h->ev_h2d[b], 0));
         // virtual origin: staging (row 0, byte 0) is source (row wy0, column wx0)
-        const uint8_t* origin = stage - static_cast<int64_t>(wy0) * static_cast<int64_t>(pitch) - static_cast<int64_t>(wx0) * 3;
-        if ((rc = launch_preprocess(h, origin, nc, height, width, static_cast<int64_t>(fpitch),
-                                    static_cast<int64_t>(pitch), resize_mode, h->ws_patches, nullptr, st)))
-            return rc;
+        const int64_t ip = static_cast<int64_t>(pitch);
+        if (nv12) {
+            rc = launch_preprocess_nv12(h, stage - wy0 * ip - wx0, stage_uv - uv0 * ip - wx0, nc, height, width,
+                                        static_cast<int64_t>(fpitch), static_cast<int64_t>(uvfpitch), ip, resize_mode,
+                                        h->ws_patches, nullptr, st);
+        } else {
+            rc = launch_preprocess(h, stage - wy0 * ip - static_cast<int64_t>(wx0) * 3, nc, height, width,
+                                   static_cast<int64_t>(fpitch), ip, resize_mode, h->ws_patches, nullptr, st);
+        }
+        if (rc) return rc;
         if ((rc = encode_patches_chunk(h, h->ws_patches, nc, emb_dev + static_cast<size_t>(i0) * h->cfg.embed_dim,
                                        B200CLIP_F32, l2norm, st)))
             return rc;
@@ -759,6 +777,74 @@ extern "C" int b200clip_encode_frames_u8_host(b200clip_handle* h, const uint8_t*
     B200_CUDA(h, cudaMemcpyAsync(emb_out_host, h->ws_emb, emb_el * sizeof(float), cudaMemcpyDeviceToHost, st));
     h->d2h_bytes += static_cast<int64_t>(emb_el * sizeof(float));
     B200_CUDA(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int b200clip_encode_frames_u8_host(b200clip_handle* h, const uint8_t* frames_host, int n, int height,
+                                              int width, int resize_mode, float* emb_out_host, int l2norm,
+                                              void* stream) {
+    return encode_frames_host(h, frames_host, n, height, width, false, resize_mode, emb_out_host, l2norm, stream,
+                              "encode_frames_u8_host");
+}
+
+extern "C" int b200clip_encode_frames_nv12_host(b200clip_handle* h, const uint8_t* nv12_host, int n, int height,
+                                                int width, int resize_mode, float* emb_out_host, int l2norm,
+                                                void* stream) {
+    return encode_frames_host(h, nv12_host, n, height, width, true, resize_mode, emb_out_host, l2norm, stream,
+                              "encode_frames_nv12_host");
+}
+
+// ---- NV12 frames resident on the device (what NVDEC writes): Y plane + interleaved UV plane, common row pitch
+static int check_nv12_args(b200clip_handle* h, const void* y, const void* uv, int n, int height, int width, int64_t y_fs,
+                           int64_t uv_fs, int64_t rs, const void* out, const char* what) {
+    if (n < 0 || (n > 0 && (!y || !uv || !out))) return b200_fail(h, B200CLIP_E_ARG, "%s: bad argument", what);
+    if (n > 0 && (height <= 0 || width <= 0 || ((height | width) & 1)))
+        return b200_fail(h, B200CLIP_E_SHAPE, "%s: NV12 needs positive even width and height (%dx%d)", what, width, height);
+    if (n > 0 && (rs < width || y_fs < rs * height || uv_fs < rs * (height / 2)))
+        return b200_fail(h, B200CLIP_E_ARG, "%s: bad strides %lld/%lld/%lld for %dx%d", what, (long long)rs, (long long)y_fs,
+                         (long long)uv_fs, width, height);
+    return 0;
+}
+
+extern "C" int b200clip_preprocess_nv12(b200clip_handle* h, const uint8_t* y_dev, const uint8_t* uv_dev, int n, int height,
+                                        int width, int64_t y_frame_stride, int64_t uv_frame_stride, int64_t row_stride,
+                                        int resize_mode, void* patches_out_dev, float* chw_out_dev, void* stream) {
+    if (!h) return b200_fail(h, B200CLIP_E_ARG, "preprocess_nv12: null handle");
+    if (!patches_out_dev && !chw_out_dev) return b200_fail(h, B200CLIP_E_ARG, "preprocess_nv12: no output buffer");
+    if (int rc = check_nv12_args(h, y_dev, uv_dev, n, height, width, y_frame_stride, uv_frame_stride, row_stride,
+                                 patches_out_dev ? patches_out_dev : chw_out_dev, "preprocess_nv12"))
+        return rc;
+    B200_CUDA(h, cudaSetDevice(h->device));
+    return launch_preprocess_nv12(h, y_dev, uv_dev, n, height, width, y_frame_stride, uv_frame_stride, row_stride,
+                                  resize_mode, static_cast<bf16*>(patches_out_dev), chw_out_dev,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200clip_encode_frames_nv12(b200clip_handle* h, const uint8_t* y_dev, const uint8_t* uv_dev, int n,
+                                           int height, int width, int64_t y_frame_stride, int64_t uv_frame_stride,
+                                           int64_t row_stride, int resize_mode, void* emb_out_dev, int out_dtype,
+                                           int l2norm, void* stream) {
+    int rc = check_ready(h, "encode_frames_nv12");
+    if (rc) return rc;
+    if ((rc = check_nv12_args(h, y_dev, uv_dev, n, height, width, y_frame_stride, uv_frame_stride, row_stride, emb_out_dev,
+                              "encode_frames_nv12")))
+        return rc;
+    if (out_dtype != B200CLIP_F32 && out_dtype != B200CLIP_BF16) return b200_fail(h, B200CLIP_E_ARG, "bad out_dtype");
+    if (n == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int chunk = chunk_images(h, n);
+    if ((rc = ensure_workspace(h, chunk, 0, st))) return rc;
+    for (int i = 0; i < n; i += chunk) {
+        const int nc = (n - i) < chunk ? (n - i) : chunk;
+        if ((rc = launch_preprocess_nv12(h, y_dev + static_cast<int64_t>(i) * y_frame_stride,
+                                         uv_dev + static_cast<int64_t>(i) * uv_frame_stride, nc, height, width, y_frame_stride,
+                                         uv_frame_stride, row_stride, resize_mode, h->ws_patches, nullptr, st)))
+            return rc;
+        if ((rc = encode_patches_chunk(h, h->ws_patches, nc,
+                                       static_cast<uint8_t*>(emb_out_dev) + static_cast<size_t>(i) * h->cfg.embed_dim * out_elem(out_dtype),
+                                       out_dtype, l2norm, st)))
+            return rc;
+    }
     return 0;
 }
 

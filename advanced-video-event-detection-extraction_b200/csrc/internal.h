@@ -81,6 +81,8 @@ struct b200clip_handle {
     float* pre_lut = nullptr;      // [3][256] ToTensor+Normalize lookup
     uint8_t* ws_pre = nullptr;     // preprocess intermediates
     size_t ws_pre_bytes = 0;
+    uint8_t* ws_nv12 = nullptr;    // RGB scratch of the generic (unfused) NV12 path
+    size_t ws_nv12_bytes = 0;
     void* ws_topk = nullptr;       // sim/top-k partial candidates
     size_t ws_topk_bytes = 0;
     bf16* ws_patches2 = nullptr;   // second patch buffer: K1 of chunk i+1 overlaps the tower of chunk i
@@ -159,5 +161,8 @@ int launch_similarity(b200clip_handle* h, const void* img, int dtype, int64_t n,
 int launch_topk_merge(b200clip_handle* h, const float* cs, const int64_t* ci, int g, int q, int k, float thr,
                       const double* ts, double clip_dur, double vid_dur, float* top_scores, int64_t* top_idx,
                       double* intervals, int32_t* counts, cudaStream_t st);
+int launch_preprocess_nv12(b200clip_handle* h, const uint8_t* y, const uint8_t* uv, int n, int H, int W, int64_t y_fs,
+                           int64_t uv_fs, int64_t rs, int mode, bf16* patches, float* chw, cudaStream_t st);
+int preprocess_source_window_nv12(b200clip_handle* h, int H, int W, int mode, int* x0, int* x1, int* y0, int* y1);
 void preprocess_free_plans(b200clip_handle* h);
 int preprocess_source_window(b200clip_handle* h, int H, int W, int mode, int* x0, int* x1, int* y0, int* y1);

@@ -778,14 +778,58 @@ __device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) 
 // (Re-reading the per-column constants -- packed IDP.2A weights, Pillow coefficients -- from their L1-resident tables
 // once per area row instead of holding them in ~38 registers buys a fourth CTA per SM but measured 15 % slower.)
 // NST: stages (source rows) of the bulk-copy ring, a power of two.
-template <int MAXT, int MINB, int VW, int PA, int PB, int NST>
+//
+// NV12 = true (the decoder-output frame feed): the source is a 4:2:0 frame as a hardware decoder leaves
+// it -- a Y plane and an interleaved half-resolution UV plane -- instead of packed RGB.  The producer streams, per
+// source row, the window's luma bytes and the chroma bytes of row r/2 into the stage (1.5 B/px of HBM traffic instead
+// of 3); consumer t converts ITS 8 pixels to the 24 RGB bytes OpenCV's COLOR_YUV2RGB_NV12 would produce (BT.601
+// limited range, 20-bit fixed point, bit-exact: oracle/nv12_ref.py) in registers and from there on runs the very same
+// integer pipeline on them.  RGB never exists in HBM.  One slice = 8 px = 24 bytes = 6 words (RGB source: 16 bytes).
+__device__ __forceinline__ uint32_t pack_sat_u8(int hi, int lo, uint32_t upper) {
+    uint32_t d;     // d = sat_u8(lo) | sat_u8(hi) << 8 | upper << 16
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(upper));
+    return d;
+}
+// 8 luma bytes + 4 (U, V) pairs -> 24 RGB bytes in memory order (R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3 | ...)
+__device__ __forceinline__ void nv12_convert8(uint2 yy, uint2 uv, uint32_t (&w)[6]) {
+    constexpr int CY = 1220542, CUB = 2116026, CUG = -409993, CVG = -852492, CVR = 1673527;
+    constexpr int RND = 1 << 19;
+    const uint32_t ys[2] = {__vsubus4(yy.x, 0x10101010u), __vsubus4(yy.y, 0x10101010u)};    // max(0, Y - 16), 4 at a time
+    int c[8][3];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const uint32_t word = p < 2 ? uv.x : uv.y;
+        const int u = static_cast<int>(__byte_perm(word, 0u, 0x4440u | (2 * (p & 1))));
+        const int v = static_cast<int>(__byte_perm(word, 0u, 0x4440u | (2 * (p & 1) + 1)));
+        const int ruv = v * CVR + (RND - 128 * CVR);
+        const int guv = u * CUG + (v * CVG + (RND - 128 * CVG - 128 * CUG));
+        const int buv = u * CUB + (RND - 128 * CUB);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int px = 2 * p + e;
+            const int y = static_cast<int>(__byte_perm(ys[px >> 2], 0u, 0x4440u | (px & 3)));
+            c[px][0] = (y * CY + ruv) >> 20;
+            c[px][1] = (y * CY + guv) >> 20;
+            c[px][2] = (y * CY + buv) >> 20;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {       // word k holds RGB bytes 4k .. 4k+3; byte n is pixel n/3, channel n%3
+        const int n = 4 * k;
+        w[k] = pack_sat_u8(c[(n + 1) / 3][(n + 1) % 3], c[n / 3][n % 3],
+                           pack_sat_u8(c[(n + 3) / 3][(n + 3) % 3], c[(n + 2) / 3][(n + 2) % 3], 0u));
+    }
+}
+template <int MAXT, int MINB, int VW, int PA, int PB, int NST, bool NV12>
 __global__ void __launch_bounds__(MAXT, MINB)
 area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride,
+                         const uint8_t* __restrict__ src_uv, int64_t uv_frame_stride, int segpx,
                          uint8_t* __restrict__ mid2, int64_t mid2_frame_stride, int oy0, int ny, int ox0, int nx,
                          int rows_per_strip, int xb0, int seg_bytes, int stage_bytes, int arow_pitch, int vpitch,
                          int left, int S, DevTaps ax, DevTaps ay, DevTaps bx, AhIntParams ip,
                          const uint32_t* __restrict__ aq /*[area columns][8] packed weights, see build_plan*/,
                          int null_consumers /*probe: 1 = consumers only drain the ring (load path alone), 2 = no loads (consumers alone)*/) {
+    constexpr int WPS = NV12 ? 6 : 4;        // words per slice
     extern __shared__ __align__(128) uint8_t ah_smem[];
     const int ncons = blockDim.x - 32;                 // consumer threads; the last warp is the producer
     const int tid = threadIdx.x;
@@ -803,7 +847,8 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
     const int r_lo = __ldg(ay.start + dy_a);
     const int nrows = __ldg(ay.start + dy_b - 1) + __ldg(ay.cnt + dy_b - 1) - r_lo;
     const uint8_t* gbase = src + f * frame_stride + xb0;
-    const int delta = static_cast<int>(reinterpret_cast<uintptr_t>(gbase) & 15);
+    // (NV12: the launcher guarantees 16-byte aligned planes, pitches and window start -> delta = 0)
+    const int delta = NV12 ? 0 : static_cast<int>(reinterpret_cast<uintptr_t>(gbase) & 15);
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ncons >> 5); }
@@ -834,24 +879,33 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
         // ------------------------------------------------------------------ producer warp
         if (tid == ncons) {
             const uint8_t* g = gbase - delta + static_cast<int64_t>(r_lo) * row_stride;
+            const uint8_t* guv = NV12 ? src_uv + f * uv_frame_stride + xb0 : nullptr;
             for (int i = 0; i < nrows; ++i, g += row_stride) {
                 const int s = i % NST;
                 if (i >= NST) mbar_wait(&empty_bar[s], ((i / NST) - 1) & 1, 11);
                 if (null_consumers == 2) { mbar_arrive(&full_bar[s]); continue; }   // probe: no loads, consumers at full speed
-                mbar_arrive_expect_tx(&full_bar[s], seg_bytes);
-                bulk_load_1d(ring + s * stage_bytes, g, seg_bytes, &full_bar[s]);
+                if (NV12) {     // luma row r and chroma row r / 2 of the window: [Y: segpx bytes | UV: segpx bytes]
+                    mbar_arrive_expect_tx(&full_bar[s], 2 * segpx);
+                    bulk_load_1d(ring + s * stage_bytes, g, segpx, &full_bar[s]);
+                    bulk_load_1d(ring + s * stage_bytes + segpx, guv + static_cast<int64_t>((r_lo + i) >> 1) * row_stride, segpx,
+                                 &full_bar[s]);
+                } else {
+                    mbar_arrive_expect_tx(&full_bar[s], seg_bytes);
+                    bulk_load_1d(ring + s * stage_bytes, g, seg_bytes, &full_bar[s]);
+                }
             }
         }
         return;
     }
     // ---------------------------------------------------------------------- consumers
-    // slices [16 (tid + v*ncons), +16) of every stage row; a slice past the segment re-reads slice 0 and is never parked
+    // slices [16 (tid + v*ncons), +16) of every stage row (NV12: pixels [8 (tid + v*ncons), +8), i.e. RGB bytes
+    // [24 (tid + v*ncons), +24)); a slice past the segment re-reads slice 0 and is never parked
     bool v_active[VW];
-    uint32_t v_off[VW];
+    uint32_t v_off[VW];     // byte offset of the slice in the (RGB) row == offset of its lanes in the parked streams
 #pragma unroll
     for (int v = 0; v < VW; ++v) {
-        v_active[v] = (tid + v * ncons) * 16 < seg_bytes;
-        v_off[v] = v_active[v] ? 16u * static_cast<uint32_t>(tid + v * ncons) : 0u;
+        v_active[v] = (tid + v * ncons) * (4 * WPS) < seg_bytes;
+        v_off[v] = v_active[v] ? static_cast<uint32_t>(4 * WPS) * static_cast<uint32_t>(tid + v * ncons) : 0u;
     }
     // area columns tid + p*ncons: stream addresses, realignment shifts and the packed IDP.2A weights
     bool a_active[PA];
@@ -862,7 +916,8 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
         a_active[p] = tid + p * ncons < nx;
         xcol[p] = min(tid + p * ncons, nx - 1);
         const int dx = ox0 + xcol[p];
-        const int s0 = __ldg(ax.start + dx) * 3 - xb0 + delta;        // first byte of this column inside a stage row
+        // first (RGB) byte of this column inside a stage row (NV12: xb0 is the first PIXEL of the converted window)
+        const int s0 = NV12 ? (__ldg(ax.start + dx) - xb0) * 3 : __ldg(ax.start + dx) * 3 - xb0 + delta;
         const int parity = s0 & 1, ex = s0 >> 1, ey = ex + parity;    // X_i = V[s0 + 2i], Y_i = V[s0 + 1 + 2i]
         // bit 31 = "stream starts in the high lane" (funnel shift by 16); the shift count is taken as (word >> 27)
         xoff[p] = static_cast<uint32_t>((parity ? vpitch : 0) + 4 * (ex >> 1)) | (static_cast<uint32_t>(ex & 1) << 31);
@@ -910,11 +965,11 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
     };
 
     const int lane = tid & 31;
-    uint32_t aL[VW][4], aH[VW][4];
+    uint32_t aL[VW][WPS], aH[VW][WPS];
 #pragma unroll
     for (int v = 0; v < VW; ++v)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) aL[v][k] = aH[v][k] = 0u;
+        for (int k = 0; k < WPS; ++k) aL[v][k] = aH[v][k] = 0u;
     int par = 0;         // parity of the parked-row / stream double buffers
     int nfin = 0;        // area rows finished so far
     uint8_t* out_row = mid2 + f * mid2_frame_stride + static_cast<int64_t>(dy_a - oy0) * S * 3;
@@ -939,23 +994,35 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
                 } while (!ok);
             }
         }
-        uint32_t w[VW][4];
+        uint32_t w[VW][WPS];
+        uint2 nvy[VW], nvc[VW];
 #pragma unroll
-        for (int v = 0; v < VW; ++v)
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[v][0]), "=r"(w[v][1]), "=r"(w[v][2]), "=r"(w[v][3]) : "r"(soff + v_off[v]));
+        for (int v = 0; v < VW; ++v) {
+            if constexpr (NV12) {       // 8 luma bytes and their 4 (U, V) pairs; v_off = 24 * slice -> byte 8 * slice
+                const uint32_t o = v_off[v] / 3u;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nvy[v].x), "=r"(nvy[v].y) : "r"(soff + o));
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nvc[v].x), "=r"(nvc[v].y) : "r"(soff + static_cast<uint32_t>(segpx) + o));
+            } else {
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[v][0]), "=r"(w[v][1]), "=r"(w[v][2]), "=r"(w[v][3]) : "r"(soff + v_off[v]));
+            }
+        }
         uint32_t fin, wts;
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(fin), "=r"(wts) : "r"(ria + 8));
         ria += 16;
         __syncwarp();
         if (lane == 0)                                // this warp holds its bytes in registers now
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(eb) : "memory");
+        if constexpr (NV12) {
+#pragma unroll
+            for (int v = 0; v < VW; ++v) nv12_convert8(nvy[v], nvc[v], w[v]);
+        }
         if (null_consumers == 1) { aL[0][0] ^= w[0][0] ^ w[VW - 1][3]; continue; }
         const uint32_t iyc = wts & 0xffffu;
-        uint32_t lo[VW][4], hi[VW][4];
+        uint32_t lo[VW][WPS], hi[VW][WPS];
 #pragma unroll
         for (int v = 0; v < VW; ++v)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < WPS; ++k) {
                 lo[v][k] = __byte_perm(w[v][k], 0u, 0x4240);     // bytes 0 and 2 in 16-bit lanes
                 hi[v][k] = __byte_perm(w[v][k], 0u, 0x4341);     // bytes 1 and 3
                 aL[v][k] += iyc * lo[v][k];
@@ -966,15 +1033,23 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
 #pragma unroll
             for (int v = 0; v < VW; ++v) {
                 if (v_active[v]) {
-                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(vb + v_off[v]), "r"(aL[v][0]), "r"(aL[v][1]), "r"(aL[v][2]), "r"(aL[v][3]) : "memory");
-                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(vb + vpitch + v_off[v]), "r"(aH[v][0]), "r"(aH[v][1]), "r"(aH[v][2]), "r"(aH[v][3]) : "memory");
+                    if constexpr (NV12) {       // 24-byte slices: 8-byte aligned
+#pragma unroll
+                        for (int k = 0; k < WPS; k += 2) {
+                            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(vb + v_off[v] + 4u * k), "r"(aL[v][k]), "r"(aL[v][k + 1]) : "memory");
+                            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(vb + vpitch + v_off[v] + 4u * k), "r"(aH[v][k]), "r"(aH[v][k + 1]) : "memory");
+                        }
+                    } else {
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(vb + v_off[v]), "r"(aL[v][0]), "r"(aL[v][1]), "r"(aL[v][2]), "r"(aL[v][3]) : "memory");
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(vb + vpitch + v_off[v]), "r"(aH[v][0]), "r"(aH[v][1]), "r"(aH[v][2]), "r"(aH[v][3]) : "memory");
+                    }
                 }
             }
             const uint32_t iyn = wts >> 16;           // a straddling row opens the next output row
 #pragma unroll
             for (int v = 0; v < VW; ++v)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { aL[v][k] = iyn * lo[v][k]; aH[v][k] = iyn * hi[v][k]; }
+                for (int k = 0; k < WPS; ++k) { aL[v][k] = iyn * lo[v][k]; aH[v][k] = iyn * hi[v][k]; }
             named_bar_sync(1, ncons);            // streams of this row complete; the previous parked row complete
             uint8_t* ar = arow + par * arow_pitch;
 #pragma unroll
@@ -1454,6 +1529,51 @@ int preprocess_source_window(b200clip_handle* h, int H, int W, int mode, int* x0
     return 0;
 }
 
+// Stage C (+ the K padding of the patch rows) on `cur`: the image after the horizontal pass (or the source itself when
+// no pass ran), whose element (0, 0) sits at stage coordinates (cur_y0, cur_x0).
+static int run_stage_c(b200clip_handle* h, const Plan& p, const uint8_t* cur, int64_t cur_fs, int64_t cur_rs, int cur_x0,
+                       int cur_y0, int n, bf16* patches, float* chw, cudaStream_t st) {
+    const int S = h->cfg.image_size, P = h->cfg.patch;
+    float* lut = get_lut(h);
+    if (!lut) return b200_fail(h, B200CLIP_E_NOMEM, "preprocess: LUT allocation failed");
+    {
+        // stage C reads output-column x0 at cur column (x0 + xoff - cur_x0): after B the crop is already applied
+        const int src_x0 = p.has_b ? 0 : cur_x0 - p.left;  // so that (x0 - src_x0) = x0 + left - cur_x0
+        dim3 grid((static_cast<unsigned>(S) * ((S + 7) >> 3) + 127) / 128, n);
+        ProfScope psc(h, PROF_PRE_C, static_cast<double>(n) * ((p.ry1 - p.ry0) * S * 3.0 + (patches ? static_cast<double>(h->grid) * h->grid * h->patch_k * 2.0 : 3.0 * S * S * 4.0)), st);
+        // tile form: bf16 patch output, 8-pixel groups never straddle a patch, every 24-byte group 8-byte aligned
+        const bool no_tile = b200_knobs().vpass_generic;   // parity tests cover both forms
+        const int xoff = -src_x0 * 3;
+        const bool tile = !no_tile && patches && !chw && (P & 7) == 0 && (S & 7) == 0 && (S >> 3) <= 256 &&
+                          (!p.has_c || p.c_max_cnt <= 7) && (cur_rs & 7) == 0 && (cur_fs & 7) == 0 &&
+                          ((reinterpret_cast<uintptr_t>(cur) + xoff) & 7) == 0;
+        if (tile) {
+            const int xchunks = S >> 3;
+            const int threads = xchunks * (256 / xchunks);
+            const int rows_per_block = 32;
+            dim3 tgrid((S + rows_per_block - 1) / rows_per_block, n);
+            if (p.has_c)
+                vpass_store_tile_kernel<true><<<tgrid, threads, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, xoff, p.top, p.cy, S, P,
+                                                                         h->grid, h->patch_k, rows_per_block, lut, patches);
+            else
+                vpass_store_tile_kernel<false><<<tgrid, threads, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, xoff, p.top, p.cy, S, P,
+                                                                          h->grid, h->patch_k, rows_per_block, lut, patches);
+        } else {
+            vpass_store_kernel<<<grid, 128, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, src_x0, p.has_c ? 1 : 0, p.top, p.cy, S, P,
+                                                     h->grid, h->patch_k, lut, patches, chw);
+        }
+        h->launches++;
+    }
+    if (patches && h->patch_k != 3 * P * P) {
+        const int64_t rows = static_cast<int64_t>(n) * h->grid * h->grid;
+        zero_pad_kernel<<<grid_for(h, rows * (h->patch_k - 3 * P * P), 256), 256, 0, st>>>(patches, rows, 3 * P * P,
+                                                                                          h->patch_k);
+        h->launches++;
+    }
+    B200_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
 int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
                       int64_t row_stride, int mode, bf16* patches, float* chw, cudaStream_t st) {
     if (n <= 0) return 0;
@@ -1465,9 +1585,7 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
     if (row_stride < static_cast<int64_t>(p.sx1 - p.sx0) * 3 || frame_stride < row_stride * (p.sy1 - p.sy0))
         return b200_fail(h, B200CLIP_E_ARG, "preprocess: bad frame geometry %dx%d strides %lld/%lld", W, H,
                          (long long)row_stride, (long long)frame_stride);
-    const int S = h->cfg.image_size, P = h->cfg.patch;
-    float* lut = get_lut(h);
-    if (!lut) return b200_fail(h, B200CLIP_E_NOMEM, "preprocess: LUT allocation failed");
+    const int S = h->cfg.image_size;
     // intermediates
     const size_t need = (p.mid1_per_frame + p.mid2_per_frame) * static_cast<size_t>(n);
     if (need > h->ws_pre_bytes) {
@@ -1523,7 +1641,7 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
                                 static_cast<size_t>(max_rows) * sizeof(AhRowInfo);
             if (smem <= 200 * 1024) {
                 AhIntParams ip{p.a_dx, p.a_dy, p.a_dx * p.a_dy, p.a_div_shift, p.a_div_mul};
-                auto kern = area_hpass_vfirst_kernel<160, 3, 2, 3, 2, AH_NSTAGE>;
+                auto kern = area_hpass_vfirst_kernel<160, 3, 2, 3, 2, AH_NSTAGE, false>;
                 if (!(h->attr_done & ATTR_K1_VFIRST)) {
                     B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                     // ~45 KB per CTA: without the maximum carve-out the driver's default split allows only 3 CTAs per SM
@@ -1532,7 +1650,7 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
                 }
                 ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(p.sy1 - p.sy0) * (p.sx1 - p.sx0) * 3.0 + ny * S * 3.0), st);
                 dim3 fgrid((ny + rows - 1) / rows, n);
-                kern<<<fgrid, ncv + 32, smem, st>>>(cur, cur_fs, cur_rs, mid2, p.mid2_per_frame, p.ry0, ny, p.rx0, nx, rows, xb0,
+                kern<<<fgrid, ncv + 32, smem, st>>>(cur, cur_fs, cur_rs, nullptr, 0, 0, mid2, p.mid2_per_frame, p.ry0, ny, p.rx0, nx, rows, xb0,
                                                    seg, stage_bytes, arow_pitch, vpitch, p.left, S, p.ax, p.ay, p.bx, ip, p.aq,
                                                    area_null_probe());
                 h->launches++;
@@ -1611,39 +1729,148 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         cur = mid2; cur_fs = p.mid2_per_frame; cur_rs = static_cast<int64_t>(S) * 3;
         cur_x0 = 0 /* column 0 of mid2 is output column `left`, handled below */; cur_y0 = p.ry0;
     }
-    {
-        // stage C reads output-column x0 at cur column (x0 + xoff - cur_x0): after B the crop is already applied
-        const int src_x0 = p.has_b ? 0 : cur_x0 - p.left;  // so that (x0 - src_x0) = x0 + left - cur_x0
-        dim3 grid((static_cast<unsigned>(S) * ((S + 7) >> 3) + 127) / 128, n);
-        ProfScope psc(h, PROF_PRE_C, static_cast<double>(n) * ((p.ry1 - p.ry0) * S * 3.0 + (patches ? static_cast<double>(h->grid) * h->grid * h->patch_k * 2.0 : 3.0 * S * S * 4.0)), st);
-        // tile form: bf16 patch output, 8-pixel groups never straddle a patch, every 24-byte group 8-byte aligned
-        const bool no_tile = b200_knobs().vpass_generic;   // parity tests cover both forms
-        const int xoff = -src_x0 * 3;
-        const bool tile = !no_tile && patches && !chw && (P & 7) == 0 && (S & 7) == 0 && (S >> 3) <= 256 &&
-                          (!p.has_c || p.c_max_cnt <= 7) && (cur_rs & 7) == 0 && (cur_fs & 7) == 0 &&
-                          ((reinterpret_cast<uintptr_t>(cur) + xoff) & 7) == 0;
-        if (tile) {
-            const int xchunks = S >> 3;
-            const int threads = xchunks * (256 / xchunks);
-            const int rows_per_block = 32;
-            dim3 tgrid((S + rows_per_block - 1) / rows_per_block, n);
-            if (p.has_c)
-                vpass_store_tile_kernel<true><<<tgrid, threads, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, xoff, p.top, p.cy, S, P,
-                                                                         h->grid, h->patch_k, rows_per_block, lut, patches);
-            else
-                vpass_store_tile_kernel<false><<<tgrid, threads, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, xoff, p.top, p.cy, S, P,
-                                                                          h->grid, h->patch_k, rows_per_block, lut, patches);
-        } else {
-            vpass_store_kernel<<<grid, 128, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, src_x0, p.has_c ? 1 : 0, p.top, p.cy, S, P,
-                                                     h->grid, h->patch_k, lut, patches, chw);
-        }
-        h->launches++;
+    return run_stage_c(h, p, cur, cur_fs, cur_rs, cur_x0, cur_y0, n, patches, chw, st);
+}
+
+
+// ---------------------------------------------------------------------------------------------- NV12 frame feed
+// Generic NV12 -> RGB conversion of the window K1 reads (every geometry / resize mode the fused kernel does not cover,
+// and the B200CLIP_NV12_UNFUSED parity variant): one thread per horizontal pixel pair (one chroma sample), 6 bytes
+// out.  Same arithmetic as nv12_convert8 (cv2 COLOR_YUV2RGB_NV12, oracle/nv12_ref.py).
+__global__ void __launch_bounds__(256)
+nv12_window_to_rgb_kernel(const uint8_t* __restrict__ yp, const uint8_t* __restrict__ uvp, int64_t y_fs, int64_t uv_fs,
+                          int64_t rs, uint8_t* __restrict__ dst, int64_t dst_fs, int64_t dst_pitch, int x0, int y0, int pairs,
+                          int rows) {
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= static_cast<unsigned>(pairs * rows)) return;
+    const int r = id / pairs, c = id - r * pairs;
+    const int64_t f = blockIdx.y;
+    const int x = x0 + 2 * c, y = y0 + r;
+    constexpr int CY = 1220542, CUB = 2116026, CUG = -409993, CVG = -852492, CVR = 1673527;
+    const uint8_t* yrow = yp + f * y_fs + static_cast<int64_t>(y) * rs + x;
+    const uint8_t* uvrow = uvp + f * uv_fs + static_cast<int64_t>(y >> 1) * rs + x;
+    const int u = static_cast<int>(uvrow[0]) - 128, v = static_cast<int>(uvrow[1]) - 128;
+    const int ruv = (1 << 19) + CVR * v, guv = (1 << 19) + CVG * v + CUG * u, buv = (1 << 19) + CUB * u;
+    uint8_t* o = dst + f * dst_fs + static_cast<int64_t>(r) * dst_pitch + c * 6;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int yy = max(0, static_cast<int>(yrow[e]) - 16) * CY;
+        o[e * 3 + 0] = static_cast<uint8_t>(min(max((yy + ruv) >> 20, 0), 255));
+        o[e * 3 + 1] = static_cast<uint8_t>(min(max((yy + guv) >> 20, 0), 255));
+        o[e * 3 + 2] = static_cast<uint8_t>(min(max((yy + buv) >> 20, 0), 255));
     }
-    if (patches && h->patch_k != 3 * P * P) {
-        const int64_t rows = static_cast<int64_t>(n) * h->grid * h->grid;
-        zero_pad_kernel<<<grid_for(h, rows * (h->patch_k - 3 * P * P), 256), 256, 0, st>>>(patches, rows, 3 * P * P,
-                                                                                          h->patch_k);
-        h->launches++;
+}
+
+// Window of an NV12 frame K1 needs for this geometry: pixel columns [x0, x1) (x0 a multiple of 16, x1 of 16 or W) and
+// rows [y0, y1); chroma rows [y0 / 2, (y1 + 1) / 2).  The host-frame path uploads exactly this.
+int preprocess_source_window_nv12(b200clip_handle* h, int H, int W, int mode, int* x0, int* x1, int* y0, int* y1) {
+    int rc = preprocess_source_window(h, H, W, mode, x0, x1, y0, y1);
+    if (rc) return rc;
+    *x0 &= ~15;
+    *x1 = (*x1 + 15) & ~15;
+    if (*x1 > W) *x1 = W;
+    return 0;
+}
+
+// NV12 frames (Y plane at y, interleaved UV plane at uv, common row pitch rs) -> patch rows / CHW, bit-identical to
+// cv2.cvtColor(COLOR_YUV2RGB_NV12) followed by launch_preprocess.
+int launch_preprocess_nv12(b200clip_handle* h, const uint8_t* y, const uint8_t* uv, int n, int H, int W, int64_t y_fs,
+                           int64_t uv_fs, int64_t rs, int mode, bf16* patches, float* chw, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if ((H & 1) || (W & 1)) return b200_fail(h, B200CLIP_E_SHAPE, "preprocess_nv12: width and height must be even (%dx%d)", W, H);
+    const Plan* pp = nullptr;
+    int rc = get_plan(h, H, W, mode, &pp);
+    if (rc) return rc;
+    const Plan& p = *pp;
+    int x0, x1, y0, y1;
+    if ((rc = preprocess_source_window_nv12(h, H, W, mode, &x0, &x1, &y0, &y1))) return rc;
+    // strides are checked against the window (a compacted upload of it is a valid input)
+    if (rs < x1 - x0 || y_fs < rs * (y1 - y0) || uv_fs < rs * (((y1 + 1) >> 1) - (y0 >> 1)))
+        return b200_fail(h, B200CLIP_E_ARG, "preprocess_nv12: bad frame geometry %dx%d strides %lld/%lld/%lld", W, H,
+                         (long long)rs, (long long)y_fs, (long long)uv_fs);
+    if (n > 65535) return b200_fail(h, B200CLIP_E_SHAPE, "preprocess: at most 65535 frames per call (got %d)", n);
+    const int S = h->cfg.image_size;
+    const int ny = p.ry1 - p.ry0, nx = p.rx1 - p.rx0;
+    const int segpx = x1 - x0;
+    constexpr int NCV = 160;        // consumers of the fused NV12 kernel: 8 px, two area and two Pillow columns each
+    const bool aligned = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(uv) | static_cast<uintptr_t>(rs) |
+                           static_cast<uintptr_t>(y_fs) | static_cast<uintptr_t>(uv_fs)) & 15) == 0 && (segpx & 15) == 0;
+    const bool fused = !b200_knobs().nv12_unfused && !b200_knobs().k1_unfused && p.has_a && p.has_b && !p.a_fast && p.a_seq &&
+                       p.a_max_cx <= 5 && p.b_max_cnt <= 7 && p.a_int && p.aq != nullptr && aligned && segpx <= 8 * NCV &&
+                       nx <= 2 * NCV && S <= 2 * NCV && p.a_dy * 255 < 65536 && p.a_dx <= 255;
+    if (fused) {
+        const size_t need = p.mid2_per_frame * static_cast<size_t>(n);
+        if (need > h->ws_pre_bytes) {
+            B200_CUDA(h, cudaStreamSynchronize(st));
+            if (h->ws_pre) cudaFree(h->ws_pre);
+            h->ws_pre = nullptr; h->ws_pre_bytes = 0;
+            B200_CUDA(h, cudaMalloc(&h->ws_pre, need));
+            h->ws_pre_bytes = need;
+        }
+        uint8_t* mid2 = h->ws_pre;
+        int rows = 24;
+        while (rows > 4 && static_cast<int64_t>(n) * ((ny + rows - 1) / rows) < static_cast<int64_t>(h->num_sms) * 6)
+            rows = (rows + 1) / 2;
+        const int seg_bytes = 3 * segpx, stage_bytes = 2 * segpx, arow_pitch = (nx * 3 + 32 + 15) & ~15, vpitch = seg_bytes + 32;
+        const int max_rows = rows * p.ay.stride;
+        const size_t smem = 2 * AH_NSTAGE * sizeof(uint64_t) + static_cast<size_t>(AH_NSTAGE) * stage_bytes +
+                            4 * static_cast<size_t>(vpitch) + 2 * static_cast<size_t>(arow_pitch) +
+                            static_cast<size_t>(max_rows) * sizeof(AhRowInfo);
+        if (smem <= 200 * 1024) {
+            AhIntParams ip{p.a_dx, p.a_dy, p.a_dx * p.a_dy, p.a_div_shift, p.a_div_mul};
+            auto kern = area_hpass_vfirst_kernel<NCV + 32, 3, 1, 2, 2, AH_NSTAGE, true>;
+            if (!(h->attr_done & ATTR_K1_NV12)) {
+                B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                B200_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                h->attr_done |= ATTR_K1_NV12;
+            }
+            // algorithmic bytes: the NV12 frame in (1.5 B/px), the patch rows (or fp32 CHW) out
+            ProfScope ps(h, PROF_PRE, static_cast<double>(n) * (static_cast<double>(H) * W * 1.5 +
+                         (patches ? static_cast<double>(h->grid) * h->grid * h->patch_k * 2.0 : 0.0) +
+                         (chw ? 3.0 * S * S * 4.0 : 0.0)), st);
+            {
+                ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(y1 - y0) * segpx * 1.5 + ny * S * 3.0), st);
+                dim3 fgrid((ny + rows - 1) / rows, n);
+                kern<<<fgrid, NCV + 32, smem, st>>>(y, y_fs, rs, uv, uv_fs, segpx, mid2, p.mid2_per_frame, p.ry0, ny, p.rx0, nx, rows,
+                                                   x0, seg_bytes, stage_bytes, arow_pitch, vpitch, p.left, S, p.ax, p.ay, p.bx, ip,
+                                                   p.aq, 0);
+                h->launches++;
+            }
+            return run_stage_c(h, p, mid2, p.mid2_per_frame, static_cast<int64_t>(S) * 3, 0, p.ry0, n, patches, chw, st);
+        }
+    }
+    // generic form: convert the window to packed RGB in a bounded scratch buffer, group by group, and hand each group
+    // to the RGB chain with a virtual frame origin in front of the compacted window
+    const int xe = x0 & ~1, pairs = (x1 - xe + 1) >> 1, wrows = y1 - y0;
+    const size_t pitch = (static_cast<size_t>(pairs) * 6 + 63) & ~size_t(63), fpitch = pitch * wrows, lead = 64;
+    int group = static_cast<int>((size_t(256) << 20) / fpitch);
+    if (group < 1) group = 1;
+    if (group > n) group = n;
+    const size_t need = static_cast<size_t>(group) * fpitch + 2 * lead;
+    if (need > h->ws_nv12_bytes) {
+        B200_CUDA(h, cudaStreamSynchronize(st));
+        if (h->ws_nv12) cudaFree(h->ws_nv12);
+        h->ws_nv12 = nullptr; h->ws_nv12_bytes = 0;
+        B200_CUDA(h, cudaMalloc(&h->ws_nv12, need));
+        h->ws_nv12_bytes = need;
+    }
+    const size_t prow = static_cast<size_t>(h->grid) * h->grid * h->patch_k;
+    for (int i0 = 0; i0 < n; i0 += group) {
+        const int nc = (n - i0) < group ? (n - i0) : group;
+        uint8_t* stage = h->ws_nv12 + lead;
+        {
+            ProfScope ps(h, PROF_MISC, static_cast<double>(nc) * wrows * pairs * (3.0 + 6.0), st);
+            dim3 grid((static_cast<unsigned>(pairs) * wrows + 255) / 256, nc);
+            nv12_window_to_rgb_kernel<<<grid, 256, 0, st>>>(y + i0 * y_fs, uv + i0 * uv_fs, y_fs, uv_fs, rs, stage,
+                                                           static_cast<int64_t>(fpitch), static_cast<int64_t>(pitch), xe, y0,
+                                                           pairs, wrows);
+            h->launches++;
+        }
+        const uint8_t* origin = stage - static_cast<int64_t>(y0) * static_cast<int64_t>(pitch) - static_cast<int64_t>(xe) * 3;
+        rc = launch_preprocess(h, origin, nc, H, W, static_cast<int64_t>(fpitch), static_cast<int64_t>(pitch), mode,
+                               patches ? patches + static_cast<size_t>(i0) * prow : nullptr,
+                               chw ? chw + static_cast<size_t>(i0) * 3 * S * S : nullptr, st);
+        if (rc) return rc;
     }
     B200_CUDA(h, cudaGetLastError());
     return 0;

@@ -133,6 +133,61 @@ class B200CLIP:
                          int(normalize), self._stream())
         return out
 
+    # ---- NV12 frame feed (decoder output; cv2 layout uint8 [N, H*3/2, W]: Y rows then interleaved UV rows) ----------
+    def _check_nv12(self, frames, device_type: str):
+        if isinstance(frames, np.ndarray):
+            frames = torch.from_numpy(np.ascontiguousarray(frames))
+        if frames.dim() != 3 or frames.dtype != torch.uint8 or frames.shape[1] % 3 or frames.shape[2] % 2 or \
+                (frames.shape[1] * 2 // 3) % 2:
+            raise ValueError(f"expected NV12 uint8 [N, H*3/2, W] with even H and W, got {frames.dtype} {tuple(frames.shape)}")
+        if frames.device.type != device_type:
+            raise ValueError(f"NV12 frames must live on the {device_type} for this call")
+        return frames.contiguous()
+
+    def preprocess_nv12(self, frames: torch.Tensor, resize_mode: int = capi.RESIZE_REFERENCE,
+                        chw: bool = False) -> torch.Tensor:
+        """NV12 uint8 [N, H*3/2, W] (cuda) -> bf16 patch rows [N*g*g, patch_k] or fp32 [N,3,S,S]; pixels identical to
+        cv2.cvtColor(COLOR_YUV2RGB_NV12) + preprocess_u8."""
+        f = self._check_nv12(frames, "cuda")
+        n, hh, w = (int(v) for v in f.shape)
+        h = hh * 2 // 3
+        y_ptr = f.data_ptr()
+        if chw:
+            out = torch.empty(n, 3, self.cfg.image_size, self.cfg.image_size, device=self.device, dtype=torch.float32)
+            po, co = None, out
+        else:
+            g = self.cfg.image_size // self.cfg.patch
+            out = torch.empty(n * g * g, self.cfg.patch_k, device=self.device, dtype=torch.bfloat16)
+            po, co = out, None
+        self.handle.call("b200clip_preprocess_nv12", capi._p(y_ptr), capi._p(y_ptr + h * w), n, h, w, hh * w, hh * w, w,
+                         resize_mode, capi._p(po), capi._p(co), self._stream())
+        return out
+
+    def encode_frames_nv12(self, frames: torch.Tensor, resize_mode: int = capi.RESIZE_REFERENCE, normalize: bool = True,
+                           out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        """Device-resident NV12 frames [N, H*3/2, W] -> embeddings [N,E] (colour conversion fused into K1)."""
+        f = self._check_nv12(frames, "cuda")
+        n, hh, w = (int(v) for v in f.shape)
+        h = hh * 2 // 3
+        out = torch.empty(n, self.embed_dim, device=self.device, dtype=out_dtype)
+        dt = capi.BF16 if out_dtype == torch.bfloat16 else capi.F32
+        y_ptr = f.data_ptr()
+        self.handle.call("b200clip_encode_frames_nv12", capi._p(y_ptr), capi._p(y_ptr + h * w), n, h, w, hh * w, hh * w, w,
+                         resize_mode, capi._p(out), dt, int(normalize), self._stream())
+        return out
+
+    def encode_frames_nv12_host(self, frames, resize_mode: int = capi.RESIZE_REFERENCE, normalize: bool = True,
+                                out=None):
+        """HOST NV12 frames (numpy / CPU tensor uint8 [N, H*3/2, W]) -> float32 [N,E] (host numpy, or the device tensor
+        passed as `out`): half the PCIe bytes of encode_frames_u8_host."""
+        f = self._check_nv12(frames, "cpu")
+        n, hh, w = (int(v) for v in f.shape)
+        if out is None:
+            out = np.empty((n, self.embed_dim), np.float32)
+        self.handle.call("b200clip_encode_frames_nv12_host", capi._p(f), n, hh * 2 // 3, w, resize_mode, capi._p(out),
+                         int(normalize), self._stream())
+        return out
+
     def similarity(self, img_emb: torch.Tensor, txt_emb: torch.Tensor) -> torch.Tensor:
         """compute_similarity: [N,E] x [Q,E] -> fp32 [N,Q]."""
         img = img_emb.contiguous()

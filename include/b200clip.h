@@ -119,6 +119,28 @@ int b200clip_encode_frames_u8(b200clip_handle* h, const uint8_t* frames_dev, int
 int b200clip_encode_frames_u8_host(b200clip_handle* h, const uint8_t* frames_host, int n, int height, int width,
                                    int resize_mode, float* emb_out_host, int l2norm, void* stream);
 
+/* ---- frame feed: 4:2:0 frames as a video decoder leaves them, converted inside K1.
+ *      Replaces the CPU colour conversion the reference's decoders run before handing RGB to Python
+ *      (src/services/frame_extractor.py:38-235: decord.VideoReader / cv2.VideoCapture + cvtColor :191) and, like the
+ *      *_u8 calls, MemoryManager.resize_frame_for_memory + the open_clip transform.  Pixels are bit-identical to
+ *      cv2.cvtColor(frame, cv2.COLOR_YUV2RGB_NV12) followed by the *_u8 chain; RGB never exists in HBM on the fused path
+ *      (1080p / 720p class geometries with 16-byte aligned planes; everything else converts the crop window first).
+ *      NV12: y_dev = luma plane [height rows], uv_dev = interleaved chroma plane [height/2 rows], both with
+ *      row_stride bytes per row (NVDEC: uv_dev = y_dev + row_stride * aligned_height); frame i at
+ *      y_dev + i*y_frame_stride / uv_dev + i*uv_frame_stride.  width and height must be even. */
+int b200clip_preprocess_nv12(b200clip_handle* h, const uint8_t* y_dev, const uint8_t* uv_dev, int n, int height,
+                             int width, int64_t y_frame_stride, int64_t uv_frame_stride, int64_t row_stride,
+                             int resize_mode, void* patches_out_dev /* bf16 patch rows or NULL */,
+                             float* chw_out_dev /* fp32 [n,3,S,S] or NULL */, void* stream);
+int b200clip_encode_frames_nv12(b200clip_handle* h, const uint8_t* y_dev, const uint8_t* uv_dev, int n, int height,
+                                int width, int64_t y_frame_stride, int64_t uv_frame_stride, int64_t row_stride,
+                                int resize_mode, void* emb_out_dev, int out_dtype, int l2norm, void* stream);
+/* HOST NV12 frames (frame i at nv12_host + i*height*width*3/2: Y plane then UV plane, the layout cv2 takes for
+ * COLOR_YUV2RGB_NV12) -> embeddings; same staging, window upload and emb_out rules as
+ * b200clip_encode_frames_u8_host, at half the PCIe bytes. */
+int b200clip_encode_frames_nv12_host(b200clip_handle* h, const uint8_t* nv12_host, int n, int height, int width,
+                                     int resize_mode, float* emb_out_host, int l2norm, void* stream);
+
 /* ---- text tower.  Replaces model.encode_text(tokens[Q,77]) (+ L2 norm, openclip_model.py:200-210). */
 int b200clip_encode_text(b200clip_handle* h, const int64_t* tokens_dev, int q, float* emb_out_dev, int l2norm,
                          void* stream);
