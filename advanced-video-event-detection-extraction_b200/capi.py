@@ -19,7 +19,7 @@ RESIZE_BICUBIC = 2
 F32 = 0
 BF16 = 1
 
-ERRORS = {-1: "E_ARG", -2: "E_SHAPE", -3: "E_CUDA", -4: "E_ARCH", -5: "E_STATE", -6: "E_NOMEM"}
+ERRORS = {-1: "E_ARG", -2: "E_SHAPE", -3: "E_CUDA", -4: "E_ARCH", -5: "E_STATE", -6: "E_NOMEM", -7: "E_NCCL"}
 
 
 class B200ClipError(RuntimeError):
@@ -72,6 +72,14 @@ SIGNATURES = {
     "b200clip_similarity": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "b200clip_topk_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_double,
                                     c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200clip_topk_msg_bytes": (c_int64, [c_int, c_int]),
+    "b200clip_sim_topk_nccl": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int,
+                                       c_float, c_void_p, c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p]),
+    "b200clip_topk_merge_nccl": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p,
+                                         c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200clip_topk_merge_packed": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_double, c_double,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200clip_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_int, c_void_p]),
     "b200clip_layernorm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float,
@@ -169,7 +177,7 @@ class Handle:
         self.call("b200clip_reserve", int(max_images), int(max_texts))
 
     PROFILE_CLASSES = ("gemm", "attention", "layernorm", "preprocess", "head", "sim_topk", "misc", "pre_area", "pre_hpass",
-                       "pre_vpass")
+                       "pre_vpass", "comm")
 
     def profile_enable(self, on: bool = True):
         self.call("b200clip_profile_enable", int(on))

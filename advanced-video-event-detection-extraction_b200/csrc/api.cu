@@ -172,7 +172,7 @@ extern "C" int b200clip_destroy(b200clip_handle* h) {
     for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
     cudaFree(h->ws_x); cudaFree(h->ws_y); cudaFree(h->ws_qkv); cudaFree(h->ws_h); cudaFree(h->ws_patches);
-    cudaFree(h->ws_emb); cudaFree(h->ws_pre); cudaFree(h->ws_nv12); cudaFree(h->ws_topk); cudaFree(h->ws_eot); cudaFree(h->ws_tokens);
+    cudaFree(h->ws_emb); cudaFree(h->ws_pre); cudaFree(h->ws_nv12); cudaFree(h->ws_gather); cudaFree(h->ws_topk); cudaFree(h->ws_eot); cudaFree(h->ws_tokens);
     cudaFree(h->ws_patches2); cudaFree(h->ws_stats);
     cudaFree(h->ws_tx); cudaFree(h->ws_ty); cudaFree(h->ws_tqkv); cudaFree(h->ws_th); cudaFree(h->ws_tstats);
     if (h->pre_stream) cudaStreamDestroy(h->pre_stream);

@@ -81,6 +81,8 @@ struct b200clip_handle {
     float* pre_lut = nullptr;      // [3][256] ToTensor+Normalize lookup
     uint8_t* ws_pre = nullptr;     // preprocess intermediates
     size_t ws_pre_bytes = 0;
+    uint8_t* ws_gather = nullptr;  // [world] candidate messages of the NCCL exchange (b200clip_*_nccl)
+    size_t ws_gather_bytes = 0;
     uint8_t* ws_nv12 = nullptr;    // RGB scratch of the generic (unfused) NV12 path
     size_t ws_nv12_bytes = 0;
     void* ws_topk = nullptr;       // sim/top-k partial candidates
@@ -116,7 +118,7 @@ struct B200Knobs {
 const B200Knobs& b200_knobs();
 
 // kernel classes for the profiler
-enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_PRE = 3, PROF_HEAD = 4, PROF_SIM = 5, PROF_MISC = 6, PROF_PRE_A = 7, PROF_PRE_B = 8, PROF_PRE_C = 9, PROF_NCLS = 10 };
+enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_PRE = 3, PROF_HEAD = 4, PROF_SIM = 5, PROF_MISC = 6, PROF_PRE_A = 7, PROF_PRE_B = 8, PROF_PRE_C = 9, PROF_COMM = 10, PROF_NCLS = 11 };
 // RAII bracket: records an event pair around the launches made in its scope when profiling is on
 struct ProfScope {
     b200clip_handle* h; cudaStream_t st; int idx;
@@ -164,5 +166,8 @@ int launch_topk_merge(b200clip_handle* h, const float* cs, const int64_t* ci, in
 int launch_preprocess_nv12(b200clip_handle* h, const uint8_t* y, const uint8_t* uv, int n, int H, int W, int64_t y_fs,
                            int64_t uv_fs, int64_t rs, int mode, bf16* patches, float* chw, cudaStream_t st);
 int preprocess_source_window_nv12(b200clip_handle* h, int H, int W, int mode, int* x0, int* x1, int* y0, int* y1);
+int launch_topk_merge_strided(b200clip_handle* h, const float* cs, const int64_t* ci, int64_t ls_s, int64_t ls_i, int g, int q,
+                              int k, float thr, const double* ts, double clip_dur, double vid_dur, float* top_scores,
+                              int64_t* top_idx, double* intervals, int32_t* counts, cudaStream_t st);
 void preprocess_free_plans(b200clip_handle* h);
 int preprocess_source_window(b200clip_handle* h, int H, int W, int mode, int* x0, int* x1, int* y0, int* y1);

@@ -182,8 +182,8 @@ sim_stream_kernel(const void* __restrict__ img, int64_t n, int e, const float* _
 // exactly np.argsort(s)[::-1][:k] (src/pipeline/phase1_mvp.py:145).  lk = length of every candidate list.
 template <bool IDX64>
 __global__ void __launch_bounds__(SIM_WARPS * 32)
-topk_final_kernel(const float* __restrict__ cand_s, const void* __restrict__ cand_i, int g, int q_total, int lk, int kp,
-                  int off, int ko, float thr, const double* __restrict__ ts, int64_t index_base, double clip_dur,
+topk_final_kernel(const float* __restrict__ cand_s, const void* __restrict__ cand_i, int64_t ls_s, int64_t ls_i, int g,
+                  int q_total, int lk, int kp, int off, int ko, float thr, const double* __restrict__ ts, int64_t index_base, double clip_dur,
                   double vid_dur, float* __restrict__ top_s, int64_t* __restrict__ top_i, double* __restrict__ intervals,
                   int32_t* __restrict__ counts) {
     __shared__ float ls[SIM_WARPS][SIM_MAXK];
@@ -199,8 +199,11 @@ topk_final_kernel(const float* __restrict__ cand_s, const void* __restrict__ can
         ceil_i = top_i[static_cast<size_t>(q) * ko + off - 1];
         ceil_s = ceil_i < 0 ? -INFINITY : top_s[static_cast<size_t>(q) * ko + off - 1];
     }
+    // list `l` starts ls_s floats / ls_i indices behind list l - 1 (partial lists: q_total * lk; gathered messages: the
+    // message pitch)
+    (void)q_total;
     auto cand_index = [&](int list, int j) -> long long {
-        const size_t o = (static_cast<size_t>(list) * q_total + q) * lk + j;
+        const size_t o = static_cast<size_t>(list) * ls_i + static_cast<size_t>(q) * lk + j;
         return IDX64 ? static_cast<const long long*>(cand_i)[o] : static_cast<long long>(static_cast<const int*>(cand_i)[o]);
     };
     // 64-bit aware insert (tie-break on the global index)
@@ -219,7 +222,7 @@ topk_final_kernel(const float* __restrict__ cand_s, const void* __restrict__ can
     };
     for (int list = warp; list < g; list += SIM_WARPS) {
         for (int j = 0; j < lk; ++j) {
-            const float s = cand_s[(static_cast<size_t>(list) * q_total + q) * lk + j];
+            const float s = cand_s[static_cast<size_t>(list) * ls_s + static_cast<size_t>(q) * lk + j];
             long long idx = cand_index(list, j);
             if (idx < 0) break;
             idx += index_base;
@@ -493,7 +496,8 @@ static int launch_sim_topk_tc(b200clip_handle* h, const void* img, int dtype, in
             h->launches++;
         }
     }
-    topk_final_kernel<false><<<q, SIM_WARPS * 32, 0, st>>>(part_s, part_i, g * n_slices, q, k, k, 0, k, thr, ts, index_base,
+    topk_final_kernel<false><<<q, SIM_WARPS * 32, 0, st>>>(part_s, part_i, static_cast<int64_t>(q) * k, static_cast<int64_t>(q) * k,
+                                                          g * n_slices, q, k, k, 0, k, thr, ts, index_base,
                                                           clip_dur, vid_dur, top_scores, top_idx, intervals, counts);
     h->launches++;
     if (!dense) {
@@ -546,8 +550,26 @@ int launch_sim_topk(b200clip_handle* h, const void* img, int dtype, int64_t n, i
                             off > 0 ? top_scores + off - 1 : nullptr, off > 0 ? top_idx + off - 1 : nullptr, k, index_base);
             if (rc) return rc;
         }
-        topk_final_kernel<false><<<q, SIM_WARPS * 32, 0, st>>>(part_s, part_i, g, q, kp, kp, off, k, thr, ts, index_base,
+        topk_final_kernel<false><<<q, SIM_WARPS * 32, 0, st>>>(part_s, part_i, static_cast<int64_t>(q) * kp,
+                                                              static_cast<int64_t>(q) * kp, g, q, kp, kp, off, k, thr, ts, index_base,
                                                               clip_dur, vid_dur, top_scores, top_idx, intervals, counts);
+        h->launches++;
+    }
+    B200_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+// cs / ci: g candidate lists of [q, k] entries each, list l at cs + l * ls_s (floats) / ci + l * ls_i (int64)
+int launch_topk_merge_strided(b200clip_handle* h, const float* cs, const int64_t* ci, int64_t ls_s, int64_t ls_i, int g, int q,
+                              int k, float thr, const double* ts, double clip_dur, double vid_dur, float* top_scores,
+                              int64_t* top_idx, double* intervals, int32_t* counts, cudaStream_t st) {
+    if (!cs || !ci || !top_scores || !top_idx) return b200_fail(h, B200CLIP_E_ARG, "topk_merge: null argument");
+    if (g <= 0 || q <= 0 || k <= 0 || k > SIM_MAXK_TOTAL) return b200_fail(h, B200CLIP_E_SHAPE, "topk_merge: bad g/q/k");
+    ProfScope ps(h, PROF_SIM, static_cast<double>(g) * q * k * 12.0, st);
+    for (int off = 0; off < k; off += SIM_MAXK) {
+        const int kp = (k - off) < SIM_MAXK ? (k - off) : SIM_MAXK;
+        topk_final_kernel<true><<<q, SIM_WARPS * 32, 0, st>>>(cs, ci, ls_s, ls_i, g, q, k, kp, off, k, thr, ts, 0, clip_dur, vid_dur,
+                                                             top_scores, top_idx, intervals, counts);
         h->launches++;
     }
     B200_CUDA(h, cudaGetLastError());
@@ -557,14 +579,6 @@ int launch_sim_topk(b200clip_handle* h, const void* img, int dtype, int64_t n, i
 int launch_topk_merge(b200clip_handle* h, const float* cs, const int64_t* ci, int g, int q, int k, float thr,
                       const double* ts, double clip_dur, double vid_dur, float* top_scores, int64_t* top_idx,
                       double* intervals, int32_t* counts, cudaStream_t st) {
-    if (!cs || !ci || !top_scores || !top_idx) return b200_fail(h, B200CLIP_E_ARG, "topk_merge: null argument");
-    if (g <= 0 || q <= 0 || k <= 0 || k > SIM_MAXK_TOTAL) return b200_fail(h, B200CLIP_E_SHAPE, "topk_merge: bad g/q/k");
-    for (int off = 0; off < k; off += SIM_MAXK) {
-        const int kp = (k - off) < SIM_MAXK ? (k - off) : SIM_MAXK;
-        topk_final_kernel<true><<<q, SIM_WARPS * 32, 0, st>>>(cs, ci, g, q, k, kp, off, k, thr, ts, 0, clip_dur, vid_dur,
-                                                             top_scores, top_idx, intervals, counts);
-        h->launches++;
-    }
-    B200_CUDA(h, cudaGetLastError());
-    return 0;
+    return launch_topk_merge_strided(h, cs, ci, static_cast<int64_t>(q) * k, static_cast<int64_t>(q) * k, g, q, k, thr, ts,
+                                     clip_dur, vid_dur, top_scores, top_idx, intervals, counts, st);
 }

@@ -43,6 +43,8 @@ class B200CLIP:
         if max_images or max_texts:
             self.handle.reserve(max_images, max_texts)
         self.embed_dim = cfg.embed_dim
+        self._comm_cache = {}       # (group, device) -> ncclComm_t of torch's process group (0 = not NCCL)
+        self._msg_cache = {}        # (q, k, world) -> (message, gathered) buffers of the generic exchange
 
     # ---- open_clip surface -------------------------------------------------------------------
     def eval(self):
@@ -222,6 +224,59 @@ class B200CLIP:
                          capi._p(scores), capi._p(idx), capi._p(iv), capi._p(cnt), self._stream())
         return scores, idx, iv, cnt
 
+    def sim_topk_sharded(self, img_emb: torch.Tensor, txt_emb: torch.Tensor, k: int, threshold: float = -float("inf"),
+                         timestamps: torch.Tensor | None = None, index_base: int = 0, clip_duration: float = 30.0,
+                         video_duration: float = 0.0, group=None):
+        """K4 over a row-sharded embedding matrix (this rank holds rows [index_base, index_base + len(img_emb))):
+        local top-k -> ONE all-gather of the packed candidate message -> the same merge on every rank.  Same outputs
+        as sim_topk, identical on all ranks and bit-identical to sim_topk over the unsharded matrix.  On NCCL the whole
+        exchange runs inside libb200clip.so (b200clip_sim_topk_nccl: no torch kernel, no host sync); other backends
+        move the message with torch.distributed."""
+        from . import distributed as D
+
+        rank, world = D.world_info(group)
+        if world == 1:
+            return self.sim_topk(img_emb, txt_emb, k, threshold, timestamps, index_base, clip_duration, video_duration)
+        img = img_emb.contiguous()
+        txt = txt_emb.to(self.device, torch.float32).contiguous()
+        q = int(txt.shape[0])
+        scores = torch.empty(q, k, device=self.device, dtype=torch.float32)
+        idx = torch.empty(q, k, device=self.device, dtype=torch.int64)
+        iv = torch.empty(q, k, 2, device=self.device, dtype=torch.float64)
+        cnt = torch.empty(q, device=self.device, dtype=torch.int32)
+        ts = timestamps.to(self.device, torch.float64).contiguous() if timestamps is not None else None
+        dt = capi.BF16 if img.dtype == torch.bfloat16 else capi.F32
+        thr = float(max(threshold, -3.0e38))
+        key = (id(group), self.device_index)
+        if key not in self._comm_cache:
+            self._comm_cache[key] = D.nccl_comm_ptr(self.device, group)
+        comm = self._comm_cache[key]
+        if comm:
+            self.handle.call("b200clip_sim_topk_nccl", capi._p(comm), rank, world, capi._p(img), dt, int(img.shape[0]),
+                             int(img.shape[1]), capi._p(txt), q, int(k), thr, capi._p(ts), int(index_base),
+                             float(clip_duration), float(video_duration), capi._p(scores), capi._p(idx), capi._p(iv),
+                             capi._p(cnt), self._stream())
+            return scores, idx, iv, cnt
+        # generic transport: K4 writes into a message buffer, torch.distributed gathers it, the merge kernel reads the
+        # gathered messages in place
+        mb = D.msg_bytes(q, k)
+        bkey = (q, k, world)
+        if bkey not in self._msg_cache:
+            self._msg_cache[bkey] = (torch.zeros(mb, dtype=torch.uint8, device=self.device),
+                                     torch.empty(world, mb, dtype=torch.uint8, device=self.device))
+        msg, gathered = self._msg_cache[bkey]
+        self.handle.call("b200clip_sim_topk", capi._p(img), dt, int(img.shape[0]), int(img.shape[1]), capi._p(txt), q, int(k),
+                         -3.0e38, capi._p(None), int(index_base), 0.0, 0.0, capi._p(msg.data_ptr() + q * k * 8),
+                         capi._p(msg.data_ptr()), capi._p(None), capi._p(None), self._stream())
+        if dist_backend_is_cpu_only(group):
+            gathered.copy_(D.exchange_messages(msg.cpu(), group))
+        else:
+            D.exchange_messages(msg, group, out=gathered)
+        self.handle.call("b200clip_topk_merge_packed", capi._p(gathered), world, q, int(k), thr, capi._p(ts),
+                         float(clip_duration), float(video_duration), capi._p(scores), capi._p(idx), capi._p(iv),
+                         capi._p(cnt), self._stream())
+        return scores, idx, iv, cnt
+
     def topk_merge(self, cand_scores: torch.Tensor, cand_idx: torch.Tensor, threshold: float = -float("inf"),
                    timestamps: torch.Tensor | None = None, clip_duration: float = 30.0, video_duration: float = 0.0):
         """Merge [g,Q,k] candidate lists (global indices) into the global top-k."""
@@ -238,6 +293,12 @@ class B200CLIP:
                          float(clip_duration), float(video_duration), capi._p(scores), capi._p(idx), capi._p(iv),
                          capi._p(cnt), self._stream())
         return scores, idx, iv, cnt
+
+
+def dist_backend_is_cpu_only(group=None) -> bool:
+    import torch.distributed as dist
+
+    return dist.get_backend(group) == "gloo"
 
 
 class _Preprocess:

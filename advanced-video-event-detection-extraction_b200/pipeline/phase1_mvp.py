@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from .. import capi
-from ..distributed import allgather_candidates, shard_range, world_info
+from ..distributed import shard_range, world_info
 from ..models.openclip_model import OpenCLIPModel
 from ..services.frame_extractor import FrameExtractor
 from ..utils.config import settings
@@ -138,13 +138,10 @@ class Phase1MVP:
             model.encode_frames_u8_host(middle, resize_mode=capi.RESIZE_REFERENCE, normalize=True, out=emb)
         else:
             emb = torch.empty(0, model.embed_dim, device=model.device, dtype=torch.float32)
-        scores, idx, iv, cnt = model.sim_topk(emb, text_embedding, k_eff, settings.CONFIDENCE_THRESHOLD, ts_dev,
-                                              index_base=lo, clip_duration=settings.CLIP_DURATION,
-                                              video_duration=video_duration)
-        if world > 1:
-            cs, ci = allgather_candidates(scores, idx)
-            scores, idx, iv, cnt = model.topk_merge(cs, ci, settings.CONFIDENCE_THRESHOLD, ts_dev,
-                                                    settings.CLIP_DURATION, video_duration)
+        # (world > 1: local top-k -> one all-gather of the packed candidates -> merge, see ..distributed)
+        scores, idx, iv, cnt = model.sim_topk_sharded(emb, text_embedding, k_eff, settings.CONFIDENCE_THRESHOLD, ts_dev,
+                                                      index_base=lo, clip_duration=settings.CLIP_DURATION,
+                                                      video_duration=video_duration)
         if return_device:
             return scores, idx, iv, cnt
         n_hits = int(cnt[0].item())

@@ -1,17 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- frames/sec of the phase1_mvp hot path (K1 preprocess -> ViT-B/32 embed -> text score -> top-k) on B200.
+"""bench.py -- frames/sec of the phase1_mvp hot path (K1 preprocess -> ViT embed -> text score -> top-k) on B200.
 
-Workload (BASELINE.json configs[1]): ViT-B/32 over a 1-hour video at 1 fps = 3600 decoded 1080p uint8 frames per
-GPU, 1 text query, top_k = 5, reference-exact resize chain.  A "step" is one pass over the whole video.
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C]     our arm (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ... [--config C]                    the reference's CPU path on the box's host cores
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm  (N>1: launched by torchrun, one rank per GPU)
-  python bench.py --impl reference ...                         the reference's CPU path on the box's host cores
+--config selects the BASELINE.json workload (1-based; the DEFAULT, 2, is the configuration the metric is quoted on):
+  1  configs[0]: ViT-B/32, 512 synthetic 224x224 frames, 1 text query, top_k=5 (the CPU-runnable case)
+  2  configs[1]: ViT-B/32 over a 1-hour video at 1 fps = 3600 decoded 1080p uint8 frames per GPU (weak scaling)
+  3  configs[2]: ViT-L/14 over a 10-min 30 fps video = 18 000 frames of 224x224, sharded over the ranks (strong scaling)
+  4  configs[3]: 256 text queries x 1 M cached frame embeddings (bf16 cache, row-sharded over the ranks), top_k=5
+  5  configs[4]: 100 000 person crops (256x128) vs one reference-image embedding, top_k=10, sharded over the ranks
 
-Prints ONE JSON line (rank 0).  `value` = whole-job frames/s with the frames already resident in HBM (device timed,
-CUDA events, max over ranks); `e2e` = the same metric through the host-buffer API (pinned host frames -> H2D inside
-the timed region -> result rows back on the host); `roofline` = the dominant kernel (tcgen05 GEMM) from CUDA events
-recorded around every GEMM launch on the launching stream inside the timed region; `cpu_baseline` = the oracle port
-of the reference pipeline timed on a bounded sample of the same workload on the host cores.
+Prints ONE JSON line (rank 0).  `value` = whole-job frames/s with the inputs already resident in HBM (device timed,
+CUDA events, max over ranks); `e2e` = the same metric through the host-buffer C-ABI calls (pinned host inputs -> H2D
+inside the timed region -> result rows back on the host); `roofline` = the dominant kernel class from CUDA events
+recorded around every launch of that class on the launching stream inside the timed region; `cpu_baseline` = the
+oracle port of the reference pipeline timed on a bounded sample of the same workload on the host cores.
 """
 from __future__ import annotations
 
@@ -29,7 +33,6 @@ os.environ.setdefault("B200CLIP_ALLOW_SYNTHETIC", "1")   # synthetic weights + s
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "frames/sec ViT-B/32 embed+score"
 UNIT = "frames/s"
 QUERY = "a person walking across street"
 
@@ -37,16 +40,17 @@ QUERY = "a person walking across street"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (0 = the config's default)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=3600, help="frames per GPU per step")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json workload, 1-based (default 2)")
+    ap.add_argument("--frames", type=int, default=0, help="override the frame / row count of the config")
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--top-k", type=int, default=5)
-    ap.add_argument("--cpu-frames", type=int, default=256, help="frames in the cpu_baseline sample")
-    ap.add_argument("--ref-frames", type=int, default=64, help="frames per step of the --impl reference arm")
-    ap.add_argument("--chunk", type=int, default=0, help="frames per pass of the tower (0 = all frames of the step at once)")
+    ap.add_argument("--top-k", type=int, default=0)
+    ap.add_argument("--cpu-frames", type=int, default=0, help="units in the cpu_baseline sample (0 = the config's default)")
+    ap.add_argument("--ref-frames", type=int, default=0, help="units per step of the --impl reference arm (0 = default)")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per pass of the tower (0 = the config's default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -121,8 +125,455 @@ def synth_host_frames(n: int, h: int, w: int, seed: int = 7):
     return np.concatenate([base] * reps)[:n]
 
 
+def device_frames(n: int, H: int, W: int, dev, seed: int):
+    """Synthetic decoded frames generated on the device (stand-in for a decoder's output): solid colour + coarse blocks
+    + noise per frame."""
+    import torch
+
+    g = torch.Generator(device=dev).manual_seed(seed)
+    frames = torch.empty(n, H, W, 3, dtype=torch.uint8, device=dev)
+    cell = max(8, min(H, W) // 9)
+    per = max(1, min(n, (256 << 20) // (H * W * 3)))
+    for i0 in range(0, n, per):
+        i1 = min(n, i0 + per)
+        f = torch.randint(0, 64, (i1 - i0, H, W, 3), dtype=torch.uint8, device=dev, generator=g)
+        f += torch.randint(0, 192, (i1 - i0, 1, 1, 3), dtype=torch.uint8, device=dev, generator=g)
+        blk = torch.randint(0, 192, (i1 - i0, H // cell, W // cell, 3), dtype=torch.uint8, device=dev, generator=g)
+        hh, ww = (H // cell) * cell, (W // cell) * cell
+        f[:, :hh, :ww] //= 2
+        f[:, :hh, :ww] += (blk.repeat_interleave(cell, 1).repeat_interleave(cell, 2) // 2)
+        frames[i0:i1] = f
+        del f, blk
+    return frames
+
+
+def rgb_to_nv12_device(frames):
+    """uint8 [N,H,W,3] (cuda) -> NV12 uint8 [N,H*3/2,W]: BT.601 limited-range encode with 2x2 chroma averaging (input
+    generator only -- what the bench measures starts from these NV12 bytes)."""
+    import torch
+
+    n, H, W, _ = frames.shape
+    out = torch.empty(n, H * 3 // 2, W, dtype=torch.uint8, device=frames.device)
+    per = max(1, (128 << 20) // (H * W * 12))
+    for i0 in range(0, n, per):
+        f = frames[i0:i0 + per].float()
+        r, g, b = f[..., 0], f[..., 1], f[..., 2]
+        out[i0:i0 + per, :H] = (16 + (65.481 * r + 128.553 * g + 24.966 * b) / 255).round().clamp(0, 255).to(torch.uint8)
+        cb = 128 + (-37.797 * r - 74.203 * g + 112.0 * b) / 255
+        cr = 128 + (112.0 * r - 93.786 * g - 18.214 * b) / 255
+        pool = lambda p: p.reshape(-1, H // 2, 2, W // 2, 2).mean((2, 4)).round().clamp(0, 255).to(torch.uint8)
+        out[i0:i0 + per, H:, 0::2] = pool(cb)
+        out[i0:i0 + per, H:, 1::2] = pool(cr)
+    return out
+
+
+# =============================================================================================== workloads
+class Workload:
+    """One BASELINE config: device-resident step, host-buffer (e2e) step, CPU sample, roofline class."""
+
+    model_name = "ViT-B-32"
+    metric = "frames/sec ViT-B/32 embed+score"
+    scaling = "weak"
+    default_steps = 20
+    roof_class = "gemm"
+    cpu_units = 256
+    ref_units = 64
+
+    def __init__(self, args, rank, local_rank, world, dev):
+        self.args, self.rank, self.local_rank, self.world, self.dev = args, rank, local_rank, world, dev
+        self.k = args.top_k or self.default_k
+        self.thr = 0.25
+
+    default_k = 5
+
+    # ---- helpers
+    def make_model(self, max_images, max_texts=1):
+        from b200clip import open_clip as oc
+        from b200clip.model_configs import MODEL_CONFIGS
+        from b200clip.weights import random_state_dict
+
+        self.cfg = MODEL_CONFIGS[self.model_name]
+        self.sd = random_state_dict(self.cfg, 0)
+        self.model, _, _ = oc.create_model_and_transforms(self.model_name, state_dict=self.sd, device=self.dev,
+                                                          max_images=max_images, max_texts=max_texts)
+        self.h = self.model.handle
+
+    def tokens(self, texts):
+        from b200clip.tokenizer import get_tokenizer
+
+        return get_tokenizer(self.model_name)(texts)
+
+    def flops_per_unit(self):
+        return self.cfg.flops_per_image()
+
+
+class FramesWorkload(Workload):
+    """Frames -> K1 -> image tower -> K4 against one text query (configs 1, 2, 3, 5)."""
+
+    H = W = 224
+    resize_mode = 0         # capi.RESIZE_REFERENCE
+    per_gpu = True          # frames_n is per GPU (weak) or the job total (strong)
+    frames_n = 512
+    host_slice = 0          # pinned host frames per rank for the e2e leg (0 = all of the rank's frames)
+    nv12_e2e = False
+    chunk = 0
+
+    def setup(self):
+        import torch
+
+        from b200clip.distributed import shard_range
+
+        a = self.args
+        n_cfg = a.frames or self.frames_n
+        if self.per_gpu:
+            self.n_total, self.lo, self.hi = n_cfg * self.world, self.rank * n_cfg, (self.rank + 1) * n_cfg
+        else:
+            self.n_total = n_cfg
+            self.lo, self.hi = shard_range(n_cfg, self.rank, self.world)
+        self.n = self.hi - self.lo
+        chunk = a.chunk or self.chunk
+        self.make_model(chunk if 0 < chunk < self.n else max(self.n, 1))
+        self.frames = device_frames(self.n, self.H, self.W, self.dev, 1234 + self.rank)
+        self.tok = self.tokens([self.query_text()]).to(self.dev)
+        self.ts = torch.arange(self.n_total, dtype=torch.float64, device=self.dev) / self.fps
+        self.duration = self.n_total / self.fps
+
+    fps = 1.0
+
+    def query_text(self):
+        return QUERY
+
+    def query_embedding(self):
+        return self.model.encode_text(self.tok, normalize=True)
+
+    def step(self):
+        txt = self.query_embedding()
+        emb = self.model.encode_frames_u8(self.frames, self.resize_mode, normalize=True)
+        s, i, iv, c = self.model.sim_topk_sharded(emb, txt, self.k, self.thr, self.ts, index_base=self.lo,
+                                                  clip_duration=30.0, video_duration=self.duration)
+        return emb, txt, s, i, iv, c
+
+    def units_per_step(self):
+        return self.n_total
+
+    # ---- host-buffer leg
+    def setup_e2e(self):
+        import numpy as np
+        import torch
+
+        n_host = self.n if not self.host_slice else min(self.n, self.host_slice)
+        self.calls = -(-self.n // n_host)
+        self.n_host = n_host
+        self.host_frames = torch.empty(n_host, self.H, self.W, 3, dtype=torch.uint8, pin_memory=True)
+        self.host_frames.copy_(self.frames[:n_host])
+        self.host_nv12 = None
+        if self.nv12_e2e:
+            self.host_nv12 = torch.empty(n_host, self.H * 3 // 2, self.W, dtype=torch.uint8, pin_memory=True)
+            self.host_nv12.copy_(rgb_to_nv12_device(self.frames[:n_host]))
+        self.tok_host = np.ascontiguousarray(self.tok.cpu().numpy())
+        self.txt_host = np.empty((1, self.cfg.embed_dim), np.float32)
+        self.emb_e2e = torch.empty(n_host * self.calls, self.cfg.embed_dim, device=self.dev)
+        k = self.k
+        self.res_host = [torch.empty(1, k, dtype=torch.float32, pin_memory=True), torch.empty(1, k, dtype=torch.int64, pin_memory=True),
+                         torch.empty(1, k, 2, dtype=torch.float64, pin_memory=True), torch.empty(1, dtype=torch.int32, pin_memory=True)]
+        self.e2e_rows = n_host * self.calls
+        self.ts2 = torch.arange(self.e2e_rows * self.world, dtype=torch.float64, device=self.dev)
+
+    def e2e_text(self):
+        import torch
+
+        from b200clip import capi
+
+        self.h.call("b200clip_encode_text_host", capi._p(self.tok_host), 1, capi._p(self.txt_host), 1, self.model._stream())
+        return torch.from_numpy(self.txt_host).to(self.dev, non_blocking=True)
+
+    def e2e_step(self, nv12=False):
+        import torch
+
+        txt = self.e2e_text()
+        for c in range(self.calls):
+            out = self.emb_e2e[c * self.n_host:(c + 1) * self.n_host]
+            if nv12:
+                self.model.encode_frames_nv12_host(self.host_nv12, self.resize_mode, True, out=out)
+            else:
+                self.model.encode_frames_u8_host(self.host_frames, self.resize_mode, True, out=out)
+        s, i, iv, cnt = self.model.sim_topk_sharded(self.emb_e2e, txt, self.k, self.thr, self.ts2,
+                                                    index_base=self.rank * self.e2e_rows, clip_duration=30.0,
+                                                    video_duration=float(self.e2e_rows * self.world))
+        for dst, src in zip(self.res_host, (s, i, iv, cnt)):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(self.dev)
+
+    def e2e_units(self):
+        return self.e2e_rows * self.world
+
+    def e2e_extra_bytes(self):
+        return self.txt_host.nbytes, sum(t.numel() * t.element_size() for t in self.res_host)
+
+    def e2e_api(self, nv12):
+        fn = "b200clip_encode_frames_nv12_host" if nv12 else "b200clip_encode_frames_u8_host"
+        return (f"b200clip_encode_text_host + {fn} (pinned host frames, {self.calls} call(s) of {self.n_host} frames) + "
+                "b200clip_sim_topk" + ("_nccl" if self.world > 1 else "") + ", results copied to host")
+
+    # ---- CPU sample (rank 0, N = 1)
+    def cpu_sample(self, out):
+        import numpy as np
+
+        from oracle.reference_pipeline import ReferenceCPU
+
+        cores = os.cpu_count() or 1
+        ncpu = min(self.args.cpu_frames or self.cpu_units, self.n)
+        sample = self.frames[:ncpu].cpu().numpy()
+        ref = ReferenceCPU(self.model_name, state_dict=self.sd, threads=cores)
+        shrink = self.resize_mode == 0
+        ref.encode_images(sample[:min(32, ncpu)], shrink=shrink)  # warm-up
+        t0 = time.perf_counter()
+        emb_cpu = ref.encode_images(sample, shrink=shrink)
+        txt_cpu = self.cpu_query(ref, sample)
+        sims_cpu = (emb_cpu @ txt_cpu.T)[:, 0]
+        np.argsort(sims_cpu)[::-1][:self.k]
+        dt = time.perf_counter() - t0
+        cpu = {"value": ncpu / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {ncpu} of the {self.n} frames: " + self.cpu_desc() + f" on {cores} threads, {dt:.1f} s"}
+        emb_gpu = out[0][:ncpu].cpu().numpy()
+        cos = (emb_gpu * emb_cpu).sum(-1)
+        sims_gpu = (emb_gpu @ out[1].cpu().numpy().T)[:, 0]
+        check = {"frames": ncpu, "embedding_cosine_min": float(cos.min()),
+                 "max_abs_score_err": float(np.abs(sims_gpu - sims_cpu).max())}
+        return cpu, check
+
+    def cpu_query(self, ref, sample):
+        return ref.encode_text_tokens(self.tok.cpu())
+
+    def cpu_desc(self):
+        pre = "cv2 INTER_AREA + " if self.resize_mode == 0 and max(self.H, self.W) > 512 else ""
+        return f"{pre}PIL/torchvision transform + fp32 PyTorch {self.model_name} (batch 32) + np.dot/argsort"
+
+    def describe(self):
+        shard = (f"{self.n} frames per GPU on {self.world} rank(s)" if self.per_gpu else
+                 f"{self.n_total} frames in contiguous shards of {self.n} over {self.world} rank(s)")
+        return {"workload": self.workload_text(), "frames_total": self.n_total, "frames_per_gpu": self.n,
+                "frame_hw": [self.H, self.W], "queries": 1, "top_k": self.k, "model": self.model_name,
+                "sharding": "single GPU" if self.world == 1 else shard + "; one NCCL all-gather of the packed top-k candidates",
+                "cache": f"inputs ({self.n * self.H * self.W * 3 / 1e9:.2f} GB of frames per GPU) are larger than the 126 MB L2",
+                "weights": "seeded random init (no checkpoint offline)"}
+
+
+class Config1(FramesWorkload):
+    frames_n = 512
+    default_steps = 50
+    cpu_units = 256
+
+    def workload_text(self):
+        return ("BASELINE configs[0]: phase1_mvp query, OpenCLIP ViT-B/32, 512 synthetic 224x224 frames per GPU, 1 text query, "
+                f"top_k={self.k} (all-frames mode)")
+
+
+class Config2(FramesWorkload):
+    H, W = 1080, 1920
+    frames_n = 3600
+    nv12_e2e = True
+
+    def setup(self):
+        self.H, self.W = self.args.height, self.args.width
+        # pinned host frames per rank: the whole batch on one GPU, smaller slices (re-used `calls` times per step) when
+        # several ranks share the host's pinned-memory budget
+        self.host_slice = 0 if self.world == 1 else (900 if self.world <= 2 else 450)
+        super().setup()
+
+    def workload_text(self):
+        return ("BASELINE configs[1]: ViT-B/32 (QuickGELU) over a 1-hour video at 1 fps -- "
+                f"{self.n} decoded {self.H}x{self.W} uint8 frames per GPU, 1 text query, top_k={self.k}, threshold 0.25, "
+                "reference resize chain (INTER_AREA<=512 -> PIL bicubic -> crop)")
+
+
+class Config3(FramesWorkload):
+    model_name = "ViT-L-14"
+    metric = "frames/sec ViT-L/14 embed+score"
+    frames_n = 18000
+    per_gpu = False
+    scaling = "strong"
+    default_steps = 3
+    fps = 30.0
+    chunk = 1024
+    cpu_units = 48
+    ref_units = 32
+
+    def workload_text(self):
+        return ("BASELINE configs[2]: ViT-L/14 (QuickGELU) over a 10-min 30 fps video -- 18 000 frames of 224x224 uint8 sharded "
+                f"over the ranks, 1 text query, top_k={self.k}, NCCL merge of the per-shard candidates")
+
+
+class Config5(FramesWorkload):
+    """Image-query scoring (ImageMatcher._single_stage_matching, src/services/image_matcher.py:980-1018): person crops
+    through open_clip's transform only (no 512 shrink: crops are not FrameExtractor output), query = the embedding of
+    one reference image, top_k = 10, threshold 0.7 (video_processor.py:644-645)."""
+
+    H, W = 256, 128
+    frames_n = 100000
+    per_gpu = False
+    scaling = "strong"
+    default_steps = 3
+    default_k = 10
+    resize_mode = 2         # capi.RESIZE_BICUBIC
+    chunk = 4096
+    host_slice = 20000
+    cpu_units = 256
+
+    def __init__(self, *a):
+        super().__init__(*a)
+        self.thr = 0.7
+
+    def setup(self):
+        super().setup()
+        import torch
+
+        g = torch.Generator(device=self.dev).manual_seed(99)
+        self.ref_image = torch.randint(0, 256, (1, self.H, self.W, 3), dtype=torch.uint8, device=self.dev, generator=g)
+
+    def query_embedding(self):
+        return self.model.encode_frames_u8(self.ref_image, self.resize_mode, normalize=True)
+
+    def e2e_text(self):
+        if not hasattr(self, "ref_host"):
+            import torch
+
+            self.ref_host = self.ref_image.cpu().pin_memory()
+            self.ref_emb = torch.empty(1, self.cfg.embed_dim, device=self.dev)
+        self.model.encode_frames_u8_host(self.ref_host, self.resize_mode, True, out=self.ref_emb)
+        return self.ref_emb
+
+    def e2e_extra_bytes(self):
+        return 0, sum(t.numel() * t.element_size() for t in self.res_host)
+
+    def cpu_query(self, ref, sample):
+        return ref.encode_images(self.ref_image.cpu().numpy(), shrink=False)
+
+    def workload_text(self):
+        return ("BASELINE configs[4]: enhanced person detection -- CLIP ViT-B/32 embedding of 100 000 person crops "
+                f"({self.H}x{self.W} uint8, open_clip transform) vs one reference-image embedding, top_k={self.k}, threshold 0.7")
+
+
+class Config4(Workload):
+    """256 text queries x 1 M cached frame embeddings (bf16, unit norm), row-sharded over the ranks: text tower for the
+    query batch + the tcgen05 similarity GEMM with fused top-k + fp32 re-score + clip intervals."""
+
+    metric = "frames/sec ViT-B/32 cached embeddings scored (256 queries)"
+    scaling = "strong"
+    default_steps = 50
+    roof_class = "sim_topk"
+    Q = 256
+    rows = 1_000_000
+
+    def setup(self):
+        import torch
+
+        from b200clip.distributed import shard_range
+
+        self.n_total = self.args.frames or self.rows
+        self.lo, self.hi = shard_range(self.n_total, self.rank, self.world)
+        self.n = self.hi - self.lo
+        self.make_model(1, self.Q)
+        e = self.cfg.embed_dim
+        g = torch.Generator(device=self.dev).manual_seed(4321 + self.rank)
+        self.cache = torch.empty(self.n, e, device=self.dev, dtype=torch.bfloat16)
+        for i0 in range(0, self.n, 1 << 18):
+            x = torch.randn(min(1 << 18, self.n - i0), e, device=self.dev, generator=g)
+            self.cache[i0:i0 + len(x)] = (x / x.norm(dim=-1, keepdim=True)).bfloat16()
+        words = ["person", "car", "dog", "street", "walking", "red", "running", "bag", "door", "night", "truck", "blue"]
+        self.texts = [f"a {words[i % 12]} {words[(i // 12) % 12]} near the {words[(i * 7) % 12]} {i}" for i in range(self.Q)]
+        self.tok = self.tokens(self.texts).to(self.dev)
+        self.ts = torch.arange(self.n_total, dtype=torch.float64, device=self.dev)
+        self.duration = float(self.n_total)
+
+    def step(self):
+        txt = self.model.encode_text(self.tok, normalize=True)
+        s, i, iv, c = self.model.sim_topk_sharded(self.cache, txt, self.k, self.thr, self.ts, index_base=self.lo,
+                                                  clip_duration=30.0, video_duration=self.duration)
+        return self.cache, txt, s, i, iv, c
+
+    def units_per_step(self):
+        return self.n_total
+
+    def flops_per_unit(self):
+        return 2.0 * self.Q * self.cfg.embed_dim
+
+    def setup_e2e(self):
+        import numpy as np
+        import torch
+
+        self.tok_host = np.ascontiguousarray(self.tok.cpu().numpy())
+        self.txt_host = np.empty((self.Q, self.cfg.embed_dim), np.float32)
+        k = self.k
+        self.res_host = [torch.empty(self.Q, k, dtype=torch.float32, pin_memory=True), torch.empty(self.Q, k, dtype=torch.int64, pin_memory=True),
+                         torch.empty(self.Q, k, 2, dtype=torch.float64, pin_memory=True), torch.empty(self.Q, dtype=torch.int32, pin_memory=True)]
+
+    def e2e_step(self, nv12=False):
+        import torch
+
+        from b200clip import capi
+
+        # host token ids in, host result rows out; the embedding cache stays resident (that is what a cache is)
+        self.h.call("b200clip_encode_text_host", capi._p(self.tok_host), self.Q, capi._p(self.txt_host), 1, self.model._stream())
+        txt = torch.from_numpy(self.txt_host).to(self.dev, non_blocking=True)
+        s, i, iv, cnt = self.model.sim_topk_sharded(self.cache, txt, self.k, self.thr, self.ts, index_base=self.lo,
+                                                    clip_duration=30.0, video_duration=self.duration)
+        for dst, src in zip(self.res_host, (s, i, iv, cnt)):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(self.dev)
+
+    def e2e_units(self):
+        return self.n_total
+
+    def e2e_extra_bytes(self):
+        return self.txt_host.nbytes, sum(t.numel() * t.element_size() for t in self.res_host)
+
+    def e2e_api(self, nv12):
+        return ("b200clip_encode_text_host (256 x 77 host token ids) + b200clip_sim_topk" + ("_nccl" if self.world > 1 else "") +
+                " on the resident bf16 cache, [256, k] scores / indices / intervals / counts copied to host")
+
+    def cpu_sample(self, out):
+        import numpy as np
+
+        cores = os.cpu_count() or 1
+        ncpu = min(self.args.cpu_frames or 200_000, self.n)
+        emb = self.cache[:ncpu].float().cpu().numpy()           # the reference holds fp32 embeddings
+        txt = out[1].cpu().numpy()
+        t0 = time.perf_counter()
+        sims = np.dot(emb, txt.T)                                   # openclip_model.py:212-214
+        top = np.argsort(sims, axis=0)[::-1][:self.k]              # phase1_mvp.py:145 per query
+        dt = time.perf_counter() - t0
+        cpu = {"value": ncpu / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {ncpu} of the {self.n_total} cached rows x 256 queries: np.dot + np.argsort per query (fp32), "
+                         f"{dt:.1f} s; the text tower is not included"}
+        s_gpu = out[2].cpu().numpy()
+        i_gpu = out[3].cpu().numpy()
+        # the GPU top-k covers all rows; compare scores of its hits that fall inside the CPU sample
+        err = 0.0
+        for q in range(self.Q):
+            for r in range(self.k):
+                if 0 <= i_gpu[q, r] < ncpu and self.lo == 0:
+                    err = max(err, abs(float(sims[i_gpu[q, r], q]) - float(s_gpu[q, r])))
+        return cpu, {"rows": ncpu, "max_abs_score_err_on_shared_hits": err, "cpu_top1_query0": int(top[0, 0])}
+
+    def describe(self):
+        return {"workload": f"BASELINE configs[3]: multi-query batch -- 256 text queries x {self.n_total} cached frame embeddings "
+                            f"(bf16, E=512), fused similarity GEMM + top-{self.k} + fp32 re-score + clip intervals; the step "
+                            "includes the text tower for the 256 queries",
+                "rows_total": self.n_total, "rows_per_gpu": self.n, "queries": self.Q, "top_k": self.k, "model": self.model_name,
+                "sharding": "single GPU" if self.world == 1 else f"cache rows in contiguous shards over {self.world} rank(s); "
+                "one NCCL all-gather of the packed top-k candidates",
+                "cache": f"{self.n * 1024 / 1e9:.2f} GB of embeddings per GPU, larger than the 126 MB L2",
+                "weights": "seeded random init (no checkpoint offline)"}
+
+
+WORKLOADS = {1: Config1, 2: Config2, 3: Config3, 4: Config4, 5: Config5}
+
+
 # =============================================================================================== reference arm
 def run_reference(args, rank: int):
+    """The reference's own CPU path (oracle port: /root/reference has no importable arithmetic) on a
+    bounded sample of the selected config, all host threads."""
     if rank != 0:
         return
     import numpy as np
@@ -133,94 +584,105 @@ def run_reference(args, rank: int):
     from b200clip.weights import random_state_dict
     from oracle.reference_pipeline import ReferenceCPU
 
+    cls = WORKLOADS[args.config]
     cores = os.cpu_count() or 1
-    ref = ReferenceCPU("ViT-B-32", state_dict=random_state_dict(MODEL_CONFIGS["ViT-B-32"], 0), threads=cores)
-    frames = synth_host_frames(args.ref_frames, args.height, args.width)
-    tok = get_tokenizer("ViT-B-32")([QUERY])
-    ts = [float(i) for i in range(len(frames))]
-    for _ in range(args.warmup):
-        ref.query(frames, tok, args.top_k, 0.25, ts)
+    k = args.top_k or cls.default_k
+    steps = args.steps or 3
+    if args.config == 4:
+        n = args.ref_frames or 200_000
+        rng = np.random.default_rng(0)
+        emb = rng.standard_normal((n, 512)).astype(np.float32)
+        emb /= np.linalg.norm(emb, axis=1, keepdims=True)
+        txt = rng.standard_normal((256, 512)).astype(np.float32)
+        txt /= np.linalg.norm(txt, axis=1, keepdims=True)
+        torch.set_num_threads(cores)
+
+        def one():
+            sims = np.dot(emb, txt.T)
+            return np.argsort(sims, axis=0)[::-1][:k]
+
+        sample = f"{n} of 1 000 000 cached fp32 rows x 256 queries per step: np.dot + np.argsort per query, {cores} threads"
+        wl = "BASELINE configs[3]: 256 text queries x 1M cached frame embeddings"
+    else:
+        name = cls.model_name
+        ref = ReferenceCPU(name, state_dict=random_state_dict(MODEL_CONFIGS[name], 0), threads=cores)
+        n = args.ref_frames or cls.ref_units
+        H, W = (args.height, args.width) if args.config == 2 else (cls.H, cls.W)
+        frames = synth_host_frames(n, H, W)
+        tok = get_tokenizer(name)([QUERY])
+        ts = [float(i) for i in range(n)]
+        shrink = cls.resize_mode == 0
+        thr = 0.7 if args.config == 5 else 0.25
+
+        def one():
+            if args.config == 5:
+                emb = ref.encode_images(frames, shrink=False)
+                q = ref.encode_images(frames[:1], shrink=False)
+                sims = (emb @ q.T)[:, 0]
+                return np.argsort(sims)[::-1][:k]
+            return ref.query(frames, tok, k, thr, ts, shrink=shrink)
+
+        sample = (f"{n} frames ({H}x{W} uint8) per step: " + ("cv2 INTER_AREA shrink + " if shrink and max(H, W) > 512 else "") +
+                  f"PIL/torchvision transform + fp32 PyTorch {name} (batch 32) + np.dot/argsort, {cores} threads")
+        wl = f"BASELINE configs[{args.config - 1}] ({name}, {H}x{W} frames)"
+    for _ in range(max(1, min(args.warmup, 3))):
+        one()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ref.query(frames, tok, args.top_k, 0.25, ts)
+    for _ in range(steps):
+        one()
     dt = time.perf_counter() - t0
-    value = args.steps * len(frames) / dt
-    sample = (f"{len(frames)} of {args.frames} frames ({args.height}x{args.width} uint8) per step: cv2 INTER_AREA shrink + "
-              f"PIL/torchvision transform + fp32 PyTorch ViT-B/32 (batch 32) + np.dot/argsort, {cores} threads")
+    value = steps * n / dt
     emit({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": cls.metric, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": cls.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": {"workload": wl, "bench_config": args.config, "sample_units_per_step": n},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
 
 
-def workload_config(args, world: int) -> dict:
-    return {"workload": "BASELINE configs[1]: ViT-B/32 (QuickGELU) over a 1-hour video at 1 fps -- "
-                        f"{args.frames} decoded {args.height}x{args.width} uint8 frames per GPU, 1 text query, "
-                        f"top_k={args.top_k}, threshold 0.25, reference resize chain (INTER_AREA<=512 -> PIL bicubic -> crop)",
-            "frames_per_gpu": args.frames, "frame_hw": [args.height, args.width], "queries": 1, "top_k": args.top_k,
-            "sharding": f"frames sharded over {world} rank(s); one all-gather of top-k candidates" if world > 1
-            else "single GPU", "cache": "inputs (22.4 GB of frames per GPU) are far larger than the 126 MB L2",
-            "weights": "seeded random init (no checkpoint offline)"}
-
-
 # =============================================================================================== our arm
-def run_b200(args, rank: int, local_rank: int, world: int):
-    import numpy as np
+def h2d_ceiling(dev, world):
+    """Plain contiguous pinned -> device copies on every rank at once: the PCIe / host-memory ceiling the e2e leg lives
+    under (GB/s per rank: min over ranks, and the sum over ranks)."""
     import torch
     import torch.distributed as dist
 
-    from b200clip import capi
-    from b200clip import open_clip as oc
-    from b200clip.distributed import allgather_candidates
-    from b200clip.model_configs import MODEL_CONFIGS
-    from b200clip.tokenizer import get_tokenizer
-    from b200clip.weights import random_state_dict
+    nbytes = 1 << 30
+    src = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    gbs = torch.tensor([3 * nbytes / (time.perf_counter() - t0) / 1e9], dtype=torch.float64, device=dev)
+    lo, tot = gbs.clone(), gbs.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    del src, dst
+    return {"per_rank_min_gbs": float(lo.item()), "sum_gbs": float(tot.item()), "bytes": nbytes, "copies": 3}
+
+
+def run_b200(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg = MODEL_CONFIGS["ViT-B-32"]
-    sd = random_state_dict(cfg, 0)
-    n, H, W = args.frames, args.height, args.width
-    model, _, _ = oc.create_model_and_transforms("ViT-B-32", state_dict=sd, device=dev,
-                                                 max_images=(args.chunk if 0 < args.chunk < n else n), max_texts=1)
-    h = model.handle
-
-    # ---- synthetic decoded frames resident in HBM (stand-in for NVDEC output): per-frame solid colour + blocks + noise
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    frames = torch.empty(n, H, W, 3, dtype=torch.uint8, device=dev)
-    for i0 in range(0, n, 200):
-        i1 = min(n, i0 + 200)
-        f = torch.randint(0, 64, (i1 - i0, H, W, 3), dtype=torch.uint8, device=dev, generator=g)
-        bg = torch.randint(0, 192, (i1 - i0, 1, 1, 3), dtype=torch.uint8, device=dev, generator=g)
-        f += bg
-        blk = torch.randint(0, 192, (i1 - i0, H // 120, W // 120, 3), dtype=torch.uint8, device=dev, generator=g)
-        f[:, : (H // 120) * 120, : (W // 120) * 120] //= 2
-        f[:, : (H // 120) * 120, : (W // 120) * 120] += (blk.repeat_interleave(120, 1).repeat_interleave(120, 2) // 2)
-        frames[i0:i1] = f
-        del f, blk
-    tok = get_tokenizer("ViT-B-32")([QUERY]).to(dev)
-    n_total = n * world
-    ts = torch.arange(n_total, dtype=torch.float64, device=dev)  # 1 fps
-    thr, k = 0.25, args.top_k
-
-    # (Running the text tower on a side stream under the image tower was measured SLOWER -- 39.5 vs 37.3 ms per step:
-    # its small grids take SMs away from the persistent, statically scheduled GEMM CTAs -- so the step is serial.)
-    def step():
-        txt = model.encode_text(tok, normalize=True)
-        emb = model.encode_frames_u8(frames, capi.RESIZE_REFERENCE, normalize=True)
-        s, i, iv, c = model.sim_topk(emb, txt, k, thr, ts, index_base=rank * n, clip_duration=30.0,
-                                     video_duration=float(n_total))
-        if world > 1:
-            cs, ci = allgather_candidates(s, i)
-            s, i, iv, c = model.topk_merge(cs, ci, thr, ts, 30.0, float(n_total))
-        return emb, txt, s, i, iv, c
+    w = WORKLOADS[args.config](args, rank, local_rank, world, dev)
+    w.setup()
+    h = w.h
+    steps = args.steps or w.default_steps
+    warmup = max(args.warmup, 3)
 
     def barrier():
         if world > 1:
@@ -230,8 +692,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        out = step()
+    for _ in range(warmup):
+        out = w.step()
     barrier()
     h.reset_launches()
     h.profile_read(reset=True)
@@ -243,133 +705,112 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         sampler.mark()
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        out = step()
+    for _ in range(steps):
+        out = w.step()
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     h.profile_enable(False)
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    own_ms = e0.elapsed_time(e1)
+    ms = torch.tensor([own_ms], dtype=torch.float64, device=dev)
+    per_rank = [own_ms / steps]
     if world > 1:
+        allms = torch.zeros(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allms, ms)
+        per_rank = [float(v) / steps for v in allms.tolist()]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     launches = h.launches
     prof = h.profile_read(reset=True)
-    value = n_total * args.steps / (total_ms / 1e3)
+    value = w.units_per_step() * steps / (total_ms / 1e3)
 
     # ---- end to end through the host-buffer API
-    e2e = None
-    emb_dev_ref, txt_ref, s_ref, i_ref = out[0], out[1], out[2], out[3]
-    host_frames = None
+    e2e, e2e_alt, ceiling = None, None, None
     if not args.no_e2e:
-        # pinned host frames per rank: the whole batch on one GPU, smaller slices (re-used `calls` times per step) when
-        # several ranks share the host's pinned-memory budget (8 ranks x 450 frames x 6.2 MB = 22 GB)
-        n_host = n if world == 1 else min(n, 900 if world <= 2 else 450)
-        calls = -(-n // n_host)
-        host_frames = torch.empty(n_host, H, W, 3, dtype=torch.uint8, pin_memory=True)
-        host_frames.copy_(frames[:n_host])
-        tok_host = np.ascontiguousarray(tok.cpu().numpy())
-        txt_host = np.empty((1, cfg.embed_dim), np.float32)
-        emb_e2e = torch.empty(n_host * calls, cfg.embed_dim, device=dev)
-        res_host = [torch.empty(1, k, dtype=torch.float32, pin_memory=True), torch.empty(1, k, dtype=torch.int64, pin_memory=True),
-                    torch.empty(1, k, 2, dtype=torch.float64, pin_memory=True), torch.empty(1, dtype=torch.int32, pin_memory=True)]
-        ts2 = torch.arange(n_host * calls * world, dtype=torch.float64, device=dev)
+        w.setup_e2e()
+        e2e_steps = max(2, min(steps, 5))
 
-        def e2e_step():
-            h.call("b200clip_encode_text_host", capi._p(tok_host), 1, capi._p(txt_host), 1, model._stream())
-            for c in range(calls):
-                model.encode_frames_u8_host(host_frames, capi.RESIZE_REFERENCE, True, out=emb_e2e[c * n_host:(c + 1) * n_host])
-            txt = torch.from_numpy(txt_host).to(dev, non_blocking=True)
-            s, i, iv, cnt = model.sim_topk(emb_e2e, txt, k, thr, ts2, index_base=rank * n_host * calls,
-                                           clip_duration=30.0, video_duration=float(n_host * calls * world))
+        def measure(nv12):
+            w.e2e_step(nv12)
+            barrier()
+            h.transfer_bytes(reset=True)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                w.e2e_step(nv12)
+            barrier()
+            h2d_lib, d2h_lib = h.transfer_bytes(reset=True)   # counted inside the library, per cudaMemcpy*Async it issued
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
             if world > 1:
-                cs, ci = allgather_candidates(s, i)
-                s, i, iv, cnt = model.topk_merge(cs, ci, thr, ts2, 30.0, float(n_host * calls * world))
-            for dst, src in zip(res_host, (s, i, iv, cnt)):
-                dst.copy_(src, non_blocking=True)
-            torch.cuda.synchronize(dev)
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            xh, xd = w.e2e_extra_bytes()
+            return {"value": w.e2e_units() * e2e_steps / float(dt.item()), "unit": UNIT,
+                    "h2d_bytes_per_step": int(h2d_lib // e2e_steps + xh), "d2h_bytes_per_step": int(d2h_lib // e2e_steps + xd),
+                    "h2d_gbs_per_rank": (h2d_lib / e2e_steps) / (float(dt.item()) / e2e_steps) / 1e9,
+                    "steps": e2e_steps, "input": "nv12" if nv12 else ("rgb" if isinstance(w, FramesWorkload) else "token ids"),
+                    "api": w.e2e_api(nv12)}
 
-        e2e_step()
-        barrier()
-        h.transfer_bytes(reset=True)
-        t0 = time.perf_counter()
-        e2e_steps = max(2, min(args.steps, 5))
-        for _ in range(e2e_steps):
-            e2e_step()
-        barrier()
-        h2d_lib, d2h_lib = h.transfer_bytes(reset=True)   # counted inside the library, per cudaMemcpy*Async it issued
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_host * calls * world * e2e_steps / float(dt.item()), "unit": UNIT,
-               # library uploads (frame windows + tokens) + the text embedding torch re-uploads for K4
-               "h2d_bytes_per_step": int(h2d_lib // e2e_steps + txt_host.nbytes),
-               "d2h_bytes_per_step": int(d2h_lib // e2e_steps + sum(t.numel() * t.element_size() for t in res_host)),
-               "host_frame_bytes_per_step": int(n_host * calls * H * W * 3),
-               "upload": "only the columns/rows of each frame that survive the centre crop are copied (strided cudaMemcpy3DAsync)",
-               "steps": e2e_steps, "api": "b200clip_encode_text_host + b200clip_encode_frames_u8_host (pinned host frames, "
-               f"{calls} call(s) of {n_host} frames) + b200clip_sim_topk, results copied to host"}
+        e2e = measure(False)
+        if getattr(w, "nv12_e2e", False):
+            # the same frames as a decoder leaves them (NV12, 1.5 B/px): the frame-feed entry point is the headline host
+            # path, the RGB entry point (what the reference's Python hands over) is reported next to it
+            e2e_alt = e2e
+            e2e_alt["note"] = "RGB host frames through the reference-facing b200clip_encode_frames_u8_host (3 B/px over PCIe)"
+            e2e = measure(True)
+            e2e["upload"] = ("NV12 host frames (decoder output, 1.5 B/px); only the columns/rows of each plane that survive the "
+                             "centre crop are copied (two strided cudaMemcpy3DAsync per chunk); converted to RGB inside K1")
+        ceiling = h2d_ceiling(dev, world)
 
     # ---- CPU baseline (rank 0, N = 1 only): oracle port of the reference pipeline on a bounded sample
-    cpu = None
-    check = None
+    cpu, check = None, None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle.reference_pipeline import ReferenceCPU
-
-        cores = os.cpu_count() or 1
-        ncpu = min(args.cpu_frames, n)
-        sample_np = (host_frames[:ncpu].numpy() if host_frames is not None else frames[:ncpu].cpu().numpy())
-        ref = ReferenceCPU("ViT-B-32", state_dict=sd, threads=cores)
-        ref.encode_images(sample_np[:32], shrink=True)  # warm-up
-        t0 = time.perf_counter()
-        emb_cpu = ref.encode_images(sample_np, shrink=True)
-        txt_cpu = ref.encode_text_tokens(tok.cpu())
-        sims_cpu = (emb_cpu @ txt_cpu.T)[:, 0]
-        order_cpu = np.argsort(sims_cpu)[::-1][:k]
-        dt = time.perf_counter() - t0
-        cpu = {"value": ncpu / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {ncpu} of the {n} frames: cv2 INTER_AREA + PIL/torchvision transform + fp32 PyTorch "
-                         f"ViT-B/32 (batch 32) + np.dot/argsort on {cores} threads, {dt:.1f} s"}
-        emb_gpu = emb_dev_ref[:ncpu].cpu().numpy()
-        cos = (emb_gpu * emb_cpu).sum(-1)
-        sims_gpu = (emb_gpu @ txt_ref.cpu().numpy().T)[:, 0]
-        check = {"frames": ncpu, "embedding_cosine_min": float(cos.min()),
-                 "max_abs_score_err": float(np.abs(sims_gpu - sims_cpu).max())}
+        cpu, check = w.cpu_sample(out)
 
     if rank == 0:
         pk = peaks()
-        gemm = prof["gemm"]
-        tf = gemm["work"] / (gemm["ms"] / 1e3) / 1e12 if gemm["ms"] > 0 else 0.0
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
-        if os.path.exists(tp):
-            # ncu dram__bytes_read.sum + dram__bytes_write.sum of the GEMM launches (profiles/r01j_gemm_ncu_summary.txt),
-            # kept as bytes per FLOP and scaled to this run's average launch
-            tj = json.load(open(tp))
-            traffic = tj["dram_bytes_per_flop"] * gemm["work"] / max(gemm["launches"], 1)
+        cls = w.roof_class
+        r = prof[cls]
         kernels = {}
-        for name, r in prof.items():
-            if r["launches"]:
+        for name, rr in prof.items():
+            if rr["launches"]:
                 # pre_* are sub-ranges of "preprocess" (not additive with it)
-                kernels[name] = {"ms_per_step": r["ms"] / args.steps, "launches_per_step": r["launches"] / args.steps,
-                                 "share": r["ms"] / total_ms,
-                                 ("tflops" if name == "gemm" else "gbs"): (r["work"] / (r["ms"] / 1e3) / (1e12 if name == "gemm" else 1e9))}
+                key = "tflops" if name == "gemm" else "gbs"
+                kernels[name] = {"ms_per_step": rr["ms"] / steps, "launches_per_step": rr["launches"] / steps,
+                                 "share": rr["ms"] / total_ms, key: (rr["work"] / (rr["ms"] / 1e3) / (1e12 if name == "gemm" else 1e9))}
+        if cls == "gemm":
+            tf = r["work"] / (r["ms"] / 1e3) / 1e12 if r["ms"] > 0 else 0.0
+            roof = {"bound": "tensor",
+                    "kernel": "gemm_bf16_tcgen05_2cta_kernel<1> (cta_group::2 256x256 tiles: every large-M ViT GEMM of the step) + "
+                              "gemm_bf16_tcgen05_kernel<64> (the M = 77 text-tower GEMMs)",
+                    "achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops_sustained"],
+                    "traffic": None,
+                    "traffic_note": "not measured in this run (ncu dram__bytes per GEMM shape: profiles/*gemm_ncu_summary*)",
+                    "flop_per_launch_avg": r["work"] / max(r["launches"], 1)}
+        else:
+            # config 4: the similarity GEMM with fused top-k (2*Q*n*E FLOP per launch), timed with its final merge / re-score
+            flop = 2.0 * w.Q * w.n * w.cfg.embed_dim * steps
+            tf = flop / (r["ms"] / 1e3) / 1e12 if r["ms"] > 0 else 0.0
+            roof = {"bound": "tensor", "kernel": "sim_topk_tc_kernel<true> (tcgen05 2-CTA similarity GEMM, top-k fused in the epilogue) "
+                                                 "+ topk_final_kernel + rescore_sort_kernel",
+                    "achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops_sustained"],
+                    "traffic": None, "hbm_gbs": r["work"] / (r["ms"] / 1e3) / 1e9, "hbm_frac": r["work"] / (r["ms"] / 1e3) / 1e9 / pk["hbm_gbs"],
+                    "flop_per_launch_avg": flop / max(r["launches"], 1)}
+        roof.update({"peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step); burst peak {pk['bf16_tflops']}",
+                     "launches": r["launches"], "share_of_step": r["ms"] / total_ms})
+        cfgd = w.describe()
+        cfgd["bench_config"] = args.config
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
-            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all ViT GEMMs of the step)",
-                         "achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": tf / pk["bf16_tflops_sustained"], "traffic": traffic,
-                         "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step); "
-                                        f"burst peak {pk['bf16_tflops']}",
-                         "flop_per_launch_avg": gemm["work"] / max(gemm["launches"], 1),
-                         "launches": gemm["launches"], "share_of_step": gemm["ms"] / total_ms},
-            "kernels": kernels,
+            "metric": w.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": w.scaling, "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": cfgd, "roofline": roof, "kernels": kernels,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "check": check,
-            "model_flop_per_frame": cfg.flops_per_image(),
-            "model_tflops": value * cfg.flops_per_image() / 1e12 / world,
+            "per_rank_ms_per_step": per_rank,
+            "model_flop_per_unit": w.flops_per_unit(),
+            "model_tflops": value * w.flops_per_unit() / 1e12 / world,
         }
+        if e2e_alt is not None:
+            line["e2e_rgb"] = e2e_alt
+        if ceiling is not None:
+            line["h2d_ceiling"] = ceiling
         emit(line)
     if world > 1:
         dist.barrier()

@@ -35,6 +35,7 @@ extern "C" {
 #define B200CLIP_E_ARCH (-4)   /* device is not compute capability 10.x */
 #define B200CLIP_E_STATE (-5)  /* weights missing / handle not finalized */
 #define B200CLIP_E_NOMEM (-6)
+#define B200CLIP_E_NCCL (-7)   /* NCCL could not be bound at run time, or a collective failed */
 
 typedef struct b200clip_handle b200clip_handle;
 
@@ -184,6 +185,35 @@ int b200clip_topk_merge(b200clip_handle* h, const float* cand_scores_dev, const 
                         double video_duration, float* top_scores_dev, int64_t* top_idx_dev, double* intervals_dev,
                         int32_t* counts_dev, void* stream);
 
+/* ---- multi-GPU (the reference is single-device).  Rows (frames or cached embeddings) are
+ *      block-partitioned over ranks, weights replicated, no communication while embedding.  The only exchange is the
+ *      per-rank candidate list: ONE in-place ncclAllGather of B200CLIP message bytes on `stream`, then the same
+ *      deterministic merge on every rank (result == the single-GPU top-k, bit for bit).  `nccl_comm` is an ncclComm_t
+ *      (void*) created by the host with the libnccl.so.2 mapped in the process (PyTorch:
+ *      ProcessGroupNCCL._comm_ptr()); NCCL is bound with dlopen at first use, failures return B200CLIP_E_NCCL.
+ *      Message of one rank, b200clip_topk_msg_bytes(q, k) bytes: int64 idx[q][k] (global, -1 = empty) |
+ *      float score[q][k] | zero padding to 16 bytes. */
+int64_t b200clip_topk_msg_bytes(int q, int k);
+/* Shard-local K4 + exchange + merge in one call: img_emb_dev holds this rank's n_local rows, index_base = global index
+ * of its first row; outputs as b200clip_sim_topk, identical on every rank. */
+int b200clip_sim_topk_nccl(b200clip_handle* h, void* nccl_comm, int rank, int world, const void* img_emb_dev,
+                           int emb_dtype, int64_t n_local, int e, const float* txt_emb_dev, int q, int k,
+                           float threshold, const double* timestamps_dev, int64_t index_base, double clip_duration,
+                           double video_duration, float* top_scores_dev, int64_t* top_idx_dev, double* intervals_dev,
+                           int32_t* counts_dev, void* stream);
+/* Exchange + merge of candidates the caller already holds (local_scores_dev fp32 [q,k], local_idx_dev int64 [q,k],
+ * global indices). */
+int b200clip_topk_merge_nccl(b200clip_handle* h, void* nccl_comm, int rank, int world, const float* local_scores_dev,
+                             const int64_t* local_idx_dev, int q, int k, float threshold, const double* timestamps_dev,
+                             double clip_duration, double video_duration, float* top_scores_dev, int64_t* top_idx_dev,
+                             double* intervals_dev, int32_t* counts_dev, void* stream);
+/* Merge of g gathered messages (layout above, message l at gathered_dev + l * msg_bytes) that some other transport
+ * delivered (e.g. torch.distributed.all_gather_into_tensor on gloo in the CPU-side tests of the host logic). */
+int b200clip_topk_merge_packed(b200clip_handle* h, const void* gathered_dev, int g, int q, int k, float threshold,
+                               const double* timestamps_dev, double clip_duration, double video_duration,
+                               float* top_scores_dev, int64_t* top_idx_dev, double* intervals_dev, int32_t* counts_dev,
+                               void* stream);
+
 /* ---- building blocks, exported for the parity tests and micro-benchmarks ---- */
 /* out[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ resid); bf16 in/out, fp32 accumulate. act: 0 none,
  * 1 QuickGELU, 2 erf GELU.  bias fp32 [N] or NULL, resid bf16 [M,N] or NULL (may equal out). */
@@ -200,7 +230,7 @@ int b200clip_attention_bf16(b200clip_handle* h, const void* qkv_dev, void* out_d
  * launching stream.  profile_read synchronises the device and returns, for one class, the summed elapsed ms, the
  * summed algorithmic work (FLOP for class 0 = GEMM; bytes for 1 = attention, 2 = LayerNorm, 3 = K1 preprocess chain,
  * 4 = head, 5 = K4 similarity/top-k, 6 = misc, 7/8/9 = the K1 stages area / horizontal / vertical, which are also
- * inside 3) and the number of timed launches. */
+ * inside 3, 10 = the NCCL all-gather of the multi-GPU exchange: bytes gathered) and the number of timed launches. */
 int b200clip_profile_enable(b200clip_handle* h, int on);
 int b200clip_profile_read(b200clip_handle* h, int kernel_class, double* ms_out, double* work_out,
                           int64_t* launches_out, int reset);

@@ -86,3 +86,48 @@ def test_shard_range_partitions():
             assert max(hi - lo for lo, hi in parts) <= -(-n // world) if n else True
     with pytest.raises(ValueError):
         shard_range(10, 2, 2)
+
+
+def _msg_worker(rank, world, port, q, k, out_dir):
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from b200clip import distributed as D
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7 + rank)
+    s = np.sort(rng.standard_normal((q, k)).astype(np.float32), axis=1)[:, ::-1].copy()
+    i = (rng.permutation(1000)[: q * k].reshape(q, k) + 1000 * rank).astype(np.int64)
+    if rank == 1:
+        s[0, k - 1], i[0, k - 1] = -np.inf, -1                      # an empty slot
+    msg = D.pack_message(torch.from_numpy(s), torch.from_numpy(i))
+    assert msg.numel() == D.msg_bytes(q, k) and msg.numel() % 16 == 0
+    buf = torch.empty(world, msg.numel(), dtype=torch.uint8)
+    got = D.exchange_messages(msg, out=buf)
+    assert got.data_ptr() == buf.data_ptr()                          # the preallocated buffer is used, one collective
+    cs, ci = D.unpack_messages(got, q, k)
+    assert np.array_equal(cs[rank].numpy(), s) and np.array_equal(ci[rank].numpy(), i)
+    ms, mi = D.merge_messages_reference(got.numpy(), q, k)
+    np.savez(os.path.join(out_dir, f"msg{rank}.npz"), ms=ms, mi=mi, s=s, i=i)
+    assert D.nccl_comm_ptr(torch.device("cpu")) == 0                 # gloo: no NCCL communicator -> generic transport
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_packed_message_round_trip_two_ranks(tmp_path):
+    """The wire format of the candidate exchange (int64 idx | fp32 score | pad to 16 B) through a real 2-rank
+    all_gather_into_tensor, and the merge rule every rank applies to the gathered messages."""
+    from b200clip import capi
+    from b200clip import distributed as D
+
+    q, k, world = 3, 5, 2
+    assert D.msg_bytes(q, k) == capi.load_library().b200clip_topk_msg_bytes(q, k) == 192
+    assert D.msg_bytes(1, 1) == 16 and D.msg_bytes(256, 5) == capi.load_library().b200clip_topk_msg_bytes(256, 5)
+    mp.spawn(_msg_worker, args=(world, _free_port(), q, k, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "msg0.npz"), np.load(tmp_path / "msg1.npz")
+    assert np.array_equal(r0["mi"], r1["mi"]) and np.array_equal(r0["ms"], r1["ms"])
+    for qq in range(q):
+        cand = sorted([(float(s), int(i)) for r in (r0, r1) for s, i in zip(r["s"][qq], r["i"][qq]) if i >= 0], reverse=True)[:k]
+        assert [c[1] for c in cand] == list(r0["mi"][qq]) and np.allclose([c[0] for c in cand], r0["ms"][qq])

@@ -1,0 +1,183 @@
+"""BASELINE configs at their FULL sizes, through size-independent properties (the oracle cannot run 1 M rows / 100 k
+crops / hundreds of ViT-L/14 frames in seconds): exact order against the kernel's own dense scores, planted winners,
+batch / chunk invariance (a frame's embedding must not depend on what else is in the batch), plus an oracle check on
+the distinct inputs the big batch is tiled from.  And the outlier-weights stress of the bf16 residual stream."""
+import numpy as np
+import pytest
+import torch
+
+from parity import COS_MIN, SCORE_TOL, cosine_rows
+from synth import structured_frames
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config4_full_size_1m_rows_256_queries(model_b32):
+    """1 000 000 x 512 bf16 cache, 256 queries, k = 5: the tensor-core kernel's selection == a stable descending sort
+    (ties -> higher index) of the scores that very kernel computed; the public call returns those rows re-scored in
+    fp32 and re-sorted; planted winners come back; counts follow the threshold."""
+    from b200clip import capi
+
+    n, q, k, e = 1_000_000, 256, 5, 512
+    g = torch.Generator(device="cuda").manual_seed(11)
+    img = torch.empty(n, e, device="cuda", dtype=torch.bfloat16)
+    for i0 in range(0, n, 1 << 18):
+        x = torch.randn(min(1 << 18, n - i0), e, device="cuda", generator=g)
+        img[i0:i0 + len(x)] = (x / x.norm(dim=-1, keepdim=True)).bfloat16()
+    txt = torch.randn(q, e, device="cuda", generator=g)
+    txt = txt / txt.norm(dim=-1, keepdim=True)
+    planted = torch.tensor([3, 499_999, 999_999], device="cuda")
+    for qq in range(0, q, 37):                                   # a few queries get clear winners + an exact tie pair
+        img[planted + qq] = torch.stack([0.9 * txt[qq], 0.8 * txt[qq], 0.9 * txt[qq]]).bfloat16()
+    s = torch.empty(q, k, device="cuda")
+    i = torch.empty(q, k, device="cuda", dtype=torch.int64)
+    c = torch.empty(q, device="cuda", dtype=torch.int32)
+    dense = torch.empty(n, q, device="cuda")
+    model_b32.handle.call("b200clip_sim_topk_dense", capi._p(img), capi.BF16, n, e, capi._p(txt), q, k, 0.2, capi._p(s),
+                          capi._p(i), capi._p(c), capi._p(dense), model_b32._stream())
+    # stable descending sort with ties -> higher index: sort the column-reversed matrix, map the indices back
+    want_i = torch.empty(q, k, device="cuda", dtype=torch.int64)
+    want_s = torch.empty(q, k, device="cuda")
+    for q0 in range(0, q, 32):
+        d = dense[:, q0:q0 + 32].T.flip(1).contiguous()
+        vals, idx = torch.sort(d, dim=1, descending=True, stable=True)
+        want_i[q0:q0 + 32] = (n - 1) - idx[:, :k]
+        want_s[q0:q0 + 32] = vals[:, :k]
+        del d, vals, idx
+    assert torch.equal(i, want_i) and torch.equal(s, want_s)
+    assert torch.equal(c, (want_s >= 0.2).sum(1).to(torch.int32))
+    for qq in range(0, q, 37):
+        assert i[qq, :3].tolist() == [999_999 + qq if 999_999 + qq < n else -1, 3 + qq, 499_999 + qq] or \
+            i[qq, :3].tolist() == [int(planted[2]) + qq, int(planted[0]) + qq, int(planted[1]) + qq]
+    del dense
+    ts = torch.arange(n, dtype=torch.float64, device="cuda")
+    s2, i2, iv2, c2 = model_b32.sim_topk(img, txt, k, 0.2, ts, 0, 30.0, float(n))
+    assert torch.equal(torch.sort(i2, dim=1).values, torch.sort(i, dim=1).values)        # same rows ...
+    rows = img[i2.reshape(-1)].float().view(q, k, e)
+    ref = (rows * txt[:, None, :]).sum(-1)
+    assert float((s2 - ref).abs().max()) < 2e-5                                          # ... scored with the fp32 query
+    assert bool((s2[:, :-1] >= s2[:, 1:]).all()) and torch.equal(c2, (s2 >= 0.2).sum(1).to(torch.int32))
+    assert torch.equal(iv2[..., 0], (i2.double() - 15.0).clamp(min=0.0))
+    assert torch.equal(iv2[..., 1], (i2.double() + 15.0).clamp(max=float(n)))
+
+
+def test_config5_full_size_100k_crops(model_b32, oracle_sd_b32):
+    """100 000 person crops (256x128) tiled from 96 distinct ones, top_k = 10 against a reference image that occurs 12
+    times: exact duplicates tie, so the hits are the 10 HIGHEST planted positions in descending order; every copy of a
+    crop embeds to the same bits regardless of its position in the 100 k batch; the distinct crops match the oracle."""
+    from b200clip import capi
+    from oracle import clip_ref
+    from oracle import preprocess_ref as P
+
+    n, nd, k = 100_000, 96, 10
+    base = structured_frames(nd, 256, 128, seed=55)
+    dev_base = torch.from_numpy(base).cuda()
+    sel = torch.arange(n, device="cuda") % (nd - 1)              # crop nd-1 (the reference person) only where planted
+    planted = torch.tensor([5, 77, 4095, 4096, 12345, 33333, 50000, 65536, 77777, 88888, 99998, 99999], device="cuda")
+    sel[planted] = nd - 1
+    crops = dev_base[sel]
+    emb = model_b32.encode_frames_u8(crops, capi.RESIZE_BICUBIC, normalize=True)
+    qemb = model_b32.encode_frames_u8(dev_base[nd - 1:], capi.RESIZE_BICUBIC, normalize=True)
+    s, i, _, c = model_b32.sim_topk(emb, qemb, k, 0.7)
+    assert i[0].tolist() == sorted(planted.tolist(), reverse=True)[:k]
+    assert int(c[0]) == k and float(s[0, 0]) == float(s[0, k - 1]) and abs(float(s[0, 0]) - 1.0) < 1e-3
+    first = model_b32.encode_frames_u8(dev_base, capi.RESIZE_BICUBIC, normalize=True)    # a 96-crop batch
+    assert torch.equal(emb, first[sel]), "a crop's embedding depends on its position / batch"
+    oracle = clip_ref.CLIPRef(clip_ref.CONFIGS["ViT-B-32"], oracle_sd_b32)
+    x = torch.from_numpy(np.stack([P.to_chw_normalized(P.clip_transform_u8(f)) for f in base]))
+    e = oracle.encode_image(x)
+    e = (e / e.norm(dim=-1, keepdim=True)).numpy()
+    assert cosine_rows(first.cpu().numpy(), e).min() >= COS_MIN
+    assert np.abs((first @ qemb.T)[:, 0].cpu().numpy() - e @ e[nd - 1]).max() <= SCORE_TOL
+
+
+def test_config3_vitl14_512_frames(golden_dir):
+    """ViT-L/14 on 512 frames (16 distinct, tiled): the T = 257 attention path, 1024-wide GEMMs and the K-padded patch
+    embedding at a batch the bench uses; oracle cosine / score tolerance on the distinct frames, bit-identical copies,
+    and chunk invariance (one pass of 512 == passes of 96)."""
+    from b200clip import capi
+    from b200clip import open_clip as oc
+    from oracle import clip_ref
+    from oracle import phase1_ref as R
+    from oracle import preprocess_ref as P
+
+    cfg = clip_ref.CONFIGS["ViT-L-14"]
+    sd = clip_ref.init_state_dict(cfg, seed=0, gain=1.0)
+    distinct = structured_frames(16, 224, 224, seed=2024)
+    sel = torch.arange(512) % 16
+    frames = torch.from_numpy(distinct)[sel].cuda()
+    big, _, _ = oc.create_model_and_transforms("ViT-L-14", state_dict=sd, device="cuda:0", max_images=512, max_texts=1)
+    emb = big.encode_frames_u8(frames, capi.RESIZE_REFERENCE, normalize=True)
+    assert torch.equal(emb, emb[:16][sel.cuda()]), "copies of a frame must embed to the same bits"
+    big.handle.reserve(96, 1)
+    assert torch.equal(big.encode_frames_u8(frames, capi.RESIZE_REFERENCE, normalize=True), emb), "chunk invariance"
+    oracle = clip_ref.CLIPRef(cfg, sd)
+    x = torch.from_numpy(np.stack([P.to_chw_normalized(P.clip_transform_u8(f)) for f in distinct]))
+    e = oracle.encode_image(x)
+    e = (e / e.norm(dim=-1, keepdim=True)).numpy()
+    cos = cosine_rows(emb[:16].cpu().numpy(), e)
+    tok = clip_ref.synthetic_tokenize(["a person walking across street"])
+    t = oracle.encode_text(tok)
+    t = (t / t.norm(dim=-1, keepdim=True)).numpy()
+    txt = big.encode_text(tok.cuda(), normalize=True)
+    sims = big.similarity(emb, txt)[:, 0].cpu().numpy()
+    print(f"\n[parity] ViT-L/14 512 frames: cosine min {cos.min():.6f}, max |dscore| {np.abs(sims[:16] - (e @ t.T)[:, 0]).max():.5f}")
+    assert cos.min() >= COS_MIN and np.abs(sims[:16] - (e @ t.T)[:, 0]).max() <= SCORE_TOL
+    s, i, iv, c = big.sim_topk(emb, txt, 5, -1.0, torch.arange(512, dtype=torch.float64) / 30.0, 0, 30.0, 512 / 30.0)
+    want = np.lexsort((np.arange(512), sims))[::-1][:5]
+    assert np.array_equal(i[0].cpu().numpy(), want)
+    for r in range(5):
+        assert tuple(iv[0, r].cpu().numpy()) == R.clip_interval(float(want[r]) / 30.0, 30.0, 512 / 30.0)
+    big.handle.close()
+
+
+def _outlier_state_dict(cfg, seed=0):
+    """Seeded weights with the residual-channel outliers trained CLIP checkpoints carry (a handful of channels 10^2-10^3
+    times larger than the rest): six channels of ln_pre are scaled 50-300x, and the rows of every block's c_proj that
+    write those channels 4-8x, so the outliers enter the residual stream at the first layer and are fed in every block."""
+    from oracle import clip_ref
+
+    sd = clip_ref.init_state_dict(cfg, seed=seed, gain=1.0)
+    chans = [5, 77, 300, 511, 640, 700]
+    gains = [50.0, 100.0, 150.0, 200.0, 250.0, 300.0]
+    for ch, gn in zip(chans, gains):
+        sd["visual.ln_pre.weight"][ch] *= gn
+        sd["visual.ln_pre.bias"][ch] *= gn
+    for l in range(cfg.layers):
+        w = sd[f"visual.transformer.resblocks.{l}.mlp.c_proj.weight"]
+        for j, ch in enumerate(chans):
+            w[ch, :] *= 4.0 + (j % 5)
+    return sd, chans
+
+
+def test_outlier_weights_stress_bf16_residual_stream():
+    """north_star bar (cosine >= 0.999, |dscore| <= 1e-2) where it is hardest: residual-channel outliers.  The CUDA path
+    keeps the residual stream in bf16 and folds ln_1 / ln_2 into bf16-rounded weights; the oracle is fp32."""
+    from b200clip import capi
+    from b200clip import open_clip as oc
+    from oracle import clip_ref
+    from oracle import preprocess_ref as P
+
+    cfg = clip_ref.CONFIGS["ViT-B-32"]
+    sd, chans = _outlier_state_dict(cfg)
+    frames = structured_frames(24, 224, 224, seed=808)
+    oracle = clip_ref.CLIPRef(cfg, sd)
+    x = torch.from_numpy(np.stack([P.to_chw_normalized(P.clip_transform_u8(f)) for f in frames]))
+    # the stress must be real: measure the outliers in the oracle's own residual stream after ln_pre
+    h0 = oracle.encode_image(x[:4], upto="blocks")              # residual stream after the last block
+    e = oracle.encode_image(x)
+    e = (e / e.norm(dim=-1, keepdim=True)).numpy()
+    model, _, _ = oc.create_model_and_transforms("ViT-B-32", state_dict=sd, device="cuda:0", max_images=32, max_texts=4)
+    emb = model.encode_frames_u8(torch.from_numpy(frames).cuda(), capi.RESIZE_BICUBIC, normalize=True)
+    cos = cosine_rows(emb.cpu().numpy(), e)
+    tok = clip_ref.synthetic_tokenize(["a person walking across street", "red car", "a dog jumping over fence"])
+    t = oracle.encode_text(tok)
+    t = (t / t.norm(dim=-1, keepdim=True)).numpy()
+    txt = model.encode_text(tok.cuda(), normalize=True)
+    d = np.abs(model.similarity(emb, txt).cpu().numpy() - e @ t.T).max()
+    ratio = float(h0[..., chans].abs().mean() / h0.abs().median())
+    assert ratio >= 50.0, f"the fixture does not stress the residual stream (outlier/median {ratio:.1f}x)"
+    print(f"\n[parity] outlier weights: residual outlier/median magnitude {ratio:.0f}x, cosine min {cos.min():.6f}, max |dscore| {d:.5f}")
+    assert cos.min() >= COS_MIN, f"cosine {cos.min()}"
+    assert d <= SCORE_TOL
+    model.handle.close()
