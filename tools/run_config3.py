@@ -19,7 +19,7 @@ import torch.distributed as dist
 
 from b200clip import capi
 from b200clip import open_clip as oc
-from b200clip.distributed import allgather_candidates, shard_range
+from b200clip.distributed import shard_range
 from b200clip.model_configs import MODEL_CONFIGS
 from b200clip.tokenizer import get_tokenizer
 from b200clip.weights import random_state_dict
@@ -70,10 +70,7 @@ def main() -> int:
     def step():
         txt = model.encode_text(tok, normalize=True)
         emb = model.encode_frames_u8(frames, capi.RESIZE_REFERENCE, normalize=True)
-        s, i, iv, c = model.sim_topk(emb, txt, k, thr, ts, index_base=lo, clip_duration=30.0, video_duration=dur)
-        if world > 1:
-            cs, ci = allgather_candidates(s, i)
-            s, i, iv, c = model.topk_merge(cs, ci, thr, ts, 30.0, dur)
+        s, i, iv, c = model.sim_topk_sharded(emb, txt, k, thr, ts, index_base=lo, clip_duration=30.0, video_duration=dur)
         return txt, s, i, iv, c
 
     def barrier():
