@@ -721,19 +721,18 @@ static int encode_frames_host(b200clip_handle* h, const uint8_t* frames_host, in
         h->ws_emb_elems = emb_el;
     }
     float* emb_dev = out_on_device ? emb_out_host : h->ws_emb;
-    // the copy stream must not overwrite a staging buffer the compute stream of a previous call still reads
-    cudaEvent_t& e0 = h->ev_done[0];
-    B200_CUDA(h, cudaEventRecord(e0, st));
-    B200_CUDA(h, cudaStreamWaitEvent(h->copy_stream, e0, 0));
+    // The two staging buffers alternate ACROSS calls too (stage_seq), and an upload into buffer b only waits for the
+    // last compute that read buffer b (ev_done[b], possibly recorded by an earlier call): the first upload of a call
+    // overlaps the tower of the previous call instead of waiting for the whole compute stream to drain.
     const int nchunks = (n + chunk - 1) / chunk;
     for (int ci = 0; ci < nchunks; ++ci) {
-        const int b = ci & 1;
+        const int b = static_cast<int>((h->stage_seq + ci) & 1);
         const int i0 = ci * chunk;
         const int nc = (n - i0) < chunk ? (n - i0) : chunk;
         const uint8_t* src = frames_host + static_cast<size_t>(i0) * fbytes;
-        if (ci >= 2) B200_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));
+        B200_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));   // (a never-recorded event is a no-op)
         if (!pinned) {
-            if (ci >= 2) B200_CUDA(h, cudaEventSynchronize(h->ev_h2d[b]));  // bounce buffer b is free again
+            B200_CUDA(h, cudaEventSynchronize(h->ev_h2d[b]));                   // bounce buffer b is free again
             memcpy(h->ws_stage_host[b], src, static_cast<size_t>(nc) * fbytes);
             src = h->ws_stage_host[b];
         }
@@ -769,6 +768,7 @@ static int encode_frames_host(b200clip_handle* h, const uint8_t* frames_host, in
             return rc;
         B200_CUDA(h, cudaEventRecord(h->ev_done[b], st));
     }
+    h->stage_seq += nchunks;
     if (out_on_device) {
         // frames_host may be reused by the caller once the uploads are done; compute stays asynchronous on `st`
         B200_CUDA(h, cudaStreamSynchronize(h->copy_stream));

@@ -72,6 +72,7 @@ struct b200clip_handle {
     uint8_t* ws_stage_dev[2] = {nullptr, nullptr};   // device staging for host-frame calls
     uint8_t* ws_stage_host[2] = {nullptr, nullptr};  // pinned
     size_t ws_stage_bytes = 0, ws_stage_host_bytes = 0;
+    uint64_t stage_seq = 0;                          // chunks uploaded so far: parity picks the staging buffer
     float* ws_stats = nullptr;     // [rows, LN_SLOTS, 2] per-row (sum, sum of squares) partials of the residual stream
     int32_t* ws_eot = nullptr;     // [ws_texts] row of the EOT token per text
     int64_t* ws_tokens = nullptr;  // [ws_texts * ctx]

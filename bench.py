@@ -218,19 +218,23 @@ class FramesWorkload(Workload):
     nv12_e2e = False
     chunk = 0
 
-    def setup(self):
-        import torch
-
+    def plan(self):
+        """Sizes only (no device): shared by both arms so that their `config` objects are the same."""
         from b200clip.distributed import shard_range
 
-        a = self.args
-        n_cfg = a.frames or self.frames_n
+        n_cfg = self.args.frames or self.frames_n
         if self.per_gpu:
             self.n_total, self.lo, self.hi = n_cfg * self.world, self.rank * n_cfg, (self.rank + 1) * n_cfg
         else:
             self.n_total = n_cfg
             self.lo, self.hi = shard_range(n_cfg, self.rank, self.world)
         self.n = self.hi - self.lo
+
+    def setup(self):
+        import torch
+
+        a = self.args
+        self.plan()
         chunk = a.chunk or self.chunk
         self.make_model(chunk if 0 < chunk < self.n else max(self.n, 1))
         self.frames = device_frames(self.n, self.H, self.W, self.dev, 1234 + self.rank)
@@ -374,12 +378,12 @@ class Config2(FramesWorkload):
     frames_n = 3600
     nv12_e2e = True
 
-    def setup(self):
+    def plan(self):
         self.H, self.W = self.args.height, self.args.width
         # pinned host frames per rank: the whole batch on one GPU, smaller slices (re-used `calls` times per step) when
         # several ranks share the host's pinned-memory budget
         self.host_slice = 0 if self.world == 1 else (900 if self.world <= 2 else 450)
-        super().setup()
+        super().plan()
 
     def workload_text(self):
         return ("BASELINE configs[1]: ViT-B/32 (QuickGELU) over a 1-hour video at 1 fps -- "
@@ -465,14 +469,17 @@ class Config4(Workload):
     Q = 256
     rows = 1_000_000
 
-    def setup(self):
-        import torch
-
+    def plan(self):
         from b200clip.distributed import shard_range
 
         self.n_total = self.args.frames or self.rows
         self.lo, self.hi = shard_range(self.n_total, self.rank, self.world)
         self.n = self.hi - self.lo
+
+    def setup(self):
+        import torch
+
+        self.plan()
         self.make_model(1, self.Q)
         e = self.cfg.embed_dim
         g = torch.Generator(device=self.dev).manual_seed(4321 + self.rank)
@@ -564,6 +571,7 @@ class Config4(Workload):
                 "sharding": "single GPU" if self.world == 1 else f"cache rows in contiguous shards over {self.world} rank(s); "
                 "one NCCL all-gather of the packed top-k candidates",
                 "cache": f"{self.n * 1024 / 1e9:.2f} GB of embeddings per GPU, larger than the 126 MB L2",
+                "text_tower": "in the step (256 x 77 tokens)",
                 "weights": "seeded random init (no checkpoint offline)"}
 
 
@@ -587,6 +595,10 @@ def run_reference(args, rank: int):
     cls = WORKLOADS[args.config]
     cores = os.cpu_count() or 1
     k = args.top_k or cls.default_k
+    shape = cls(args, 0, 0, max(1, int(os.environ.get("WORLD_SIZE", "1"))), None)   # sizes only: the same `config` object as our arm
+    shape.plan()
+    cfgd = shape.describe()
+    cfgd["bench_config"] = args.config
     steps = args.steps or 3
     if args.config == 4:
         n = args.ref_frames or 200_000
@@ -602,7 +614,6 @@ def run_reference(args, rank: int):
             return np.argsort(sims, axis=0)[::-1][:k]
 
         sample = f"{n} of 1 000 000 cached fp32 rows x 256 queries per step: np.dot + np.argsort per query, {cores} threads"
-        wl = "BASELINE configs[3]: 256 text queries x 1M cached frame embeddings"
     else:
         name = cls.model_name
         ref = ReferenceCPU(name, state_dict=random_state_dict(MODEL_CONFIGS[name], 0), threads=cores)
@@ -624,7 +635,6 @@ def run_reference(args, rank: int):
 
         sample = (f"{n} frames ({H}x{W} uint8) per step: " + ("cv2 INTER_AREA shrink + " if shrink and max(H, W) > 512 else "") +
                   f"PIL/torchvision transform + fp32 PyTorch {name} (batch 32) + np.dot/argsort, {cores} threads")
-        wl = f"BASELINE configs[{args.config - 1}] ({name}, {H}x{W} frames)"
     for _ in range(max(1, min(args.warmup, 3))):
         one()
     t0 = time.perf_counter()
@@ -636,7 +646,7 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": cls.metric, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": cls.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl, "bench_config": args.config, "sample_units_per_step": n},
+        "config": cfgd, "sample_units_per_step": n,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -722,6 +732,12 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     total_ms = float(ms.item())
     launches = h.launches
     prof = h.profile_read(reset=True)
+    # time each rank spent inside the candidate all-gather (on its stream: NCCL latency + waiting for the slowest peer)
+    per_rank_comm = [prof["comm"]["ms"] / steps]
+    if world > 1:
+        allc = torch.zeros(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allc, torch.tensor([prof["comm"]["ms"] / steps], dtype=torch.float64, device=dev))
+        per_rank_comm = [float(v) for v in allc.tolist()]
     value = w.units_per_step() * steps / (total_ms / 1e3)
 
     # ---- end to end through the host-buffer API
@@ -803,7 +819,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": w.scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": cfgd, "roofline": roof, "kernels": kernels,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "check": check,
-            "per_rank_ms_per_step": per_rank,
+            "per_rank_ms_per_step": per_rank, "per_rank_allgather_ms_per_step": per_rank_comm,
             "model_flop_per_unit": w.flops_per_unit(),
             "model_tflops": value * w.flops_per_unit() / 1e12 / world,
         }
