@@ -38,7 +38,7 @@ const B200Knobs& b200_knobs() {
         b.sim_simt = on("B200CLIP_SIM_SIMT"); b.sim_stream_a = on("B200CLIP_SIM_STREAM_A");
         b.attn_oneshot = on("B200CLIP_ATTN_ONESHOT"); b.attn_tc = on("B200CLIP_ATTN_TC"); b.attn_tiled = on("B200CLIP_ATTN_TILED");
         b.overlap = on("B200CLIP_OVERLAP"); b.full_upload = on("B200CLIP_FULL_UPLOAD");
-        b.nv12_unfused = on("B200CLIP_NV12_UNFUSED");
+        b.nv12_unfused = on("B200CLIP_NV12_UNFUSED"); b.k1_persistent = on("B200CLIP_K1_PERSISTENT");
         return b;
     }();
     return k;

@@ -100,6 +100,7 @@ struct b200clip_handle {
     int chunk_cap = 0;             // images per pass of the tower fixed by an explicit b200clip_reserve (0 = default)
     // cudaFuncSetAttribute is per DEVICE: which kernels of this handle's device already carry their opt-in (ATTR_*)
     uint32_t attr_done = 0;
+    int k1_ctas_per_sm[2] = {0, 0};          // resident CTAs per SM of the persistent K1 area kernels (RGB, NV12)
     int g2_clusters[5] = {0, 0, 0, 0, 0};   // co-resident clusters of the 2-CTA GEMM on this device, per pairs
 };
 enum { ATTR_GEMM64 = 1u << 0, ATTR_GEMM128 = 1u << 1, ATTR_GEMM256 = 1u << 2, ATTR_GEMM_2CTA = 1u << 3, ATTR_SIM_TC = 1u << 4,
@@ -114,7 +115,7 @@ struct B200Knobs {
     bool sim_simt, sim_stream_a;
     bool attn_oneshot, attn_tc, attn_tiled;
     bool overlap, full_upload;
-    bool nv12_unfused;
+    bool nv12_unfused, k1_persistent;
 };
 const B200Knobs& b200_knobs();
 

@@ -153,6 +153,9 @@ struct Plan {
     const uint32_t* aq = nullptr;   // [w1][8] packed IDP.2A weights of the vertical-first area kernel (a_int only)
     size_t mid1_per_frame = 0, mid2_per_frame = 0;
     std::vector<void*> dev;  // device allocations holding the tables
+    AxisTaps h_ay;           // host copy of the vertical area taps (strip row programs are built from it)
+    struct StripTable { const void* rinfo = nullptr; const void* meta = nullptr; int nstrips = 0, max_rows = 0; };
+    mutable std::map<int, StripTable> strips;   // rows per strip -> row programs of the fused area kernels (device)
 };
 
 template <class T>
@@ -828,7 +831,15 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
                          int rows_per_strip, int xb0, int seg_bytes, int stage_bytes, int arow_pitch, int vpitch,
                          int left, int S, DevTaps ax, DevTaps ay, DevTaps bx, AhIntParams ip,
                          const uint32_t* __restrict__ aq /*[area columns][8] packed weights, see build_plan*/,
+                         int nstrips, int nitems, int max_rows,
+                         const AhRowInfo* __restrict__ strip_rinfo /*[nstrips][max_rows] row programs, host built*/,
+                         const int2* __restrict__ strip_meta /*[nstrips] (first source row, source rows)*/,
                          int null_consumers /*probe: 1 = consumers only drain the ring (load path alone), 2 = no loads (consumers alone)*/) {
+    // PERSISTENT: a CTA walks work items (strip, frame) = blockIdx.x, + gridDim.x, ...  The per-thread constants (packed
+    // area weights, Pillow coefficients, stream offsets), the barriers and the zeroed slack are set up once per CTA,
+    // the row program of every strip comes ready-made from a host-built table (double buffered in shared memory), and
+    // the bulk-copy ring keeps running across items: the producer streams the first rows of the next item while the
+    // consumers finish the current one.
     constexpr int WPS = NV12 ? 6 : 4;        // words per slice
     extern __shared__ __align__(128) uint8_t ah_smem[];
     const int ncons = blockDim.x - 32;                 // consumer threads; the last warp is the producer
@@ -840,58 +851,43 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
     uint8_t* arow = vbuf + 4 * vpitch;                  // [2] parked uint8 area rows
     AhRowInfo* rinfo = reinterpret_cast<AhRowInfo*>(arow + 2 * arow_pitch);
 
-    const int strip = blockIdx.x;
-    const int64_t f = blockIdx.y;
-    const int dy_a = oy0 + strip * rows_per_strip;
-    const int dy_b = min(dy_a + rows_per_strip, oy0 + ny);
-    const int r_lo = __ldg(ay.start + dy_a);
-    const int nrows = __ldg(ay.start + dy_b - 1) + __ldg(ay.cnt + dy_b - 1) - r_lo;
-    const uint8_t* gbase = src + f * frame_stride + xb0;
-    // (NV12: the launcher guarantees 16-byte aligned planes, pitches and window start -> delta = 0)
-    const int delta = NV12 ? 0 : static_cast<int>(reinterpret_cast<uintptr_t>(gbase) & 15);
+    const uint8_t* gbase0 = src + xb0;
+    // (RGB: row and frame pitches are multiples of 16 bytes, so the misalignment of a row segment is the same for every
+    // row of every frame; NV12: the launcher guarantees 16-byte aligned planes, pitches and window start -> delta = 0)
+    const int delta = NV12 ? 0 : static_cast<int>(reinterpret_cast<uintptr_t>(gbase0) & 15);
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ncons >> 5); }
         fence_mbar_init();
     }
-    // row program of the strip (see area_hpass_bulk_kernel): pad = integer weights, low half into the output row being
-    // accumulated, high half into the next one
-    for (int i = tid; i < nrows; i += blockDim.x) rinfo[i].beta_next = 0.f, rinfo[i].finish = 0, rinfo[i].pad = 0;
     // the slack words behind the streams are read (with weight 0, or shifted out) but never written per row
     for (int i = tid; i < vpitch; i += blockDim.x) reinterpret_cast<uint32_t*>(vbuf)[i] = 0u;
-    __syncthreads();
-    for (int d = tid; d < dy_b - dy_a; d += blockDim.x) {
-        const int dy = dy_a + d;
-        const int sy0 = __ldg(ay.start + dy), cy = __ldg(ay.cnt + dy);
-        const bool shared_first = d > 0 && sy0 == __ldg(ay.start + dy - 1) + __ldg(ay.cnt + dy - 1) - 1;
-        for (int j = 0; j < cy; ++j) {
-            const float beta = __ldg(ay.wf + dy * ay.stride + j);
-            AhRowInfo& ri = rinfo[sy0 + j - r_lo];
-            const int ib = __float2int_rn(beta * static_cast<float>(ip.dy));
-            if (j == 0 && shared_first) { ri.beta_next = beta; atomicOr(&ri.pad, ib << 16); }
-            else { ri.beta_cur = beta; atomicOr(&ri.pad, ib); }
-            if (j == cy - 1) ri.finish = 1;
-        }
-    }
     __syncthreads();
 
     if (tid >= ncons) {
         // ------------------------------------------------------------------ producer warp
         if (tid == ncons) {
-            const uint8_t* g = gbase - delta + static_cast<int64_t>(r_lo) * row_stride;
-            const uint8_t* guv = NV12 ? src_uv + f * uv_frame_stride + xb0 : nullptr;
-            for (int i = 0; i < nrows; ++i, g += row_stride) {
-                const int s = i % NST;
-                if (i >= NST) mbar_wait(&empty_bar[s], ((i / NST) - 1) & 1, 11);
-                if (null_consumers == 2) { mbar_arrive(&full_bar[s]); continue; }   // probe: no loads, consumers at full speed
-                if (NV12) {     // luma row r and chroma row r / 2 of the window: [Y: segpx bytes | UV: segpx bytes]
-                    mbar_arrive_expect_tx(&full_bar[s], 2 * segpx);
-                    bulk_load_1d(ring + s * stage_bytes, g, segpx, &full_bar[s]);
-                    bulk_load_1d(ring + s * stage_bytes + segpx, guv + static_cast<int64_t>((r_lo + i) >> 1) * row_stride, segpx,
-                                 &full_bar[s]);
-                } else {
-                    mbar_arrive_expect_tx(&full_bar[s], seg_bytes);
-                    bulk_load_1d(ring + s * stage_bytes, g, seg_bytes, &full_bar[s]);
+            uint32_t it = 0;                              // rows issued so far: the ring runs across items
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int strip = item % nstrips;
+                const int64_t f = item / nstrips;
+                const int2 meta = __ldg(strip_meta + strip);
+                const int r_lo = meta.x, nrows = meta.y;
+                const uint8_t* g = gbase0 + f * frame_stride - delta + static_cast<int64_t>(r_lo) * row_stride;
+                const uint8_t* guv = NV12 ? src_uv + f * uv_frame_stride + xb0 : nullptr;
+                for (int i = 0; i < nrows; ++i, ++it, g += row_stride) {
+                    const uint32_t s = it & (NST - 1);
+                    if (it >= NST) mbar_wait(&empty_bar[s], ((it / NST) - 1) & 1, 11);
+                    if (null_consumers == 2) { mbar_arrive(&full_bar[s]); continue; }   // probe: no loads, consumers at full speed
+                    if (NV12) {     // luma row r and chroma row r / 2 of the window: [Y: segpx bytes | UV: segpx bytes]
+                        mbar_arrive_expect_tx(&full_bar[s], 2 * segpx);
+                        bulk_load_1d(ring + s * stage_bytes, g, segpx, &full_bar[s]);
+                        bulk_load_1d(ring + s * stage_bytes + segpx, guv + static_cast<int64_t>((r_lo + i) >> 1) * row_stride, segpx,
+                                     &full_bar[s]);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[s], seg_bytes);
+                        bulk_load_1d(ring + s * stage_bytes, g, seg_bytes, &full_bar[s]);
+                    }
                 }
             }
         }
@@ -966,144 +962,161 @@ area_hpass_vfirst_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, 
 
     const int lane = tid & 31;
     uint32_t aL[VW][WPS], aH[VW][WPS];
-#pragma unroll
-    for (int v = 0; v < VW; ++v)
-#pragma unroll
-        for (int k = 0; k < WPS; ++k) aL[v][k] = aH[v][k] = 0u;
-    int par = 0;         // parity of the parked-row / stream double buffers
-    int nfin = 0;        // area rows finished so far
-    uint8_t* out_row = mid2 + f * mid2_frame_stride + static_cast<int64_t>(dy_a - oy0) * S * 3;
+    int par = 0;         // parity of the parked-row / stream double buffers (runs across items)
     // 32-bit shared addresses, made opaque so that they stay in registers (ptxas otherwise re-derives them from
     // SR_CgaCtaId in every row: an S2R round trip on the critical path of the row loop)
-    uint32_t full0 = smem_u32(full_bar), ring0 = smem_u32(ring), vb0 = smem_u32(vbuf), ria = smem_u32(rinfo);
+    uint32_t full0 = smem_u32(full_bar), ring0 = smem_u32(ring), vb0 = smem_u32(vbuf), ri0 = smem_u32(rinfo);
     uint32_t sbytes = static_cast<uint32_t>(stage_bytes);
-    asm volatile("" : "+r"(full0), "+r"(ring0), "+r"(vb0), "+r"(ria), "+r"(sbytes));
-    for (int i = 0; i < nrows; ++i) {
-        const uint32_t s = static_cast<uint32_t>(i) & (NST - 1), phase = (static_cast<uint32_t>(i) / NST) & 1u;
-        const uint32_t fb = full0 + 8u * s, eb = fb + 8u * NST, soff = ring0 + s * sbytes;
-        {
-            uint32_t ok;
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(fb), "r"(phase) : "memory");
-            if (!ok) {                                 // slow path: bounded spin (a protocol bug must trap, not hang)
-                uint32_t spins = 0;
-                do {
-                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(fb), "r"(phase) : "memory");
-                    if (!ok && ++spins > (1u << 24)) __trap();
-                } while (!ok);
-            }
+    asm volatile("" : "+r"(full0), "+r"(ring0), "+r"(vb0), "+r"(ri0), "+r"(sbytes));
+    const uint32_t ri_bytes = static_cast<uint32_t>(max_rows) * static_cast<uint32_t>(sizeof(AhRowInfo));
+    uint32_t it = 0;     // rows consumed so far: ring stage = it % NST, phase = (it / NST) & 1
+    uint32_t ibuf = 0;   // row-program buffer of the current item
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ibuf ^= 1u) {
+        const int strip = item % nstrips;
+        const int64_t f = item / nstrips;
+        const int nrows = __ldg(strip_meta + strip).y;
+        const int dy_a = oy0 + strip * rows_per_strip;
+        // this item's row program -> buffer ibuf.  Every consumer has left the previous item (which used the other
+        // buffer) once it passes the barrier, and the item before that is long finished.
+        for (int i = tid; i < nrows; i += ncons) {
+            const uint4 e = __ldg(reinterpret_cast<const uint4*>(strip_rinfo + static_cast<size_t>(strip) * max_rows + i));
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ri0 + ibuf * ri_bytes + 16u * i), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w) : "memory");
         }
-        uint32_t w[VW][WPS];
-        uint2 nvy[VW], nvc[VW];
-#pragma unroll
-        for (int v = 0; v < VW; ++v) {
-            if constexpr (NV12) {       // 8 luma bytes and their 4 (U, V) pairs; v_off = 24 * slice -> byte 8 * slice
-                const uint32_t o = v_off[v] / 3u;
-                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nvy[v].x), "=r"(nvy[v].y) : "r"(soff + o));
-                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nvc[v].x), "=r"(nvc[v].y) : "r"(soff + static_cast<uint32_t>(segpx) + o));
-            } else {
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[v][0]), "=r"(w[v][1]), "=r"(w[v][2]), "=r"(w[v][3]) : "r"(soff + v_off[v]));
-            }
-        }
-        uint32_t fin, wts;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(fin), "=r"(wts) : "r"(ria + 8));
-        ria += 16;
-        __syncwarp();
-        if (lane == 0)                                // this warp holds its bytes in registers now
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(eb) : "memory");
-        if constexpr (NV12) {
-#pragma unroll
-            for (int v = 0; v < VW; ++v) nv12_convert8(nvy[v], nvc[v], w[v]);
-        }
-        if (null_consumers == 1) { aL[0][0] ^= w[0][0] ^ w[VW - 1][3]; continue; }
-        const uint32_t iyc = wts & 0xffffu;
-        uint32_t lo[VW][WPS], hi[VW][WPS];
+        named_bar_sync(1, ncons);
+        uint32_t ria = ri0 + ibuf * ri_bytes;
 #pragma unroll
         for (int v = 0; v < VW; ++v)
 #pragma unroll
-            for (int k = 0; k < WPS; ++k) {
-                lo[v][k] = __byte_perm(w[v][k], 0u, 0x4240);     // bytes 0 and 2 in 16-bit lanes
-                hi[v][k] = __byte_perm(w[v][k], 0u, 0x4341);     // bytes 1 and 3
-                aL[v][k] += iyc * lo[v][k];
-                aH[v][k] += iyc * hi[v][k];
+            for (int k = 0; k < WPS; ++k) aL[v][k] = aH[v][k] = 0u;
+        int nfin = 0;        // area rows of this item finished so far
+        uint8_t* out_row = mid2 + f * mid2_frame_stride + static_cast<int64_t>(dy_a - oy0) * S * 3;
+        for (int i = 0; i < nrows; ++i, ++it) {
+            const uint32_t s = it & (NST - 1), phase = (it / NST) & 1u;
+            const uint32_t fb = full0 + 8u * s, eb = fb + 8u * NST, soff = ring0 + s * sbytes;
+            {
+                uint32_t ok;
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                             "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(fb), "r"(phase) : "memory");
+                if (!ok) {                                 // slow path: bounded spin (a protocol bug must trap, not hang)
+                    uint32_t spins = 0;
+                    do {
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(fb), "r"(phase) : "memory");
+                        if (!ok && ++spins > (1u << 24)) __trap();
+                    } while (!ok);
+                }
             }
-        if (fin != 0) {                               // uniform over the CTA: an area-output row is complete
-            const uint32_t vb = vb0 + static_cast<uint32_t>(par) * 2u * static_cast<uint32_t>(vpitch);
-#pragma unroll
+            uint32_t w[VW][WPS];
+            uint2 nvy[VW], nvc[VW];
+    #pragma unroll
             for (int v = 0; v < VW; ++v) {
-                if (v_active[v]) {
-                    if constexpr (NV12) {       // 24-byte slices: 8-byte aligned
-#pragma unroll
-                        for (int k = 0; k < WPS; k += 2) {
-                            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(vb + v_off[v] + 4u * k), "r"(aL[v][k]), "r"(aL[v][k + 1]) : "memory");
-                            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(vb + vpitch + v_off[v] + 4u * k), "r"(aH[v][k]), "r"(aH[v][k + 1]) : "memory");
-                        }
-                    } else {
-                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(vb + v_off[v]), "r"(aL[v][0]), "r"(aL[v][1]), "r"(aL[v][2]), "r"(aL[v][3]) : "memory");
-                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(vb + vpitch + v_off[v]), "r"(aH[v][0]), "r"(aH[v][1]), "r"(aH[v][2]), "r"(aH[v][3]) : "memory");
-                    }
+                if constexpr (NV12) {       // 8 luma bytes and their 4 (U, V) pairs; v_off = 24 * slice -> byte 8 * slice
+                    const uint32_t o = v_off[v] / 3u;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nvy[v].x), "=r"(nvy[v].y) : "r"(soff + o));
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(nvc[v].x), "=r"(nvc[v].y) : "r"(soff + static_cast<uint32_t>(segpx) + o));
+                } else {
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[v][0]), "=r"(w[v][1]), "=r"(w[v][2]), "=r"(w[v][3]) : "r"(soff + v_off[v]));
                 }
             }
-            const uint32_t iyn = wts >> 16;           // a straddling row opens the next output row
-#pragma unroll
+            uint32_t fin, wts;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(fin), "=r"(wts) : "r"(ria + 8));
+            ria += 16;
+            __syncwarp();
+            if (lane == 0)                                // this warp holds its bytes in registers now
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(eb) : "memory");
+            if constexpr (NV12) {
+    #pragma unroll
+                for (int v = 0; v < VW; ++v) nv12_convert8(nvy[v], nvc[v], w[v]);
+            }
+            if (null_consumers == 1) { aL[0][0] ^= w[0][0] ^ w[VW - 1][3]; continue; }
+            const uint32_t iyc = wts & 0xffffu;
+            uint32_t lo[VW][WPS], hi[VW][WPS];
+    #pragma unroll
             for (int v = 0; v < VW; ++v)
-#pragma unroll
-                for (int k = 0; k < WPS; ++k) { aL[v][k] = iyn * lo[v][k]; aH[v][k] = iyn * hi[v][k]; }
-            named_bar_sync(1, ncons);            // streams of this row complete; the previous parked row complete
-            uint8_t* ar = arow + par * arow_pitch;
-#pragma unroll
-            for (int p = 0; p < PA; ++p) {
-                if (a_active[p]) {
-                    const uint32_t xa = vb + (xoff[p] & 0x7fffffffu), ya = vb + (yoff[p] & 0x7fffffffu);
-                    const uint32_t xsh = xoff[p] >> 27, ysh = yoff[p] >> 27;      // 0 or 16
-                    uint32_t xr[5], yr[5], x[4], y[4];
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(xr[k]) : "r"(xa + 4u * k));
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(yr[k]) : "r"(ya + 4u * k));
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        x[k] = __funnelshift_r(xr[k], xr[k + 1], xsh);
-                        y[k] = __funnelshift_r(yr[k], yr[k + 1], ysh);
-                    }
-                    const uint32_t (&qq)[8] = q[p];
-                    uint32_t n0 = dp2a_lo(x[0], qq[0], 0u);
-                    n0 = dp2a_hi(x[1], qq[0], n0);
-                    n0 = dp2a_lo(x[3], qq[1], n0);
-                    n0 = dp2a_hi(y[0], qq[1], n0);
-                    n0 = dp2a_lo(y[2], qq[2], n0);
-                    uint32_t n1 = dp2a_hi(x[1], qq[2], 0u);
-                    n1 = dp2a_lo(x[2], qq[3], n1);
-                    n1 = dp2a_hi(y[0], qq[3], n1);
-                    n1 = dp2a_lo(y[1], qq[4], n1);
-                    n1 = dp2a_hi(y[3], qq[4], n1);
-                    uint32_t n2 = dp2a_lo(x[0], qq[5], 0u);
-                    n2 = dp2a_hi(x[2], qq[5], n2);
-                    n2 = dp2a_lo(x[3], qq[6], n2);
-                    n2 = dp2a_hi(y[1], qq[6], n2);
-                    n2 = dp2a_lo(y[2], qq[7], n2);
-                    // rint(N / D) == floor((2N + D) / 2D): no ties for odd D
-                    uint8_t* o = ar + xcol[p] * 3;
-                    o[0] = static_cast<uint8_t>(__umulhi(2u * n0 + ip.d, ip.div_mul) >> ip.div_shift);
-                    o[1] = static_cast<uint8_t>(__umulhi(2u * n1 + ip.d, ip.div_mul) >> ip.div_shift);
-                    o[2] = static_cast<uint8_t>(__umulhi(2u * n2 + ip.d, ip.div_mul) >> ip.div_shift);
+    #pragma unroll
+                for (int k = 0; k < WPS; ++k) {
+                    lo[v][k] = __byte_perm(w[v][k], 0u, 0x4240);     // bytes 0 and 2 in 16-bit lanes
+                    hi[v][k] = __byte_perm(w[v][k], 0u, 0x4341);     // bytes 1 and 3
+                    aL[v][k] += iyc * lo[v][k];
+                    aH[v][k] += iyc * hi[v][k];
                 }
+            if (fin != 0) {                               // uniform over the CTA: an area-output row is complete
+                const uint32_t vb = vb0 + static_cast<uint32_t>(par) * 2u * static_cast<uint32_t>(vpitch);
+    #pragma unroll
+                for (int v = 0; v < VW; ++v) {
+                    if (v_active[v]) {
+                        if constexpr (NV12) {       // 24-byte slices: 8-byte aligned
+    #pragma unroll
+                            for (int k = 0; k < WPS; k += 2) {
+                                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(vb + v_off[v] + 4u * k), "r"(aL[v][k]), "r"(aL[v][k + 1]) : "memory");
+                                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(vb + vpitch + v_off[v] + 4u * k), "r"(aH[v][k]), "r"(aH[v][k + 1]) : "memory");
+                            }
+                        } else {
+                            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(vb + v_off[v]), "r"(aL[v][0]), "r"(aL[v][1]), "r"(aL[v][2]), "r"(aL[v][3]) : "memory");
+                            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(vb + vpitch + v_off[v]), "r"(aH[v][0]), "r"(aH[v][1]), "r"(aH[v][2]), "r"(aH[v][3]) : "memory");
+                        }
+                    }
+                }
+                const uint32_t iyn = wts >> 16;           // a straddling row opens the next output row
+    #pragma unroll
+                for (int v = 0; v < VW; ++v)
+    #pragma unroll
+                    for (int k = 0; k < WPS; ++k) { aL[v][k] = iyn * lo[v][k]; aH[v][k] = iyn * hi[v][k]; }
+                named_bar_sync(1, ncons);            // streams of this row complete; the previous parked row complete
+                uint8_t* ar = arow + par * arow_pitch;
+    #pragma unroll
+                for (int p = 0; p < PA; ++p) {
+                    if (a_active[p]) {
+                        const uint32_t xa = vb + (xoff[p] & 0x7fffffffu), ya = vb + (yoff[p] & 0x7fffffffu);
+                        const uint32_t xsh = xoff[p] >> 27, ysh = yoff[p] >> 27;      // 0 or 16
+                        uint32_t xr[5], yr[5], x[4], y[4];
+    #pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(xr[k]) : "r"(xa + 4u * k));
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(yr[k]) : "r"(ya + 4u * k));
+                        }
+    #pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            x[k] = __funnelshift_r(xr[k], xr[k + 1], xsh);
+                            y[k] = __funnelshift_r(yr[k], yr[k + 1], ysh);
+                        }
+                        const uint32_t (&qq)[8] = q[p];
+                        uint32_t n0 = dp2a_lo(x[0], qq[0], 0u);
+                        n0 = dp2a_hi(x[1], qq[0], n0);
+                        n0 = dp2a_lo(x[3], qq[1], n0);
+                        n0 = dp2a_hi(y[0], qq[1], n0);
+                        n0 = dp2a_lo(y[2], qq[2], n0);
+                        uint32_t n1 = dp2a_hi(x[1], qq[2], 0u);
+                        n1 = dp2a_lo(x[2], qq[3], n1);
+                        n1 = dp2a_hi(y[0], qq[3], n1);
+                        n1 = dp2a_lo(y[1], qq[4], n1);
+                        n1 = dp2a_hi(y[3], qq[4], n1);
+                        uint32_t n2 = dp2a_lo(x[0], qq[5], 0u);
+                        n2 = dp2a_hi(x[2], qq[5], n2);
+                        n2 = dp2a_lo(x[3], qq[6], n2);
+                        n2 = dp2a_hi(y[1], qq[6], n2);
+                        n2 = dp2a_lo(y[2], qq[7], n2);
+                        // rint(N / D) == floor((2N + D) / 2D): no ties for odd D
+                        uint8_t* o = ar + xcol[p] * 3;
+                        o[0] = static_cast<uint8_t>(__umulhi(2u * n0 + ip.d, ip.div_mul) >> ip.div_shift);
+                        o[1] = static_cast<uint8_t>(__umulhi(2u * n1 + ip.d, ip.div_mul) >> ip.div_shift);
+                        o[2] = static_cast<uint8_t>(__umulhi(2u * n2 + ip.d, ip.div_mul) >> ip.div_shift);
+                    }
+                }
+                if (nfin > 0) {
+                    hpass_row(arow + (par ^ 1) * arow_pitch, out_row);
+                    out_row += S * 3;
+                }
+                ++nfin;
+                par ^= 1;
             }
-            if (nfin > 0) {
-                hpass_row(arow + (par ^ 1) * arow_pitch, out_row);
-                out_row += S * 3;
-            }
-            ++nfin;
-            par ^= 1;
+        }
+        if (nfin > 0) {
+            named_bar_sync(1, ncons);                // the last parked row of the item is complete
+            hpass_row(arow + (par ^ 1) * arow_pitch, out_row);
         }
     }
     if (null_consumers == 1 && aL[0][0] == 0x12345678u) mid2[0] = 1;   // keeps the probe's loads alive
-    if (nfin > 0) {
-        named_bar_sync(1, ncons);                // the last parked row is complete
-        hpass_row(arow + (par ^ 1) * arow_pitch, out_row);
-    }
 }
 
 // B: Pillow horizontal pass for output columns [ocol0, ocol0+S) on rows [0, ny) of the (possibly compacted)
@@ -1334,6 +1347,75 @@ static int common_denominator(const AxisTaps& t, int o0, int o1) {
     return 0;
 }
 
+// Row programs of the vertical-first area kernel for strips of `rows` area rows: per strip the first source row and the
+// number of source rows, and per source row (AhRowInfo) its weights into the output row being accumulated / the next
+// one (a straddling row feeds both), the integer forms of the two (pad: low / high half) and the "output row
+// complete" flag.  Built once per (geometry, rows) on the host; the persistent CTAs copy a strip's program into shared
+// memory per work item instead of deriving it from the tap tables.
+static int get_strip_table(b200clip_handle* h, const Plan& p, int rows, Plan::StripTable* out) {
+    auto it = p.strips.find(rows);
+    if (it != p.strips.end()) { *out = it->second; return 0; }
+    const AxisTaps& ay = p.h_ay;
+    const int oy0 = p.ry0, ny = p.ry1 - p.ry0;
+    const int nstrips = (ny + rows - 1) / rows;
+    const int max_rows = rows * ay.stride;
+    std::vector<AhRowInfo> prog(static_cast<size_t>(nstrips) * max_rows, AhRowInfo{0.f, 0.f, 0, 0});
+    std::vector<int2> meta(nstrips);
+    for (int s = 0; s < nstrips; ++s) {
+        const int dy_a = oy0 + s * rows, dy_b = std::min(dy_a + rows, oy0 + ny);
+        const int r_lo = ay.start[dy_a];
+        const int nrows = ay.start[dy_b - 1] + ay.cnt[dy_b - 1] - r_lo;
+        if (nrows > max_rows) return b200_fail(h, B200CLIP_E_SHAPE, "preprocess: strip of %d rows needs %d source rows", rows, nrows);
+        meta[s] = make_int2(r_lo, nrows);
+        AhRowInfo* e = &prog[static_cast<size_t>(s) * max_rows];
+        for (int dy = dy_a; dy < dy_b; ++dy) {
+            const int sy0 = ay.start[dy], cy = ay.cnt[dy];
+            const bool shared_first = dy > dy_a && sy0 == ay.start[dy - 1] + ay.cnt[dy - 1] - 1;
+            for (int j = 0; j < cy; ++j) {
+                const float beta = ay.wf[static_cast<size_t>(dy) * ay.stride + j];
+                AhRowInfo& ri = e[sy0 + j - r_lo];
+                const int ib = static_cast<int>(lrintf(beta * static_cast<float>(p.a_dy)));
+                if (j == 0 && shared_first) { ri.beta_next = beta; ri.pad |= ib << 16; }
+                else { ri.beta_cur = beta; ri.pad |= ib; }
+                if (j == cy - 1) ri.finish = 1;
+            }
+        }
+    }
+    Plan::StripTable t;
+    void* d = nullptr;
+    B200_CUDA(h, cudaMalloc(&d, prog.size() * sizeof(AhRowInfo)));
+    h->allocs.push_back(d);
+    B200_CUDA(h, cudaMemcpy(d, prog.data(), prog.size() * sizeof(AhRowInfo), cudaMemcpyHostToDevice));
+    t.rinfo = d;
+    B200_CUDA(h, cudaMalloc(&d, meta.size() * sizeof(int2)));
+    h->allocs.push_back(d);
+    B200_CUDA(h, cudaMemcpy(d, meta.data(), meta.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    t.meta = d;
+    t.nstrips = nstrips; t.max_rows = max_rows;
+    p.strips[rows] = t;
+    *out = t;
+    return 0;
+}
+
+// CTAs of a K1 area launch.  Default: one CTA per work item.  B200CLIP_K1_PERSISTENT=1: every SM filled to the kernel's
+// occupancy and each CTA walking many items -- measured on one box back to back (profiles/r02g_k1_persistent_ab.txt): 5.07 /
+// 4.96 ms per 3600 frames persistent vs 4.99 / 4.76 one-shot, i.e. the per-CTA prologue is already hidden by the block
+// scheduler with 3 resident CTAs per SM; kept as a parity-tested launch form.
+template <class K>
+static int persistent_grid(b200clip_handle* h, K kern, int threads, size_t smem, int nitems, int* cached) {
+    if (!b200_knobs().k1_persistent) return nitems;
+    if (*cached <= 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm <= 0) {
+            cudaGetLastError();
+            per_sm = 2;
+        }
+        *cached = per_sm;
+    }
+    const int g = *cached * h->num_sms;
+    return nitems < g ? nitems : g;
+}
+
 static int build_plan(b200clip_handle* h, int H, int W, int mode, Plan& p) {
     const int S = h->cfg.image_size;
     p.H = H; p.W = W; p.mode = mode;
@@ -1424,6 +1506,7 @@ static int build_plan(b200clip_handle* h, int H, int W, int mode, Plan& p) {
     }
     p.ax = upload_taps(h, p, ax, rc);
     p.ay = upload_taps(h, p, ay, rc);
+    p.h_ay = ay;
     p.bx = upload_taps(h, p, bx, rc);
     p.cy = upload_taps(h, p, cy, rc);
     if (p.a_int && p.a_max_cx <= 5 && p.a_dx <= 255) {
@@ -1635,10 +1718,12 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
             while (rows > 4 && static_cast<int64_t>(n) * ((ny + rows - 1) / rows) < static_cast<int64_t>(h->num_sms) * 6)
                 rows = (rows + 1) / 2;
             const int stage_bytes = seg + 16, arow_pitch = (nx * 3 + 32 + 15) & ~15, vpitch = seg + 32;
-            const int max_rows = rows * p.ay.stride;
+            Plan::StripTable stt;
+            if (int src = get_strip_table(h, p, rows, &stt)) return src;
+            const int max_rows = stt.max_rows;
             const size_t smem = 2 * AH_NSTAGE * sizeof(uint64_t) + static_cast<size_t>(AH_NSTAGE) * stage_bytes +
                                 4 * static_cast<size_t>(vpitch) + 2 * static_cast<size_t>(arow_pitch) +
-                                static_cast<size_t>(max_rows) * sizeof(AhRowInfo);
+                                2 * static_cast<size_t>(max_rows) * sizeof(AhRowInfo);
             if (smem <= 200 * 1024) {
                 AhIntParams ip{p.a_dx, p.a_dy, p.a_dx * p.a_dy, p.a_div_shift, p.a_div_mul};
                 auto kern = area_hpass_vfirst_kernel<160, 3, 2, 3, 2, AH_NSTAGE, false>;
@@ -1649,10 +1734,12 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
                     h->attr_done |= ATTR_K1_VFIRST;
                 }
                 ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(p.sy1 - p.sy0) * (p.sx1 - p.sx0) * 3.0 + ny * S * 3.0), st);
-                dim3 fgrid((ny + rows - 1) / rows, n);
+                const int nitems = stt.nstrips * n;
+                const int fgrid = persistent_grid(h, kern, ncv + 32, smem, nitems, &h->k1_ctas_per_sm[0]);
                 kern<<<fgrid, ncv + 32, smem, st>>>(cur, cur_fs, cur_rs, nullptr, 0, 0, mid2, p.mid2_per_frame, p.ry0, ny, p.rx0, nx, rows, xb0,
                                                    seg, stage_bytes, arow_pitch, vpitch, p.left, S, p.ax, p.ay, p.bx, ip, p.aq,
-                                                   area_null_probe());
+                                                   stt.nstrips, nitems, max_rows, static_cast<const AhRowInfo*>(stt.rinfo),
+                                                   static_cast<const int2*>(stt.meta), area_null_probe());
                 h->launches++;
                 fused_ab = true;
                 cur = mid2; cur_fs = p.mid2_per_frame; cur_rs = static_cast<int64_t>(S) * 3;
@@ -1812,10 +1899,12 @@ int launch_preprocess_nv12(b200clip_handle* h, const uint8_t* y, const uint8_t* 
         while (rows > 4 && static_cast<int64_t>(n) * ((ny + rows - 1) / rows) < static_cast<int64_t>(h->num_sms) * 6)
             rows = (rows + 1) / 2;
         const int seg_bytes = 3 * segpx, stage_bytes = 2 * segpx, arow_pitch = (nx * 3 + 32 + 15) & ~15, vpitch = seg_bytes + 32;
-        const int max_rows = rows * p.ay.stride;
+        Plan::StripTable stt;
+        if ((rc = get_strip_table(h, p, rows, &stt))) return rc;
+        const int max_rows = stt.max_rows;
         const size_t smem = 2 * AH_NSTAGE * sizeof(uint64_t) + static_cast<size_t>(AH_NSTAGE) * stage_bytes +
                             4 * static_cast<size_t>(vpitch) + 2 * static_cast<size_t>(arow_pitch) +
-                            static_cast<size_t>(max_rows) * sizeof(AhRowInfo);
+                            2 * static_cast<size_t>(max_rows) * sizeof(AhRowInfo);
         if (smem <= 200 * 1024) {
             AhIntParams ip{p.a_dx, p.a_dy, p.a_dx * p.a_dy, p.a_div_shift, p.a_div_mul};
             auto kern = area_hpass_vfirst_kernel<NCV + 32, 3, 1, 2, 2, AH_NSTAGE, true>;
@@ -1830,10 +1919,12 @@ int launch_preprocess_nv12(b200clip_handle* h, const uint8_t* y, const uint8_t* 
                          (chw ? 3.0 * S * S * 4.0 : 0.0)), st);
             {
                 ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(y1 - y0) * segpx * 1.5 + ny * S * 3.0), st);
-                dim3 fgrid((ny + rows - 1) / rows, n);
+                const int nitems = stt.nstrips * n;
+                const int fgrid = persistent_grid(h, kern, NCV + 32, smem, nitems, &h->k1_ctas_per_sm[1]);
                 kern<<<fgrid, NCV + 32, smem, st>>>(y, y_fs, rs, uv, uv_fs, segpx, mid2, p.mid2_per_frame, p.ry0, ny, p.rx0, nx, rows,
                                                    x0, seg_bytes, stage_bytes, arow_pitch, vpitch, p.left, S, p.ax, p.ay, p.bx, ip,
-                                                   p.aq, 0);
+                                                   p.aq, stt.nstrips, nitems, max_rows, static_cast<const AhRowInfo*>(stt.rinfo),
+                                                   static_cast<const int2*>(stt.meta), 0);
                 h->launches++;
             }
             return run_stage_c(h, p, mid2, p.mid2_per_frame, static_cast<int64_t>(S) * 3, 0, p.ry0, n, patches, chw, st);

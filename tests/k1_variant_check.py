@@ -44,6 +44,20 @@ def main() -> int:
             if not np.array_equal(patches[i * 49:(i + 1) * 49], want_patches):
                 print(f"{w}x{h} frame {i}: bf16 patch rows differ")
                 bad += 1
+    # a batch large enough that every persistent CTA walks several (strip, frame) items with the ring running across them:
+    # 600 frames of 720p (4 distinct) -> 7200 items on <= 444 resident CTAs; every copy must give the same bytes
+    base = np.concatenate([noise_frames(3, 720, 1280, seed=5), structured_frames(1, 720, 1280, seed=6)])
+    many = torch.from_numpy(base).cuda()[torch.arange(600, device="cuda") % 4]
+    pm = model.preprocess_u8(many, capi.RESIZE_REFERENCE, chw=False).view(600, -1)
+    first = model.preprocess_u8(torch.from_numpy(base).cuda(), capi.RESIZE_REFERENCE, chw=False).view(4, -1)
+    if not torch.equal(pm.view(torch.int16), first[torch.arange(600, device="cuda") % 4].view(torch.int16)):
+        print("600-frame batch: copies of a frame differ")
+        bad += 1
+    for i in range(4):
+        want = torch.from_numpy(P.patchify(P.to_chw_normalized(P.reference_preprocess_u8(base[i])), 32)).bfloat16().reshape(-1)
+        if not torch.equal(first[i].cpu().view(torch.int16), want.view(torch.int16)):
+            print(f"720p frame {i}: bf16 patch rows differ from the oracle")
+            bad += 1
     print("variant ok" if not bad else "variant FAILED", {k: v for k, v in os.environ.items() if k.startswith("B200CLIP_")})
     return 1 if bad else 0
 

@@ -172,8 +172,8 @@ for h, w in [(1080, 1920), (720, 1280)]:
 print("variant ok", model.handle.launches)
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     launches = {}
-    for name, env in (("fused", {}), ("unfused", {"B200CLIP_NV12_UNFUSED": "1"})):
-        e = {k: v for k, v in os.environ.items() if k != "B200CLIP_NV12_UNFUSED"}
+    for name, env in (("fused", {}), ("unfused", {"B200CLIP_NV12_UNFUSED": "1"}), ("persistent", {"B200CLIP_K1_PERSISTENT": "1"})):
+        e = {k: v for k, v in os.environ.items() if k not in ("B200CLIP_NV12_UNFUSED", "B200CLIP_K1_PERSISTENT")}
         e.update(env)
         r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "variant ok" in r.stdout, (name, r.stdout[-1500:], r.stderr[-1500:])
