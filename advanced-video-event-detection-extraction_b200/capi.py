@@ -177,7 +177,7 @@ class Handle:
         self.call("b200clip_reserve", int(max_images), int(max_texts))
 
     PROFILE_CLASSES = ("gemm", "attention", "layernorm", "preprocess", "head", "sim_topk", "misc", "pre_area", "pre_hpass",
-                       "pre_vpass", "comm")
+                       "pre_vpass", "comm", "gemm_small")
 
     def profile_enable(self, on: bool = True):
         self.call("b200clip_profile_enable", int(on))

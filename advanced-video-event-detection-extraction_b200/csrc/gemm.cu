@@ -61,7 +61,9 @@ static int launch_gemm_bn(b200clip_handle* h, const bf16* a, int lda, const bf16
     const int tiles = m_blocks * n_blocks;
     const int grid = tiles < h->num_sms ? tiles : h->num_sms;
     {
-        ProfScope ps(h, PROF_GEMM, 2.0 * M * static_cast<double>(N) * K, st);
+        // (class "gemm_small": the single-CTA kernel serves M < 2048 -- the 77-row text-tower GEMMs, heads of tiny
+        // batches; the roofline class "gemm" is the cta_group::2 kernel alone)
+        ProfScope ps(h, PROF_GEMM_SMALL, 2.0 * M * static_cast<double>(N) * K, st);
         kern<<<grid, b200::GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tw, out, ldc, M, N, K, ep);
     }
     h->launches++;

@@ -120,7 +120,7 @@ struct B200Knobs {
 const B200Knobs& b200_knobs();
 
 // kernel classes for the profiler
-enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_PRE = 3, PROF_HEAD = 4, PROF_SIM = 5, PROF_MISC = 6, PROF_PRE_A = 7, PROF_PRE_B = 8, PROF_PRE_C = 9, PROF_COMM = 10, PROF_NCLS = 11 };
+enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_PRE = 3, PROF_HEAD = 4, PROF_SIM = 5, PROF_MISC = 6, PROF_PRE_A = 7, PROF_PRE_B = 8, PROF_PRE_C = 9, PROF_COMM = 10, PROF_GEMM_SMALL = 11, PROF_NCLS = 12 };
 // RAII bracket: records an event pair around the launches made in its scope when profiling is on
 struct ProfScope {
     b200clip_handle* h; cudaStream_t st; int idx;

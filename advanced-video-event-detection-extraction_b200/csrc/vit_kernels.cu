@@ -1107,7 +1107,7 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
 // ============================================================================ head (K3)
 // For each selected row: LayerNorm (ln_post / ln_final) -> @ proj[width, embed] -> optional L2 normalise.
 // HEAD_IMGS rows per CTA share one pass over the projection matrix.
-constexpr int HEAD_IMGS = 16, HEAD_THREADS = 256, HEAD_MAXCOL = 4;  // embed <= 1024; 16 rows share one walk over proj
+constexpr int HEAD_IMGS = 8, HEAD_THREADS = 256, HEAD_MAXCOL = 4;  // embed <= 1024
 
 // MAXCOL = ceil(embed / HEAD_THREADS): output columns per thread (2 for E = 512), so that no zero-weight columns
 // are multiplied; the normalised rows are read from shared memory four features at a time.
@@ -1121,7 +1121,7 @@ head_kernel(const bf16* __restrict__ x, int64_t row_stride, const int32_t* __res
     float* red = hs + HEAD_IMGS * width;  // [HEAD_IMGS][HEAD_THREADS/32]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int img0 = blockIdx.x * HEAD_IMGS;
-    // (1) LayerNorm: warp w handles images img0 + w and img0 + w + 8
+    // (1) LayerNorm: warp w handles image img0 + w (+ 8, ... if a CTA owns more images than warps)
     for (int li = warp; li < HEAD_IMGS; li += HEAD_THREADS / 32) {
         const int img = img0 + li;
         float* dst = xs + li * width;
@@ -1158,33 +1158,27 @@ head_kernel(const bf16* __restrict__ x, int64_t row_stride, const int32_t* __res
     for (int c = 0; c < MAXCOL; ++c)
 #pragma unroll
         for (int i = 0; i < HEAD_IMGS; ++i) acc[c][i] = 0.f;
-    // The walk over the projection matrix is a chain of L2 round trips: HEAD_DEPTH rows of it are fetched ahead of the
-    // FMAs that consume them (8 rows x MAXCOL loads in flight per thread instead of 4), and 16 instead of 8 images share
-    // one walk (3600 images = 225 CTAs: a single wave at 3 CTAs per SM; 450 CTAs of 78 registers were two waves).
-    constexpr int HEAD_DEPTH = MAXCOL <= 2 ? 8 : 4;
-    for (int d0 = 0; d0 < width; d0 += HEAD_DEPTH) {      // width % 4 == 0 (checked by the launcher)
-        float w[HEAD_DEPTH][MAXCOL];
+    // Measured alternatives (profiles/r02i_head_variants.txt), all SLOWER than this form (0.32 ms per 3600 rows): 16 / 8
+    // projection rows in flight per thread (0.53 / 0.51 ms: at 78 / 64 registers only 3 / 4 CTAs share an SM's L1, and
+    // the kernel lives on L1 reuse of the projection matrix between co-resident CTAs), 16 images per CTA (0.48 ms).
+    for (int d0 = 0; d0 < width; d0 += 4) {      // width % 4 == 0 (checked by the launcher)
+        float w[4][MAXCOL];
 #pragma unroll
-        for (int dd = 0; dd < HEAD_DEPTH; ++dd)
+        for (int dd = 0; dd < 4; ++dd)
 #pragma unroll
             for (int c = 0; c < MAXCOL; ++c) {
                 const int col = threadIdx.x + c * HEAD_THREADS;
-                w[dd][c] = (col < embed && d0 + dd < width) ? __bfloat162float(proj[static_cast<int64_t>(d0 + dd) * embed + col]) : 0.f;
+                w[dd][c] = col < embed ? __bfloat162float(proj[static_cast<int64_t>(d0 + dd) * embed + col]) : 0.f;
             }
 #pragma unroll
-        for (int d4 = 0; d4 < HEAD_DEPTH; d4 += 4) {
-            if (d0 + d4 < width) {
+        for (int i = 0; i < HEAD_IMGS; ++i) {
+            const float4 xv = *reinterpret_cast<const float4*>(xs + i * width + d0);
 #pragma unroll
-                for (int i = 0; i < HEAD_IMGS; ++i) {
-                    const float4 xv = *reinterpret_cast<const float4*>(xs + i * width + d0 + d4);
-#pragma unroll
-                    for (int c = 0; c < MAXCOL; ++c) {
-                        float a = acc[c][i];
-                        a = fmaf(xv.x, w[d4][c], a); a = fmaf(xv.y, w[d4 + 1][c], a);
-                        a = fmaf(xv.z, w[d4 + 2][c], a); a = fmaf(xv.w, w[d4 + 3][c], a);
-                        acc[c][i] = a;
-                    }
-                }
+            for (int c = 0; c < MAXCOL; ++c) {
+                float a = acc[c][i];
+                a = fmaf(xv.x, w[0][c], a); a = fmaf(xv.y, w[1][c], a);
+                a = fmaf(xv.z, w[2][c], a); a = fmaf(xv.w, w[3][c], a);
+                acc[c][i] = a;
             }
         }
     }

@@ -228,7 +228,7 @@ int b200clip_attention_bf16(b200clip_handle* h, const void* qkv_dev, void* out_d
 
 /* Opt-in per-kernel-class device timing: while enabled, every launch is bracketed by a CUDA event pair on the
  * launching stream.  profile_read synchronises the device and returns, for one class, the summed elapsed ms, the
- * summed algorithmic work (FLOP for class 0 = GEMM; bytes for 1 = attention, 2 = LayerNorm, 3 = K1 preprocess chain,
+ * summed algorithmic work (FLOP for class 0 = the cta_group::2 GEMM and 11 = the single-CTA GEMM, M < 2048; bytes for 1 = attention, 2 = LayerNorm, 3 = K1 preprocess chain,
  * 4 = head, 5 = K4 similarity/top-k, 6 = misc, 7/8/9 = the K1 stages area / horizontal / vertical, which are also
  * inside 3, 10 = the NCCL all-gather of the multi-GPU exchange: bytes gathered) and the number of timed launches. */
 int b200clip_profile_enable(b200clip_handle* h, int on);

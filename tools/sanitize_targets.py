@@ -36,7 +36,8 @@ s, i, iv, c = model.sim_topk(img, txt[:2], 70, 0.0, torch.arange(5000, dtype=tor
 s2, i2, iv2, c2 = model.sim_topk(img.bfloat16(), txt, 5, 0.0, None, 0, 30.0, 0.0)              # tensor-core path + re-score
 q, k = 2, 70
 msg = D.pack_message(s, i)
-gathered = torch.stack([msg, msg])
+empty = D.pack_message(torch.full_like(s, float("-inf")), torch.full_like(i, -1))
+gathered = torch.stack([empty, msg])
 o = [torch.empty(q, k, device=dev), torch.empty(q, k, device=dev, dtype=torch.int64), torch.empty(q, k, 2, device=dev, dtype=torch.float64),
      torch.empty(q, device=dev, dtype=torch.int32)]
 model.handle.call("b200clip_topk_merge_packed", capi._p(gathered), 2, q, k, 0.0, capi._p(None), 30.0, 0.0, capi._p(o[0]), capi._p(o[1]),
