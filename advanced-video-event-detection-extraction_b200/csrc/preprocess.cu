@@ -811,6 +811,8 @@ __device__ __forceinline__ void nv12_convert8(uint2 yy, uint2 uv, uint32_t (&w)[
         for (int e = 0; e < 2; ++e) {
             const int px = 2 * p + e;
             const int y = static_cast<int>(__byte_perm(ys[px >> 2], 0u, 0x4440u | (px & 3)));
+            // (the shift as IMAD.HI -- high word of x * 2^12, FMA pipe instead of the ALU pipe that the byte permutes keep
+            // at 58 % -- measured SLOWER: 2.36 vs 2.0 ms per 1024 frames)
             c[px][0] = (y * CY + ruv) >> 20;
             c[px][1] = (y * CY + guv) >> 20;
             c[px][2] = (y * CY + buv) >> 20;
