@@ -564,6 +564,10 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* 
 // of the 6 warps walks its 16-row query tiles (tile = warp, warp + 6, warp + 12 ...) over the resident key blocks with
 // an online softmax -- no block-wide barrier inside the key loop and no re-read of K/V per query tile (the tiled
 // kernel above re-loads them for each of its 5 query tiles and synchronises the CTA twice per key block).
+// (Measured and dropped in round 2: 8 warps at 128 registers, two CTAs per SM, the 16 full query tiles of T = 257 in two
+// rounds and the odd 257th row scored by all warps on the CUDA cores -- 20.5 ms per 512 ViT-L/14 frames against 18.2 ms for
+// this 6-warp / 162-register form: the SM is throughput bound -- legacy tensor pipe 47 %, shared-memory pipe 57 %,
+// profiles/r02f_attention_seq_ncu_summary.txt -- and the thinner warps lose more than the third round costs.)
 constexpr int ATS_WARPS = 6, ATS_THREADS = ATS_WARPS * 32, ATS_MAX_BLOCKS = 5;      // T <= 320
 __global__ void __launch_bounds__(ATS_THREADS, 2)
 attention_seq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* __restrict__ qkv,
@@ -780,6 +784,93 @@ attention_seq_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* _
     }
 }
 
+// One query row against ALL keys of a head whose K / V boxes are resident in shared memory (64-row boxes of 128-byte
+// rows in the TMA 128-byte swizzle), computed by NW warps together on the CUDA cores: key-per-lane scores, a block-wide
+// softmax through `scratch`, P.V with two output dimensions per lane.  Used for the odd last row of T = 128 m + 1
+// sequences (ViT-L/14: 257), which would otherwise cost a whole extra 128-row tensor-core tile.
+template <int NW, int MAXKEYS>
+__device__ __forceinline__ void attention_odd_row(const uint8_t* sK, const uint8_t* sV, float* scratch, const bf16* qrow,
+                                                  bf16* orow, int T, int warp, int lane, int bar_id) {
+    float* xs_q = scratch;                                 // [64]
+    float* xs_p = xs_q + 64;                               // [MAXKEYS]
+    float* xs_red = xs_p + MAXKEYS;                        // [2][NW]
+    float* xs_o = xs_red + 2 * NW;                         // [NW][64]
+    const float scale_log2 = 0.125f * 1.4426950408889634f;
+    if (warp == 0) {
+        const float2 qv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qrow + lane * 2));
+        xs_q[lane * 2] = qv.x; xs_q[lane * 2 + 1] = qv.y;
+    }
+    named_bar_sync(bar_id, NW * 32);
+    constexpr int KPL = (MAXKEYS + NW * 32 - 1) / (NW * 32);      // keys per lane
+    float sc[KPL];
+    float mloc = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+        const int key = warp * 32 + lane + j * (NW * 32);
+        sc[j] = -INFINITY;
+        if (key < T) {
+            const uint8_t* kr = sK + (key >> 6) * ATT_BK * 128 + (key & 63) * 128;
+            float a = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 kv = *reinterpret_cast<const uint4*>(kr + ((c ^ (key & 7)) << 4));
+                const float4 q0v = *reinterpret_cast<const float4*>(xs_q + c * 8);
+                const float4 q1v = *reinterpret_cast<const float4*>(xs_q + c * 8 + 4);
+                float2 f;
+                f = unpack_bf16x2(kv.x); a = fmaf(f.x, q0v.x, a); a = fmaf(f.y, q0v.y, a);
+                f = unpack_bf16x2(kv.y); a = fmaf(f.x, q0v.z, a); a = fmaf(f.y, q0v.w, a);
+                f = unpack_bf16x2(kv.z); a = fmaf(f.x, q1v.x, a); a = fmaf(f.y, q1v.y, a);
+                f = unpack_bf16x2(kv.w); a = fmaf(f.x, q1v.z, a); a = fmaf(f.y, q1v.w, a);
+            }
+            sc[j] = a;
+            mloc = fmaxf(mloc, a);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
+    if (lane == 0) xs_red[warp] = mloc;
+    named_bar_sync(bar_id, NW * 32);
+    float gmax = xs_red[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) gmax = fmaxf(gmax, xs_red[w]);
+    float sloc = 0.f;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+        const int key = warp * 32 + lane + j * (NW * 32);
+        if (key < T) {
+            const float pk = ex2_approx((sc[j] - gmax) * scale_log2);
+            xs_p[key] = pk;
+            sloc += pk;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sloc += __shfl_xor_sync(0xffffffffu, sloc, o);
+    if (lane == 0) xs_red[NW + warp] = sloc;
+    named_bar_sync(bar_id, NW * 32);
+    float o0 = 0.f, o1 = 0.f;       // P . V: warp w takes keys w, w + NW, ...; lane l owns output dimensions 2l, 2l + 1
+    for (int key = warp; key < T; key += NW) {
+        const float pk = xs_p[key];
+        const uint8_t* vr = sV + (key >> 6) * ATT_BK * 128 + (key & 63) * 128;
+        const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vr + (((lane >> 2) ^ (key & 7)) << 4) + (lane & 3) * 4));
+        o0 = fmaf(pk, v.x, o0);
+        o1 = fmaf(pk, v.y, o1);
+    }
+    xs_o[warp * 64 + lane * 2] = o0;
+    xs_o[warp * 64 + lane * 2 + 1] = o1;
+    named_bar_sync(bar_id, NW * 32);
+    if (warp == 0) {
+        float tot = 0.f, r0 = 0.f, r1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            tot += xs_red[NW + w];
+            r0 += xs_o[w * 64 + lane * 2];
+            r1 += xs_o[w * 64 + lane * 2 + 1];
+        }
+        const float inv = 1.f / tot;
+        *reinterpret_cast<uint32_t*>(orow + lane * 2) = pack_bf16x2(r0 * inv, r1 * inv);
+    }
+}
+
 // ---------------------------------------------------------------------------- tcgen05 variant
 // Attention on the 5th-generation tensor cores for mid-length sequences without a mask (ViT-L/14: T = 257).
 // One CTA per (sequence, head); K and V of the head are TMA-loaded once and stay resident, Q streams tile by tile.
@@ -815,7 +906,8 @@ __host__ __device__ inline AtcLayout atc_layout(int T) {
 
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constant__ CUtensorMap tmap_kv64,
-                    const __grid_constant__ CUtensorMap tmap_kv16, bf16* __restrict__ out, int T, int heads) {
+                    const __grid_constant__ CUtensorMap tmap_kv16, const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                    int T, int heads) {
     extern __shared__ uint8_t atc_raw[];
     uint8_t* base = atc_raw + ((1024u - (smem_u32(atc_raw) & 1023u)) & 1023u)   /* pointer arithmetic keeps the shared address space: LDS/STS, not generic LD/ST */;
     const AtcLayout L = atc_layout(T);
@@ -837,7 +929,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
     const int head = blockIdx.x;
     const int seq = blockIdx.y;
     const int D = heads * ATT_D;
-    const int nq = (T + ATC_BM - 1) / ATC_BM;
+    // T = 128 m + 1 (ViT-L/14: 257): the odd last query row is scored on the CUDA cores after the tiles instead of
+    // costing a whole extra 128-row tile (a third of the S -> softmax -> P -> PV chain for one row)
+    const int xq = (T > ATC_BM && T % ATC_BM == 1) ? 1 : 0;
+    const int Tq = T - xq;
+    const int nq = (Tq + ATC_BM - 1) / ATC_BM;
     const int nk = (T + ATC_BN - 1) / ATC_BN;
     const int last_keys = T - (nk - 1) * ATC_BN;
     const bool last_small = last_keys <= 16;
@@ -933,7 +1029,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
         for (int i = 0; i < nsteps; ++i) {
             const int t = i / nk, b = i - t * nk;
             const int kv_valid = (b == nk - 1) ? last_keys : ATC_BN;
-            const bool warp_rows = t * ATC_BM + warp * 32 < T;          // warp-uniform
+            const bool warp_rows = t * ATC_BM + warp * 32 < Tq;         // warp-uniform
             // (1) the PV of the previous block of this tile joins O (still relative to the previous maximum); waiting
             //     for it also guarantees that the tensor core has finished reading the previous P from shared memory
             if (i > 0) {
@@ -997,7 +1093,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
                 tc_fence_after();
                 add_pv();
                 const int row = t * ATC_BM + row_in_tile;
-                if (row < T) {
+                if (row < Tq) {
                     const float inv = 1.f / l_run;
                     bf16* orow = out + (static_cast<int64_t>(seq) * T + row) * D + head * ATT_D;
 #pragma unroll
@@ -1014,6 +1110,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
                 for (int j = 0; j < ATT_D; ++j) o[j] = 0.f;
                 m_run = -INFINITY; l_run = 0.f;
             }
+        }
+        if (xq) {
+            // every softmax warp is past its last pv_full wait: the tensor core no longer reads sP, which becomes the
+            // scratch of the odd row
+            named_bar_sync(2, 128);
+            attention_odd_row<4, ATC_MAX_KB * ATC_BN>(sK, sV, reinterpret_cast<float*>(sP),
+                                                      qkv + (static_cast<int64_t>(seq) * T + T - 1) * 3 * D + head * ATT_D,
+                                                      out + (static_cast<int64_t>(seq) * T + T - 1) * D + head * ATT_D, T, warp, lane, 2);
         }
     }
     tc_fence_before();
@@ -1068,7 +1172,7 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
         const int smem = atc_layout(t).total + 1024;
         B200_CUDA(h, cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         ProfScope ps(h, PROF_ATTN, static_cast<double>(n_seq) * t * heads * ATT_D * 2.0 * 4.0, st);
-        attention_tc_kernel<<<dim3(heads, n_seq), ATC_THREADS, smem, st>>>(tq, t64, t16, out, t, heads);
+        attention_tc_kernel<<<dim3(heads, n_seq), ATC_THREADS, smem, st>>>(tq, t64, t16, qkv, out, t, heads);
         h->launches++;
         B200_CUDA(h, cudaGetLastError());
         return 0;

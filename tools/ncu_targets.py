@@ -43,4 +43,10 @@ else:
     for _ in range(3):
         h.call("b200clip_attention_bf16", capi._p(qkv), capi._p(out), n_seq, t, heads, 0, st)
     torch.cuda.synchronize()
-    print("l14attn ok", float(out.float().abs().sum()))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(48):         # two ViT-L/14 passes' worth of layers, back to back
+        h.call("b200clip_attention_bf16", capi._p(qkv), capi._p(out), n_seq, t, heads, 0, st)
+    e1.record()
+    torch.cuda.synchronize()
+    print("l14attn ok", float(out.float().abs().sum()), "ms per layer call (512 seq x 16 heads, T = 257):", round(e0.elapsed_time(e1) / 48, 4))
