@@ -219,6 +219,7 @@ class FramesWorkload(Workload):
     host_slice = 0          # pinned host frames per rank for the e2e leg (0 = all of the rank's frames)
     nv12_e2e = False
     chunk = 0
+    overlap_query = True    # the query runs on the TEXT tower (own workspace): it may overlap K1 of the image tower
 
     def plan(self):
         """Sizes only (no device): shared by both arms so that their `config` objects are the same."""
@@ -253,7 +254,7 @@ class FramesWorkload(Workload):
         return self.model.encode_text(self.tok, normalize=True)
 
     def step(self):
-        if not self.args.no_text_overlap:
+        if self.overlap_query and not self.args.no_text_overlap:
             # The query's text tower (60 latency-bound launches of a few CTAs each, ~0.7 ms) runs on a high-priority side
             # stream while K1 -- an ordinary, non-persistent grid -- preprocesses the frames; the towers of one handle have
             # disjoint workspaces.  It has finished long before the first persistent GEMM of the image tower starts.
@@ -443,6 +444,7 @@ class Config5(FramesWorkload):
     chunk = 4096
     host_slice = 20000
     cpu_units = 256
+    overlap_query = False   # the query is an IMAGE: it needs the image tower's workspace, one in-flight call per handle
 
     def __init__(self, *a):
         super().__init__(*a)
