@@ -104,7 +104,7 @@ struct b200clip_handle {
     int g2_clusters[5] = {0, 0, 0, 0, 0};   // co-resident clusters of the 2-CTA GEMM on this device, per pairs
 };
 enum { ATTR_GEMM64 = 1u << 0, ATTR_GEMM128 = 1u << 1, ATTR_GEMM256 = 1u << 2, ATTR_GEMM_2CTA = 1u << 3, ATTR_SIM_TC = 1u << 4,
-       ATTR_ATTN_PERSIST = 1u << 5, ATTR_SIM_STREAM = 1u << 6, ATTR_K1_VFIRST = 1u << 7, ATTR_K1_NV12 = 1u << 8 };
+       ATTR_ATTN_PERSIST = 1u << 5, ATTR_SIM_STREAM = 1u << 6, ATTR_K1_VFIRST = 1u << 7, ATTR_K1_NV12 = 1u << 8, ATTR_K1_MMA = 1u << 9 };
 
 // Environment switches, read ONCE per process (first use).  They select between code paths that are all valid and
 // parity-tested (fallback kernels that other geometries use anyway); measurement probes that invalidate results or
@@ -116,6 +116,8 @@ struct B200Knobs {
     bool attn_oneshot, attn_tc, attn_tiled;
     bool overlap, full_upload;
     bool nv12_unfused, k1_persistent;
+    bool k1_verbose;           // B200CLIP_K1_VERBOSE: report the K1 code path on stderr
+    bool area_mma;             // K1 stages A + B on the integer tensor cores (preprocess_mma.cuh)
 };
 const B200Knobs& b200_knobs();
 

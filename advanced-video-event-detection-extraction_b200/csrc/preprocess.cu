@@ -154,6 +154,13 @@ struct Plan {
     size_t mid1_per_frame = 0, mid2_per_frame = 0;
     std::vector<void*> dev;  // device allocations holding the tables
     AxisTaps h_ay;           // host copy of the vertical area taps (strip row programs are built from it)
+    AxisTaps h_ax, h_bx;     // host copies of the horizontal area / Pillow taps (fragment tables of the IMMA kernel)
+    struct MmaTables {       // device tables of area_hpass_mma_kernel for one alignment of the source window
+        const void *a1 = nullptr, *kb1 = nullptr, *b2 = nullptr, *gmeta = nullptr, *ap = nullptr, *kbp = nullptr;
+        int ntx = 0, npt = 0, ngroups = 0, nb = 0, seg = 0, pitch1 = 0, pitchA = 0;
+        bool ok = false;
+    };
+    mutable std::map<int, MmaTables> mma;       // keyed by delta = (window start address) & 15
     struct StripTable { const void* rinfo = nullptr; const void* meta = nullptr; int nstrips = 0, max_rows = 0; };
     mutable std::map<int, StripTable> strips;   // rows per strip -> row programs of the fused area kernels (device)
 };
@@ -1399,6 +1406,111 @@ static int get_strip_table(b200clip_handle* h, const Plan& p, int rows, Plan::St
     return 0;
 }
 
+#include "preprocess_mma.cuh"
+
+// Fragment tables of area_hpass_mma_kernel (see preprocess_mma.cuh) for source windows whose first byte sits `delta`
+// bytes behind a 16-byte boundary.  Every weight is placed at the (register, byte) position at which the MMA fragment
+// layouts of m16n8k32 expect it.  Stage 1 reads its K window with 32-bit loads in the natural order (K index kk of K step
+// s = byte kb + 32 s + kk of the ring row, kb a multiple of 4); stage 3 with 64-bit loads, so K is enumerated in the
+// order those deliver the bytes: kk of step s, lane (g, t4) = byte kb + 32 s + 8 t4 + 4 (kk >= 16) + (kk & 3).
+static int get_mma_tables(b200clip_handle* h, const Plan& p, int delta, Plan::MmaTables* out) {
+    auto it = p.mma.find(delta);
+    if (it != p.mma.end()) { *out = it->second; return 0; }
+    Plan::MmaTables t;
+    const AxisTaps &ax = p.h_ax, &ay = p.h_ay, &bx = p.h_bx;
+    const int S = h->cfg.image_size;
+    const int nx = p.rx1 - p.rx0, ny = p.ry1 - p.ry0;
+    const int gstart = p.sx0 * 3 - delta;                     // source-row byte held by byte 0 of a ring row
+    auto pitch32 = [](int need) { int v = (need + 127) / 128 * 128 + 32; return v - 128 >= need ? v - 128 : v; };
+    t.seg = (delta + (p.sx1 - p.sx0) * 3 + 15) & ~15;
+    t.pitch1 = pitch32(t.seg + 64);
+    t.pitchA = pitch32(nx + 64);
+    t.ntx = (nx + 4) / 5;
+    t.npt = (S + 15) / 16;
+    t.ngroups = (ny + 7) / 8;
+    bool ok = p.a_int && p.a_dx <= 255 && 2 * p.a_dy <= 255 && gstart >= 0;
+    std::vector<uint32_t> a1(static_cast<size_t>(t.ntx) * 2 * 32 * 4, 0u), b2(static_cast<size_t>(t.ngroups) * 32 * 2, 0u),
+        ap(static_cast<size_t>(t.npt) * 3 * 2 * 32 * 4, 0u);
+    std::vector<int> kb1(t.ntx, 0), kbp(t.npt, 0);
+    std::vector<int2> gmeta(t.ngroups);
+    auto put = [](uint32_t& word, int j, uint32_t byte) { word |= (byte & 0xffu) << (8 * j); };
+    // stage 1: 5 area pixels (15 interleaved columns) per tile against the <= 64 source-row bytes under them
+    for (int ti = 0; ti < t.ntx && ok; ++ti) {
+        const int px0 = p.rx0 + 5 * ti, px1 = std::min(px0 + 5, p.rx1);
+        int lastb = 0;
+        for (int x = px0; x < px1; ++x) lastb = std::max(lastb, 3 * (ax.start[x] + ax.cnt[x]) - gstart);
+        const int kb = (3 * ax.start[px0] - gstart) & ~3;
+        if (kb < 0 || lastb - kb > 64 || kb + 64 > t.pitch1) { ok = false; break; }
+        kb1[ti] = kb;
+        for (int s = 0; s < 2; ++s)
+            for (int lane = 0; lane < 32; ++lane)
+                for (int r = 0; r < 4; ++r)
+                    for (int j = 0; j < 4; ++j) {
+                        const int g = lane >> 2, t4 = lane & 3, m = g + 8 * (r & 1);
+                        const int sb = kb + 32 * s + 16 * (r >> 1) + 4 * t4 + j + gstart;    // byte of the source row
+                        const int sx = sb / 3, sc = sb % 3, x = px0 + m / 3;
+                        if (m >= 15 || x >= px1 || sc != m % 3 || sx < ax.start[x] || sx >= ax.start[x] + ax.cnt[x]) continue;
+                        const long iw = lrintf(ax.wf[static_cast<size_t>(x) * ax.stride + (sx - ax.start[x])] * static_cast<float>(p.a_dx));
+                        if (iw < 0 || iw > 255) ok = false;
+                        put(a1[((static_cast<size_t>(ti) * 2 + s) * 32 + lane) * 4 + r], j, static_cast<uint32_t>(iw));
+                    }
+    }
+    // stage 2: 8 area rows per group against its <= 32 source rows, in the order the repacked accumulators hold them
+    for (int gi = 0; gi < t.ngroups && ok; ++gi) {
+        const int y0 = p.ry0 + 8 * gi, y1 = std::min(y0 + 8, p.ry1);
+        const int r_lo = ay.start[y0];
+        int r_hi = r_lo;
+        for (int y = y0; y < y1; ++y) r_hi = std::max(r_hi, ay.start[y] + ay.cnt[y]);
+        if (r_hi - r_lo > 32) { ok = false; break; }
+        gmeta[gi] = make_int2(r_lo, r_hi - r_lo);
+        t.nb = std::max(t.nb, (r_hi - r_lo + 7) / 8);
+        for (int lane = 0; lane < 32; ++lane)
+            for (int hh = 0; hh < 2; ++hh)
+                for (int j = 0; j < 4; ++j) {
+                    const int n = lane >> 2, t4 = lane & 3, y = y0 + n;
+                    const int sr = r_lo + 16 * hh + (j < 2 ? 2 * t4 + j : 8 + 2 * t4 + (j - 2));
+                    if (y >= y1 || sr < ay.start[y] || sr >= ay.start[y] + ay.cnt[y]) continue;
+                    const long iw = 2 * lrintf(ay.wf[static_cast<size_t>(y) * ay.stride + (sr - ay.start[y])] * static_cast<float>(p.a_dy));
+                    if (iw < 0 || iw > 255) ok = false;
+                    put(b2[(static_cast<size_t>(gi) * 32 + lane) * 2 + hh], j, static_cast<uint32_t>(iw));
+                }
+    }
+    // stage 3: 16 Pillow output columns per tile against the <= 64 area columns under them, three byte planes of the
+    // 22-bit coefficients (two's complement: w = p0 + 256 p1 + 65536 p2, p2 signed)
+    for (int pt = 0; pt < t.npt && ok; ++pt) {
+        const int o0 = p.left + 16 * pt, o1 = std::min(o0 + 16, p.left + S);
+        int lasta = 0;
+        for (int o = o0; o < o1; ++o) lasta = std::max(lasta, bx.start[o] + bx.cnt[o] - p.rx0);
+        const int kb = (bx.start[o0] - p.rx0) & ~7;
+        if (kb < 0 || lasta - kb > 64 || kb + 64 > t.pitchA) { ok = false; break; }
+        kbp[pt] = kb;
+        for (int pl = 0; pl < 3; ++pl)
+            for (int s = 0; s < 2; ++s)
+                for (int lane = 0; lane < 32; ++lane)
+                    for (int r = 0; r < 4; ++r)
+                        for (int j = 0; j < 4; ++j) {
+                            const int g = lane >> 2, t4 = lane & 3, o = o0 + g + 8 * (r & 1);
+                            const int acol = kb + 32 * s + 8 * t4 + 4 * (r >> 1) + j + p.rx0;   // column of the area image
+                            if (o >= o1 || acol < bx.start[o] || acol >= bx.start[o] + bx.cnt[o]) continue;
+                            const int wv = bx.wi[static_cast<size_t>(o) * bx.stride + (acol - bx.start[o])];
+                            if (wv < -(1 << 23) || wv >= (1 << 23)) ok = false;
+                            put(ap[(((static_cast<size_t>(pt) * 3 + pl) * 2 + s) * 32 + lane) * 4 + r], j,
+                                static_cast<uint32_t>(wv >> (8 * pl)));
+                        }
+    }
+    if (ok) {
+        Plan& pm = const_cast<Plan&>(p);
+        int rc = 0;
+        t.a1 = upload(h, pm, a1, rc); t.kb1 = upload(h, pm, kb1, rc); t.b2 = upload(h, pm, b2, rc);
+        t.gmeta = upload(h, pm, gmeta, rc); t.ap = upload(h, pm, ap, rc); t.kbp = upload(h, pm, kbp, rc);
+        if (rc) return b200_fail(h, rc, "preprocess: uploading the IMMA fragment tables failed");
+    }
+    t.ok = ok;
+    p.mma[delta] = t;
+    *out = t;
+    return 0;
+}
+
 // CTAs of a K1 area launch.  Default: one CTA per work item.  B200CLIP_K1_PERSISTENT=1: every SM filled to the kernel's
 // occupancy and each CTA walking many items -- measured on one box back to back (profiles/r02g_k1_persistent_ab.txt): 5.07 /
 // 4.96 ms per 3600 frames persistent vs 4.99 / 4.76 one-shot, i.e. the per-CTA prologue is already hidden by the block
@@ -1509,6 +1621,8 @@ static int build_plan(b200clip_handle* h, int H, int W, int mode, Plan& p) {
     p.ax = upload_taps(h, p, ax, rc);
     p.ay = upload_taps(h, p, ay, rc);
     p.h_ay = ay;
+    p.h_ax = ax;
+    p.h_bx = bx;
     p.bx = upload_taps(h, p, bx, rc);
     p.cy = upload_taps(h, p, cy, rc);
     if (p.a_int && p.a_max_cx <= 5 && p.a_dx <= 255) {
@@ -1713,7 +1827,53 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         const int ncv = 128;
         const bool vfirst = intx && !no_vfirst && p.aq != nullptr && (seg >> 4) <= 2 * ncv && nx <= 3 * ncv && S <= 2 * ncv &&
                             p.a_dy * 255 < 65536 && p.a_dx <= 255 && xb0 - delta >= 0 && xb0 - delta + seg <= W * 3;
-        if (vfirst) {
+        // IMMA form (preprocess_mma.cuh): the three separable passes as integer tensor-core products, one persistent CTA
+        // per SM.  Same integer arithmetic as the vertical-first kernel, so the same exactness conditions apply.
+        if (intx && b200_knobs().area_mma && xb0 - delta >= 0) {
+            Plan::MmaTables mt;
+            if (int mrc = get_mma_tables(h, p, delta, &mt)) return mrc;
+            constexpr int NCW = 15, TPW = 4;
+            const size_t fixed = 256 + NBUF * 3 * 8 * static_cast<size_t>(mt.pitchA);
+            const size_t blockbytes = 8 * static_cast<size_t>(mt.pitch1);
+            int nst = mt.ok ? static_cast<int>((216 * 1024 - fixed) / blockbytes) : 0;
+            nst = nst > MMA_MAX_NST ? MMA_MAX_NST : nst;
+            if (b200_knobs().k1_verbose)
+                fprintf(stderr, "b200clip K1 %dx%d: IMMA tables ok=%d ntx=%d npt=%d groups=%d nb=%d seg=%d pitch1=%d pitchA=%d nst=%d\n", W, H,
+                        (int)mt.ok, mt.ntx, mt.npt, mt.ngroups, mt.nb, mt.seg, mt.pitch1, mt.pitchA, nst);
+            if (mt.ok && mt.ntx <= NCW * TPW && mt.nb >= 1 && mt.nb <= 4 && nst >= 3 && xb0 - delta + mt.seg <= W * 3) {
+                int gps = 3;         // groups of 8 area rows per work item
+                while (gps > 1 && static_cast<int64_t>(n) * ((mt.ngroups + gps - 1) / gps) < static_cast<int64_t>(h->num_sms) * 4) --gps;
+                MmaParams mp{};
+                mp.src = cur + xb0 - delta; mp.frame_stride = cur_fs; mp.row_stride = cur_rs;
+                mp.mid2 = mid2; mp.mid2_frame_stride = static_cast<int64_t>(p.mid2_per_frame);
+                mp.S = S; mp.ny = ny; mp.nx = nx; mp.seg = mt.seg; mp.pitch1 = mt.pitch1; mp.pitchA = mt.pitchA;
+                mp.ntx = mt.ntx; mp.npt = mt.npt; mp.gps = gps; mp.nstrips = (mt.ngroups + gps - 1) / gps; mp.ngroups = mt.ngroups;
+                mp.nitems = mp.nstrips * n; mp.nst = nst;
+                mp.d = static_cast<uint32_t>(p.a_dx * p.a_dy); mp.div_mul = p.a_div_mul; mp.div_shift = p.a_div_shift;
+                mp.a1 = static_cast<const uint4*>(mt.a1); mp.kb1 = static_cast<const int*>(mt.kb1);
+                mp.b2 = static_cast<const uint2*>(mt.b2); mp.gmeta = static_cast<const int2*>(mt.gmeta);
+                mp.ap = static_cast<const uint4*>(mt.ap); mp.kbp = static_cast<const int*>(mt.kbp);
+                const size_t smem = fixed + nst * blockbytes;
+                void (*kern)(const MmaParams) = mt.nb == 4 ? area_hpass_mma_kernel<NCW, TPW, 4>
+                                              : mt.nb == 3 ? area_hpass_mma_kernel<NCW, TPW, 3>
+                                              : mt.nb == 2 ? area_hpass_mma_kernel<NCW, TPW, 2> : area_hpass_mma_kernel<NCW, TPW, 1>;
+                if (!(h->attr_done & ATTR_K1_MMA)) {
+                    B200_CUDA(h, cudaFuncSetAttribute(area_hpass_mma_kernel<NCW, TPW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+                    B200_CUDA(h, cudaFuncSetAttribute(area_hpass_mma_kernel<NCW, TPW, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+                    B200_CUDA(h, cudaFuncSetAttribute(area_hpass_mma_kernel<NCW, TPW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+                    B200_CUDA(h, cudaFuncSetAttribute(area_hpass_mma_kernel<NCW, TPW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+                    h->attr_done |= ATTR_K1_MMA;
+                }
+                ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(p.sy1 - p.sy0) * (p.sx1 - p.sx0) * 3.0 + ny * S * 3.0), st);
+                const int fgrid = mp.nitems < h->num_sms ? mp.nitems : h->num_sms;
+                kern<<<fgrid, (NCW + 1) * 32, smem, st>>>(mp);
+                h->launches++;
+                fused_ab = true;
+                cur = mid2; cur_fs = p.mid2_per_frame; cur_rs = static_cast<int64_t>(S) * 3;
+                cur_x0 = 0; cur_y0 = p.ry0;
+            }
+        }
+        if (!fused_ab && vfirst) {
             // strip length: 24, 48, 96 and 288 rows measured within noise of each other on B200 (the per-CTA prologue
             // is ~10 % of the stall samples at 24 rows, but longer strips lose as much to the tail) -> keep 24
             int rows = 24;
