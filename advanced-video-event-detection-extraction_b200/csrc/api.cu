@@ -39,7 +39,7 @@ const B200Knobs& b200_knobs() {
         b.attn_oneshot = on("B200CLIP_ATTN_ONESHOT"); b.attn_tc = on("B200CLIP_ATTN_TC"); b.attn_tiled = on("B200CLIP_ATTN_TILED");
         b.overlap = on("B200CLIP_OVERLAP"); b.full_upload = on("B200CLIP_FULL_UPLOAD");
         b.nv12_unfused = on("B200CLIP_NV12_UNFUSED"); b.k1_persistent = on("B200CLIP_K1_PERSISTENT");
-        b.area_mma = on("B200CLIP_AREA_MMA"); b.k1_verbose = on("B200CLIP_K1_VERBOSE");
+        b.area_mma = !on("B200CLIP_AREA_NOMMA"); b.k1_verbose = on("B200CLIP_K1_VERBOSE");
         return b;
     }();
     return k;

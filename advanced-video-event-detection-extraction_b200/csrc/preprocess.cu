@@ -1421,10 +1421,12 @@ static int get_mma_tables(b200clip_handle* h, const Plan& p, int delta, Plan::Mm
     const int S = h->cfg.image_size;
     const int nx = p.rx1 - p.rx0, ny = p.ry1 - p.ry0;
     const int gstart = p.sx0 * 3 - delta;                     // source-row byte held by byte 0 of a ring row
-    auto pitch32 = [](int need) { int v = (need + 127) / 128 * 128 + 32; return v - 128 >= need ? v - 128 : v; };
+    // smallest pitch >= need that is `rem` modulo 128: the 8 rows a warp reads at once (stage 1: 16 bytes per row and
+    // LDS.32; stage 3: 32 bytes per row and half-warp of an LDS.64) then fall on distinct shared-memory banks
+    auto pitch_mod = [](int need, int rem) { int v = (need + 127) / 128 * 128 + rem; return v - 128 >= need ? v - 128 : v; };
     t.seg = (delta + (p.sx1 - p.sx0) * 3 + 15) & ~15;
-    t.pitch1 = pitch32(t.seg + 64);
-    t.pitchA = pitch32(nx + 64);
+    t.pitch1 = pitch_mod(t.seg + 64, 16);
+    t.pitchA = pitch_mod(nx + 64, 32);
     t.ntx = (nx + 4) / 5;
     t.npt = (S + 15) / 16;
     t.ngroups = (ny + 7) / 8;
@@ -1829,11 +1831,14 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
                             p.a_dy * 255 < 65536 && p.a_dx <= 255 && xb0 - delta >= 0 && xb0 - delta + seg <= W * 3;
         // IMMA form (preprocess_mma.cuh): the three separable passes as integer tensor-core products, one persistent CTA
         // per SM.  Same integer arithmetic as the vertical-first kernel, so the same exactness conditions apply.
-        if (intx && b200_knobs().area_mma && xb0 - delta >= 0) {
+        // (the switches that pick among the CUDA-core kernels -- horizontal-first, one column per thread, persistent launch
+        // form -- imply them)
+        const bool want_mma = b200_knobs().area_mma && !b200_knobs().area_hfirst && !b200_knobs().area_px1 && !b200_knobs().k1_persistent;
+        if (intx && want_mma && xb0 - delta >= 0) {
             Plan::MmaTables mt;
             if (int mrc = get_mma_tables(h, p, delta, &mt)) return mrc;
             constexpr int NCW = 15, TPW = 4;
-            const size_t fixed = 256 + NBUF * 3 * 8 * static_cast<size_t>(mt.pitchA);
+            const size_t fixed = 256 + NBUF * 3 * (8 * static_cast<size_t>(mt.pitchA) + 8);
             const size_t blockbytes = 8 * static_cast<size_t>(mt.pitch1);
             int nst = mt.ok ? static_cast<int>((216 * 1024 - fixed) / blockbytes) : 0;
             nst = nst > MMA_MAX_NST ? MMA_MAX_NST : nst;

@@ -33,7 +33,7 @@ struct MmaParams {
     const uint8_t* src; int64_t frame_stride, row_stride;
     uint8_t* mid2; int64_t mid2_frame_stride;
     int S, ny, nx;                 // Pillow output columns, area rows and area columns of the window
-    int seg, pitch1, pitchA;       // bytes per bulk-copied row, ring row pitch, parked-row pitch (both = 32 mod 128)
+    int seg, pitch1, pitchA;       // bytes per bulk-copied row, ring row pitch (16 mod 128), parked-row pitch (32 mod 128)
     int ntx, npt;                  // stage-1 tiles (5 area pixels), Pillow tiles (16 output pixels)
     int gps, nstrips, ngroups, nitems, nst;
     uint32_t d, div_mul; int div_shift;
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) area_hpass_mma_kernel(const
     uint64_t* aempty_bar = afull_bar + NBUF;
     uint8_t* ring = mma_smem + 256;
     const uint32_t blockbytes = 8u * static_cast<uint32_t>(P.pitch1);
-    const uint32_t planebytes = 8u * static_cast<uint32_t>(P.pitchA);
+    const uint32_t planebytes = 8u * static_cast<uint32_t>(P.pitchA) + 8u;    // + 8: the three colour planes of a pixel on distinct banks
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {

@@ -2,7 +2,8 @@
 per process from environment switches (B200CLIP_AREA_FP32: fp32 area arithmetic instead of the integer-exact one;
 B200CLIP_K1_UNFUSED: separate area / horizontal kernels; B200CLIP_AREA_NOSTRIP: per-pixel area kernel;
 B200CLIP_AREA_HFIRST: horizontal-first integer area kernel instead of the vertical-first one;
-B200CLIP_VPASS_GENERIC: per-item vertical-pass kernel instead of the tile form for the bf16 patch output), so each
+B200CLIP_VPASS_GENERIC: per-item vertical-pass kernel instead of the tile form for the bf16 patch output;
+B200CLIP_AREA_NOMMA: the CUDA-core kernels instead of the integer tensor-core (IMMA) form of stages A + B), so each
 variant needs its own process.  Checks 1080p and 720p frames byte for byte against the oracle (which is itself pinned
 to cv2 / Pillow / torchvision)."""
 import os
