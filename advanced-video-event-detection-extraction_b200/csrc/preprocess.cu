@@ -1838,14 +1838,15 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
             Plan::MmaTables mt;
             if (int mrc = get_mma_tables(h, p, delta, &mt)) return mrc;
             constexpr int NCW = 15, TPW = 4;
-            const size_t fixed = 256 + NBUF * 3 * (8 * static_cast<size_t>(mt.pitchA) + 8);
+            constexpr size_t kMmaSmem = 227 * 1024;      // the whole shared memory of an SM: one CTA per SM
+            const size_t fixed = 256 + NBUF * 3 * (8 * static_cast<size_t>(mt.pitchA) + 8) + static_cast<size_t>(mt.npt) * 3 * 2 * 32 * 16 + NCW * 384;
             const size_t blockbytes = 8 * static_cast<size_t>(mt.pitch1);
-            int nst = mt.ok ? static_cast<int>((216 * 1024 - fixed) / blockbytes) : 0;
+            int nst = mt.ok && fixed < kMmaSmem ? static_cast<int>((kMmaSmem - fixed) / blockbytes) : 0;
             nst = nst > MMA_MAX_NST ? MMA_MAX_NST : nst;
             if (b200_knobs().k1_verbose)
                 fprintf(stderr, "b200clip K1 %dx%d: IMMA tables ok=%d ntx=%d npt=%d groups=%d nb=%d seg=%d pitch1=%d pitchA=%d nst=%d\n", W, H,
                         (int)mt.ok, mt.ntx, mt.npt, mt.ngroups, mt.nb, mt.seg, mt.pitch1, mt.pitchA, nst);
-            if (mt.ok && mt.ntx <= NCW * TPW && mt.nb >= 1 && mt.nb <= 4 && nst >= 3 && xb0 - delta + mt.seg <= W * 3) {
+            if (mt.ok && S % 16 == 0 && mt.ntx <= NCW * TPW && mt.nb >= 1 && mt.nb <= 4 && nst >= 3 && xb0 - delta + mt.seg <= W * 3) {
                 int gps = 3;         // groups of 8 area rows per work item
                 while (gps > 1 && static_cast<int64_t>(n) * ((mt.ngroups + gps - 1) / gps) < static_cast<int64_t>(h->num_sms) * 4) --gps;
                 MmaParams mp{};
@@ -1863,10 +1864,10 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
                                               : mt.nb == 3 ? area_hpass_mma_kernel<NCW, TPW, 3>
                                               : mt.nb == 2 ? area_hpass_mma_kernel<NCW, TPW, 2> : area_hpass_mma_kernel<NCW, TPW, 1>;
                 if (!(h->attr_done & ATTR_K1_MMA)) {
-                    B200_CUDA(h, cudaFuncSetAttribute(area_hpass_mma_kernel<NCW, TPW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-                    B200_CUDA(h, cudaFuncSetAttribute(area_hpass_mma_kernel<NCW, TPW, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-                    B200_CUDA(h, cudaFuncSetAttribute(area_hpass_mma_kernel<NCW, TPW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-                    B200_CUDA(h, cudaFuncSetAttribute(area_hpass_mma_kernel<NCW, TPW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+                    B200_CUDA(h, cudaFuncSetAttribute(area_hpass_mma_kernel<NCW, TPW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMmaSmem)));
+                    B200_CUDA(h, cudaFuncSetAttribute(area_hpass_mma_kernel<NCW, TPW, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMmaSmem)));
+                    B200_CUDA(h, cudaFuncSetAttribute(area_hpass_mma_kernel<NCW, TPW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMmaSmem)));
+                    B200_CUDA(h, cudaFuncSetAttribute(area_hpass_mma_kernel<NCW, TPW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMmaSmem)));
                     h->attr_done |= ATTR_K1_MMA;
                 }
                 ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(p.sy1 - p.sy0) * (p.sx1 - p.sx0) * 3.0 + ny * S * 3.0), st);

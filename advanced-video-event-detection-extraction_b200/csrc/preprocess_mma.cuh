@@ -59,6 +59,11 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -110,6 +115,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) area_hpass_mma_kernel(const
         for (int s = 0; s < P.nst; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NCW); }
         for (int s = 0; s < NBUF; ++s) { mbar_init(&afull_bar[s], NCW); mbar_init(&aempty_bar[s], NCW); }
         fence_mbar_init();
+    }
+    {   // the Pillow coefficient fragments stay in shared memory for the whole kernel
+        uint4* apd = reinterpret_cast<uint4*>(ring + P.nst * blockbytes + NBUF * 3u * planebytes);
+        for (int i = tid; i < P.npt * 3 * 2 * 32; i += blockDim.x) apd[i] = __ldg(P.ap + i);
     }
     __syncthreads();
 
@@ -164,27 +173,30 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) area_hpass_mma_kernel(const
 
     uint32_t full0 = smem_u32(full_bar), ring0 = smem_u32(ring), bbytes = blockbytes, pitchA = static_cast<uint32_t>(P.pitchA);
     uint32_t arows0 = ring0 + static_cast<uint32_t>(P.nst) * blockbytes;     // [NBUF][3 planes][8 rows][pitchA]
+    uint32_t ap0 = arows0 + NBUF * 3u * planebytes;                         // Pillow fragments, then the per-warp scratch
     uint32_t afull0 = smem_u32(afull_bar), aempty0 = smem_u32(aempty_bar);
-    asm volatile("" : "+r"(full0), "+r"(ring0), "+r"(bbytes), "+r"(arows0), "+r"(pitchA));
+    asm volatile("" : "+r"(full0), "+r"(ring0), "+r"(bbytes), "+r"(arows0), "+r"(pitchA), "+r"(ap0));
     const uint32_t lane_offA = static_cast<uint32_t>(g) * pitchA + 8u * t4;
     const int S3 = P.S * 3;
     const uint32_t dinit = P.d, dmul = P.div_mul;
     const int dsh = P.div_shift;
 
-    // Pillow pass over the parked rows of one group: buffer pp, `nvalid` rows, to `out` (row 0 of the group in mid2)
+    // Pillow pass over the parked rows of one group: buffer pp, `nvalid` rows, to `out` (row 0 of the group in mid2).
+    // A tile's 8 rows x 16 pixels go through a per-warp scratch so that they leave as 16-byte stores.
+    const uint32_t scr0 = ap0 + static_cast<uint32_t>(P.npt) * (3u * 2u * 32u * 16u) + static_cast<uint32_t>(w) * 384u;
+    const uint32_t scr_w = scr0 + (2u * t4) * 48u + static_cast<uint32_t>(g) * 3u;     // (area row 2 t4, pixel g, channel 0)
+    const uint32_t scr_r = scr0 + static_cast<uint32_t>(lane) * 16u;                   // row lane / 3, 16-byte part lane % 3
     auto pillow = [&](uint32_t pp, uint32_t wait_parity, uint8_t* out, int nvalid) {
         for (int pt = w; pt < P.npt; pt += NCW) {
+            const uint32_t kbp = static_cast<uint32_t>(__ldg(P.kbp + pt));
+            if (pt == w) mbar_wait_u32(afull0 + 8u * pp, wait_parity, 22);
+            const uint32_t abase = arows0 + pp * 3u * planebytes + lane_offA + kbp;
+            const uint32_t apl = ap0 + static_cast<uint32_t>(pt) * (3u * 2u * 32u * 16u) + static_cast<uint32_t>(lane) * 16u;
             uint4 ap[3][2];
 #pragma unroll
             for (int pl = 0; pl < 3; ++pl)
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) ap[pl][ks] = __ldg(P.ap + ((pt * 3 + pl) * 2 + ks) * 32 + lane);
-            const uint32_t kbp = static_cast<uint32_t>(__ldg(P.kbp + pt));
-            if (pt == w) mbar_wait_u32(afull0 + 8u * pp, wait_parity, 22);
-            const uint32_t abase = arows0 + pp * 3u * planebytes + lane_offA + kbp;
-            uint8_t* o0 = out + (2 * t4) * S3 + (pt * 16 + g) * 3;       // (area row 2 t4, output column pt * 16 + g)
-            const bool okx0 = pt * 16 + g < P.S, okx1 = pt * 16 + g + 8 < P.S;
-            const bool oky0 = 2 * t4 < nvalid, oky1 = 2 * t4 + 1 < nvalid;
+                for (int ks = 0; ks < 2; ++ks) ap[pl][ks] = lds128(apl + static_cast<uint32_t>(pl * 2 + ks) * 512u);
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 const uint2 b0 = lds64(abase + ch * planebytes);
@@ -200,11 +212,16 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) area_hpass_mma_kernel(const
                 for (int e = 0; e < 4; ++e) {
                     const int acc = c0[e] + (c1[e] << 8) + (c2[e] << 16);      // wraps like the 32-bit sum it stands for
                     const int v = min(max(acc >> 22, 0), 255);
-                    if (((e >> 1) ? okx1 : okx0) && ((e & 1) ? oky1 : oky0)) o0[(e & 1) * S3 + (e >> 1) * 24 + ch] = static_cast<uint8_t>(v);
+                    sts8(scr_w + (e & 1) * 48u + (e >> 1) * 24u + ch, static_cast<uint32_t>(v));
                 }
             }
+            __syncwarp();
+            if (lane < 24 && lane / 3 < nvalid) {
+                const uint4 v = lds128(scr_r);
+                *reinterpret_cast<uint4*>(out + (lane / 3) * S3 + pt * 48 + (lane % 3) * 16) = v;
+            }
+            __syncwarp();
         }
-        __syncwarp();
         if (lane == 0) mbar_arrive_u32(aempty0 + 8u * pp);
     };
 
@@ -222,6 +239,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) area_hpass_mma_kernel(const
             const uint2 b2 = __ldg(P.b2 + gi * 32 + lane);
             uint32_t pA[TPW], pB[TPW];
             int acc[TPW][4];
+#pragma unroll
+            for (int k = 0; k < TPW; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = static_cast<int>(dinit);
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 mbar_wait_u32(full0 + 8u * s, ph, 23);
@@ -252,14 +271,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) area_hpass_mma_kernel(const
                     // fragment of a K = 16 step of the vertical product; the two planes are folded after each step
                     const uint32_t eA = (b & 1) ? pA[k] : wA, oA = (b & 1) ? wA : 0u;
                     const uint32_t eB = (b & 1) ? pB[k] : wB, oB = (b & 1) ? wB : 0u;
-                    int cl[4], ch[4] = {0, 0, 0, 0};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) cl[e] = b < 2 ? static_cast<int>(dinit) : acc[k][e];
+                    int ch[4] = {0, 0, 0, 0};
                     const uint32_t bw = (b >> 1) ? b2.y : b2.x;
-                    imma16816(cl, __byte_perm(eA, oA, 0x6420), __byte_perm(eB, oB, 0x6420), bw);
+                    imma16816(acc[k], __byte_perm(eA, oA, 0x6420), __byte_perm(eB, oB, 0x6420), bw);
                     imma16816(ch, __byte_perm(eA, oA, 0x7531), __byte_perm(eB, oB, 0x7531), bw);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[k][e] = cl[e] + (ch[e] << 8);
+                    for (int e = 0; e < 4; ++e) acc[k][e] += ch[e] << 8;
                 }
             }
             // ---- stage 2 epilogue: acc = 2 N + D for the 8 area rows of the group -> parked planar in buffer `par`
