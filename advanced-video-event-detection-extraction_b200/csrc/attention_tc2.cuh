@@ -1,0 +1,282 @@
+// Attention for T = 257 (ViT-L/14, H/14, g/14 at 224 px: 256 patches + class token), unmasked, head dim 64, on the
+// 5th-generation tensor cores with the probabilities handed over IN TENSOR MEMORY.  Included by vit_kernels.cu only.
+//
+// One persistent CTA per SM walks (sequence, head) items; Q, K and V of an item (100 KB) arrive by TMA into one of two
+// shared-memory buffers, so the loads of the next item run under the arithmetic of the current one.  An item is two
+// "units" = 128-row query tiles (rows 0..127 and 128..255); unit u lives in TMEM slot u & 1 (256 columns each) and is
+// served by softmax warpgroup u & 1 (4 warps, one query row per thread).  The 257th row is scored on the CUDA cores by
+// four more warps at the same time (attention_odd_row, as in attention_tc_kernel).
+//
+//   S   = Q_tile[128 x 64] . K[256 keys x 64]^T      4 x tcgen05.mma M=128 N=256 K=16, fp32 into slot columns [0, 256)
+//   s'  = Q_tile . k_256                             the 257th key cannot join the N = 256 tile (and TMEM has no room for
+//                                                    a second one): two mma.sync m16n8k16 tiles per warp, one shuffle set
+//   P   = exp2(scale (S - max))                      FULL-ROW softmax (all of a row's scores are resident, so there is no
+//                                                    running maximum and no rescaling of O): pass 1 = max over 8 tcgen05.ld
+//                                                    of 32 columns, pass 2 = exponentials; P (bf16, two keys per column)
+//                                                    is written back over S with tcgen05.st, columns [0, 128) + 8 columns
+//                                                    for key 256 and its 15 zero partners -- it never touches shared memory
+//   O   = P[128 x 272] . V[272 keys x 64]            17 x tcgen05.mma with A FROM TENSOR MEMORY (pinned by
+//                                                    tools/probes/umma_tmem_a_probe.cu) and V as an MN-major B operand,
+//                                                    fp32 into slot columns [192, 256) (S columns already consumed)
+//   out = O / sum                                    tcgen05.ld, normalise, bf16 rows to global
+//
+// A single thread issues all MMAs in the order S(u), PV(u - 1): while one warpgroup exponentiates unit u - 1 the tensor
+// core already produces S(u) for the other one, and the two warpgroups drift half a period apart by themselves (the
+// exponentials, 16 per clock and SM, are the per-SM limit: 2 x 128 x 257 per item = 4.1 k clocks; the HBM share of an
+// SM allows 5.7 k clocks per item, so the kernel is memory bound when the pipeline holds).
+#pragma once
+
+constexpr int A2_T = 257, A2_SM_WARPS = 8, A2_ODD_WARPS = 4;
+constexpr int A2_TMA_WARP = A2_SM_WARPS + A2_ODD_WARPS, A2_MMA_WARP = A2_TMA_WARP + 1;
+constexpr int A2_THREADS = (A2_MMA_WARP + 1) * 32;                 // 448
+constexpr int A2_Q_BYTES = 2 * 128 * 128;                          // two 128-row tiles of 128-byte rows
+constexpr int A2_KV_ROWS = 272;                                    // 257 keys, padded to the 16-key MMA step
+constexpr int A2_KV_BYTES = A2_KV_ROWS * 128;
+constexpr int A2_BUF_BYTES = A2_Q_BYTES + 2 * A2_KV_BYTES;         // 102400
+constexpr int A2_SCRATCH_BYTES = 4096;                             // odd-row scratch (648 floats)
+constexpr int A2_SMEM_BYTES = 1024 + 2 * A2_BUF_BYTES + A2_SCRATCH_BYTES + 256;
+
+__device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]: A is read from tensor memory (128 lanes x K/2 columns, two bf16 per column)
+__device__ __forceinline__ void umma_bf16_tmem_a(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __launch_bounds__(A2_THREADS, 1)
+attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constant__ CUtensorMap tmap_kv64,
+                     const __grid_constant__ CUtensorMap tmap_kv16, const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                     int heads, int n_items) {
+    extern __shared__ uint8_t a2_raw[];
+    uint8_t* base = a2_raw + ((1024u - (smem_u32(a2_raw) & 1023u)) & 1023u);
+    float* scratch = reinterpret_cast<float*>(base + 2 * A2_BUF_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * A2_BUF_BYTES + A2_SCRATCH_BYTES);
+    uint64_t* full = bars;              // [2] Q, K, V of an item landed in buffer b
+    uint64_t* empty = bars + 2;         // [2] buffer b no longer read (tensor core + softmax warps + odd-row warps)
+    uint64_t* s_full = bars + 4;        // [2] S of the unit in slot s is in TMEM
+    uint64_t* p_full = bars + 6;        // [2] P of the unit in slot s is in TMEM
+    uint64_t* o_full = bars + 8;        // [2] O of the unit in slot s is in TMEM (and P consumed)
+    uint64_t* slot_free = bars + 10;    // [2] O read out: the slot may take the next S
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = A2_T, D = heads * ATT_D;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + A2_SM_WARPS + A2_ODD_WARPS);
+            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&slot_free[i], 4);
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmap_q128); tma_prefetch_desc(&tmap_kv64); tma_prefetch_desc(&tmap_kv16);
+    }
+    if (warp == A2_MMA_WARP) tmem_alloc<1>(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == A2_TMA_WARP) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int j = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+                const int b = j & 1;
+                mbar_wait(&empty[b], ((j >> 1) & 1) ^ 1, 61);
+                const int seq = item / heads, head = item - seq * heads;
+                const int row0 = seq * T;
+                uint8_t* sQ = base + b * A2_BUF_BYTES;
+                uint8_t* sK = sQ + A2_Q_BYTES;
+                uint8_t* sV = sK + A2_KV_BYTES;
+                mbar_arrive_expect_tx(&full[b], A2_BUF_BYTES);
+                tma_load_2d(sQ, &tmap_q128, &full[b], head * ATT_D, row0);
+                tma_load_2d(sQ + 128 * 128, &tmap_q128, &full[b], head * ATT_D, row0 + 128);
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb) {
+                    tma_load_2d(sK + kb * 64 * 128, &tmap_kv64, &full[b], D + head * ATT_D, row0 + kb * 64);
+                    tma_load_2d(sV + kb * 64 * 128, &tmap_kv64, &full[b], 2 * D + head * ATT_D, row0 + kb * 64);
+                }
+                // rows 256 .. 271: key 256 and 15 rows of the next sequence (or zero fill), which P multiplies by zero
+                tma_load_2d(sK + 256 * 128, &tmap_kv16, &full[b], D + head * ATT_D, row0 + 256);
+                tma_load_2d(sV + 256 * 128, &tmap_kv16, &full[b], 2 * D + head * ATT_D, row0 + 256);
+            }
+        }
+    } else if (warp == A2_MMA_WARP) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc_bf16(128, 256);
+            const uint32_t idesc_pv = make_idesc_bf16(128, ATT_D) | (1u << 16);     // B (= V) MN-major
+            auto issue_pv = [&](int u) {        // unit u = 2 j + tile
+                const int slot = u & 1, j = u >> 1, b = j & 1;
+                mbar_wait(&p_full[slot], j & 1, 62);
+                tc_fence_after();
+                const uint32_t tbase = tmem + slot * 256;
+                const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(base + b * A2_BUF_BYTES + A2_Q_BYTES + A2_KV_BYTES));
+#pragma unroll
+                for (int k = 0; k < A2_KV_ROWS / 16; ++k)
+                    umma_bf16_tmem_a(tbase + 192, tbase + 8 * k, bdesc + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv, k != 0);
+                umma_commit(&o_full[slot]);
+                if (slot == 1) umma_commit(&empty[b]);     // every MMA that reads buffer b has been issued
+            };
+            int j = 0, u = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+                const int b = j & 1;
+                mbar_wait(&full[b], (j >> 1) & 1, 63);
+                uint8_t* sQ = base + b * A2_BUF_BYTES;
+                const uint64_t kdesc = make_sw128_kmajor_desc(smem_u32(sQ + A2_Q_BYTES));
+                for (int tile = 0; tile < 2; ++tile, ++u) {
+                    mbar_wait(&slot_free[tile], (j & 1) ^ 1, 64);
+                    tc_fence_after();
+                    const uint64_t qdesc = make_sw128_kmajor_desc(smem_u32(sQ + tile * 128 * 128));
+#pragma unroll
+                    for (int k = 0; k < ATT_D / 16; ++k)
+                        umma_bf16<1>(tmem + tile * 256, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+                    umma_commit(&s_full[tile]);
+                    if (u >= 1) issue_pv(u - 1);
+                }
+            }
+            if (u >= 1) issue_pv(u - 1);
+        }
+    } else if (warp >= A2_SM_WARPS) {
+        // ===================== odd-row warps: query row 256 on the CUDA cores =====================
+        const int ow = warp - A2_SM_WARPS;
+        int j = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+            const int b = j & 1;
+            mbar_wait(&full[b], (j >> 1) & 1, 65);
+            const int seq = item / heads, head = item - seq * heads;
+            const uint8_t* sK = base + b * A2_BUF_BYTES + A2_Q_BYTES;
+            attention_odd_row<A2_ODD_WARPS, 320>(sK, sK + A2_KV_BYTES, scratch,
+                                                 qkv + (static_cast<int64_t>(seq) * T + T - 1) * 3 * D + head * ATT_D,
+                                                 out + (static_cast<int64_t>(seq) * T + T - 1) * D + head * ATT_D, T, ow, lane, 2);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[b]);
+        }
+    } else {
+        // ===================== softmax warps: warpgroup = query tile, one row per thread =====================
+        const int tile = warp >> 2, wq = warp & 3;
+        const int row_in_tile = wq * 32 + lane;
+        const uint32_t tbase = tmem + (static_cast<uint32_t>(wq * 32) << 16) + tile * 256;
+        const float scale_log2 = 0.125f * 1.4426950408889634f;
+        const int g = lane >> 2, t4 = lane & 3;
+        int j = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+            const int b = j & 1;
+            const int seq = item / heads, head = item - seq * heads;
+            // ---- s' = q_row . k_256 for the 32 rows of this warp: two m16n8k16 tiles (only column 0 of B is non-zero)
+            mbar_wait(&full[b], (j >> 1) & 1, 66);
+            float s_last;
+            {
+                const uint32_t qa = smem_u32(base + b * A2_BUF_BYTES + tile * 128 * 128);
+                const uint32_t ka = smem_u32(base + b * A2_BUF_BYTES + A2_Q_BYTES + 256 * 128);    // row 256: chunks unswizzled
+                float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t b0 = 0u, b1 = 0u;
+                    if (g == 0) {
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(b0) : "r"(ka + 32u * ks + 4u * t4));
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(b1) : "r"(ka + 32u * ks + 16u + 4u * t4));
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        uint32_t a[4];
+                        const int r = wq * 32 + mt * 16 + (lane & 15);
+                        ldmatrix_x4(qa + sw_off(r, ks * 2 + (lane >> 4)), a[0], a[1], a[2], a[3]);
+                        mma_bf16_16816(c[mt], a, b0, b1);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[b]);       // this warp's shared-memory reads of the item are done
+                // row L of the warp = m-tile L >> 4, fragment row L & 15: column 0 sits in lane 4 (L & 7), c[.][0] / c[.][2]
+                const int src = 4 * (lane & 7);
+                const float v00 = __shfl_sync(0xffffffffu, c[0][0], src), v02 = __shfl_sync(0xffffffffu, c[0][2], src);
+                const float v10 = __shfl_sync(0xffffffffu, c[1][0], src), v12 = __shfl_sync(0xffffffffu, c[1][2], src);
+                s_last = (lane & 16) ? ((lane & 8) ? v12 : v10) : ((lane & 8) ? v02 : v00);
+            }
+            // ---- pass 1: row maximum over the 256 scores in TMEM (+ s')
+            mbar_wait(&s_full[tile], j & 1, 67);
+            tc_fence_after();
+            float mx = s_last;
+#pragma unroll 1
+            for (int cchunk = 0; cchunk < 8; cchunk += 2) {
+                uint32_t sa[32], sb[32];
+                tmem_ld_32x32(tbase + cchunk * 32, sa);
+                tmem_ld_32x32(tbase + cchunk * 32 + 32, sb);
+                tmem_ld_wait_regs(sa);
+                tmem_ld_wait_regs(sb);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(sa[i]), __uint_as_float(sb[i])));
+            }
+            // ---- pass 2: exponentials, row sum, P (bf16 pairs) back over S
+            const float nm = -mx * scale_log2;
+            float rs = 0.f;
+#pragma unroll 1
+            for (int cchunk = 0; cchunk < 8; ++cchunk) {
+                uint32_t sa[32];
+                tmem_ld_32x32(tbase + cchunk * 32, sa);
+                tmem_ld_wait_regs(sa);
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(sa[2 * i]), scale_log2, nm));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(sa[2 * i + 1]), scale_log2, nm));
+                    rs += p0 + p1;
+                    pk[i] = pack_bf16x2(p0, p1);
+                }
+                tmem_st_32x32_x16(tbase + cchunk * 16, pk);       // columns [16 c, 16 c + 16): S chunks <= c, already read
+            }
+            {
+                const float pl = ex2_approx(fmaf(s_last, scale_log2, nm));
+                rs += pl;
+                uint32_t pk[8] = {pack_bf16x2(pl, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                tmem_st_32x32_x8(tbase + 128, pk);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[tile]);
+            // ---- O of the unit: normalise and store this thread's row
+            mbar_wait(&o_full[tile], j & 1, 68);
+            tc_fence_after();
+            const float inv = 1.f / rs;
+            bf16* orow = out + (static_cast<int64_t>(seq) * T + tile * 128 + row_in_tile) * D + head * ATT_D;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t o[32];
+                tmem_ld_32x32(tbase + 192 + hh * 32, o);
+                tmem_ld_wait_regs(o);
+                if (hh == 1) {      // everything this warp needs from the slot is in registers
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&slot_free[tile]);
+                }
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    uint4 wv;
+                    wv.x = pack_bf16x2(__uint_as_float(o[cc * 8 + 0]) * inv, __uint_as_float(o[cc * 8 + 1]) * inv);
+                    wv.y = pack_bf16x2(__uint_as_float(o[cc * 8 + 2]) * inv, __uint_as_float(o[cc * 8 + 3]) * inv);
+                    wv.z = pack_bf16x2(__uint_as_float(o[cc * 8 + 4]) * inv, __uint_as_float(o[cc * 8 + 5]) * inv);
+                    wv.w = pack_bf16x2(__uint_as_float(o[cc * 8 + 6]) * inv, __uint_as_float(o[cc * 8 + 7]) * inv);
+                    *reinterpret_cast<uint4*>(orow + hh * 32 + cc * 8) = wv;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == A2_MMA_WARP) { tc_fence_after(); tmem_dealloc<1>(tmem, 512); }
+}

@@ -1125,6 +1125,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
     if (warp == 5) { tc_fence_after(); tmem_dealloc<1>(tmem, 256); }
 }
 
+#include "attention_tc2.cuh"
+
 int make_tmap_bf16_2d(b200clip_handle* h, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz);
 
@@ -1154,6 +1156,26 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
         ProfScope ps(h, PROF_ATTN, static_cast<double>(n_seq) * t * heads * ATT_D * 2.0 * 4.0, st);
         attention_persistent_kernel<<<static_cast<unsigned>(grid), ATT_THREADS, ATP_SMEM_BYTES, st>>>(
             tq, out, t, heads, static_cast<int>(n_items));
+        h->launches++;
+        B200_CUDA(h, cudaGetLastError());
+        return 0;
+    }
+    // T = 257 (ViT-L/14 and larger at 224 px): persistent tcgen05 kernel with the probabilities handed over in TMEM
+    if (!causal && t == A2_T && b200_knobs().attn_tc2 && n_items >= 1 && n_items < (int64_t(1) << 31) &&
+        static_cast<int64_t>(n_seq) * t < (int64_t(1) << 31) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) {
+        CUtensorMap tq, t64, t16;
+        const uint64_t rows = static_cast<uint64_t>(n_seq) * t, cols = 3ull * heads * ATT_D;
+        int rc;
+        if ((rc = make_tmap_bf16_2d(h, &tq, qkv, rows, cols, cols, 128, ATT_D, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tmap_bf16_2d(h, &t64, qkv, rows, cols, cols, 64, ATT_D, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tmap_bf16_2d(h, &t16, qkv, rows, cols, cols, 16, ATT_D, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if (!(h->attr_done & ATTR_ATTN_TC2)) {
+            B200_CUDA(h, cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES));
+            h->attr_done |= ATTR_ATTN_TC2;
+        }
+        const int grid = n_items < h->num_sms ? static_cast<int>(n_items) : h->num_sms;
+        ProfScope ps(h, PROF_ATTN, static_cast<double>(n_seq) * t * heads * ATT_D * 2.0 * 4.0, st);
+        attention_tc2_kernel<<<grid, A2_THREADS, A2_SMEM_BYTES, st>>>(tq, t64, t16, qkv, out, heads, static_cast<int>(n_items));
         h->launches++;
         B200_CUDA(h, cudaGetLastError());
         return 0;
