@@ -58,10 +58,19 @@ __device__ __forceinline__ void umma_bf16_tmem_a(uint32_t tmem_d, uint32_t tmem_
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+#ifdef B200CLIP_PROBES
+// development probe: clock64 stamps of CTA 0 (softmax warps 0 and 4, MMA issuer) for items 8 .. 15, read back with
+// b200clip_debug_a2_probe (tools/attn_tc2_check.py prints the timeline)
+__device__ long long g_a2_probe[3 * 8 * 8];
+#define A2_STAMP(who, j, k) do { if (blockIdx.x == 0 && (j) >= 8 && (j) < 16) g_a2_probe[((who) * 8 + ((j) - 8)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define A2_STAMP(who, j, k) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_constant__ CUtensorMap tmap_kv64,
-                     const __grid_constant__ CUtensorMap tmap_kv16, const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                     int heads, int n_items) {
+                     const __grid_constant__ CUtensorMap tmap_kv16, const __grid_constant__ CUtensorMap tmap_o,
+                     const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, int n_items) {
     extern __shared__ uint8_t a2_raw[];
     uint8_t* base = a2_raw + ((1024u - (smem_u32(a2_raw) & 1023u)) & 1023u);
     float* scratch = reinterpret_cast<float*>(base + 2 * A2_BUF_BYTES);
@@ -78,11 +87,11 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + A2_SM_WARPS + A2_ODD_WARPS);
+            mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + 2 + A2_ODD_WARPS);
             mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&slot_free[i], 4);
         }
         fence_mbar_init();
-        tma_prefetch_desc(&tmap_q128); tma_prefetch_desc(&tmap_kv64); tma_prefetch_desc(&tmap_kv16);
+        tma_prefetch_desc(&tmap_q128); tma_prefetch_desc(&tmap_kv64); tma_prefetch_desc(&tmap_kv16); tma_prefetch_desc(&tmap_o);
     }
     if (warp == A2_MMA_WARP) tmem_alloc<1>(tmem_slot, 512);
     tc_fence_before();
@@ -96,7 +105,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
             int j = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
                 const int b = j & 1;
-                mbar_wait(&empty[b], ((j >> 1) & 1) ^ 1, 61);
+                mbar_wait_relaxed(&empty[b], ((j >> 1) & 1) ^ 1, 61);
                 const int seq = item / heads, head = item - seq * heads;
                 const int row0 = seq * T;
                 uint8_t* sQ = base + b * A2_BUF_BYTES;
@@ -123,6 +132,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
             auto issue_pv = [&](int u) {        // unit u = 2 j + tile
                 const int slot = u & 1, j = u >> 1, b = j & 1;
                 mbar_wait(&p_full[slot], j & 1, 62);
+                A2_STAMP(2, j, 4 + slot * 2);          // P ready, PV issue
                 tc_fence_after();
                 const uint32_t tbase = tmem + slot * 256;
                 const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(base + b * A2_BUF_BYTES + A2_Q_BYTES + A2_KV_BYTES));
@@ -140,6 +150,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
                 const uint64_t kdesc = make_sw128_kmajor_desc(smem_u32(sQ + A2_Q_BYTES));
                 for (int tile = 0; tile < 2; ++tile, ++u) {
                     mbar_wait(&slot_free[tile], (j & 1) ^ 1, 64);
+                    A2_STAMP(2, j, tile * 2);              // slot free, S issue
                     tc_fence_after();
                     const uint64_t qdesc = make_sw128_kmajor_desc(smem_u32(sQ + tile * 128 * 128));
 #pragma unroll
@@ -157,7 +168,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
         int j = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
             const int b = j & 1;
-            mbar_wait(&full[b], (j >> 1) & 1, 65);
+            mbar_wait_relaxed(&full[b], (j >> 1) & 1, 65);
             const int seq = item / heads, head = item - seq * heads;
             const uint8_t* sK = base + b * A2_BUF_BYTES + A2_Q_BYTES;
             attention_odd_row<A2_ODD_WARPS, 320>(sK, sK + A2_KV_BYTES, scratch,
@@ -178,7 +189,10 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
             const int b = j & 1;
             const int seq = item / heads, head = item - seq * heads;
             // ---- s' = q_row . k_256 for the 32 rows of this warp: two m16n8k16 tiles (only column 0 of B is non-zero)
+            const bool stamp = lane == 0 && wq == 0;
+            if (stamp) A2_STAMP(tile, j, 0);
             mbar_wait(&full[b], (j >> 1) & 1, 66);
+            if (stamp) A2_STAMP(tile, j, 1);
             float s_last;
             {
                 const uint32_t qa = smem_u32(base + b * A2_BUF_BYTES + tile * 128 * 128);
@@ -199,8 +213,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
                         mma_bf16_16816(c[mt], a, b0, b1);
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[b]);       // this warp's shared-memory reads of the item are done
                 // row L of the warp = m-tile L >> 4, fragment row L & 15: column 0 sits in lane 4 (L & 7), c[.][0] / c[.][2]
                 const int src = 4 * (lane & 7);
                 const float v00 = __shfl_sync(0xffffffffu, c[0][0], src), v02 = __shfl_sync(0xffffffffu, c[0][2], src);
@@ -208,40 +220,59 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
                 s_last = (lane & 16) ? ((lane & 8) ? v12 : v10) : ((lane & 8) ? v02 : v00);
             }
             // ---- pass 1: row maximum over the 256 scores in TMEM (+ s')
+            if (stamp) A2_STAMP(tile, j, 2);
             mbar_wait(&s_full[tile], j & 1, 67);
+            if (stamp) A2_STAMP(tile, j, 3);
             tc_fence_after();
-            float mx = s_last;
-#pragma unroll 1
-            for (int cchunk = 0; cchunk < 8; cchunk += 2) {
-                uint32_t sa[32], sb[32];
-                tmem_ld_32x32(tbase + cchunk * 32, sa);
-                tmem_ld_32x32(tbase + cchunk * 32 + 32, sb);
-                tmem_ld_wait_regs(sa);
-                tmem_ld_wait_regs(sb);
+            // (the TMEM loads are software pipelined: chunk c + 1 is in flight while chunk c is worked on)
+            float mx4[4] = {s_last, s_last, s_last, s_last};     // four independent chains: FMNMX3 has ~5 clocks of latency
+            {
+                uint32_t sa[2][32];
+                tmem_ld_32x32(tbase, sa[0]);
+                tmem_ld_wait_regs(sa[0]);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(sa[i]), __uint_as_float(sb[i])));
-            }
-            // ---- pass 2: exponentials, row sum, P (bf16 pairs) back over S
-            const float nm = -mx * scale_log2;
-            float rs = 0.f;
-#pragma unroll 1
-            for (int cchunk = 0; cchunk < 8; ++cchunk) {
-                uint32_t sa[32];
-                tmem_ld_32x32(tbase + cchunk * 32, sa);
-                tmem_ld_wait_regs(sa);
-                uint32_t pk[16];
+                for (int cchunk = 0; cchunk < 8; ++cchunk) {
+                    if (cchunk + 1 < 8) tmem_ld_32x32(tbase + (cchunk + 1) * 32, sa[(cchunk + 1) & 1]);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(sa[2 * i]), scale_log2, nm));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(sa[2 * i + 1]), scale_log2, nm));
-                    rs += p0 + p1;
-                    pk[i] = pack_bf16x2(p0, p1);
+                    for (int i = 0; i < 32; i += 2)
+                        mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sa[cchunk & 1][i]), __uint_as_float(sa[cchunk & 1][i + 1])));
+                    if (cchunk + 1 < 8) tmem_ld_wait_regs(sa[(cchunk + 1) & 1]);
                 }
-                tmem_st_32x32_x16(tbase + cchunk * 16, pk);       // columns [16 c, 16 c + 16): S chunks <= c, already read
+            }
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            // ---- pass 2: exponentials, row sum, P (bf16 pairs) back over S
+            if (stamp) A2_STAMP(tile, j, 4);
+            const float nm = -mx * scale_log2;
+            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+            {
+                uint32_t sa[2][32];
+                tmem_ld_32x32(tbase, sa[0]);
+                tmem_ld_wait_regs(sa[0]);
+#pragma unroll
+                for (int cchunk = 0; cchunk < 8; ++cchunk) {
+                    if (cchunk + 1 < 8) tmem_ld_32x32(tbase + (cchunk + 1) * 32, sa[(cchunk + 1) & 1]);
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+#ifdef A2_NO_EX2
+                        const float p0 = fmaf(__uint_as_float(sa[cchunk & 1][2 * i]), scale_log2, nm);
+                        const float p1 = fmaf(__uint_as_float(sa[cchunk & 1][2 * i + 1]), scale_log2, nm);
+#else
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(sa[cchunk & 1][2 * i]), scale_log2, nm));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(sa[cchunk & 1][2 * i + 1]), scale_log2, nm));
+#endif
+                        rs4[i & 3] += p0 + p1;
+                        pk[i] = pack_bf16x2(p0, p1);
+                    }
+                    // columns [16 c, 16 c + 16) hold scores of chunks <= c: chunk c is in registers and the load of chunk
+                    // c + 1 (columns >= 32 (c + 1) > 16 c + 16) does not overlap them
+                    if (cchunk + 1 < 8) tmem_ld_wait_regs(sa[(cchunk + 1) & 1]);
+                    tmem_st_32x32_x16(tbase + cchunk * 16, pk);
+                }
             }
             {
                 const float pl = ex2_approx(fmaf(s_last, scale_log2, nm));
-                rs += pl;
+                rs4[0] += pl;
                 uint32_t pk[8] = {pack_bf16x2(pl, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
                 tmem_st_32x32_x8(tbase + 128, pk);
             }
@@ -249,11 +280,15 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[tile]);
+            if (stamp) A2_STAMP(tile, j, 5);
             // ---- O of the unit: normalise and store this thread's row
             mbar_wait(&o_full[tile], j & 1, 68);
+            if (stamp) A2_STAMP(tile, j, 6);
             tc_fence_after();
-            const float inv = 1.f / rs;
-            bf16* orow = out + (static_cast<int64_t>(seq) * T + tile * 128 + row_in_tile) * D + head * ATT_D;
+            const float inv = 1.f / ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+            // the rows leave through the unit's Q tile (the tensor core is done with it: S is complete, and so are the
+            // ldmatrix reads of every warp once the warpgroup meets below) as ONE TMA store of 128 x 64 bf16
+            uint8_t* stage = base + b * A2_BUF_BYTES + tile * 128 * 128;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 uint32_t o[32];
@@ -264,6 +299,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&slot_free[tile]);
                 }
+                if (hh == 0) named_bar_sync(3 + tile, 128);      // every warp of the group has finished reading the Q tile
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     uint4 wv;
@@ -271,10 +307,20 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
                     wv.y = pack_bf16x2(__uint_as_float(o[cc * 8 + 2]) * inv, __uint_as_float(o[cc * 8 + 3]) * inv);
                     wv.z = pack_bf16x2(__uint_as_float(o[cc * 8 + 4]) * inv, __uint_as_float(o[cc * 8 + 5]) * inv);
                     wv.w = pack_bf16x2(__uint_as_float(o[cc * 8 + 6]) * inv, __uint_as_float(o[cc * 8 + 7]) * inv);
-                    *reinterpret_cast<uint4*>(orow + hh * 32 + cc * 8) = wv;
+                    *reinterpret_cast<uint4*>(stage + sw_off(row_in_tile, hh * 4 + cc)) = wv;
                 }
             }
+            fence_proxy_async_smem();
+            named_bar_sync(3 + tile, 128);
+            if (wq == 0 && lane == 0) {
+                tma_store_2d(&tmap_o, stage, head * ATT_D, seq * T + tile * 128);
+                tma_store_commit();
+                tma_store_wait_read<0>();
+                mbar_arrive(&empty[b]);          // the warpgroup is done with buffer b
+            }
+            if (stamp) A2_STAMP(tile, j, 7);
         }
+        if (wq == 0 && lane == 0) tma_store_wait<0>();
     }
     tc_fence_before();
     __syncthreads();

@@ -1130,6 +1130,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
 int make_tmap_bf16_2d(b200clip_handle* h, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz);
 
+#ifdef B200CLIP_PROBES
+extern "C" int b200clip_debug_a2_probe(long long* out, int n) {
+    return cudaMemcpyFromSymbol(out, g_a2_probe, sizeof(long long) * (n < 192 ? n : 192)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, int t, int heads, int causal,
                      cudaStream_t st) {
     if (n_seq <= 0) return 0;
@@ -1169,13 +1175,16 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
         if ((rc = make_tmap_bf16_2d(h, &tq, qkv, rows, cols, cols, 128, ATT_D, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
         if ((rc = make_tmap_bf16_2d(h, &t64, qkv, rows, cols, cols, 64, ATT_D, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
         if ((rc = make_tmap_bf16_2d(h, &t16, qkv, rows, cols, cols, 16, ATT_D, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        CUtensorMap to;
+        if ((rc = make_tmap_bf16_2d(h, &to, out, rows, static_cast<uint64_t>(heads) * ATT_D, static_cast<uint64_t>(heads) * ATT_D, 128, ATT_D,
+                                    CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
         if (!(h->attr_done & ATTR_ATTN_TC2)) {
             B200_CUDA(h, cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES));
             h->attr_done |= ATTR_ATTN_TC2;
         }
         const int grid = n_items < h->num_sms ? static_cast<int>(n_items) : h->num_sms;
         ProfScope ps(h, PROF_ATTN, static_cast<double>(n_seq) * t * heads * ATT_D * 2.0 * 4.0, st);
-        attention_tc2_kernel<<<grid, A2_THREADS, A2_SMEM_BYTES, st>>>(tq, t64, t16, qkv, out, heads, static_cast<int>(n_items));
+        attention_tc2_kernel<<<grid, A2_THREADS, A2_SMEM_BYTES, st>>>(tq, t64, t16, to, qkv, out, heads, static_cast<int>(n_items));
         h->launches++;
         B200_CUDA(h, cudaGetLastError());
         return 0;

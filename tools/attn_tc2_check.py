@@ -38,4 +38,15 @@ for _ in range(48):
 e1.record()
 torch.cuda.synchronize()
 print("ms per layer call (512 seq x 16 heads, T = 257):", round(e0.elapsed_time(e1) / 48, 4), {k: v for k, v in os.environ.items() if k.startswith("B200CLIP_ATTN")})
+lib = capi.load_library()
+if hasattr(lib, "b200clip_debug_a2_probe"):       # PROBES build: timeline of CTA 0, items 8 .. 15 (clock64, relative)
+    buf = (ctypes.c_longlong * 192)()
+    lib.b200clip_debug_a2_probe(buf, 192)
+    v = [buf[i] for i in range(192)]
+    t0 = min(x for x in v if x > 0)
+    names = ["top", "full", "s'", "s_full", "pass1", "P", "o_full", "stored"]
+    for j in range(8):
+        for who, nm in ((0, "WG0"), (1, "WG1")):
+            print(nm, "item", 8 + j, " ".join(f"{names[k]}={v[(who * 8 + j) * 8 + k] - t0}" for k in range(8)))
+        print("MMA item", 8 + j, " ".join(f"{n}={v[(2 * 8 + j) * 8 + k] - t0}" for k, n in ((0, "S0"), (2, "S1"), (4, "PV0"), (6, "PV1"))))
 sys.exit(1 if bad else 0)
