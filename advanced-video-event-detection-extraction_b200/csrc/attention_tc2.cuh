@@ -26,14 +26,14 @@
 // SM allows 5.7 k clocks per item, so the kernel is memory bound when the pipeline holds).
 #pragma once
 
-constexpr int A2_T = 257, A2_SM_WARPS = 8, A2_ODD_WARPS = 4;
-constexpr int A2_TMA_WARP = A2_SM_WARPS + A2_ODD_WARPS, A2_MMA_WARP = A2_TMA_WARP + 1;
-constexpr int A2_THREADS = (A2_MMA_WARP + 1) * 32;                 // 448
+constexpr int A2_T = 257, A2_SM_WARPS = 16, A2_ODD_WARPS = 4;
+constexpr int A2_TMA_WARP = A2_SM_WARPS + A2_ODD_WARPS, A2_MMA_WARP = A2_TMA_WARP + 1, A2_ST_WARP = A2_MMA_WARP + 1;
+constexpr int A2_THREADS = (A2_ST_WARP + 1) * 32;                  // 736
 constexpr int A2_Q_BYTES = 2 * 128 * 128;                          // two 128-row tiles of 128-byte rows
 constexpr int A2_KV_ROWS = 272;                                    // 257 keys, padded to the 16-key MMA step
 constexpr int A2_KV_BYTES = A2_KV_ROWS * 128;
 constexpr int A2_BUF_BYTES = A2_Q_BYTES + 2 * A2_KV_BYTES;         // 102400
-constexpr int A2_SCRATCH_BYTES = 4096;                             // odd-row scratch (648 floats)
+constexpr int A2_SCRATCH_BYTES = 8192;                             // odd-row scratch (648 floats) + row max / sum exchange
 constexpr int A2_SMEM_BYTES = 1024 + 2 * A2_BUF_BYTES + A2_SCRATCH_BYTES + 256;
 
 __device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -47,6 +47,19 @@ __device__ __forceinline__ void tmem_st_32x32_x8(uint32_t taddr, const uint32_t 
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_regs16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 : : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem desc]: A is read from tensor memory (128 lanes x K/2 columns, two bf16 per column)
@@ -81,14 +94,15 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
     uint64_t* p_full = bars + 6;        // [2] P of the unit in slot s is in TMEM
     uint64_t* o_full = bars + 8;        // [2] O of the unit in slot s is in TMEM (and P consumed)
     uint64_t* slot_free = bars + 10;    // [2] O read out: the slot may take the next S
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* stage_full = bars + 12;   // [2] the unit's output rows are staged in its Q tile
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = A2_T, D = heads * ATT_D;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + 2 + A2_ODD_WARPS);
-            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&slot_free[i], 4);
+            mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + 1 + A2_ODD_WARPS); mbar_init(&stage_full[i], 8);
+            mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); mbar_init(&o_full[i], 1); mbar_init(&slot_free[i], 8);
         }
         fence_mbar_init();
         tma_prefetch_desc(&tmap_q128); tma_prefetch_desc(&tmap_kv64); tma_prefetch_desc(&tmap_kv16); tma_prefetch_desc(&tmap_o);
@@ -129,38 +143,72 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
         if (lane == 0) {
             const uint32_t idesc_s = make_idesc_bf16(128, 256);
             const uint32_t idesc_pv = make_idesc_bf16(128, ATT_D) | (1u << 16);     // B (= V) MN-major
-            auto issue_pv = [&](int u) {        // unit u = 2 j + tile
-                const int slot = u & 1, j = u >> 1, b = j & 1;
-                mbar_wait(&p_full[slot], j & 1, 62);
-                A2_STAMP(2, j, 4 + slot * 2);          // P ready, PV issue
-                tc_fence_after();
-                const uint32_t tbase = tmem + slot * 256;
-                const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(base + b * A2_BUF_BYTES + A2_Q_BYTES + A2_KV_BYTES));
-#pragma unroll
-                for (int k = 0; k < A2_KV_ROWS / 16; ++k)
-                    umma_bf16_tmem_a(tbase + 192, tbase + 8 * k, bdesc + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv, k != 0);
-                umma_commit(&o_full[slot]);
-                if (slot == 1) umma_commit(&empty[b]);     // every MMA that reads buffer b has been issued
+            auto test = [](uint64_t* bar, uint32_t parity) {       // non-blocking: has the phase of that parity completed?
+                uint32_t ok;
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+                return ok != 0;
             };
-            int j = 0, u = 0;
+            int my_items = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) ++my_items;
+            const int U = 2 * my_items;
+            // S(us) needs the item's data and a free slot, PV(up) the unit's probabilities: whichever is ready goes to the
+            // tensor core, S first (it releases a whole warpgroup, PV only an epilogue); a fixed S(u), PV(u - 1) order
+            // would park PV behind the load of the next item
+            int us = 0, up = 0;
+            uint32_t idle = 0;
+            while (up < U) {
+                bool did = false;
+                if (us < U) {
+                    const int tile = us & 1, j = us >> 1, b = j & 1;
+                    if (test(&full[b], (j >> 1) & 1) && test(&slot_free[tile], (j & 1) ^ 1)) {
+                        A2_STAMP(2, j, tile * 2);
+                        tc_fence_after();
+                        uint8_t* sQ = base + b * A2_BUF_BYTES;
+                        const uint64_t kdesc = make_sw128_kmajor_desc(smem_u32(sQ + A2_Q_BYTES));
+                        const uint64_t qdesc = make_sw128_kmajor_desc(smem_u32(sQ + tile * 128 * 128));
+#pragma unroll
+                        for (int k = 0; k < ATT_D / 16; ++k)
+                            umma_bf16<1>(tmem + tile * 256, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+                        umma_commit(&s_full[tile]);
+                        ++us; did = true;
+                    }
+                }
+                if (up < us) {
+                    const int slot = up & 1, j = up >> 1, b = j & 1;
+                    if (test(&p_full[slot], j & 1)) {
+                        A2_STAMP(2, j, 4 + slot * 2);
+                        tc_fence_after();
+                        const uint32_t tbase = tmem + slot * 256;
+                        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(base + b * A2_BUF_BYTES + A2_Q_BYTES + A2_KV_BYTES));
+#pragma unroll
+                        for (int k = 0; k < A2_KV_ROWS / 16; ++k)     // P: keys 0..127 at columns [0, 64), 128..255 at [128, 192), 256.. at [192, 200)
+                            umma_bf16_tmem_a(tbase + 64, tbase + (k < 8 ? 8 * k : 64 + 8 * k), bdesc + static_cast<uint64_t>(k) * (2048 >> 4), idesc_pv, k != 0);
+                        umma_commit(&o_full[slot]);
+                        if (slot == 1) umma_commit(&empty[b]);     // every MMA that reads buffer b has been issued
+                        ++up; did = true;
+                    }
+                }
+                if (did) idle = 0;
+                else if (++idle > (1u << 26)) { printf("b200clip: attention_tc2 MMA issuer stuck (block %d, us %d, up %d)\n", (int)blockIdx.x, us, up); __trap(); }
+            }
+        }
+    } else if (warp == A2_ST_WARP) {
+        // ===================== output store: one TMA store per unit out of its (recycled) Q tile =====================
+        if (lane == 0) {
+            int j = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
                 const int b = j & 1;
-                mbar_wait(&full[b], (j >> 1) & 1, 63);
-                uint8_t* sQ = base + b * A2_BUF_BYTES;
-                const uint64_t kdesc = make_sw128_kmajor_desc(smem_u32(sQ + A2_Q_BYTES));
-                for (int tile = 0; tile < 2; ++tile, ++u) {
-                    mbar_wait(&slot_free[tile], (j & 1) ^ 1, 64);
-                    A2_STAMP(2, j, tile * 2);              // slot free, S issue
-                    tc_fence_after();
-                    const uint64_t qdesc = make_sw128_kmajor_desc(smem_u32(sQ + tile * 128 * 128));
-#pragma unroll
-                    for (int k = 0; k < ATT_D / 16; ++k)
-                        umma_bf16<1>(tmem + tile * 256, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-                    umma_commit(&s_full[tile]);
-                    if (u >= 1) issue_pv(u - 1);
+                const int seq = item / heads, head = item - seq * heads;
+                for (int tile = 0; tile < 2; ++tile) {
+                    mbar_wait_relaxed(&stage_full[tile], j & 1, 69);
+                    tma_store_2d(&tmap_o, base + b * A2_BUF_BYTES + tile * 128 * 128, head * ATT_D, seq * T + tile * 128);
+                    tma_store_commit();
                 }
+                tma_store_wait_read<0>();
+                mbar_arrive(&empty[b]);          // both staging tiles of buffer b have been read
             }
-            if (u >= 1) issue_pv(u - 1);
+            tma_store_wait<0>();
         }
     } else if (warp >= A2_SM_WARPS) {
         // ===================== odd-row warps: query row 256 on the CUDA cores =====================
@@ -178,23 +226,26 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
             if (lane == 0) mbar_arrive(&empty[b]);
         }
     } else {
-        // ===================== softmax warps: warpgroup = query tile, one row per thread =====================
-        const int tile = warp >> 2, wq = warp & 3;
+        // ===================== softmax warps: group of 8 warps = query tile; a row is shared by the two warps of a TMEM
+        // lane quadrant, each taking 128 of its 256 key columns (half 1 also the 257th key) =====================
+        const int tile = warp >> 3, half = (warp >> 2) & 1, wq = warp & 3;
         const int row_in_tile = wq * 32 + lane;
         const uint32_t tbase = tmem + (static_cast<uint32_t>(wq * 32) << 16) + tile * 256;
         const float scale_log2 = 0.125f * 1.4426950408889634f;
         const int g = lane >> 2, t4 = lane & 3;
+        float* xmax = scratch + 1024 + tile * 512;           // [2 halves][128 rows] partial row maxima of the unit
+        float* xsum = xmax + 256;                            // [2 halves][128 rows] partial row sums
         int j = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
             const int b = j & 1;
-            const int seq = item / heads, head = item - seq * heads;
-            // ---- s' = q_row . k_256 for the 32 rows of this warp: two m16n8k16 tiles (only column 0 of B is non-zero)
-            const bool stamp = lane == 0 && wq == 0;
+            const bool stamp = lane == 0 && wq == 0 && half == 0;
             if (stamp) A2_STAMP(tile, j, 0);
             mbar_wait(&full[b], (j >> 1) & 1, 66);
             if (stamp) A2_STAMP(tile, j, 1);
-            float s_last;
-            {
+            // ---- s' = q_row . k_256 for the 32 rows of the quadrant (half 1): two m16n8k16 tiles, only column 0 of B
+            //      is non-zero
+            float s_last = -INFINITY;
+            if (half == 1) {
                 const uint32_t qa = smem_u32(base + b * A2_BUF_BYTES + tile * 128 * 128);
                 const uint32_t ka = smem_u32(base + b * A2_BUF_BYTES + A2_Q_BYTES + 256 * 128);    // row 256: chunks unswizzled
                 float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -219,108 +270,95 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid
                 const float v10 = __shfl_sync(0xffffffffu, c[1][0], src), v12 = __shfl_sync(0xffffffffu, c[1][2], src);
                 s_last = (lane & 16) ? ((lane & 8) ? v12 : v10) : ((lane & 8) ? v02 : v00);
             }
-            // ---- pass 1: row maximum over the 256 scores in TMEM (+ s')
+            // ---- pass 1: maximum over this warp's 128 of the row's scores in TMEM (+ s'), exchanged with the other half
             if (stamp) A2_STAMP(tile, j, 2);
             mbar_wait(&s_full[tile], j & 1, 67);
             if (stamp) A2_STAMP(tile, j, 3);
             tc_fence_after();
-            // (the TMEM loads are software pipelined: chunk c + 1 is in flight while chunk c is worked on)
-            float mx4[4] = {s_last, s_last, s_last, s_last};     // four independent chains: FMNMX3 has ~5 clocks of latency
+            const uint32_t scol = tbase + half * 128;
+            float mx4[4] = {s_last, s_last, s_last, s_last};     // independent chains: FMNMX3 has ~5 clocks of latency
             {
-                uint32_t sa[2][32];
-                tmem_ld_32x32(tbase, sa[0]);
-                tmem_ld_wait_regs(sa[0]);
+                uint32_t sa[2][16];          // 16-column chunks, the next one in flight while this one is reduced
+                tmem_ld_32x32_x16(scol, sa[0]);
+                tmem_ld_wait_regs16(sa[0]);
 #pragma unroll
                 for (int cchunk = 0; cchunk < 8; ++cchunk) {
-                    if (cchunk + 1 < 8) tmem_ld_32x32(tbase + (cchunk + 1) * 32, sa[(cchunk + 1) & 1]);
+                    if (cchunk + 1 < 8) tmem_ld_32x32_x16(scol + (cchunk + 1) * 16, sa[(cchunk + 1) & 1]);
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2)
+                    for (int i = 0; i < 16; i += 2)
                         mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sa[cchunk & 1][i]), __uint_as_float(sa[cchunk & 1][i + 1])));
-                    if (cchunk + 1 < 8) tmem_ld_wait_regs(sa[(cchunk + 1) & 1]);
+                    if (cchunk + 1 < 8) tmem_ld_wait_regs16(sa[(cchunk + 1) & 1]);
                 }
             }
-            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-            // ---- pass 2: exponentials, row sum, P (bf16 pairs) back over S
+            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            xmax[half * 128 + row_in_tile] = mx;
+            named_bar_sync(5 + tile, 256);
+            mx = fmaxf(mx, xmax[(half ^ 1) * 128 + row_in_tile]);
+            // ---- pass 2: exponentials, partial row sum, P (bf16 pairs) back over THIS warp's already consumed columns:
+            //      half 0 -> columns [0, 64), half 1 -> [128, 192) and key 256 (+ 15 zero partners) -> [192, 200)
             if (stamp) A2_STAMP(tile, j, 4);
             const float nm = -mx * scale_log2;
             float rs4[4] = {0.f, 0.f, 0.f, 0.f};
             {
-                uint32_t sa[2][32];
-                tmem_ld_32x32(tbase, sa[0]);
-                tmem_ld_wait_regs(sa[0]);
+                uint32_t sa[2][16];
+                tmem_ld_32x32_x16(scol, sa[0]);
+                tmem_ld_wait_regs16(sa[0]);
 #pragma unroll
                 for (int cchunk = 0; cchunk < 8; ++cchunk) {
-                    if (cchunk + 1 < 8) tmem_ld_32x32(tbase + (cchunk + 1) * 32, sa[(cchunk + 1) & 1]);
-                    uint32_t pk[16];
+                    if (cchunk + 1 < 8) tmem_ld_32x32_x16(scol + (cchunk + 1) * 16, sa[(cchunk + 1) & 1]);
+                    uint32_t pk[8];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-#ifdef A2_NO_EX2
-                        const float p0 = fmaf(__uint_as_float(sa[cchunk & 1][2 * i]), scale_log2, nm);
-                        const float p1 = fmaf(__uint_as_float(sa[cchunk & 1][2 * i + 1]), scale_log2, nm);
-#else
+                    for (int i = 0; i < 8; ++i) {
                         const float p0 = ex2_approx(fmaf(__uint_as_float(sa[cchunk & 1][2 * i]), scale_log2, nm));
                         const float p1 = ex2_approx(fmaf(__uint_as_float(sa[cchunk & 1][2 * i + 1]), scale_log2, nm));
-#endif
                         rs4[i & 3] += p0 + p1;
                         pk[i] = pack_bf16x2(p0, p1);
                     }
-                    // columns [16 c, 16 c + 16) hold scores of chunks <= c: chunk c is in registers and the load of chunk
-                    // c + 1 (columns >= 32 (c + 1) > 16 c + 16) does not overlap them
-                    if (cchunk + 1 < 8) tmem_ld_wait_regs(sa[(cchunk + 1) & 1]);
-                    tmem_st_32x32_x16(tbase + cchunk * 16, pk);
+                    // columns [8 c, 8 c + 8) of this half held scores of chunks <= c / 2: all in registers or consumed
+                    if (cchunk + 1 < 8) tmem_ld_wait_regs16(sa[(cchunk + 1) & 1]);
+                    tmem_st_32x32_x8(scol + cchunk * 8, pk);
                 }
             }
-            {
+            if (half == 1) {
                 const float pl = ex2_approx(fmaf(s_last, scale_log2, nm));
                 rs4[0] += pl;
                 uint32_t pk[8] = {pack_bf16x2(pl, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-                tmem_st_32x32_x8(tbase + 128, pk);
+                tmem_st_32x32_x8(tbase + 192, pk);
             }
+            const float rs = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+            xsum[half * 128 + row_in_tile] = rs;             // read by the other half behind the group barrier below
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[tile]);
             if (stamp) A2_STAMP(tile, j, 5);
-            // ---- O of the unit: normalise and store this thread's row
+            // ---- O of the unit (slot columns [64, 128)): this warp normalises and stages 32 of the 64 output columns
             mbar_wait(&o_full[tile], j & 1, 68);
             if (stamp) A2_STAMP(tile, j, 6);
             tc_fence_after();
-            const float inv = 1.f / ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-            // the rows leave through the unit's Q tile (the tensor core is done with it: S is complete, and so are the
-            // ldmatrix reads of every warp once the warpgroup meets below) as ONE TMA store of 128 x 64 bf16
-            uint8_t* stage = base + b * A2_BUF_BYTES + tile * 128 * 128;
+            uint8_t* stage = base + b * A2_BUF_BYTES + tile * 128 * 128;     // the unit's Q tile: S is complete, and the
+            uint32_t o[32];                                                  // ldmatrix reads end before the barrier below
+            tmem_ld_32x32(tbase + 64 + half * 32, o);
+            tmem_ld_wait_regs(o);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_free[tile]);
+            named_bar_sync(3 + tile, 256);
+            const float inv = 1.f / (rs + xsum[(half ^ 1) * 128 + row_in_tile]);
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                uint32_t o[32];
-                tmem_ld_32x32(tbase + 192 + hh * 32, o);
-                tmem_ld_wait_regs(o);
-                if (hh == 1) {      // everything this warp needs from the slot is in registers
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&slot_free[tile]);
-                }
-                if (hh == 0) named_bar_sync(3 + tile, 128);      // every warp of the group has finished reading the Q tile
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    uint4 wv;
-                    wv.x = pack_bf16x2(__uint_as_float(o[cc * 8 + 0]) * inv, __uint_as_float(o[cc * 8 + 1]) * inv);
-                    wv.y = pack_bf16x2(__uint_as_float(o[cc * 8 + 2]) * inv, __uint_as_float(o[cc * 8 + 3]) * inv);
-                    wv.z = pack_bf16x2(__uint_as_float(o[cc * 8 + 4]) * inv, __uint_as_float(o[cc * 8 + 5]) * inv);
-                    wv.w = pack_bf16x2(__uint_as_float(o[cc * 8 + 6]) * inv, __uint_as_float(o[cc * 8 + 7]) * inv);
-                    *reinterpret_cast<uint4*>(stage + sw_off(row_in_tile, hh * 4 + cc)) = wv;
-                }
+            for (int cc = 0; cc < 4; ++cc) {
+                uint4 wv;
+                wv.x = pack_bf16x2(__uint_as_float(o[cc * 8 + 0]) * inv, __uint_as_float(o[cc * 8 + 1]) * inv);
+                wv.y = pack_bf16x2(__uint_as_float(o[cc * 8 + 2]) * inv, __uint_as_float(o[cc * 8 + 3]) * inv);
+                wv.z = pack_bf16x2(__uint_as_float(o[cc * 8 + 4]) * inv, __uint_as_float(o[cc * 8 + 5]) * inv);
+                wv.w = pack_bf16x2(__uint_as_float(o[cc * 8 + 6]) * inv, __uint_as_float(o[cc * 8 + 7]) * inv);
+                *reinterpret_cast<uint4*>(stage + sw_off(row_in_tile, half * 4 + cc)) = wv;
             }
             fence_proxy_async_smem();
-            named_bar_sync(3 + tile, 128);
-            if (wq == 0 && lane == 0) {
-                tma_store_2d(&tmap_o, stage, head * ATT_D, seq * T + tile * 128);
-                tma_store_commit();
-                tma_store_wait_read<0>();
-                mbar_arrive(&empty[b]);          // the warpgroup is done with buffer b
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stage_full[tile]);      // the store warp takes it from here
             if (stamp) A2_STAMP(tile, j, 7);
         }
-        if (wq == 0 && lane == 0) tma_store_wait<0>();
     }
     tc_fence_before();
     __syncthreads();

@@ -1167,7 +1167,8 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
         return 0;
     }
     // T = 257 (ViT-L/14 and larger at 224 px): persistent tcgen05 kernel with the probabilities handed over in TMEM
-    if (!causal && t == A2_T && b200_knobs().attn_tc2 && n_items >= 1 && n_items < (int64_t(1) << 31) &&
+    // (B200CLIP_ATTN_NOTC2=1 and the switches that name another kernel keep the older ones reachable as parity variants)
+    if (!causal && t == A2_T && b200_knobs().attn_tc2 && !b200_knobs().attn_tc && !b200_knobs().attn_tiled && n_items >= 1 && n_items < (int64_t(1) << 31) &&
         static_cast<int64_t>(n_seq) * t < (int64_t(1) << 31) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) {
         CUtensorMap tq, t64, t16;
         const uint64_t rows = static_cast<uint64_t>(n_seq) * t, cols = 3ull * heads * ATT_D;

@@ -103,9 +103,11 @@ def test_attention_matches_torch(handle, n_seq, t, heads, causal):
 
 
 def test_attention_kernel_variants_in_subprocess():
-    """The attention kernel for 64 < T <= 320 is chosen once per process: default = mma.sync with resident K/V,
-    B200CLIP_ATTN_TC=1 = tcgen05 (S and PV on the 5th-generation tensor cores, V as an MN-major operand),
-    B200CLIP_ATTN_TILED=1 = the tiled fallback.  All three must match torch on the ViT-L/14 shape and friends."""
+    """The attention kernel for 64 < T <= 320 is chosen once per process: default = the persistent tcgen05 kernel with the
+    probabilities in tensor memory for T = 257 (ViT-L/14) and mma.sync with resident K/V otherwise,
+    B200CLIP_ATTN_NOTC2=1 = mma.sync also for T = 257, B200CLIP_ATTN_TC=1 = the first tcgen05 kernel (S and PV on the
+    5th-generation tensor cores, V as an MN-major operand, P through shared memory), B200CLIP_ATTN_TILED=1 = the tiled
+    fallback.  All must match torch on the ViT-L/14 shape (few and many items per persistent CTA) and friends."""
     import os
     import subprocess
     import sys
@@ -117,7 +119,7 @@ from b200clip import capi
 from b200clip.model_configs import MODEL_CONFIGS, to_capi_config
 h = capi.Handle(to_capi_config(MODEL_CONFIGS["ViT-B-32"]), 0)
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-for n_seq, t, heads in [(3, 257, 16), (5, 100, 4), (2, 320, 2), (1, 129, 1), (4, 96, 3), (2, 65, 2), (7, 145, 5), (2, 130, 2),
+for n_seq, t, heads in [(3, 257, 16), (1, 257, 1), (37, 257, 16), (5, 100, 4), (2, 320, 2), (1, 129, 1), (4, 96, 3), (2, 65, 2), (7, 145, 5), (2, 130, 2),
                           (2, 196, 3), (1, 258, 1), (3, 197, 12), (2, 260, 2), (1, 68, 1)]:
     torch.manual_seed(t * heads)
     d = heads * 64
@@ -131,7 +133,7 @@ for n_seq, t, heads in [(3, 257, 16), (5, 100, 4), (2, 320, 2), (1, 129, 1), (4,
     assert not torch.isnan(out.float()).any() and err <= 0.03, (n_seq, t, heads, err)
 print("variant ok")
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for env in ({}, {"B200CLIP_ATTN_TC": "1"}, {"B200CLIP_ATTN_TILED": "1"}):
+    for env in ({}, {"B200CLIP_ATTN_NOTC2": "1"}, {"B200CLIP_ATTN_TC": "1"}, {"B200CLIP_ATTN_TILED": "1"}):
         e = {k: v for k, v in os.environ.items() if not k.startswith("B200CLIP_ATTN")}
         e.update(env)
         r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)

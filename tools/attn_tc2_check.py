@@ -1,4 +1,4 @@
-"""Development check of attention_tc2_kernel (T = 257) against torch, several batch sizes (fewer items than SMs, a
+"""Development check of attention_tc2_kernel (T = 257, the default; B200CLIP_ATTN_NOTC2=1 = mma.sync kernel) against torch, several batch sizes (fewer items than SMs, a
 non-multiple, many items per CTA), then the per-call time of both kernels on the ViT-L/14 shape."""
 import ctypes, os, sys
 os.environ.setdefault("B200CLIP_ALLOW_SYNTHETIC", "1")
