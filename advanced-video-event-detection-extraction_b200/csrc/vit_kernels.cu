@@ -1126,6 +1126,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q128, const __grid_
 }
 
 #include "attention_tc2.cuh"
+#include "attention_tc64.cuh"
 
 int make_tmap_bf16_2d(b200clip_handle* h, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz);
@@ -1146,6 +1147,27 @@ int launch_attention(b200clip_handle* h, const bf16* qkv, bf16* out, int n_seq, 
     const int64_t per_seq_out = static_cast<int64_t>(t) * heads * ATT_D;
     const bool no_persist = b200_knobs().attn_oneshot;     // parity tests cover both
     const int64_t n_items = static_cast<int64_t>(n_seq) * heads;
+    // T <= 64: two items per 128-row tcgen05 tile, S read from TMEM once (attention_tc64.cuh)
+    if (!causal && t <= 64 && b200_knobs().attn_tc64 && !no_persist && n_items >= 2 * h->num_sms && n_items < (int64_t(1) << 31) &&
+        n_items * t < (int64_t(1) << 31) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) {
+        CUtensorMap tq, to;
+        const uint64_t rows = static_cast<uint64_t>(n_seq) * t, cols = 3ull * heads * ATT_D;
+        int rc;
+        if ((rc = make_tmap_bf16_2d(h, &tq, qkv, rows, cols, cols, t, ATT_D, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tmap_bf16_2d(h, &to, out, rows, static_cast<uint64_t>(heads) * ATT_D, static_cast<uint64_t>(heads) * ATT_D, t, ATT_D,
+                                    CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if (!(h->attr_done & ATTR_ATTN_TC64)) {
+            B200_CUDA(h, cudaFuncSetAttribute(attention_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A6_SMEM_BYTES));
+            h->attr_done |= ATTR_ATTN_TC64;
+        }
+        const int64_t n_tiles = (n_items + 1) / 2;
+        const int grid = n_tiles < h->num_sms ? static_cast<int>(n_tiles) : h->num_sms;
+        ProfScope ps(h, PROF_ATTN, static_cast<double>(n_seq) * t * heads * ATT_D * 2.0 * 4.0, st);
+        attention_tc64_kernel<<<grid, A6_THREADS, A6_SMEM_BYTES, st>>>(tq, to, t, heads, static_cast<int>(n_items));
+        h->launches++;
+        B200_CUDA(h, cudaGetLastError());
+        return 0;
+    }
     if (!causal && t <= ATT_BK && !no_persist && n_items >= 2 * h->num_sms && n_items * t < (int64_t(1) << 31) &&
         (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) {
         CUtensorMap tq;

@@ -76,9 +76,10 @@ def test_layernorm_matches_torch(handle, rows, width):
 
 @pytest.mark.parametrize("n_seq,t,heads,causal", [(3, 50, 12, 0), (2, 77, 8, 1), (2, 257, 16, 0), (5, 5, 2, 0),
                                                     (1, 16, 1, 1), (70, 50, 12, 0), (1, 64, 2, 1), (1, 65, 2, 0),
-                                                    # >= 296 (sequence, head) items, T <= 64, no mask: persistent TMA-fed kernel
+                                                    # >= 296 (sequence, head) items, T <= 64, no mask: persistent tcgen05 kernel, two
+                                                    # items per 128-row tile (odd item counts: the last tile holds one)
                                                     (300, 50, 12, 0), (40, 64, 8, 0), (100, 33, 4, 0), (500, 1, 1, 0),
-                                                    (37, 7, 9, 0),
+                                                    (37, 7, 9, 0), (301, 50, 1, 0), (2000, 50, 12, 0),
                                                     # 64 < T <= 320, no mask: K/V-resident kernel (one CTA per sequence and head)
                                                     (3, 257, 16, 0), (5, 100, 4, 0), (2, 320, 2, 0), (1, 129, 1, 0), (4, 96, 3, 0),
                                                     # beyond it / causal: the tiled kernel
@@ -107,7 +108,9 @@ def test_attention_kernel_variants_in_subprocess():
     probabilities in tensor memory for T = 257 (ViT-L/14) and mma.sync with resident K/V otherwise,
     B200CLIP_ATTN_NOTC2=1 = mma.sync also for T = 257, B200CLIP_ATTN_TC=1 = the first tcgen05 kernel (S and PV on the
     5th-generation tensor cores, V as an MN-major operand, P through shared memory), B200CLIP_ATTN_TILED=1 = the tiled
-    fallback.  All must match torch on the ViT-L/14 shape (few and many items per persistent CTA) and friends."""
+    fallback; for T <= 64 the default is the two-items-per-tile tcgen05 kernel, B200CLIP_ATTN_NOTC64=1 = the persistent
+    mma.sync kernel, B200CLIP_ATTN_ONESHOT=1 = one CTA per item.  All must match torch on the ViT-L/14 and ViT-B/32
+    shapes (few and many items per persistent CTA, odd item counts) and friends."""
     import os
     import subprocess
     import sys
@@ -119,7 +122,7 @@ from b200clip import capi
 from b200clip.model_configs import MODEL_CONFIGS, to_capi_config
 h = capi.Handle(to_capi_config(MODEL_CONFIGS["ViT-B-32"]), 0)
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-for n_seq, t, heads in [(3, 257, 16), (1, 257, 1), (37, 257, 16), (5, 100, 4), (2, 320, 2), (1, 129, 1), (4, 96, 3), (2, 65, 2), (7, 145, 5), (2, 130, 2),
+for n_seq, t, heads in [(3, 257, 16), (1, 257, 1), (37, 257, 16), (300, 50, 12), (301, 50, 1), (77, 64, 5), (150, 33, 3), (5, 100, 4), (2, 320, 2), (1, 129, 1), (4, 96, 3), (2, 65, 2), (7, 145, 5), (2, 130, 2),
                           (2, 196, 3), (1, 258, 1), (3, 197, 12), (2, 260, 2), (1, 68, 1)]:
     torch.manual_seed(t * heads)
     d = heads * 64
@@ -133,7 +136,8 @@ for n_seq, t, heads in [(3, 257, 16), (1, 257, 1), (37, 257, 16), (5, 100, 4), (
     assert not torch.isnan(out.float()).any() and err <= 0.03, (n_seq, t, heads, err)
 print("variant ok")
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for env in ({}, {"B200CLIP_ATTN_NOTC2": "1"}, {"B200CLIP_ATTN_TC": "1"}, {"B200CLIP_ATTN_TILED": "1"}):
+    for env in ({}, {"B200CLIP_ATTN_NOTC2": "1", "B200CLIP_ATTN_NOTC64": "1"}, {"B200CLIP_ATTN_TC": "1", "B200CLIP_ATTN_NOTC64": "1", "B200CLIP_ATTN_ONESHOT": "1"},
+                {"B200CLIP_ATTN_TILED": "1"}):
         e = {k: v for k, v in os.environ.items() if not k.startswith("B200CLIP_ATTN")}
         e.update(env)
         r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
