@@ -58,6 +58,15 @@ def parse_args():
     return ap.parse_args()
 
 
+def gemm_traffic(flop_per_launch):
+    """DRAM bytes per launch of the dominant GEMM kernel from its committed ncu capture, scaled by FLOP per launch
+    (None when the capture is missing)."""
+    p = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p))["dram_bytes_per_flop"] * flop_per_launch
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -822,8 +831,9 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                               "the whole image tower; the M = 77 text-tower GEMMs run on gemm_bf16_tcgen05_kernel<64|256>, "
                               "class gemm_small)",
                     "achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops_sustained"],
-                    "traffic": None,
-                    "traffic_note": "not measured in this run (ncu dram__bytes per GEMM shape: profiles/*gemm_ncu_summary*)",
+                    "traffic": gemm_traffic(r["work"] / max(r["launches"], 1)),
+                    "traffic_note": "bytes per launch = dram bytes / FLOP of the ncu --set full capture of this kernel (profiles/gemm_traffic.json: "
+                                    "its four ViT-B/32 shapes at M = 51200) x this run's FLOP per launch; not measured live (no counters outside ncu)",
                     "flop_per_launch_avg": r["work"] / max(r["launches"], 1)}
         else:
             # config 4: the similarity GEMM with fused top-k (2*Q*n*E FLOP per launch), timed with its final merge / re-score
