@@ -264,10 +264,11 @@ class FramesWorkload(Workload):
 
     def step(self):
         if self.overlap_query and not self.args.no_text_overlap:
-            # The query's text tower (60 latency-bound launches of a few CTAs each, ~0.7 ms) runs on a high-priority side
-            # stream while K1 -- an ordinary, non-persistent grid -- preprocesses the frames; the towers of one handle have
-            # disjoint workspaces.  It has finished long before the first persistent GEMM of the image tower starts.
-            # A/B on one box (profiles/r02j_text_overlap_ab.txt): 39.74 / 39.53 ms per step vs 40.06 / 40.32 serial.
+            # The query's text tower (~85 latency-bound launches of a few CTAs each, ~1.3 ms when serial) runs on a
+            # high-priority side stream next to K1 and the first kernels of the image tower; the towers of one handle have
+            # disjoint workspaces.  A/B on one box: -0.55 ms per step when K1 was an ordinary grid of short CTAs
+            # (profiles/r02j_text_overlap_ab.txt); with the persistent one-CTA-per-SM IMMA form of K1 the two orders
+            # measure equal (38.0 vs 37.9-38.5 ms), the overlapped form stays the default.
             import torch
 
             if not hasattr(self, "side"):
