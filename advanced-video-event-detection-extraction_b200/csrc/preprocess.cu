@@ -1871,7 +1871,11 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
                     h->attr_done |= ATTR_K1_MMA;
                 }
                 ProfScope psa(h, PROF_PRE_A, static_cast<double>(n) * (static_cast<double>(p.sy1 - p.sy0) * (p.sx1 - p.sx0) * 3.0 + ny * S * 3.0), st);
-                const int fgrid = mp.nitems < h->num_sms ? mp.nitems : h->num_sms;
+                int fgrid = mp.nitems < h->num_sms ? mp.nitems : h->num_sms;
+#ifdef B200CLIP_PROBES
+                // probe (profiles/r02w_*): the kernel's time is nearly proportional to the CTAs it may use
+                if (const char* e = getenv("B200CLIP_K1_CTAS")) { const int v = atoi(e); if (v > 0 && v < fgrid) fgrid = v; }
+#endif
                 kern<<<fgrid, (NCW + 1) * 32, smem, st>>>(mp);
                 h->launches++;
                 fused_ab = true;
