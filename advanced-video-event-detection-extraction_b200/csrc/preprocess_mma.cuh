@@ -5,7 +5,8 @@
 //
 // Why: the CUDA-core form (area_hpass_vfirst_kernel) is purely issue bound -- ~754 k warp instructions per 1080p frame,
 // 58 % issue utilisation, the bulk-copy feed completely hidden.  Written as matrix products the
-// three separable passes need ~4x fewer instructions, and the weights (small integers) become constant A / B fragments:
+// three separable passes need half the instructions (375 M instead of 754 M per 1024 frames), and the weights (small
+// integers) become constant A / B fragments:
 //
 //   stage 1  H^T [area col (x, c) | source row]  = Wx^T [15 area cols x 64 row bytes] . rows^T      (u8 x u8)
 //            M tile = 5 area pixels x 3 channels (15 of the 16 MMA rows), K = the <= 64 bytes of the RGB source row under
@@ -15,18 +16,22 @@
 //            H <= 255 * Dx needs 16 bits: the accumulators of stage 1 are split into a low- and a high-byte plane with
 //            three PRMT per 8 values and fed back as A fragments (the C layout of one MMA pairs up with the A layout of
 //            the next when K, the source rows, is taken in the order the fragments hold them -- the Wy table is permuted
-//            on the host to match).  N2 = 2 N + D, so the area sample is umulhi(N2, magic) >> s exactly like the
-//            CUDA-core kernel (rint(N / D) for odd D); it is parked PLANAR (R, G, B planes) in shared memory.
+//            on the host to match).  The product runs as K = 16 steps (m16n8k16), one per finished pair of 8-row
+//            blocks, with the two planes folded into one accumulator after each step, so a tile carries 6 live registers
+//            through a group instead of 10.  N2 = 2 N + D, so the area sample is umulhi(N2, magic) >> s exactly like
+//            the CUDA-core kernel (rint(N / D) for odd D); it is parked PLANAR (R, G, B planes) in shared memory.
 //   stage 3  Pillow^T [output col | area row]    = Wp^T [16 output cols x 64 area cols] . plane^T     (3 byte planes)
 //            the 22-bit signed fixed-point coefficients are split into three byte planes (u8, u8, s8); one set of weight
-//            fragments serves the three colour planes.  (acc + 2^21) >> 22, clipped, stored to mid2.
+//            fragments (resident in shared memory, 3 KB per tile) serves the three colour planes.  (acc + 2^21) >> 22,
+//            clipped; a tile's 8 rows x 48 bytes go through a per-warp scratch and leave as 16-byte stores to mid2.
 //
 // Work decomposition: a CTA is persistent and walks (strip, frame) items; a strip is `gps` groups of 8 area rows; a group
 // is NB blocks of 8 source rows = one ring stage (8 bulk copies, one per row, issued by 8 lanes of the producer warp).
 // Each of the NCW consumer warps owns TPW stage-1 tiles for the whole kernel, reads ITS 64-byte column window of every
 // block and releases the block as soon as the bytes are in registers; the only cross-warp hand-off is the parked area
-// rows of a group (mbarrier pair per parity, Pillow pass of group i deferred until after stage 2 of group i + 1, so no
-// warp waits for the others in the steady state).
+// rows of a group (NBUF = 4 buffers with an mbarrier pair each, the Pillow pass of group i deferred until after stage 2 of
+// group i + PDEF, so no warp waits for the others in the steady state).  Ring row pitch = 16 mod 128 and parked-row
+// pitch = 32 mod 128 bytes put the 8 rows a fragment load touches on distinct shared-memory banks.
 #pragma once
 
 struct MmaParams {
