@@ -4,26 +4,32 @@
 // One persistent CTA per SM walks (sequence, head) items; Q, K and V of an item (100 KB) arrive by TMA into one of two
 // shared-memory buffers, so the loads of the next item run under the arithmetic of the current one.  An item is two
 // "units" = 128-row query tiles (rows 0..127 and 128..255); unit u lives in TMEM slot u & 1 (256 columns each) and is
-// served by softmax warpgroup u & 1 (4 warps, one query row per thread).  The 257th row is scored on the CUDA cores by
-// four more warps at the same time (attention_odd_row, as in attention_tc_kernel).
+// served by softmax warp group u & 1: 8 warps, TWO per TMEM lane quadrant, each taking 128 of the row's 256 key columns
+// (partial maxima and sums are exchanged through shared memory) -- one warp per quadrant cannot overlap its own MUFU
+// and TMEM phases.  The 257th row is scored on the CUDA cores by four more warps at the same time (attention_odd_row,
+// as in attention_tc_kernel); a store warp writes the output tiles.
 //
 //   S   = Q_tile[128 x 64] . K[256 keys x 64]^T      4 x tcgen05.mma M=128 N=256 K=16, fp32 into slot columns [0, 256)
 //   s'  = Q_tile . k_256                             the 257th key cannot join the N = 256 tile (and TMEM has no room for
-//                                                    a second one): two mma.sync m16n8k16 tiles per warp, one shuffle set
+//                                                    a second one): two mma.sync m16n8k16 tiles per quadrant, one shuffle set
 //   P   = exp2(scale (S - max))                      FULL-ROW softmax (all of a row's scores are resident, so there is no
-//                                                    running maximum and no rescaling of O): pass 1 = max over 8 tcgen05.ld
-//                                                    of 32 columns, pass 2 = exponentials; P (bf16, two keys per column)
-//                                                    is written back over S with tcgen05.st, columns [0, 128) + 8 columns
-//                                                    for key 256 and its 15 zero partners -- it never touches shared memory
+//                                                    running maximum and no rescaling of O): pass 1 = maximum, pass 2 =
+//                                                    exponentials, both over double-buffered 16-column tcgen05.ld chunks;
+//                                                    P (bf16, two keys per column) is written back with tcgen05.st over
+//                                                    columns the SAME warp has already consumed: keys 0..127 -> [0, 64),
+//                                                    128..255 -> [128, 192), key 256 and 15 zero partners -> [192, 200)
+//                                                    -- it never touches shared memory
 //   O   = P[128 x 272] . V[272 keys x 64]            17 x tcgen05.mma with A FROM TENSOR MEMORY (pinned by
 //                                                    tools/probes/umma_tmem_a_probe.cu) and V as an MN-major B operand,
-//                                                    fp32 into slot columns [192, 256) (S columns already consumed)
-//   out = O / sum                                    tcgen05.ld, normalise, bf16 rows to global
+//                                                    fp32 into slot columns [64, 128) (scores of the first half, consumed)
+//   out = O / sum                                    tcgen05.ld, normalise, bf16 rows staged in the unit's Q tile (the
+//                                                    tensor core is done with it), one TMA store per tile
 //
-// A single thread issues all MMAs in the order S(u), PV(u - 1): while one warpgroup exponentiates unit u - 1 the tensor
-// core already produces S(u) for the other one, and the two warpgroups drift half a period apart by themselves (the
-// exponentials, 16 per clock and SM, are the per-SM limit: 2 x 128 x 257 per item = 4.1 k clocks; the HBM share of an
-// SM allows 5.7 k clocks per item, so the kernel is memory bound when the pipeline holds).
+// A single thread issues all MMAs; it polls (mbarrier.test_wait) which of S(next unit) -- needs the item's data and a
+// drained slot -- and PV(previous unit) -- needs its P -- is ready and sends S first, so the tensor core produces S for
+// one group while the other one exponentiates.  What bounds the kernel is the tensor-memory READ port, 64 B/clk/SM:
+// a full-row softmax reads S twice, 2 x 128 KB + 32 KB of O per unit = 9.2 k clocks per item, the measured period
+// (MUFU.EX2 would allow 4.4 k, HBM 5.7 k; profiles/r02r_attention_tc2_steps.md).
 #pragma once
 
 constexpr int A2_T = 257, A2_SM_WARPS = 16, A2_ODD_WARPS = 4;
