@@ -36,7 +36,7 @@ const B200Knobs& b200_knobs() {
         b.vpass_generic = on("B200CLIP_VPASS_GENERIC");
         b.gemm_1cta = on("B200CLIP_GEMM_1CTA"); b.gemm_spin_wait = on("B200CLIP_GEMM_SPIN_WAIT");
         b.sim_simt = on("B200CLIP_SIM_SIMT"); b.sim_stream_a = on("B200CLIP_SIM_STREAM_A");
-        b.attn_oneshot = on("B200CLIP_ATTN_ONESHOT"); b.attn_tc = on("B200CLIP_ATTN_TC"); b.attn_tiled = on("B200CLIP_ATTN_TILED"); b.attn_tc2 = !on("B200CLIP_ATTN_NOTC2"); b.attn_tc64 = !on("B200CLIP_ATTN_NOTC64");
+        b.attn_oneshot = on("B200CLIP_ATTN_ONESHOT"); b.attn_tc = on("B200CLIP_ATTN_TC"); b.attn_tiled = on("B200CLIP_ATTN_TILED"); b.attn_tc2 = !on("B200CLIP_ATTN_NOTC2"); b.attn_tc64 = !on("B200CLIP_ATTN_NOTC64"); b.head_simt = on("B200CLIP_HEAD_SIMT");
         b.overlap = on("B200CLIP_OVERLAP"); b.full_upload = on("B200CLIP_FULL_UPLOAD");
         b.nv12_unfused = on("B200CLIP_NV12_UNFUSED"); b.k1_persistent = on("B200CLIP_K1_PERSISTENT");
         b.area_mma = !on("B200CLIP_AREA_NOMMA"); b.k1_verbose = on("B200CLIP_K1_VERBOSE");

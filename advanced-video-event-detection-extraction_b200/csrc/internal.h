@@ -104,7 +104,7 @@ struct b200clip_handle {
     int g2_clusters[5] = {0, 0, 0, 0, 0};   // co-resident clusters of the 2-CTA GEMM on this device, per pairs
 };
 enum { ATTR_GEMM64 = 1u << 0, ATTR_GEMM128 = 1u << 1, ATTR_GEMM256 = 1u << 2, ATTR_GEMM_2CTA = 1u << 3, ATTR_SIM_TC = 1u << 4,
-       ATTR_ATTN_PERSIST = 1u << 5, ATTR_SIM_STREAM = 1u << 6, ATTR_K1_VFIRST = 1u << 7, ATTR_K1_NV12 = 1u << 8, ATTR_K1_MMA = 1u << 9, ATTR_ATTN_TC2 = 1u << 10, ATTR_ATTN_TC64 = 1u << 11 };
+       ATTR_ATTN_PERSIST = 1u << 5, ATTR_SIM_STREAM = 1u << 6, ATTR_K1_VFIRST = 1u << 7, ATTR_K1_NV12 = 1u << 8, ATTR_K1_MMA = 1u << 9, ATTR_ATTN_TC2 = 1u << 10, ATTR_ATTN_TC64 = 1u << 11, ATTR_HEAD_MMA = 1u << 12 };
 
 // Environment switches, read ONCE per process (first use).  They select between code paths that are all valid and
 // parity-tested (fallback kernels that other geometries use anyway); measurement probes that invalidate results or
@@ -114,6 +114,7 @@ struct B200Knobs {
     bool gemm_1cta, gemm_spin_wait;
     bool sim_simt, sim_stream_a;
     bool attn_oneshot, attn_tc, attn_tiled, attn_tc2, attn_tc64;
+    bool head_simt;            // B200CLIP_HEAD_SIMT: CUDA-core head kernel instead of the mma.sync one
     bool overlap, full_upload;
     bool nv12_unfused, k1_persistent;
     bool k1_verbose;           // B200CLIP_K1_VERBOSE: report the K1 code path on stderr

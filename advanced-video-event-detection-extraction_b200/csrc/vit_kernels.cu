@@ -1382,12 +1382,241 @@ head_kernel(const bf16* __restrict__ x, int64_t row_stride, const int32_t* __res
     }
 }
 
+// The same head on the tensor cores (mma.sync m16n8k16 bf16): a CTA owns 32 rows, keeps their LayerNorm output in
+// shared memory as TWO bf16 planes (x = hi + lo, 16 mantissa bits: the projection input keeps fp32-like precision, the
+// error against the fp32 CUDA-core kernel above is ~1e-6 relative) and streams the projection matrix ONCE through a
+// double-buffered 32-row cp.async ring (the CUDA-core kernel walks the whole 786 KB matrix per 8 rows: 354 MB of L1 / L2
+// traffic per 3600 rows, ~0.1 ms even for one row).  Warp w owns output columns [64 w, +64) of a 512-column pass;
+// per-row sums of squares are reduced in a fixed order (shuffles over the 4 lanes of a row, then the 8 warps in index
+// order), so a row's embedding does not depend on the batch it is in.
+constexpr int HM_ROWS = 32, HM_THREADS = 256, HM_KCHUNK = 32, HM_PASS = 512, HM_STAGES = 3;
+constexpr int HM_BPITCH = HM_PASS * 2 + 16;          // bytes per k-row of a staged projection chunk (+16: ldmatrix banks)
+__host__ __device__ inline size_t hm_smem_bytes(int width) {
+    return 2 * static_cast<size_t>(HM_ROWS) * (width * 2 + 16) + static_cast<size_t>(HM_STAGES) * HM_KCHUNK * HM_BPITCH + HM_ROWS * 8 * sizeof(float);
+}
+__global__ void __launch_bounds__(HM_THREADS)
+head_mma_kernel(const bf16* __restrict__ x, int64_t row_stride, const int32_t* __restrict__ row_index,
+                const float* __restrict__ gamma, const float* __restrict__ beta, const bf16* __restrict__ proj, int n,
+                int width, int embed, float eps, void* __restrict__ out, int out_dtype, int l2norm) {
+    extern __shared__ __align__(16) uint8_t hm_smem[];
+    const int apitch = width * 2 + 16;
+    uint8_t* a_hi = hm_smem;
+    uint8_t* a_lo = a_hi + HM_ROWS * apitch;
+    uint8_t* b_st = a_lo + HM_ROWS * apitch;                               // [HM_STAGES][HM_KCHUNK][HM_BPITCH]
+    float* red = reinterpret_cast<float*>(b_st + HM_STAGES * HM_KCHUNK * HM_BPITCH); // [HM_ROWS][8]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    const int row0 = blockIdx.x * HM_ROWS;
+    // (1) LayerNorm of the CTA's rows -> hi / lo bf16 planes (rows past n: zeros)
+    for (int li = warp; li < HM_ROWS; li += HM_THREADS / 32) {
+        const int img = row0 + li;
+        bf16* dh = reinterpret_cast<bf16*>(a_hi + li * apitch);
+        bf16* dl = reinterpret_cast<bf16*>(a_lo + li * apitch);
+        if (img < n) {
+            const int64_t r = row_index ? static_cast<int64_t>(row_index[img]) : static_cast<int64_t>(img);
+            const bf16* xr = x + r * row_stride;
+            float sum = 0.f;
+            for (int i = lane; i < width; i += 32) sum += __bfloat162float(xr[i]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float mean = sum / width;
+            float sq = 0.f;
+            for (int i = lane; i < width; i += 32) {
+                const float d = __bfloat162float(xr[i]) - mean;
+                sq += d * d;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            const float rstd = rsqrtf(sq / width + eps);
+            for (int i = lane; i < width; i += 32) {
+                const float v = (__bfloat162float(xr[i]) - mean) * rstd * gamma[i] + beta[i];
+                const bf16 hi = __float2bfloat16(v);
+                dh[i] = hi;
+                dl[i] = __float2bfloat16(v - __bfloat162float(hi));
+            }
+        } else {
+            for (int i = lane; i < width; i += 32) { dh[i] = __float2bfloat16(0.f); dl[i] = __float2bfloat16(0.f); }
+        }
+    }
+    const int nchunks = width / HM_KCHUNK;
+    float ssq[2][2] = {{0.f, 0.f}, {0.f, 0.f}};           // [m tile][row g / g + 8] sums of squares of this thread's columns
+    const uint32_t ahi0 = smem_u32(a_hi), alo0 = smem_u32(a_lo), bst0 = smem_u32(b_st);
+    for (int n0 = 0; n0 < embed; n0 += HM_PASS) {
+        const int ncols = min(HM_PASS, embed - n0);        // multiple of 64 (checked by the launcher)
+        const bool warp_on = warp * 64 < ncols;
+        auto load_chunk = [&](int c, int stage) {          // 32 k-rows x ncols columns of proj, 16 bytes per cp.async
+            const int per_row = ncols >> 3;
+            for (int i = threadIdx.x; i < HM_KCHUNK * per_row; i += HM_THREADS) {
+                const int kr = i / per_row, cc = i - kr * per_row;
+                cp_async_16(bst0 + (stage * HM_KCHUNK + kr) * HM_BPITCH + cc * 16,
+                            proj + static_cast<int64_t>(c * HM_KCHUNK + kr) * embed + n0 + cc * 8, true);
+            }
+            cp_async_commit();
+        };
+        float acc[2][8][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+        __syncthreads();                                   // A planes written / previous pass done with the stages
+        // HM_STAGES - 1 chunks in flight ahead of the one being multiplied (a group is committed per iteration, empty
+        // past the last chunk, so that wait_group's count always means the same thing)
+#pragma unroll
+        for (int c = 0; c < HM_STAGES - 1; ++c) { if (c < nchunks) load_chunk(c, c); else cp_async_commit(); }
+        for (int c = 0; c < nchunks; ++c) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(HM_STAGES - 2) : "memory");
+            __syncthreads();                               // chunk c visible to all; everyone is done with chunk c - 1
+            if (c + HM_STAGES - 1 < nchunks) load_chunk(c + HM_STAGES - 1, (c + HM_STAGES - 1) % HM_STAGES); else cp_async_commit();
+            if (warp_on) {
+                const uint32_t bs = bst0 + (c % HM_STAGES) * HM_KCHUNK * HM_BPITCH;
+#pragma unroll
+                for (int ks = 0; ks < HM_KCHUNK / 16; ++ks) {
+                    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const uint32_t off = static_cast<uint32_t>(mt * 16 + (lane & 15)) * apitch + static_cast<uint32_t>(c * HM_KCHUNK + ks * 16 + (lane >> 4) * 8) * 2;
+                        ldmatrix_x4(ahi0 + off, ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3]);
+                        ldmatrix_x4(alo0 + off, al[mt][0], al[mt][1], al[mt][2], al[mt][3]);
+                    }
+#pragma unroll
+                    for (int np = 0; np < 4; ++np) {           // two 8-column tiles per ldmatrix.x4.trans
+                        uint32_t b0, b1, b2, b3;
+                        const uint32_t boff = static_cast<uint32_t>(ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * HM_BPITCH +
+                                              static_cast<uint32_t>(warp * 64 + np * 16 + 8 * (lane >> 4)) * 2;
+                        ldmatrix_x4_trans(bs + boff, b0, b1, b2, b3);
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) {
+                            mma_bf16_16816(acc[mt][np * 2], ah[mt], b0, b1);
+                            mma_bf16_16816(acc[mt][np * 2], al[mt], b0, b1);
+                            mma_bf16_16816(acc[mt][np * 2 + 1], ah[mt], b2, b3);
+                            mma_bf16_16816(acc[mt][np * 2 + 1], al[mt], b2, b3);
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        // raw results of this pass (scaled in registers below when the row fits one pass) and the sums of squares
+        const bool single = embed <= HM_PASS;
+        if (warp_on) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    ssq[mt][0] += acc[mt][nt][0] * acc[mt][nt][0] + acc[mt][nt][1] * acc[mt][nt][1];
+                    ssq[mt][1] += acc[mt][nt][2] * acc[mt][nt][2] + acc[mt][nt][3] * acc[mt][nt][3];
+                }
+        }
+        if (single || !l2norm) {
+            float inv[2][2] = {{1.f, 1.f}, {1.f, 1.f}};
+            if (l2norm) {
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        float v = ssq[mt][hh];
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        if (t4 == 0) red[(mt * 16 + hh * 8 + g) * 8 + warp] = warp_on ? v : 0.f;
+                    }
+                __syncthreads();
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const float* rr = red + (mt * 16 + hh * 8 + g) * 8;
+                        float tot = 0.f;
+#pragma unroll
+                        for (int wv = 0; wv < 8; ++wv) tot += rr[wv];
+                        inv[mt][hh] = 1.0f / sqrtf(tot);       // reference divides by the norm with no epsilon
+                    }
+            }
+            if (warp_on) {
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int img = row0 + mt * 16 + hh * 8 + g;
+                        if (img >= n) continue;
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) {
+                            const int col = n0 + warp * 64 + nt * 8 + 2 * t4;
+                            const float v0 = acc[mt][nt][hh * 2] * inv[mt][hh], v1 = acc[mt][nt][hh * 2 + 1] * inv[mt][hh];
+                            if (out_dtype == B200CLIP_F32)
+                                *reinterpret_cast<float2*>(static_cast<float*>(out) + static_cast<int64_t>(img) * embed + col) = make_float2(v0, v1);
+                            else
+                                *reinterpret_cast<uint32_t*>(static_cast<bf16*>(out) + static_cast<int64_t>(img) * embed + col) = pack_bf16x2(v0, v1);
+                        }
+                    }
+            }
+        } else if (warp_on) {                              // several passes per row (fp32 output only): raw now, scaled below
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int img = row0 + mt * 16 + hh * 8 + g;
+                    if (img >= n) continue;
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) {
+                        const int col = n0 + warp * 64 + nt * 8 + 2 * t4;
+                        *reinterpret_cast<float2*>(static_cast<float*>(out) + static_cast<int64_t>(img) * embed + col) =
+                            make_float2(acc[mt][nt][hh * 2], acc[mt][nt][hh * 2 + 1]);
+                    }
+                }
+        }
+    }
+    if (embed > HM_PASS && l2norm) {
+        // the row's norm spans the passes: warps in index order, then every row of the CTA is scaled in place
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                float v = ssq[mt][hh];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (t4 == 0) red[(mt * 16 + hh * 8 + g) * 8 + warp] = v;
+            }
+        __threadfence_block();
+        __syncthreads();
+        for (int i = threadIdx.x; i < HM_ROWS * (embed >> 1); i += HM_THREADS) {
+            const int r = i / (embed >> 1), cpair = i - r * (embed >> 1);
+            const int img = row0 + r;
+            if (img >= n) continue;
+            float tot = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < 8; ++wv) tot += red[r * 8 + wv];
+            const float inv = 1.0f / sqrtf(tot);
+            float2* p = reinterpret_cast<float2*>(static_cast<float*>(out) + static_cast<int64_t>(img) * embed) + cpair;
+            float2 v = *p;
+            v.x *= inv; v.y *= inv;
+            *p = v;
+        }
+    }
+}
+
 int launch_head(b200clip_handle* h, const bf16* x, int64_t row_stride, const int32_t* row_index, const float* g,
                 const float* b, const bf16* proj, int n, int width, int embed, float eps, void* out, int out_dtype,
                 int l2norm, cudaStream_t st) {
     if (n <= 0) return 0;
     if (embed > HEAD_MAXCOL * HEAD_THREADS) return b200_fail(h, B200CLIP_E_SHAPE, "head: embed_dim %d too large", embed);
     if (width % 4 != 0) return b200_fail(h, B200CLIP_E_SHAPE, "head: width %d must be a multiple of 4", width);
+    // tensor-core form: 32 rows per CTA, the projection matrix streamed once per CTA (B200CLIP_HEAD_SIMT=1: the CUDA-core
+    // kernel below, kept for shapes the tiles do not cover and as a parity variant)
+    if (!b200_knobs().head_simt && width % HM_KCHUNK == 0 && embed % 64 == 0 && hm_smem_bytes(width) <= 226 * 1024 &&
+        (out_dtype == B200CLIP_F32 || embed <= HM_PASS) && (reinterpret_cast<uintptr_t>(proj) & 15) == 0) {
+        const size_t smem_mma = hm_smem_bytes(width);
+        if (!(h->attr_done & ATTR_HEAD_MMA)) {
+            B200_CUDA(h, cudaFuncSetAttribute(head_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            h->attr_done |= ATTR_HEAD_MMA;
+        }
+        ProfScope ps(h, PROF_HEAD, static_cast<double>(n) * (width * 2.0 + embed * 4.0) + static_cast<double>(width) * embed * 2.0, st);
+        head_mma_kernel<<<(n + HM_ROWS - 1) / HM_ROWS, HM_THREADS, smem_mma, st>>>(x, row_stride, row_index, g, b, proj, n, width, embed, eps,
+                                                                                  out, out_dtype, l2norm);
+        h->launches++;
+        B200_CUDA(h, cudaGetLastError());
+        return 0;
+    }
     const size_t smem = (static_cast<size_t>(HEAD_IMGS) * width + HEAD_IMGS * (HEAD_THREADS / 32)) * sizeof(float);
     const int maxcol = (embed + HEAD_THREADS - 1) / HEAD_THREADS;
     auto kern = maxcol <= 1 ? head_kernel<1> : maxcol == 2 ? head_kernel<2> : maxcol == 3 ? head_kernel<3> : head_kernel<4>;

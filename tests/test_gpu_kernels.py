@@ -142,3 +142,18 @@ print("variant ok")
         e.update(env)
         r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "variant ok" in r.stdout, (env, r.stdout[-1500:], r.stderr[-1500:])
+
+
+def test_head_kernel_variants_agree_in_subprocess():
+    """ln_post -> proj -> L2 (SURVEY a4/a5 tail) runs on head_mma_kernel (mma.sync, LayerNorm output split into two bf16
+    planes) by default and on the fp32 CUDA-core head_kernel with B200CLIP_HEAD_SIMT=1; the switch is read once per
+    process, so tools/head_check.py embeds the same frames / texts (1, 5, 33, 70 rows: partial and several CTAs; both
+    towers; normalised and raw; ViT-B/32 and ViT-L/14 widths) in one process per form and compares to 2e-5."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = {k: v for k, v in os.environ.items() if k != "B200CLIP_HEAD_SIMT"}
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "head_check.py")], env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
