@@ -12,7 +12,7 @@ for r in rows:
     if r is hdr or len(r) <= iv or r[im] != "gpu__time_duration.sum":
         continue
     name = r[ik].split("(")[0].replace("void ", "")
-    if not any(k in name for k in ("gemm_bf16", "area_", "attention", "head_kernel", "vpass", "layernorm", "topk", "sim_", "text_embed",
+    if not any(k in name for k in ("gemm_bf16", "area_", "attention", "head_kernel", "head_mma", "vpass", "layernorm", "topk", "sim_", "text_embed",
                                    "hpass", "zero_pad", "rescore", "nv12")):
         continue            # torch's own glue kernels (fill, copy) are not ours
     v = float(r[iv].replace(",", ""))
