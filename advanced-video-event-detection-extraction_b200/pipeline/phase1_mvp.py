@@ -46,7 +46,14 @@ class Phase1MVP:
             use_cache = False
         if use_cache:
             return self._merge(self._process_video_cached(video_path, query, top_k, keep_intervals=True), merge)
-        frames, timestamps = self.frame_extractor.extract_frames(video_path)
+        fx = self.frame_extractor
+        if settings.B200_DECODE_MIDDLES_ONLY and "extract_frames" not in vars(fx):     # a replaced decoder stays in charge
+            got = fx.extract_window_middles(video_path)
+            if got is not None:
+                middle, window_ts, n_sampled = got
+                logger.info(f"Extracted {len(middle)} window-middle frames of {n_sampled} sampled frames")
+                return self.process_middle_frames(middle, window_ts, query, top_k, debug_mode, merge=merge)
+        frames, timestamps = fx.extract_frames(video_path)
         return self.process_frames(frames, timestamps, query, top_k, debug_mode, merge=merge)
 
     @staticmethod
@@ -112,26 +119,42 @@ class Phase1MVP:
     def process_frames(self, frames: np.ndarray, timestamps: Sequence[float], query: str, top_k: int = None,
                        debug_mode: bool = None, video_duration: float = 0.0, return_device: bool = False, merge=None):
         """The body of process_video after decode (phase1_mvp.py:36-163)."""
+        mid_idx, window_ts = self.frame_extractor.window_middles(len(frames), list(timestamps))
+        logger.info(f"Extracted {len(frames)} frames, created {len(mid_idx)} sliding windows")
+        fr = np.asarray(frames)
+        return self._process_middles(lambda lo, hi: fr[np.asarray(mid_idx[lo:hi], dtype=np.int64)], window_ts, query, top_k,
+                                     debug_mode, video_duration, return_device, merge)
+
+    def process_middle_frames(self, middle_frames: np.ndarray, window_timestamps: Sequence[float], query: str,
+                              top_k: int = None, debug_mode: bool = None, video_duration: float = 0.0,
+                              return_device: bool = False, merge=None):
+        """process_frames for a caller that already holds ONLY the frame each window embeds (its middle frame,
+        phase1_mvp.py:80) and the window timestamps -- what FrameExtractor.extract_window_middles decodes."""
+        if len(middle_frames) != len(window_timestamps):
+            raise ValueError(f"Frames and timestamps length mismatch: {len(middle_frames)} vs {len(window_timestamps)}")
+        fr = np.asarray(middle_frames)
+        return self._process_middles(lambda lo, hi: fr[lo:hi], list(window_timestamps), query, top_k, debug_mode,
+                                     video_duration, return_device, merge)
+
+    def _process_middles(self, middles_of, window_ts, query, top_k, debug_mode, video_duration, return_device, merge):
+        """`middles_of(lo, hi)` -> the frames windows [lo, hi) embed, as one array."""
         if top_k is None:
             top_k = settings.TOP_K_RESULTS
         if debug_mode is not None:
             self.debug_mode = debug_mode
-        mid_idx, window_ts = self.frame_extractor.window_middles(len(frames), list(timestamps))
-        logger.info(f"Extracted {len(frames)} frames, created {len(mid_idx)} sliding windows")
-        if not mid_idx:
+        if not window_ts:
             raise ValueError("No windows could be processed due to memory constraints")
         model = self.clip_model.model
         text_embedding = torch.from_numpy(self.clip_model.encode_text(query)).to(model.device)
 
         rank, world = world_info()
-        m = len(mid_idx)
-        lo, hi = shard_range(m, rank, world)
+        lo, hi = shard_range(len(window_ts), rank, world)
         k_eff = int(top_k)      # any top_k: K4 serves k > 32 in ceil(k / 32) passes (phase1_mvp.py:145 takes any value)
         if k_eff <= 0:
             return ([], []) if self.debug_mode else []
         ts_dev = torch.tensor(window_ts, dtype=torch.float64, device=model.device)
         if hi > lo:
-            middle = np.ascontiguousarray(np.asarray(frames)[np.asarray(mid_idx[lo:hi])])
+            middle = np.ascontiguousarray(middles_of(lo, hi))
             if middle.dtype != np.uint8:
                 middle = (middle * 255).astype(np.uint8)  # openclip_model.py:188-189
             emb = torch.empty(hi - lo, model.embed_dim, device=model.device, dtype=torch.float32)
@@ -158,7 +181,7 @@ class Phase1MVP:
             norms = emb.norm(dim=-1).cpu().numpy()
             debug_info = [{"window_index": lo + j, "timestamp": window_ts[lo + j], "similarity": float(sims[j]),
                            "image_embedding_norm": float(norms[j]),
-                           "frame_shape": tuple(np.asarray(frames[mid_idx[lo + j]]).shape)} for j in range(hi - lo)]
+                           "frame_shape": tuple(middle.shape[1:])} for j in range(hi - lo)]
             if len(sims):
                 self._log_debug_analysis(sims, debug_info, query, settings.CONFIDENCE_THRESHOLD)
             return results, debug_info

@@ -54,6 +54,42 @@ class FrameExtractor:
             raise ValueError(f"No frames extracted from video: {video_path}")
         return np.stack(frames), stamps
 
+    def extract_window_middles(self, video_path: str):
+        """Frame feed for phase 1: decode ONLY the frames phase 1 embeds -- the middle frame of every
+        sliding window (phase1_mvp.py:80) -- instead of every sampled frame (frame_extractor.py:76-104 decodes all of
+        them and phase 1 then drops 7 of 8 at the default 16 / 8 windows).  Same decoder calls per kept index as
+        `extract_frames` (absolute seek + read), so the frames and timestamps are the reference's.  Returns
+        `(middle_frames [m,H,W,3] uint8 RGB, window_timestamps [m], n_sampled)`, or None when the shortcut cannot prove
+        that it is equivalent: a middle frame or the LAST sampled frame fails to decode (a truncated file shortens the
+        reference's frame list and with it the windows) -- the caller then takes the full `extract_frames` path."""
+        try:
+            import cv2
+        except ImportError as e:  # pragma: no cover
+            raise RuntimeError("video decoding needs OpenCV; pass frames to Phase1MVP.process_frames instead") from e
+        cap = cv2.VideoCapture(video_path)
+        if not cap.isOpened():
+            raise ValueError(f"Cannot open video: {video_path}")
+        try:
+            total = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+            fps = cap.get(cv2.CAP_PROP_FPS) or 30.0
+            sampled = self.sample_indices(total)
+            if not sampled:
+                return None
+            stamps = [i / fps for i in sampled]
+            mid_idx, window_ts = self.window_middles(len(sampled), stamps)
+            mid_set = set(mid_idx)
+            got = {}
+            for j in sorted(mid_set | {len(sampled) - 1}):        # + sentinel: the last sampled frame must decode
+                cap.set(cv2.CAP_PROP_POS_FRAMES, sampled[j])
+                ok, frame = cap.read()
+                if not ok:
+                    return None
+                if j in mid_set:
+                    got[j] = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+            return np.stack([got[j] for j in mid_idx]), window_ts, len(sampled)
+        finally:
+            cap.release()
+
     def window_middles(self, n_frames: int, timestamps: List[float]) -> Tuple[List[int], List[float]]:
         """Index of the frame Phase 1 embeds for every sliding window (`window[len(window)//2]`,
         phase1_mvp.py:80) and the window timestamp (frame_extractor.py:237-273) -- without materialising the

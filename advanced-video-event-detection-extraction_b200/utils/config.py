@@ -39,6 +39,10 @@ class Settings:
         # b200clip additions (not in the reference): frames per pass of the tower, frame cap compatibility
         self.B200_MAX_IMAGES_PER_PASS = _env("B200_MAX_IMAGES_PER_PASS", 1024, int)
         self.MAX_SAMPLED_FRAMES = _env("MAX_SAMPLED_FRAMES", 1000, int)  # frame_extractor.py:69-74
+        # frame feed: decode only the frame each sliding window embeds (its middle frame) instead of every sampled frame
+        # (FrameExtractor.extract_window_middles; same frames, timestamps and results, 1/8 of the decode work and host
+        # memory at the default 16 / 8 windows); 0 = decode every sampled frame like frame_extractor.py:76-104
+        self.B200_DECODE_MIDDLES_ONLY = bool(_env("B200_DECODE_MIDDLES_ONLY", 1, int))
         # embed each video once into DATA_DIR/embeddings/*.b2emb and answer later queries from the cache (off = the
         # reference's behaviour: decode + embed on every query)
         self.B200_EMBEDDING_CACHE = bool(_env("B200_EMBEDDING_CACHE", 0, int))

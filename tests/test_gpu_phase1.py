@@ -101,3 +101,50 @@ def test_process_query_contract(phase1, tmp_path):
         assert r["clip_start"] == max(0, r["timestamp"] - 15) and r["clip_end"] == r["timestamp"] + 15
     with pytest.raises(ValueError):
         vp.process_query(str(f), "dog", mode="nope")
+
+
+def test_process_video_on_a_real_mp4_matches_the_oracle_in_both_decode_modes(phase1, tmp_path, oracle_sd_b32):
+    """Phase1MVP.process_video on an mp4 written here with OpenCV (640x360, so the <=512x512 INTER_AREA shrink of
+    memory_manager.py:299-322 is on the path): the default frame feed (decode only the window-middle frames) must
+    return exactly what the decode-everything path returns, and both must agree with the CPU oracle run on the same
+    decoded frames (cv2 shrink -> PIL transform -> fp32 ViT -> dot -> argsort / threshold)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import clip_ref
+    from oracle.reference_pipeline import ReferenceCPU
+    from b200clip.pipeline.phase1_mvp import Phase1MVP
+    from b200clip.utils.config import settings
+
+    src = structured_frames(80, 360, 640, seed=7)
+    path = str(tmp_path / "clip.mp4")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 8.0, (640, 360))
+    assert vw.isOpened()
+    for f in src:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+    vw.release()
+
+    p1 = Phase1MVP(clip_model=phase1.clip_model)         # fresh extractor (other tests replace extract_frames)
+    query = "red car driving"
+    settings.CONFIDENCE_THRESHOLD = -1.0
+    try:
+        settings.B200_DECODE_MIDDLES_ONLY = True
+        fast = p1.process_video(path, query, top_k=5)
+        settings.B200_DECODE_MIDDLES_ONLY = False
+        full, debug = p1.process_video(path, query, top_k=5, debug_mode=True)
+        p1.debug_mode = False
+    finally:
+        settings.B200_DECODE_MIDDLES_ONLY = True
+        settings.CONFIDENCE_THRESHOLD = 0.25
+    assert fast == full and len(fast) == 5
+
+    frames, stamps = p1.frame_extractor.extract_frames(path)
+    mid_idx, window_ts = p1.frame_extractor.window_middles(len(frames), stamps)
+    assert len(mid_idx) == 9 and [d["timestamp"] for d in debug] == window_ts
+    ref = ReferenceCPU("ViT-B-32", state_dict=oracle_sd_b32)
+    tokens = clip_ref.synthetic_tokenize([query])
+    want, ref_sims = ref.query(frames[np.asarray(mid_idx)], tokens, 5, -1.0, timestamps=window_ts, shrink=True)
+    sims = np.array([d["similarity"] for d in debug], np.float32)
+    print(f"\n[parity] mp4 phase1 max |dscore| over 9 windows: {np.abs(sims - ref_sims).max():.5f}")
+    assert np.abs(sims - ref_sims).max() <= SCORE_TOL
+    assert_topk_equivalent(ref_sims, [r["window_index"] for r in fast], [r["confidence"] for r in fast], 5)
+    for r in fast:
+        assert r["timestamp"] == window_ts[r["window_index"]] and r["phase"] == "phase1_mvp"
