@@ -97,9 +97,17 @@ class Phase1MVP:
                     cache, resume = None, False
                     os.replace(path, path + ".bad")
             if cache is None or len(cache) != cache.meta.get("windows", len(cache)):     # absent or interrupted build
-                frames, timestamps = self.frame_extractor.extract_frames(video_path)
-                cache = EmbeddingCache.build(self.clip_model, frames, timestamps, dtype="float32", path=path,
-                                             resume=resume, fingerprint=self._fingerprint())
+                fx = self.frame_extractor
+                got = None
+                if settings.B200_DECODE_MIDDLES_ONLY and "extract_frames" not in vars(fx):
+                    got = fx.extract_window_middles(video_path)
+                if got is not None:
+                    cache = EmbeddingCache.build_from_middles(self.clip_model, got[0], got[1], dtype="float32", path=path,
+                                                              resume=resume, fingerprint=self._fingerprint())
+                else:
+                    frames, timestamps = fx.extract_frames(video_path)
+                    cache = EmbeddingCache.build(self.clip_model, frames, timestamps, dtype="float32", path=path,
+                                                 resume=resume, fingerprint=self._fingerprint())
             self._caches[path] = cache
         res = cache.query(query, top_k)
         if not keep_intervals:

@@ -263,14 +263,35 @@ class EmbeddingCache:
         """Embed the sliding-window middle frames of a decoded video (frame_extractor.py:237-273 semantics) in
         chunks; with `path` every chunk is appended to a .b2emb file as it completes, and `resume=True` skips the
         windows an earlier, interrupted run already committed."""
+        from .frame_extractor import FrameExtractor
+
+        mid_idx, window_ts = FrameExtractor().window_middles(len(frames), list(timestamps))
+        fr = np.asarray(frames)
+        return cls._build(clip_model, lambda lo, hi: fr[np.asarray(mid_idx[lo:hi], dtype=np.int64)], window_ts, dtype, duration,
+                          path, chunk, resume, resize_mode, fingerprint)
+
+    @classmethod
+    def build_from_middles(cls, clip_model, middle_frames: np.ndarray, window_timestamps: Sequence[float],
+                           dtype: str = "bfloat16", duration: float = 0.0, path: Optional[str] = None, chunk: int = 4096,
+                           resume: bool = False, resize_mode: Optional[int] = None,
+                           fingerprint: Optional[str] = None) -> "EmbeddingCache":
+        """`build` for a caller that decoded only the frame each window embeds
+        (FrameExtractor.extract_window_middles): one row per given frame, same file, same rows."""
+        if len(middle_frames) != len(window_timestamps):
+            raise ValueError(f"Frames and timestamps length mismatch: {len(middle_frames)} vs {len(window_timestamps)}")
+        fr = np.asarray(middle_frames)
+        return cls._build(clip_model, lambda lo, hi: fr[lo:hi], list(window_timestamps), dtype, duration, path, chunk,
+                          resume, resize_mode, fingerprint)
+
+    @classmethod
+    def _build(cls, clip_model, middles_of, window_ts, dtype, duration, path, chunk, resume, resize_mode, fingerprint):
         import torch
 
         from .. import capi
         from ..utils.config import settings
-        from .frame_extractor import FrameExtractor
 
         model = clip_model.model
-        mid_idx, window_ts = FrameExtractor().window_middles(len(frames), list(timestamps))
+        mid_idx = range(len(window_ts))
         tdt = torch.bfloat16 if dtype in ("bfloat16", "bf16") else torch.float32
         mode = capi.RESIZE_REFERENCE if resize_mode is None else resize_mode
         meta = {"model": settings.OPENCLIP_MODEL, "pretrained": settings.OPENCLIP_PRETRAINED, "windows": len(mid_idx),
@@ -289,7 +310,7 @@ class EmbeddingCache:
                 parts.append(prev.view(torch.bfloat16) if rows.dtype == np.uint16 else prev)
         for lo in range(done, len(mid_idx), chunk):
             hi = min(lo + chunk, len(mid_idx))
-            batch = np.ascontiguousarray(np.asarray(frames)[np.asarray(mid_idx[lo:hi])])
+            batch = np.ascontiguousarray(middles_of(lo, hi))
             if batch.dtype != np.uint8:
                 batch = (batch * 255).astype(np.uint8)
             emb = torch.empty(hi - lo, model.embed_dim, device=model.device, dtype=torch.float32)

@@ -131,6 +131,7 @@ def test_process_video_opt_in_cache(phase1, tmp_path, monkeypatch):
 
     fresh = Phase1MVP(clip_model=phase1.clip_model)
     monkeypatch.setattr(fresh.frame_extractor, "extract_frames", lambda p: (_ for _ in ()).throw(AssertionError("decoded")))
+    monkeypatch.setattr(fresh.frame_extractor, "extract_window_middles", lambda p: (_ for _ in ()).throw(AssertionError("decoded")))
     assert fresh.process_video(path, "red car", top_k=5) == want
     other = fresh.process_video(path, "dog running on grass", top_k=3)
     monkeypatch.setattr(settings, "B200_EMBEDDING_CACHE", False)
