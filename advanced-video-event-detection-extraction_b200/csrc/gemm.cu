@@ -76,6 +76,8 @@ static int launch_gemm_bn(b200clip_handle* h, const bf16* a, int lda, const bf16
 static int g2_max_clusters(b200clip_handle* h, int pairs) {
     if (!(h->attr_done & ATTR_GEMM_2CTA)) {
         cudaFuncSetAttribute(b200::gemm_bf16_tcgen05_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b200::G2_SMEM_BYTES);
+        cudaFuncSetAttribute(b200::gemm_bf16_tcgen05_2cta_kernel<1, b200::G2_DEEP_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             b200::g2_smem_bytes(b200::G2_DEEP_STAGES));
         h->g2_clusters[1] = h->num_sms / 2;
 #ifdef B200CLIP_PROBES
         cudaFuncSetAttribute(b200::gemm_bf16_tcgen05_2cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b200::G2_SMEM_BYTES);
@@ -161,6 +163,12 @@ static int launch_gemm_2cta_range(b200clip_handle* h, const bf16* a, int lda, co
             ta, tw, to, tr, outp, ldc, rows, N, K, epp, use_tma_epi);
     else
 #endif
+    // GEMMs without a residual (patch embedding, qkv, fc) run the deep-ring form: six operand stages, one staging box
+    // per epilogue warp (B200CLIP_GEMM_5STAGE=1: the five-stage / two-box form for every shape)
+    if (!epp.resid && !b200_knobs().gemm_5stage)
+        b200::gemm_bf16_tcgen05_2cta_kernel<1, b200::G2_DEEP_STAGES><<<grid, b200::GEMM_THREADS, b200::g2_smem_bytes(b200::G2_DEEP_STAGES), s>>>(
+            ta, tw, to, tr, outp, ldc, rows, N, K, epp, use_tma_epi);
+    else
         b200::gemm_bf16_tcgen05_2cta_kernel<1><<<grid, b200::GEMM_THREADS, b200::G2_SMEM_BYTES, s>>>(
             ta, tw, to, tr, outp, ldc, rows, N, K, epp, use_tma_epi);
     if (probe) {

@@ -23,6 +23,15 @@ constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_BOX_BYTES = 32 * 128;
 constexpr int G2_STAGING_BYTES = GEMM_EPI_WARPS * 2 * G2_BOX_BYTES;   // 64 KB
 constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_STAGING_BYTES + 512 + 1024;
+// Deep-ring form (STAGES = 6): the sixth 32 KB operand stage is paid for by halving the epilogue staging -- ONE box per
+// epilogue warp, reused for the warp's second 64 columns once the bulk store of the first has read it (the wait sits
+// behind the second half's epilogue math, so it is normally free).  No residual in this form (the residual tile of the
+// second half could only be requested after that wait, and a measured residual variant gained nothing on proj while
+// its extra code slowed the GELU epilogue of fc): the launcher uses it for GEMMs without a residual.
+constexpr int G2_DEEP_STAGES = 6;
+constexpr int g2_boxes(int stages) { return stages >= G2_DEEP_STAGES ? 1 : 2; }
+constexpr int g2_smem_bytes(int stages) { return stages * G2_STAGE_BYTES + GEMM_EPI_WARPS * g2_boxes(stages) * G2_BOX_BYTES + 512 + 1024; }
+static_assert(g2_smem_bytes(G2_STAGES) == G2_SMEM_BYTES && g2_smem_bytes(G2_DEEP_STAGES) <= 227 * 1024, "shared-memory budget");
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster barrier address
 
 // 32 accumulator columns of one row -> bf16 into a [32 rows][64 cols] SWIZZLE_128B box (row = lane).
@@ -30,12 +39,16 @@ constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a 
 // already holds the residual tile (TMA-loaded) and it is added in place.
 __device__ __forceinline__ void epilogue_chunk_smem(uint32_t (&acc)[32], int n0, int N, const GemmEpilogue& ep,
                                                     uint8_t* box, int lane, int chunk0, bool has_res, float mean,
-                                                    float rstd, f32x2_t& ssum, f32x2_t& ssq) {
+                                                    float rstd, f32x2_t& ssum, f32x2_t& ssq, bool wait_read = false) {
     if (n0 >= N) return;
     f32x2_t v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = f2_pack(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
     epilogue_math(v, n0, ep, nullptr, mean, rstd);
+    if (wait_read) {   // the box is being reused: the bulk store issued from it must have read it
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+    }
     uint8_t* rowp = box + lane * 128;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -67,23 +80,24 @@ __device__ __forceinline__ void epilogue_chunk_smem(uint32_t (&acc)[32], int n0,
 // a stage is written by PAIRS CTAs, so empty[s] collects the MMA commits of ALL pairs (multicast to every CTA);
 // tmem_full / tmem_empty stay inside a pair.  Multicast completions land on the full barrier of each destination
 // pair's leader (cta_group::2 address with the peer bit cleared, as in CUTLASS' SM100_TMA_2SM_LOAD_MULTICAST).
-template <int PAIRS>
+template <int PAIRS, int STAGES = G2_STAGES>
 __global__ void __cluster_dims__(2 * PAIRS, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                               __nv_bfloat16* out, int ldc, int M, int N, int K, GemmEpilogue ep, int use_tma_epi) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)   /* pointer arithmetic keeps the shared address space: LDS/STS, not generic LD/ST */;
+    constexpr int BOXES = g2_boxes(STAGES);              // staging boxes per epilogue warp
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + G2_STAGES * G2_A_BYTES;
-    uint8_t* staging = smem + G2_STAGES * G2_STAGE_BYTES;   // 1024-byte aligned
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + G2_STAGING_BYTES);
+    uint8_t* smem_b = smem + STAGES * G2_A_BYTES;
+    uint8_t* staging = smem + STAGES * G2_STAGE_BYTES;   // 1024-byte aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + GEMM_EPI_WARPS * BOXES * G2_BOX_BYTES);
     uint64_t* full_bar = bars;                           // [STAGES]  (used in the leader)
-    uint64_t* empty_bar = bars + G2_STAGES;              // [STAGES]  (both CTAs)
-    uint64_t* tmem_full_bar = bars + 2 * G2_STAGES;      // [2]       (both CTAs)
-    uint64_t* tmem_empty_bar = bars + 2 * G2_STAGES + 2; // [2]       (used in the leader)
-    uint64_t* res_bar = bars + 2 * G2_STAGES + 4;         // [GEMM_EPI_WARPS] residual-tile loads, one per warp
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4 + GEMM_EPI_WARPS);
+    uint64_t* empty_bar = bars + STAGES;                 // [STAGES]  (both CTAs)
+    uint64_t* tmem_full_bar = bars + 2 * STAGES;         // [2]       (both CTAs)
+    uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;    // [2]       (used in the leader)
+    uint64_t* res_bar = bars + 2 * STAGES + 4;            // [GEMM_EPI_WARPS] residual-tile loads, one per warp
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + GEMM_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -103,7 +117,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_w);
-        for (int s = 0; s < G2_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], PAIRS);
         }
@@ -147,7 +161,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
                                            static_cast<uint16_t>(kAllPairs << rank));
                     } else
                     tma_load_2d_cg2(smem_b + stage * G2_B_BYTES, &tmap_w, bar, kb * GEMM_BLOCK_K, n0);
-                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -178,7 +192,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
                     for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k)
                         umma_bf16<2>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     umma_commit_cg2(&empty_bar[stage], static_cast<uint16_t>((1u << (2 * PAIRS)) - 1u));   // frees the stage in every CTA that feeds it
-                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit_cg2(&tmem_full_bar[as], static_cast<uint16_t>(0b11u << (2 * pair)));   // accumulator ready in both CTAs of the pair
                 if (++as == 2) { as = 0; aphase ^= 1; }
@@ -223,12 +237,12 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
             if (use_tma_epi) {
                 // ---- staged epilogue: TMEM -> registers -> swizzled smem box -> TMA bulk store (full 128-byte
                 // lines); the residual tile is TMA-loaded into the same box while the MMAs of this tile still run.
-                uint8_t* my_stage = staging + (warp - 2) * 2 * G2_BOX_BYTES;
+                uint8_t* my_stage = staging + (warp - 2) * BOXES * G2_BOX_BYTES;
                 uint64_t* my_bar = &res_bar[warp - 2];
                 const int box_row0 = m_blk * 2 * GEMM_BLOCK_M + static_cast<int>(rank) * GEMM_BLOCK_M + q * 32;
                 if (lane == 0) tma_store_wait_read<0>();   // previous tile's stores no longer read the boxes
                 __syncwarp();
-                if (res_ptr && lane == 0) {
+                if (BOXES == 2 && res_ptr && lane == 0) {
                     mbar_arrive_expect_tx(my_bar, 2 * G2_BOX_BYTES);
                     tma_load_2d(my_stage, &tmap_res, my_bar, col0, box_row0);
                     tma_load_2d(my_stage + G2_BOX_BYTES, &tmap_res, my_bar, col0 + 64, box_row0);
@@ -238,28 +252,39 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * G2_BLOCK_N + half * COLS_PER_WARP;
                 uint32_t acc_a[32], acc_b[32];
                 tmem_ld_32x32(taddr, acc_a);
-                if (res_ptr) mbar_wait(my_bar, res_phase, 15);
+                const bool has_res = BOXES == 2 && res_ptr != nullptr;   // (the deep-ring form takes no residual)
+                if (has_res) mbar_wait(my_bar, res_phase, 15);
 #pragma unroll
-                for (int c = 0; c < NCH; c += 2) {   // one 64-column box per iteration
-                    uint8_t* box = my_stage + (c >> 1) * G2_BOX_BYTES;
+                for (int c = 0; c < NCH; c += 2) {   // one 64-column box per iteration (a rolled loop measured 1-2 % slower)
+                    uint8_t* box = my_stage + (BOXES == 2 ? (c >> 1) : 0) * G2_BOX_BYTES;
                     tmem_ld_wait_regs(acc_a);
                     tmem_ld_32x32(taddr + (c + 1) * 32, acc_b);
-                    epilogue_chunk_smem(acc_a, col0 + c * 32, N, ep, box, lane, 0, res_ptr != nullptr, mean, rstd, ssum, ssq);
+                    epilogue_chunk_smem(acc_a, col0 + c * 32, N, ep, box, lane, 0, has_res, mean, rstd, ssum, ssq, BOXES == 1 && c > 0);
                     tmem_ld_wait_regs(acc_b);
                     if (c + 2 < NCH) tmem_ld_32x32(taddr + (c + 2) * 32, acc_a);
-                    epilogue_chunk_smem(acc_b, col0 + (c + 1) * 32, N, ep, box, lane, 4, res_ptr != nullptr, mean, rstd, ssum, ssq);
-                }
-                // one generic->async proxy fence for both boxes, then the bulk stores
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-#pragma unroll
-                    for (int bx = 0; bx < NCH / 2; ++bx) {
-                        if (col0 + bx * 64 < N) tma_store_2d(&tmap_out, my_stage + bx * G2_BOX_BYTES, col0 + bx * 64, box_row0);
+                    epilogue_chunk_smem(acc_b, col0 + (c + 1) * 32, N, ep, box, lane, 4, has_res, mean, rstd, ssum, ssq);
+                    if (BOXES == 1) {   // the single box leaves right away; it is rewritten after the store has read it
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (col0 + (c >> 1) * 64 < N) tma_store_2d(&tmap_out, box, col0 + (c >> 1) * 64, box_row0);
+                            tma_store_commit();
+                        }
                     }
-                    tma_store_commit();
                 }
-                if (res_ptr) res_phase ^= 1;
+                if (BOXES == 2) {
+                    // one generic->async proxy fence for both boxes, then the bulk stores
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+#pragma unroll
+                        for (int bx = 0; bx < NCH / 2; ++bx) {
+                            if (col0 + bx * 64 < N) tma_store_2d(&tmap_out, my_stage + bx * G2_BOX_BYTES, col0 + bx * 64, box_row0);
+                        }
+                        tma_store_commit();
+                    }
+                }
+                if (has_res) res_phase ^= 1;
             } else {
                 { const long long c0 = ep.probe ? clock64() : 0; if (ep.relaxed_wait) mbar_wait_relaxed(&tmem_full_bar[as], aphase, 14); else mbar_wait(&tmem_full_bar[as], aphase, 14); if (ep.probe) p_epi += clock64() - c0; }
                 tc_fence_after();

@@ -157,3 +157,18 @@ def test_head_kernel_variants_agree_in_subprocess():
     e = {k: v for k, v in os.environ.items() if k != "B200CLIP_HEAD_SIMT"}
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "head_check.py")], env=e, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_gemm_five_stage_form_in_subprocess():
+    """GEMMs without a residual run the six-stage / one-staging-box form of the 2-CTA kernel by default;
+    B200CLIP_GEMM_5STAGE=1 (read once per process) sends them through the five-stage / two-box form that residual GEMMs
+    use.  Same parametrised comparison against torch, in its own process."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ, B200CLIP_GEMM_5STAGE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_kernels.py"), "-m", "gpu", "-x", "-q",
+                        "-k", "test_gemm_matches_torch"], env=e, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0 and " passed" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
