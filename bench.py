@@ -828,9 +828,9 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         if cls == "gemm":
             tf = r["work"] / (r["ms"] / 1e3) / 1e12 if r["ms"] > 0 else 0.0
             roof = {"bound": "tensor",
-                    "kernel": "gemm_bf16_tcgen05_2cta_kernel<1> (cta_group::2 256x256 tiles: every M >= 2048 GEMM of the step, i.e. "
-                              "the whole image tower; the M = 77 text-tower GEMMs run on gemm_bf16_tcgen05_kernel<64|256>, "
-                              "class gemm_small)",
+                    "kernel": "gemm_bf16_tcgen05_2cta_kernel<1, 6|5> (cta_group::2 256x256 tiles, six operand stages for GEMMs "
+                              "without a residual and five for out / proj: every M >= 2048 GEMM of the step, i.e. the whole image "
+                              "tower; the M = 77 text-tower GEMMs run on gemm_bf16_tcgen05_kernel<64|256>, class gemm_small)",
                     "achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops_sustained"],
                     "traffic": gemm_traffic(r["work"] / max(r["launches"], 1)),
                     "traffic_note": "bytes per launch = dram bytes / FLOP of the ncu --set full capture of this kernel (profiles/gemm_traffic.json: "
