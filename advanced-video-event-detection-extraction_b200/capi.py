@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libb200clip.so")
 RESIZE_REFERENCE = 0
 RESIZE_BILINEAR_AA = 1
 RESIZE_BICUBIC = 2
+INPUT_BGR = 0x100     # OR into resize_mode of the uint8 entry points: frames in OpenCV's BGR order (B200CLIP_INPUT_BGR)
 F32 = 0
 BF16 = 1
 

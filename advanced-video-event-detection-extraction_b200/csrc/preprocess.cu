@@ -1169,7 +1169,7 @@ hpass_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_
 __global__ void __launch_bounds__(128)
 vpass_store_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride, int src_y0, int src_x0,
                    int has_v, int top, DevTaps cy, int S, int P, int grid, int patch_k,
-                   const float* __restrict__ lut /*[3][256]*/, bf16* __restrict__ patches, float* __restrict__ chw) {
+                   const float* __restrict__ lut /*[3][256]*/, bf16* __restrict__ patches, float* __restrict__ chw, int bgr) {
     __shared__ float s_lut[768];
     for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
     __syncthreads();
@@ -1208,24 +1208,25 @@ vpass_store_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_
         const int py = oy / P, yy = oy - py * P;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
+            const int co = bgr ? 2 - c : c;     // output plane / normalisation constants of source channel c
             // the 8 pixels may straddle a patch boundary when P is not a multiple of 8 -> element stores
             const int px0 = x0 / P;
             const bool one_patch = (npx == 8) && ((x0 + 7) / P == px0) && (((x0 - px0 * P) & 7) == 0) && ((P & 7) == 0);
             if (one_patch) {
                 uint4 o;
-                o.x = pack_bf16x2(s_lut[c * 256 + u8[0 * 3 + c]], s_lut[c * 256 + u8[1 * 3 + c]]);
-                o.y = pack_bf16x2(s_lut[c * 256 + u8[2 * 3 + c]], s_lut[c * 256 + u8[3 * 3 + c]]);
-                o.z = pack_bf16x2(s_lut[c * 256 + u8[4 * 3 + c]], s_lut[c * 256 + u8[5 * 3 + c]]);
-                o.w = pack_bf16x2(s_lut[c * 256 + u8[6 * 3 + c]], s_lut[c * 256 + u8[7 * 3 + c]]);
+                o.x = pack_bf16x2(s_lut[co * 256 + u8[0 * 3 + c]], s_lut[co * 256 + u8[1 * 3 + c]]);
+                o.y = pack_bf16x2(s_lut[co * 256 + u8[2 * 3 + c]], s_lut[co * 256 + u8[3 * 3 + c]]);
+                o.z = pack_bf16x2(s_lut[co * 256 + u8[4 * 3 + c]], s_lut[co * 256 + u8[5 * 3 + c]]);
+                o.w = pack_bf16x2(s_lut[co * 256 + u8[6 * 3 + c]], s_lut[co * 256 + u8[7 * 3 + c]]);
                 const int64_t row = (f * grid + py) * grid + px0;
-                *reinterpret_cast<uint4*>(patches + row * patch_k + c * P * P + yy * P + (x0 - px0 * P)) = o;
+                *reinterpret_cast<uint4*>(patches + row * patch_k + co * P * P + yy * P + (x0 - px0 * P)) = o;
             } else {
                 for (int j = 0; j < npx; ++j) {
                     const int x = x0 + j;
                     const int px = x / P, xx = x - px * P;
                     if (px < grid && py < grid) {
                         const int64_t row = (f * grid + py) * grid + px;
-                        patches[row * patch_k + c * P * P + yy * P + xx] = __float2bfloat16(s_lut[c * 256 + u8[j * 3 + c]]);
+                        patches[row * patch_k + co * P * P + yy * P + xx] = __float2bfloat16(s_lut[co * 256 + u8[j * 3 + c]]);
                     }
                 }
             }
@@ -1234,8 +1235,9 @@ vpass_store_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_
     if (chw) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float* o = chw + ((f * 3 + c) * S + oy) * S + x0;
-            for (int j = 0; j < npx; ++j) o[j] = s_lut[c * 256 + u8[j * 3 + c]];
+            const int co = bgr ? 2 - c : c;
+            float* o = chw + ((f * 3 + co) * S + oy) * S + x0;
+            for (int j = 0; j < npx; ++j) o[j] = s_lut[co * 256 + u8[j * 3 + c]];
         }
     }
 }
@@ -1249,7 +1251,7 @@ template <bool HAS_V>
 __global__ void __launch_bounds__(256)
 vpass_store_tile_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride, int src_y0,
                         int xoff_bytes, int top, DevTaps cy, int S, int P, int grid, int patch_k, int rows_per_block,
-                        const float* __restrict__ lut /*[3][256]*/, bf16* __restrict__ patches) {
+                        const float* __restrict__ lut /*[3][256]*/, bf16* __restrict__ patches, int bgr) {
     __shared__ float s_lut[768];
     for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = __ldg(lut + i);
     __syncthreads();
@@ -1313,13 +1315,14 @@ vpass_store_tile_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, i
         bf16* orow = patches + row * patch_k + yy * P + xx;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float* l = s_lut + c * 256;
+            const int co = bgr ? 2 - c : c;     // output plane / normalisation constants of source channel c
+            const float* l = s_lut + co * 256;
             uint4 o;
             o.x = pack_bf16x2(l[byte_as_int<6>(u8w, 0 * 3 + c)], l[byte_as_int<6>(u8w, 1 * 3 + c)]);
             o.y = pack_bf16x2(l[byte_as_int<6>(u8w, 2 * 3 + c)], l[byte_as_int<6>(u8w, 3 * 3 + c)]);
             o.z = pack_bf16x2(l[byte_as_int<6>(u8w, 4 * 3 + c)], l[byte_as_int<6>(u8w, 5 * 3 + c)]);
             o.w = pack_bf16x2(l[byte_as_int<6>(u8w, 6 * 3 + c)], l[byte_as_int<6>(u8w, 7 * 3 + c)]);
-            *reinterpret_cast<uint4*>(orow + c * P * P) = o;
+            *reinterpret_cast<uint4*>(orow + co * P * P) = o;
         }
     }
 }
@@ -1724,7 +1727,7 @@ static int get_plan(b200clip_handle* h, int H, int W, int mode, const Plan** out
 // transform): the host-frame path uploads only this window.
 int preprocess_source_window(b200clip_handle* h, int H, int W, int mode, int* x0, int* x1, int* y0, int* y1) {
     const Plan* pp = nullptr;
-    int rc = get_plan(h, H, W, mode, &pp);
+    int rc = get_plan(h, H, W, mode & ~B200CLIP_INPUT_BGR, &pp);
     if (rc) return rc;
     *x0 = pp->sx0; *x1 = pp->sx1; *y0 = pp->sy0; *y1 = pp->sy1;
     return 0;
@@ -1733,7 +1736,7 @@ int preprocess_source_window(b200clip_handle* h, int H, int W, int mode, int* x0
 // Stage C (+ the K padding of the patch rows) on `cur`: the image after the horizontal pass (or the source itself when
 // no pass ran), whose element (0, 0) sits at stage coordinates (cur_y0, cur_x0).
 static int run_stage_c(b200clip_handle* h, const Plan& p, const uint8_t* cur, int64_t cur_fs, int64_t cur_rs, int cur_x0,
-                       int cur_y0, int n, bf16* patches, float* chw, cudaStream_t st) {
+                       int cur_y0, int n, bf16* patches, float* chw, cudaStream_t st, int bgr = 0) {
     const int S = h->cfg.image_size, P = h->cfg.patch;
     float* lut = get_lut(h);
     if (!lut) return b200_fail(h, B200CLIP_E_NOMEM, "preprocess: LUT allocation failed");
@@ -1755,13 +1758,13 @@ static int run_stage_c(b200clip_handle* h, const Plan& p, const uint8_t* cur, in
             dim3 tgrid((S + rows_per_block - 1) / rows_per_block, n);
             if (p.has_c)
                 vpass_store_tile_kernel<true><<<tgrid, threads, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, xoff, p.top, p.cy, S, P,
-                                                                         h->grid, h->patch_k, rows_per_block, lut, patches);
+                                                                         h->grid, h->patch_k, rows_per_block, lut, patches, bgr);
             else
                 vpass_store_tile_kernel<false><<<tgrid, threads, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, xoff, p.top, p.cy, S, P,
-                                                                          h->grid, h->patch_k, rows_per_block, lut, patches);
+                                                                          h->grid, h->patch_k, rows_per_block, lut, patches, bgr);
         } else {
             vpass_store_kernel<<<grid, 128, 0, st>>>(cur, cur_fs, cur_rs, cur_y0, src_x0, p.has_c ? 1 : 0, p.top, p.cy, S, P,
-                                                     h->grid, h->patch_k, lut, patches, chw);
+                                                     h->grid, h->patch_k, lut, patches, chw, bgr);
         }
         h->launches++;
     }
@@ -1778,6 +1781,10 @@ static int run_stage_c(b200clip_handle* h, const Plan& p, const uint8_t* cur, in
 int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
                       int64_t row_stride, int mode, bf16* patches, float* chw, cudaStream_t st) {
     if (n <= 0) return 0;
+    // B200CLIP_INPUT_BGR: every stage before the final store treats the three bytes of a pixel alike, so the channel
+    // swap of cv2.cvtColor(BGR2RGB) (frame_extractor.py:191) is applied there (run_stage_c)
+    const int bgr = (mode & B200CLIP_INPUT_BGR) ? 1 : 0;
+    mode &= ~B200CLIP_INPUT_BGR;
     const Plan* pp = nullptr;
     int prc = get_plan(h, H, W, mode, &pp);
     if (prc) return prc;
@@ -1988,7 +1995,7 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         cur = mid2; cur_fs = p.mid2_per_frame; cur_rs = static_cast<int64_t>(S) * 3;
         cur_x0 = 0 /* column 0 of mid2 is output column `left`, handled below */; cur_y0 = p.ry0;
     }
-    return run_stage_c(h, p, cur, cur_fs, cur_rs, cur_x0, cur_y0, n, patches, chw, st);
+    return run_stage_c(h, p, cur, cur_fs, cur_rs, cur_x0, cur_y0, n, patches, chw, st, bgr);
 }
 
 

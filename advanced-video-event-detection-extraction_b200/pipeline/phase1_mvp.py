@@ -48,11 +48,11 @@ class Phase1MVP:
             return self._merge(self._process_video_cached(video_path, query, top_k, keep_intervals=True), merge)
         fx = self.frame_extractor
         if settings.B200_DECODE_MIDDLES_ONLY and "extract_frames" not in vars(fx):     # a replaced decoder stays in charge
-            got = fx.extract_window_middles(video_path)
+            got = fx.extract_window_middles(video_path, bgr=True)     # BGR2RGB (frame_extractor.py:191) happens in K1
             if got is not None:
                 middle, window_ts, n_sampled = got
                 logger.info(f"Extracted {len(middle)} window-middle frames of {n_sampled} sampled frames")
-                return self.process_middle_frames(middle, window_ts, query, top_k, debug_mode, merge=merge)
+                return self.process_middle_frames(middle, window_ts, query, top_k, debug_mode, merge=merge, bgr=True)
         frames, timestamps = fx.extract_frames(video_path)
         return self.process_frames(frames, timestamps, query, top_k, debug_mode, merge=merge)
 
@@ -100,10 +100,11 @@ class Phase1MVP:
                 fx = self.frame_extractor
                 got = None
                 if settings.B200_DECODE_MIDDLES_ONLY and "extract_frames" not in vars(fx):
-                    got = fx.extract_window_middles(video_path)
+                    got = fx.extract_window_middles(video_path, bgr=True)
                 if got is not None:
                     cache = EmbeddingCache.build_from_middles(self.clip_model, got[0], got[1], dtype="float32", path=path,
-                                                              resume=resume, fingerprint=self._fingerprint())
+                                                              resume=resume, fingerprint=self._fingerprint(),
+                                                              resize_mode=capi.RESIZE_REFERENCE | capi.INPUT_BGR)
                 else:
                     frames, timestamps = fx.extract_frames(video_path)
                     cache = EmbeddingCache.build(self.clip_model, frames, timestamps, dtype="float32", path=path,
@@ -135,16 +136,18 @@ class Phase1MVP:
 
     def process_middle_frames(self, middle_frames: np.ndarray, window_timestamps: Sequence[float], query: str,
                               top_k: int = None, debug_mode: bool = None, video_duration: float = 0.0,
-                              return_device: bool = False, merge=None):
+                              return_device: bool = False, merge=None, bgr: bool = False):
         """process_frames for a caller that already holds ONLY the frame each window embeds (its middle frame,
-        phase1_mvp.py:80) and the window timestamps -- what FrameExtractor.extract_window_middles decodes."""
+        phase1_mvp.py:80) and the window timestamps -- what FrameExtractor.extract_window_middles decodes.
+        `bgr=True`: the frames are in OpenCV's BGR order (K1 swaps the channels in its final store)."""
         if len(middle_frames) != len(window_timestamps):
             raise ValueError(f"Frames and timestamps length mismatch: {len(middle_frames)} vs {len(window_timestamps)}")
         fr = np.asarray(middle_frames)
         return self._process_middles(lambda lo, hi: fr[lo:hi], list(window_timestamps), query, top_k, debug_mode,
-                                     video_duration, return_device, merge)
+                                     video_duration, return_device, merge, bgr)
 
-    def _process_middles(self, middles_of, window_ts, query, top_k, debug_mode, video_duration, return_device, merge):
+    def _process_middles(self, middles_of, window_ts, query, top_k, debug_mode, video_duration, return_device, merge,
+                         bgr: bool = False):
         """`middles_of(lo, hi)` -> the frames windows [lo, hi) embed, as one array."""
         if top_k is None:
             top_k = settings.TOP_K_RESULTS
@@ -166,7 +169,8 @@ class Phase1MVP:
             if middle.dtype != np.uint8:
                 middle = (middle * 255).astype(np.uint8)  # openclip_model.py:188-189
             emb = torch.empty(hi - lo, model.embed_dim, device=model.device, dtype=torch.float32)
-            model.encode_frames_u8_host(middle, resize_mode=capi.RESIZE_REFERENCE, normalize=True, out=emb)
+            model.encode_frames_u8_host(middle, resize_mode=capi.RESIZE_REFERENCE | (capi.INPUT_BGR if bgr else 0),
+                                        normalize=True, out=emb)
         else:
             emb = torch.empty(0, model.embed_dim, device=model.device, dtype=torch.float32)
         # (world > 1: local top-k -> one all-gather of the packed candidates -> merge, see ..distributed)

@@ -296,7 +296,7 @@ class EmbeddingCache:
         mode = capi.RESIZE_REFERENCE if resize_mode is None else resize_mode
         meta = {"model": settings.OPENCLIP_MODEL, "pretrained": settings.OPENCLIP_PRETRAINED, "windows": len(mid_idx),
                 "frame_sample_rate": settings.FRAME_SAMPLE_RATE, "max_sampled_frames": settings.MAX_SAMPLED_FRAMES,
-                "resize_mode": int(mode)}
+                "resize_mode": int(mode) & 0xff}          # (without the input-format flag capi.INPUT_BGR)
         if fingerprint:
             meta["weights_fingerprint"] = fingerprint
         writer, done, parts = None, 0, []

@@ -54,14 +54,16 @@ class FrameExtractor:
             raise ValueError(f"No frames extracted from video: {video_path}")
         return np.stack(frames), stamps
 
-    def extract_window_middles(self, video_path: str):
+    def extract_window_middles(self, video_path: str, bgr: bool = False):
         """Frame feed for phase 1: decode ONLY the frames phase 1 embeds -- the middle frame of every
         sliding window (phase1_mvp.py:80) -- instead of every sampled frame (frame_extractor.py:76-104 decodes all of
         them and phase 1 then drops 7 of 8 at the default 16 / 8 windows).  Same decoder calls per kept index as
         `extract_frames` (absolute seek + read), so the frames and timestamps are the reference's.  Returns
         `(middle_frames [m,H,W,3] uint8 RGB, window_timestamps [m], n_sampled)`, or None when the shortcut cannot prove
         that it is equivalent: a middle frame or the LAST sampled frame fails to decode (a truncated file shortens the
-        reference's frame list and with it the windows) -- the caller then takes the full `extract_frames` path."""
+        reference's frame list and with it the windows) -- the caller then takes the full `extract_frames` path.
+        `bgr=True` returns the frames as the decoder delivers them (OpenCV's BGR order) and leaves the channel swap of
+        frame_extractor.py:191 to K1 (capi.INPUT_BGR), which saves a pass over every decoded frame on the host."""
         try:
             import cv2
         except ImportError as e:  # pragma: no cover
@@ -85,7 +87,7 @@ class FrameExtractor:
                 if not ok:
                     return None
                 if j in mid_set:
-                    got[j] = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+                    got[j] = frame if bgr else cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
             return np.stack([got[j] for j in mid_idx]), window_ts, len(sampled)
         finally:
             cap.release()

@@ -66,6 +66,13 @@ typedef struct b200clip_config {
 #define B200CLIP_RESIZE_BICUBIC 2     /* open_clip's transform only (what `preprocess(PIL)` does): Pillow bicubic(aa)
                                          Resize(S) -> CenterCrop, no 512 shrink */
 
+/* OR-ed into `resize_mode` of the uint8 RGB entry points (preprocess_u8, preprocess_u8_chw, encode_frames_u8,
+   encode_frames_u8_host): the frames are in OpenCV's BGR order, as cv2.VideoCapture delivers them.  Replaces the
+   per-frame cv2.cvtColor(frame, cv2.COLOR_BGR2RGB) of /root/reference/src/services/frame_extractor.py:191: every resize
+   stage works per channel, so the swap is applied in K1's final store (normalisation constants and output plane of
+   channel 2 - c); results are bit-identical to converting first.  Not accepted by the NV12 entry points. */
+#define B200CLIP_INPUT_BGR 0x100
+
 /* element types for embedding buffers */
 #define B200CLIP_F32 0
 #define B200CLIP_BF16 1

@@ -45,6 +45,9 @@ def test_middles_only_decode_equals_full_decode(tmp_path, monkeypatch, n, over):
     middle, ts, n_sampled = got
     assert n_sampled == len(frames) and ts == window_ts and len(middle) == len(mid_idx) >= 1
     assert middle.dtype == np.uint8 and np.array_equal(middle, frames[np.asarray(mid_idx)])
+    # decoder order (BGR) on request: the same frames with the channel swap of frame_extractor.py:191 left to K1
+    raw, ts_b, n_b = fx.extract_window_middles(path, bgr=True)
+    assert ts_b == ts and n_b == n_sampled and np.array_equal(raw[..., ::-1], middle)
     # and the same windows as the reference-shaped window builder
     windows, wts = fx.create_sliding_windows(frames, stamps)
     assert wts == window_ts

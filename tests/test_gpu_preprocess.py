@@ -150,3 +150,36 @@ def test_k1_code_path_variants(env):
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "k1_variant_check.py")
     r = subprocess.run([sys.executable, script], env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("w,h,mode", [(1920, 1080, "REFERENCE"), (1280, 720, "REFERENCE"), (640, 360, "REFERENCE"),
+                                      (224, 224, "REFERENCE"), (300, 300, "BICUBIC"), (1000, 700, "BILINEAR_AA")])
+def test_bgr_input_flag_equals_converting_first(model_b32, w, h, mode):
+    """capi.INPUT_BGR (B200CLIP_INPUT_BGR): frames in OpenCV's BGR order, as cv2.VideoCapture delivers them -- the
+    per-frame cv2.cvtColor(BGR2RGB) of frame_extractor.py:191 folded into K1's final store.  Must be the same BITS as
+    converting first, for the patch rows, the fp32 CHW planes (both store kernels) and through the host-frame path."""
+    import cv2
+
+    from b200clip import capi
+
+    m = getattr(capi, "RESIZE_" + mode)
+    rgb = np.concatenate([noise_frames(1, h, w, seed=w + 7 * h), structured_frames(2, h, w, seed=w + h)])
+    bgr = np.stack([cv2.cvtColor(f, cv2.COLOR_RGB2BGR) for f in rgb])
+    d_rgb, d_bgr = torch.from_numpy(rgb).cuda(), torch.from_numpy(bgr).cuda()
+    for chw in (False, True):
+        want = model_b32.preprocess_u8(d_rgb, m, chw=chw)
+        got = model_b32.preprocess_u8(d_bgr, m | capi.INPUT_BGR, chw=chw)
+        assert torch.equal(want.view(torch.int16 if not chw else torch.int32), got.view(torch.int16 if not chw else torch.int32))
+    e_want = model_b32.encode_frames_u8(d_rgb, m, normalize=True)
+    e_got = model_b32.encode_frames_u8(d_bgr, m | capi.INPUT_BGR, normalize=True)
+    assert torch.equal(e_want, e_got)
+    h_got = model_b32.encode_frames_u8_host(bgr, m | capi.INPUT_BGR, normalize=True)
+    assert np.array_equal(np.asarray(h_got), e_want.cpu().numpy())
+
+
+def test_bgr_flag_is_refused_for_nv12(model_b32):
+    from b200clip import capi
+
+    nv12 = torch.zeros(1, 1080 * 3 // 2, 1920, dtype=torch.uint8, device="cuda")
+    with pytest.raises(RuntimeError, match="resize mode"):
+        model_b32.preprocess_nv12(nv12, capi.RESIZE_REFERENCE | capi.INPUT_BGR)
