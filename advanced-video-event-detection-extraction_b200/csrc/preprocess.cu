@@ -1220,6 +1220,20 @@ vpass_store_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_
                 o.w = pack_bf16x2(s_lut[co * 256 + u8[6 * 3 + c]], s_lut[co * 256 + u8[7 * 3 + c]]);
                 const int64_t row = (f * grid + py) * grid + px0;
                 *reinterpret_cast<uint4*>(patches + row * patch_k + co * P * P + yy * P + (x0 - px0 * P)) = o;
+            } else if ((P & 1) == 0 && (npx & 1) == 0 && (patch_k & 1) == 0) {
+                // even patch size (P = 14): an even-aligned pixel pair never straddles a patch and its element index is
+                // even, so the row leaves as 4-byte stores
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    if (j >= npx) break;
+                    const int x = x0 + j;
+                    const int px = x / P, xx = x - px * P;
+                    if (px < grid && py < grid) {
+                        const int64_t row = (f * grid + py) * grid + px;
+                        *reinterpret_cast<uint32_t*>(patches + row * patch_k + co * P * P + yy * P + xx) =
+                            pack_bf16x2(s_lut[co * 256 + u8[j * 3 + c]], s_lut[co * 256 + u8[(j + 1) * 3 + c]]);
+                    }
+                }
             } else {
                 for (int j = 0; j < npx; ++j) {
                     const int x = x0 + j;
