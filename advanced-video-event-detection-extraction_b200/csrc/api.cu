@@ -34,7 +34,7 @@ const B200Knobs& b200_knobs() {
         b.k1_unfused = on("B200CLIP_K1_UNFUSED"); b.area_fp32 = on("B200CLIP_AREA_FP32"); b.area_px1 = on("B200CLIP_AREA_PX1");
         b.area_hfirst = on("B200CLIP_AREA_HFIRST"); b.area_nostrip = on("B200CLIP_AREA_NOSTRIP");
         b.vpass_generic = on("B200CLIP_VPASS_GENERIC");
-        b.gemm_1cta = on("B200CLIP_GEMM_1CTA"); b.gemm_spin_wait = on("B200CLIP_GEMM_SPIN_WAIT"); b.gemm_5stage = on("B200CLIP_GEMM_5STAGE");
+        b.gemm_1cta = on("B200CLIP_GEMM_1CTA"); b.gemm_spin_wait = on("B200CLIP_GEMM_SPIN_WAIT"); b.gemm_5stage = on("B200CLIP_GEMM_5STAGE"); b.hpass_px1 = on("B200CLIP_HPASS_PX1");
         b.sim_simt = on("B200CLIP_SIM_SIMT"); b.sim_stream_a = on("B200CLIP_SIM_STREAM_A");
         b.attn_oneshot = on("B200CLIP_ATTN_ONESHOT"); b.attn_tc = on("B200CLIP_ATTN_TC"); b.attn_tiled = on("B200CLIP_ATTN_TILED"); b.attn_tc2 = !on("B200CLIP_ATTN_NOTC2"); b.attn_tc64 = !on("B200CLIP_ATTN_NOTC64"); b.head_simt = on("B200CLIP_HEAD_SIMT");
         b.overlap = on("B200CLIP_OVERLAP"); b.full_upload = on("B200CLIP_FULL_UPLOAD");

@@ -112,6 +112,7 @@ enum { ATTR_GEMM64 = 1u << 0, ATTR_GEMM128 = 1u << 1, ATTR_GEMM256 = 1u << 2, AT
 struct B200Knobs {
     bool k1_unfused, area_fp32, area_px1, area_hfirst, area_nostrip, vpass_generic;   // K1 fallbacks
     bool gemm_1cta, gemm_spin_wait;
+    bool hpass_px1;            // B200CLIP_HPASS_PX1: generic horizontal pass with one output pixel per thread
     bool gemm_5stage;          // B200CLIP_GEMM_5STAGE: five-stage / two-box 2-CTA GEMM for every shape
     bool sim_simt, sim_stream_a;
     bool attn_oneshot, attn_tc, attn_tiled, attn_tc2, attn_tc64;

@@ -1163,6 +1163,51 @@ hpass_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_
     o[0] = clip8(a0); o[1] = clip8(a1); o[2] = clip8(a2);
 }
 
+// B, four output pixels per thread (S % 4 == 0, 4-byte aligned rows of dst): the 12 result bytes leave as three 32-bit
+// stores instead of twelve byte stores, and the four independent tap chains give the scheduler something to overlap.
+// Same arithmetic per pixel as hpass_kernel.
+template <bool FAST>
+__global__ void __launch_bounds__(256)
+hpass4_kernel(const uint8_t* __restrict__ src, int64_t frame_stride, int64_t row_stride, int src_x0,
+              uint8_t* __restrict__ dst, int64_t dst_frame_stride, int ny, int ocol0, int S, DevTaps bx) {
+    const int sq = S >> 2;
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= static_cast<unsigned>(ny * sq)) return;
+    const int y = id / sq, x = (id - y * sq) << 2;
+    const int64_t f = blockIdx.y;
+    const uint8_t* rowp = src + f * frame_stride + static_cast<int64_t>(y) * row_stride;
+    uint32_t w[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int ox = ocol0 + x + q;
+        const int lo = __ldg(bx.start + ox), cnt = __ldg(bx.cnt + ox);
+        const int* k = bx.wi + ox * bx.stride;
+        const uint8_t* p = rowp + (lo - src_x0) * 3;
+        int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+        if (FAST) {
+            uint32_t u[6];
+            load_bytes_aligned<6>(p, cnt * 3, u);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const int kk = i < cnt ? __ldg(k + i) : 0;   // bytes past cnt may be junk: weight 0
+                a0 += kk * byte_as_int<6>(u, i * 3);
+                a1 += kk * byte_as_int<6>(u, i * 3 + 1);
+                a2 += kk * byte_as_int<6>(u, i * 3 + 2);
+            }
+        } else {
+            for (int i = 0; i < cnt; ++i) {
+                const int kk = __ldg(k + i);
+                a0 += kk * p[i * 3]; a1 += kk * p[i * 3 + 1]; a2 += kk * p[i * 3 + 2];
+            }
+        }
+        const uint32_t b[3] = {clip8(a0), clip8(a1), clip8(a2)};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) w[(q * 3 + c) >> 2] |= b[c] << (8 * ((q * 3 + c) & 3));
+    }
+    uint32_t* o = reinterpret_cast<uint32_t*>(dst + f * dst_frame_stride + (static_cast<int64_t>(y) * S + x) * 3);
+    o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
+}
+
 // C: vertical pass (or plain crop) + ToTensor/Normalize lookup + store.  One thread per 8 output pixels of one
 // output row (all 3 channels): 24 contiguous source bytes per tap, fetched as aligned words.  Output either bf16
 // patch-major rows (col = c*P*P + y*P + x, patch_k padded) or fp32 CHW.
@@ -1999,7 +2044,15 @@ int launch_preprocess(b200clip_handle* h, const uint8_t* frames, int n, int H, i
         const uint8_t* base = cur + static_cast<int64_t>(p.ry0 - cur_y0) * cur_rs;
         dim3 grid((static_cast<unsigned>(ny) * S + 255) / 256, n);
         ProfScope psb(h, PROF_PRE_B, static_cast<double>(n) * ny * (p.rx1 - p.rx0 + S) * 3.0, st);
-        if (p.b_max_cnt <= 7)
+        // four pixels per thread whenever the 12-byte groups of mid2 are word aligned (B200CLIP_HPASS_PX1=1: one pixel
+        // per thread, the form the other shapes use)
+        const bool px4 = !b200_knobs().hpass_px1 && (S & 3) == 0 && (p.mid2_per_frame & 3) == 0 && (reinterpret_cast<uintptr_t>(mid2) & 3) == 0;
+        dim3 grid4((static_cast<unsigned>(ny) * (S >> 2) + 255) / 256, n);
+        if (px4 && p.b_max_cnt <= 7)
+            hpass4_kernel<true><<<grid4, 256, 0, st>>>(base, cur_fs, cur_rs, cur_x0, mid2, p.mid2_per_frame, ny, p.left, S, p.bx);
+        else if (px4)
+            hpass4_kernel<false><<<grid4, 256, 0, st>>>(base, cur_fs, cur_rs, cur_x0, mid2, p.mid2_per_frame, ny, p.left, S, p.bx);
+        else if (p.b_max_cnt <= 7)
             hpass_kernel<true><<<grid, 256, 0, st>>>(base, cur_fs, cur_rs, cur_x0, mid2, p.mid2_per_frame, ny, p.left, S,
                                                      p.bx);
         else

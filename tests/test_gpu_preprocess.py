@@ -130,11 +130,13 @@ def test_1080p_window_alignments(model_b32, pad_w, x_off):
 @pytest.mark.parametrize("env", [{}, {"B200CLIP_AREA_FP32": "1"}, {"B200CLIP_K1_UNFUSED": "1"},
                                  {"B200CLIP_K1_UNFUSED": "1", "B200CLIP_AREA_NOSTRIP": "1"}, {"B200CLIP_VPASS_GENERIC": "1"}, {"B200CLIP_AREA_HFIRST": "1"},
                                  {"B200CLIP_AREA_HFIRST": "1", "B200CLIP_AREA_PX1": "1"}, {"B200CLIP_K1_PERSISTENT": "1"},
-                                 {"B200CLIP_AREA_NOMMA": "1"}, {"B200CLIP_AREA_NOMMA": "1", "B200CLIP_K1_PERSISTENT": "1"}],
+                                 {"B200CLIP_AREA_NOMMA": "1"}, {"B200CLIP_AREA_NOMMA": "1", "B200CLIP_K1_PERSISTENT": "1"},
+                                 {"B200CLIP_HPASS_PX1": "1"}, {"B200CLIP_HPASS_PX1": "1", "B200CLIP_K1_UNFUSED": "1"}],
                          ids=["default-imma", "fused-fp32", "unfused-strip",
                               "unfused-per-pixel", "imma-generic-vpass", "int-exact-horizontal-first-2col",
                               "int-exact-horizontal-first-1col", "vertical-first-persistent-ctas",
-                              "int-exact-vertical-first", "int-exact-vertical-first-persistent"])
+                              "int-exact-vertical-first", "int-exact-vertical-first-persistent",
+                              "generic-hpass-1px", "unfused-generic-hpass-1px"])
 def test_k1_code_path_variants(env):
     """Every K1 area-stage implementation (IMMA, integer-exact fused, fp32 fused, strip walker, per-pixel) must give the
     same bytes as cv2; the path is chosen once per process, so each variant runs tests/k1_variant_check.py in its own
@@ -144,7 +146,7 @@ def test_k1_code_path_variants(env):
 
     e = dict(os.environ)
     for k in ("B200CLIP_AREA_FP32", "B200CLIP_AREA_PX1", "B200CLIP_K1_UNFUSED", "B200CLIP_AREA_NOSTRIP", "B200CLIP_VPASS_GENERIC",
-              "B200CLIP_AREA_HFIRST", "B200CLIP_K1_PERSISTENT", "B200CLIP_AREA_NOMMA"):
+              "B200CLIP_AREA_HFIRST", "B200CLIP_K1_PERSISTENT", "B200CLIP_AREA_NOMMA", "B200CLIP_HPASS_PX1"):
         e.pop(k, None)
     e.update(env)
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "k1_variant_check.py")
