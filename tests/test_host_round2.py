@@ -119,3 +119,29 @@ def test_cache_key_covers_sampling_settings(tmp_path):
                              window_stride=8, resume=True)
     with EmbeddingCacheWriter(path, 8, "float32", True, meta, window_size=16, window_stride=8, resume=True) as w:
         assert w.rows == 3
+
+
+def test_two_plane_bf16_split_keeps_fp32_like_precision():
+    """The formulation behind head_mma_kernel (csrc/vit_kernels.cu): the LayerNorm output v (fp32) is handed to the
+    tensor cores as TWO bf16 planes, hi = bf16(v) and lo = bf16(v - hi), both multiplied with the bf16 projection and
+    accumulated in fp32.  hi + lo carries 16 mantissa bits, so the product must agree with the fp32 CUDA-core kernel
+    (v @ W in fp32 with the same bf16-rounded W) to ~2^-16 relative -- far inside the 0.999 cosine / 1e-2 score bars --
+    while a single bf16 plane would be 2^-9.  Re-enacted here with torch on the CPU."""
+    import torch
+
+    torch.manual_seed(0)
+    for width, embed in ((768, 512), (1024, 768), (512, 512)):
+        x = torch.randn(64, width) * 3.0
+        v = torch.nn.functional.layer_norm(x, (width,), torch.rand(width) + 0.5, torch.randn(width) * 0.1, 1e-5)
+        w = (torch.randn(width, embed) * width ** -0.5).bfloat16().float()
+        want = (v.double() @ w.double())
+        hi = v.bfloat16().float()
+        lo = (v - hi).bfloat16().float()
+        two = (hi @ w + lo @ w).double()
+        one = (hi @ w).double()
+        scale = want.abs().max()
+        assert float((two - want).abs().max() / scale) < 2e-5
+        assert float((one - want).abs().max() / scale) > 1e-4       # what the split buys
+        # after L2 normalisation the embeddings are indistinguishable at the parity tolerances
+        a, b = two / two.norm(dim=-1, keepdim=True), want / want.norm(dim=-1, keepdim=True)
+        assert float((a * b).sum(-1).min()) > 1 - 1e-9
