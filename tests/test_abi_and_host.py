@@ -102,3 +102,22 @@ def test_tokenizer_surface():
     assert t.shape == (2, 77) and t.dtype == torch.long
     assert torch.equal(t, synthetic_tokenize(["a person walking", "red car"]))
     assert torch.equal(tok("one two"), tok(["one two"]))
+
+
+def test_python_constants_equal_the_header():
+    """Every `#define B200CLIP_<NAME> <int>` of include/b200clip.h that the ctypes binding mirrors (resize modes, the
+    BGR input flag, element types, error codes) must carry the same value in capi -- the header is the contract, the
+    binding is a copy."""
+    import re
+
+    from b200clip import capi
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "b200clip.h")).read()
+    defs = {m.group(1): int(m.group(2).strip("()"), 0)
+            for m in re.finditer(r"^#define B200CLIP_(\w+)\s+(\(?-?(?:0x[0-9a-fA-F]+|\d+)\)?)\s*(?:/\*|$)", text, re.M)}
+    for name in ("RESIZE_REFERENCE", "RESIZE_BILINEAR_AA", "RESIZE_BICUBIC", "INPUT_BGR", "F32", "BF16"):
+        assert defs[name] == getattr(capi, name), name
+    for code, label in capi.ERRORS.items():
+        assert defs[label] == code, label
+    assert defs["OK"] == 0 and defs["INPUT_BGR"] & 0xff == 0      # the flag lives above the resize-mode byte
