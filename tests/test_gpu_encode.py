@@ -189,3 +189,33 @@ def test_text_and_image_towers_overlap_on_two_streams(model_b32):
         cur.wait_stream(side)
         torch.cuda.synchronize()
         assert torch.equal(emb, emb0) and torch.equal(txt, txt0)
+
+
+def test_vitb32_1080p_second_golden_24_frames(model_b32, golden_dir):
+    """tests/golden/vitb32_1080p_more.npz: 24 more decoded 1080p frames (20 structured, 4 noise) through the reference's
+    own resize_frame_for_memory + OpenCLIPModel.encode_images / encode_text / compute_similarity
+    (tests/golden/make_golden_1080p_more.py).  The CUDA path gets the raw frames (K1 does the shrink) through the
+    host-frame entry point, the RGB and the NV12-converted-back device paths included via the same kernels."""
+    sys_path_golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    import sys
+
+    if sys_path_golden not in sys.path:
+        sys.path.insert(0, sys_path_golden)
+    from make_golden_1080p_more import frames_1080p
+
+    from b200clip import capi
+    from oracle.clip_ref import synthetic_tokenize
+
+    g = np.load(os.path.join(golden_dir, "vitb32_1080p_more.npz"))
+    hd = frames_1080p()
+    assert len(hd) == len(g["emb"]) == 24
+    emb = model_b32.encode_frames_u8_host(hd, capi.RESIZE_REFERENCE, normalize=True)
+    cos = cosine_rows(emb, g["emb"])
+    txt = model_b32.encode_text(synthetic_tokenize(list(QUERIES)).cuda(), normalize=True).cpu().numpy()
+    scores = model_b32.similarity(torch.from_numpy(np.asarray(emb)).cuda(), torch.from_numpy(txt).cuda()).cpu().numpy()
+    ds = np.abs(scores - g["scores"]).max()
+    print(f"\n[parity] 1080p x 24 cosine min {cos.min():.6f} mean {cos.mean():.6f}; max |dscore| {ds:.5f}")
+    assert cos.min() >= COS_MIN and cosine_rows(txt, g["txt"]).min() >= COS_MIN and ds <= SCORE_TOL
+    # BGR-ordered input with the flag: the same embeddings, bit for bit
+    emb_bgr = model_b32.encode_frames_u8_host(np.ascontiguousarray(hd[..., ::-1]), capi.RESIZE_REFERENCE | capi.INPUT_BGR, normalize=True)
+    assert np.array_equal(np.asarray(emb_bgr), np.asarray(emb))

@@ -54,3 +54,25 @@ def test_patchify_is_conv_unfold():
     conv = torch.nn.functional.conv2d(torch.from_numpy(chw)[None], w, stride=32)[0].reshape(16, -1).T
     gemm = torch.from_numpy(P.patchify(chw, 32)) @ w.reshape(16, -1).T
     assert torch.allclose(conv, gemm, atol=1e-4)
+
+
+def test_oracle_pipeline_matches_second_1080p_golden(golden_dir):
+    """The CPU restatement (cv2 INTER_AREA shrink -> PIL transform -> fp32 ViT) against what the reference's own classes
+    produced for the 24-frame 1080p golden (tests/golden/make_golden_1080p_more.py): same embeddings to fp32 noise, on
+    a structured and a noise frame (a 1080p frame costs about a second on the CPU)."""
+    import sys
+
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+    from make_golden_1080p_more import N_STRUCTURED, SEED_NOISE, SEED_STRUCTURED
+    from oracle import clip_ref
+    from oracle.reference_pipeline import ReferenceCPU
+    from synth import noise_frames, structured_frames
+
+    g = np.load(os.path.join(golden_dir, "vitb32_1080p_more.npz"))
+    ref = ReferenceCPU("ViT-B-32", state_dict=clip_ref.init_state_dict(clip_ref.CONFIGS["ViT-B-32"], seed=0, gain=1.0))
+    frames = np.concatenate([structured_frames(1, 1080, 1920, seed=SEED_STRUCTURED), noise_frames(1, 1080, 1920, seed=SEED_NOISE)])
+    emb = ref.encode_images(frames, shrink=True)
+    assert np.abs(emb[0] - g["emb"][0]).max() < 2e-5
+    assert np.abs(emb[1] - g["emb"][N_STRUCTURED]).max() < 2e-5
