@@ -54,7 +54,7 @@ class FrameExtractor:
             raise ValueError(f"No frames extracted from video: {video_path}")
         return np.stack(frames), stamps
 
-    def extract_window_middles(self, video_path: str, bgr: bool = False):
+    def extract_window_middles(self, video_path: str, bgr: bool = False, only=None):
         """Frame feed for phase 1: decode ONLY the frames phase 1 embeds -- the middle frame of every
         sliding window (phase1_mvp.py:80) -- instead of every sampled frame (frame_extractor.py:76-104 decodes all of
         them and phase 1 then drops 7 of 8 at the default 16 / 8 windows).  Same decoder calls per kept index as
@@ -63,7 +63,9 @@ class FrameExtractor:
         that it is equivalent: a middle frame or the LAST sampled frame fails to decode (a truncated file shortens the
         reference's frame list and with it the windows) -- the caller then takes the full `extract_frames` path.
         `bgr=True` returns the frames as the decoder delivers them (OpenCV's BGR order) and leaves the channel swap of
-        frame_extractor.py:191 to K1 (capi.INPUT_BGR), which saves a pass over every decoded frame on the host."""
+        frame_extractor.py:191 to K1 (capi.INPUT_BGR), which saves a pass over every decoded frame on the host.
+        `only=[window indices]` decodes just those windows' frames (returned in that order, with their timestamps):
+        what a re-ranker needs for its <= 2 * top_k candidates."""
         try:
             import cv2
         except ImportError as e:  # pragma: no cover
@@ -79,6 +81,10 @@ class FrameExtractor:
                 return None
             stamps = [i / fps for i in sampled]
             mid_idx, window_ts = self.window_middles(len(sampled), stamps)
+            if only is not None:
+                if any(w < 0 or w >= len(mid_idx) for w in only):
+                    raise IndexError(f"window index out of range (video has {len(mid_idx)} windows)")
+                mid_idx, window_ts = [mid_idx[w] for w in only], [window_ts[w] for w in only]
             mid_set = set(mid_idx)
             got = {}
             for j in sorted(mid_set | {len(sampled) - 1}):        # + sentinel: the last sampled frame must decode
@@ -88,6 +94,8 @@ class FrameExtractor:
                     return None
                 if j in mid_set:
                     got[j] = frame if bgr else cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+            if not mid_idx:
+                return np.empty((0, 0, 0, 3), np.uint8), window_ts, len(sampled)
             return np.stack([got[j] for j in mid_idx]), window_ts, len(sampled)
         finally:
             cap.release()

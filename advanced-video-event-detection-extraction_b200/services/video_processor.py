@@ -26,10 +26,14 @@ _FILLERS = ["very", "really", "quite", "somewhat", "rather", "pretty"]
 
 
 class VideoProcessor:
-    def __init__(self, phase1: Phase1MVP | None = None):
+    def __init__(self, phase1: Phase1MVP | None = None, phase2=None):
+        """`phase2`: a pipeline.phase2_handoff.Phase2Reranker built around an injected captioning model (BLIP itself is
+        outside this path); without one "reranked" / "advanced" fall back to phase 1 like the reference does when its
+        phase 2 is unavailable (video_processor.py:436-447)."""
         self.phase1 = phase1 if phase1 is not None else Phase1MVP()
         self.clip_extractor = ClipExtractor()
-        self.phase2_available = False  # BLIP re-ranking is outside this path
+        self.phase2 = phase2
+        self.phase2_available = phase2 is not None
 
     def preprocess_query(self, query: str) -> str:
         query = re.sub(r"\s+", " ", query.strip())
@@ -68,9 +72,12 @@ class VideoProcessor:
                         "query": original_query, "mode": mode, "results": []}
             if mode not in ("mvp", "reranked", "advanced"):
                 raise ValueError(f"Unknown processing mode: {mode}")
-            if mode != "mvp":
-                logger.warning("Phase 2 not available, falling back to MVP mode")
-            result = self.phase1.process_video(video_path, processed_query, top_k, debug_mode=debug_mode, merge=merge)
+            if mode != "mvp" and self.phase2_available:
+                result = self.phase2.process_video(video_path, processed_query, top_k, debug_mode=debug_mode)
+            else:
+                if mode != "mvp":
+                    logger.warning("Phase 2 not available, falling back to MVP mode")
+                result = self.phase1.process_video(video_path, processed_query, top_k, debug_mode=debug_mode, merge=merge)
             debug_info = None
             if debug_mode and isinstance(result, tuple):
                 results, debug_info = result

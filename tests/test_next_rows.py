@@ -66,3 +66,122 @@ def test_single_stage_ranking_matches_reference(golden):
         conf = [w["confidence"] for w in want]
         ties += len(conf) - len(set(conf))
     assert ties > 0            # ties (lower frame index first) are covered
+
+
+def _tiny_frames(n):
+    f = np.zeros((n, 2, 2, 3), np.uint8)
+    f[:, 0, 0, 0] = np.arange(n) % 256
+    f[:, 0, 0, 1] = np.arange(n) // 256
+    return f
+
+
+def test_phase2_handoff_equals_the_reference_reranker(golden_dir):
+    """tests/golden/phase2_handoff.json = the reference's own Phase2Reranker.process_video
+    (/root/reference/src/pipeline/phase2_reranker.py:31-90) with phase 1, the frame extractor and BLIP replaced by
+    deterministic stubs (tests/golden/make_golden_phase2.py).  The same stubs around OUR hand-off must give the same
+    dicts: candidates asked of phase 1 (2 * top_k, 20 for None), captioned frame (window middle), 0.7 / 0.3 blend,
+    stable descending sort, truncation, empty result, debug tuple."""
+    import json
+
+    from b200clip.pipeline.phase2_handoff import Phase2Reranker
+    from b200clip.services.frame_extractor import FrameExtractor
+
+    cases = json.load(open(os.path.join(golden_dir, "phase2_handoff.json")))["cases"]
+    assert len(cases) >= 16
+    for c in cases:
+        n = c["n_frames"]
+        frames, stamps = _tiny_frames(n), [round(i / c["fps"], 4) for i in range(n)]
+        real = FrameExtractor()
+        m = len(real.window_middles(n, stamps)[0])
+        asked = []
+
+        class P1:
+            def process_video(self, video_path, query, top_k=None, debug_mode=None):
+                asked.append(top_k)
+                res = [dict(h) for h in c["hits"][:top_k]]
+                return (res, [{"window_index": i} for i in range(m)]) if debug_mode else res
+
+        class FX:
+            def extract_frames(self, video_path):
+                return frames, stamps
+
+            def create_sliding_windows(self, fr, ts):
+                return real.create_sliding_windows(fr, ts)
+
+        class Blip:
+            def generate_caption(self, frame):
+                return f"frame {int(frame[0, 0, 0]) + 256 * int(frame[0, 0, 1])}"
+
+            def compute_text_similarity(self, caption, query):
+                return float(c["caption_table"][int(caption.split()[1])])
+
+        r = Phase2Reranker(phase1=P1(), caption_model=Blip(), frame_extractor=FX())
+        out = r.process_video("video.mp4", "red car", c["top_k"], debug_mode=c["debug"])
+        assert asked == [c["asked_phase1_for"]]
+        assert out == c["output"]
+    with pytest.raises(RuntimeError, match="captioning model"):
+        Phase2Reranker(phase1=object(), caption_model=None, frame_extractor=object()).process_video("v.mp4", "q", 3)
+
+
+def test_phase2_candidate_frames_decode_only_what_is_captioned(tmp_path):
+    """On a real mp4 the re-ranker's frame access (extract_window_middles(only=...)) must hand BLIP the very frames the
+    reference's decode-everything + create_sliding_windows path would."""
+    cv2 = pytest.importorskip("cv2")
+    from b200clip.pipeline.phase2_handoff import Phase2Reranker
+    from b200clip.services.frame_extractor import FrameExtractor
+
+    path = str(tmp_path / "v.mp4")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 8.0, (96, 64))
+    for i in range(90):
+        f = np.zeros((64, 96, 3), np.uint8)
+        f[:, :, 0] = (3 * i) % 256
+        f[16:32, (2 * i) % 80:(2 * i) % 80 + 16, 2] = 255
+        vw.write(f)
+    vw.release()
+    fx = FrameExtractor()
+    frames, stamps = fx.extract_frames(path)
+    windows, wts = fx.create_sliding_windows(frames, stamps)
+    want = [7, 2, 9, 2, 0]
+    r = Phase2Reranker(phase1=object(), caption_model=object(), frame_extractor=fx)
+    got = r._middle_frames(path, want)
+    assert sorted(got) == [0, 2, 7, 9]
+    for w in got:
+        assert np.array_equal(got[w], windows[w][len(windows[w]) // 2])
+    sel, ts, n_sampled = fx.extract_window_middles(path, only=[9, 0])
+    assert ts == [wts[9], wts[0]] and n_sampled == len(frames) and np.array_equal(sel[0], windows[9][8])
+    with pytest.raises(IndexError):
+        fx.extract_window_middles(path, only=[len(wts)])
+
+
+def test_process_query_reranked_mode_uses_the_injected_phase2(tmp_path):
+    """video_processor.py:432-447: "reranked" / "advanced" go through phase 2 when it is available and fall back to
+    phase 1 otherwise; the threshold filter and the clip intervals apply to whichever list comes back."""
+    from b200clip.services.video_processor import VideoProcessor
+
+    f = tmp_path / "v.mp4"
+    f.write_bytes(b"0")
+    calls = []
+
+    class P1:
+        def process_video(self, video_path, query, top_k=None, debug_mode=None, merge=None):
+            calls.append(("p1", query, top_k))
+            return [{"timestamp": 4.0, "confidence": 0.5, "phase": "phase1_mvp", "window_index": 1}]
+
+    class P2:
+        def process_video(self, video_path, query, top_k=None, debug_mode=False):
+            calls.append(("p2", query, top_k))
+            return [{"timestamp": 40.0, "confidence": 0.6, "phase": "phase2_reranked", "window_index": 3, "caption": "c",
+                     "clip_score": 0.5, "caption_score": 0.83},
+                    {"timestamp": 2.0, "confidence": 0.1, "phase": "phase2_reranked", "window_index": 0, "caption": "d",
+                     "clip_score": 0.1, "caption_score": 0.1}]
+
+    vp = VideoProcessor(phase1=P1(), phase2=P2())
+    out = vp.process_query(str(f), "A dog  jumps", mode="reranked", top_k=4, threshold=0.25)
+    assert calls == [("p2", "dog jumping", 4)] and out["status"] == "success" and out["mode"] == "reranked"
+    assert [r["phase"] for r in out["results"]] == ["phase2_reranked"] and out["total_found"] == 1
+    assert out["results"][0]["clip_start"] == 25.0 and out["results"][0]["clip_end"] == 55.0
+    assert vp.process_query(str(f), "dog", mode="advanced", threshold=0.0)["total_found"] == 2
+    calls.clear()
+    fallback = VideoProcessor(phase1=P1()).process_query(str(f), "dog", mode="reranked", top_k=2, threshold=0.25)
+    assert calls == [("p1", "dog", 2)] and fallback["results"][0]["phase"] == "phase1_mvp"
+    assert vp.process_query(str(f), "dog", mode="mvp", top_k=2)["results"][0]["phase"] == "phase1_mvp"
