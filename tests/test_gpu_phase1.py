@@ -148,3 +148,48 @@ def test_process_video_on_a_real_mp4_matches_the_oracle_in_both_decode_modes(pha
     assert_topk_equivalent(ref_sims, [r["window_index"] for r in fast], [r["confidence"] for r in fast], 5)
     for r in fast:
         assert r["timestamp"] == window_ts[r["window_index"]] and r["phase"] == "phase1_mvp"
+
+
+def test_phase2_handoff_on_a_real_mp4_through_the_cuda_phase1(phase1, tmp_path):
+    """Phase2Reranker (pipeline/phase2_handoff.py) around the CUDA phase 1 and a stand-in captioner, on an mp4 decoded by
+    OpenCV: phase 1 is asked for 2 * top_k candidates, each candidate's caption comes from the RGB middle frame of ITS
+    window, scores blend 0.7 / 0.3 and the list is re-sorted and cut (phase2_reranker.py:31-90)."""
+    cv2 = pytest.importorskip("cv2")
+    from b200clip.pipeline.phase1_mvp import Phase1MVP
+    from b200clip.pipeline.phase2_handoff import Phase2Reranker
+    from b200clip.utils.config import settings
+
+    src = structured_frames(72, 240, 320, seed=11)
+    path = str(tmp_path / "clip.mp4")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 8.0, (320, 240))
+    for f in src:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+    vw.release()
+    p1 = Phase1MVP(clip_model=phase1.clip_model)
+    frames, stamps = p1.frame_extractor.extract_frames(path)
+    windows, wts = p1.frame_extractor.create_sliding_windows(frames, stamps)
+
+    class Captioner:
+        def generate_caption(self, frame):
+            return f"mean {float(frame[..., 0].mean()):.4f} {float(frame[..., 2].mean()):.4f}"     # R and B: order matters
+
+        def compute_text_similarity(self, caption, query):
+            return (float(caption.split()[1]) % 10.0) / 10.0
+
+    settings.CONFIDENCE_THRESHOLD = -1.0
+    try:
+        cands = p1.process_video(path, "red car driving", top_k=6)
+        out = Phase2Reranker(phase1=p1, caption_model=Captioner()).process_video(path, "red car driving", top_k=3)
+    finally:
+        settings.CONFIDENCE_THRESHOLD = 0.25
+    assert len(cands) == 6 and len(out) == 3 and all(r["phase"] == "phase2_reranked" for r in out)
+    cap = Captioner()
+    blended = []
+    for c in cands:
+        w = c["window_index"]
+        caption = cap.generate_caption(windows[w][len(windows[w]) // 2])
+        blended.append((0.7 * c["confidence"] + 0.3 * cap.compute_text_similarity(caption, ""), w, caption, c["confidence"]))
+    blended.sort(key=lambda t: t[0], reverse=True)
+    for r, (score, w, caption, clip) in zip(out, blended[:3]):
+        assert r["window_index"] == w and r["caption"] == caption and r["clip_score"] == clip
+        assert r["confidence"] == float(score) and r["timestamp"] == wts[w]
