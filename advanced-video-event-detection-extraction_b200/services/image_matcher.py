@@ -57,6 +57,26 @@ class ImageMatcher:
     def _compute_clip_similarity(self, reference_image: np.ndarray, frame: np.ndarray) -> float:
         return float(self.clip_similarities(reference_image, np.asarray(frame)[None])[0])
 
+    def stage2_clip_filter(self, reference_image: np.ndarray, candidates: List[Dict]) -> List[Dict]:
+        """Stage 2 of `_multi_stage_matching` (image_matcher.py:407-415): every candidate of the hash pre-filter (dicts
+        with a 'frame') gets its 'clip_similarity' and the list is cut at thresholds['clip_similarity'], order kept.
+        The reference embeds the reference image and one candidate frame per call; here the reference image is embedded
+        once and the candidate frames in one batched pass (frames of one video share a shape; mixed shapes fall back to
+        one pass per shape).  Stages 1, 3 and 4 (perceptual hash, SSIM, ORB / histogram) are CPU OpenCV code outside the
+        CLIP path and stay with the caller."""
+        if not candidates:
+            return []
+        by_shape: Dict[tuple, List[int]] = {}
+        for i, c in enumerate(candidates):
+            by_shape.setdefault(tuple(np.asarray(c["frame"]).shape), []).append(i)
+        for idx in by_shape.values():
+            sims = self.clip_similarities(reference_image, np.stack([np.asarray(candidates[i]["frame"]) for i in idx]))
+            for i, sim in zip(idx, sims):
+                candidates[i]["clip_similarity"] = float(sim)
+        kept = [c for c in candidates if c["clip_similarity"] >= self.thresholds["clip_similarity"]]
+        logger.info(f"Stage 2 filtered to {len(kept)} candidates")
+        return kept
+
     @staticmethod
     def rank_single_stage(similarities: Sequence[float], timestamps: Sequence[float], top_k: int,
                           similarity_threshold: float) -> List[Dict]:

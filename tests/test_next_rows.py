@@ -185,3 +185,32 @@ def test_process_query_reranked_mode_uses_the_injected_phase2(tmp_path):
     fallback = VideoProcessor(phase1=P1()).process_query(str(f), "dog", mode="reranked", top_k=2, threshold=0.25)
     assert calls == [("p1", "dog", 2)] and fallback["results"][0]["phase"] == "phase1_mvp"
     assert vp.process_query(str(f), "dog", mode="mvp", top_k=2)["results"][0]["phase"] == "phase1_mvp"
+
+
+def test_image_matcher_stage2_clip_filter(monkeypatch):
+    """image_matcher.py:407-415 on a table of similarities: every candidate gets its clip_similarity, the list is cut at
+    thresholds['clip_similarity'] (>=), order and the other keys are kept; frames of different shapes are batched per shape."""
+    from b200clip.services.image_matcher import ImageMatcher
+
+    # (5: float32(0.7) = 0.69999999 is below the Python-float threshold 0.7 -- also in the reference, whose
+    # similarities are float32 cosines converted with float())
+    table = {3: 0.71, 5: 0.7, 9: 0.7001, 12: 0.95, 40: 0.2}
+    m = ImageMatcher(clip_model=object())
+    batches = []
+
+    def fake(reference_image, frames):
+        batches.append(frames.shape)
+        return np.array([table[int(f[0, 0, 0])] for f in frames], np.float32)
+
+    monkeypatch.setattr(m, "clip_similarities", fake)
+    cands = []
+    for i, shape in ((3, (4, 4, 3)), (5, (4, 4, 3)), (9, (2, 6, 3)), (12, (4, 4, 3)), (40, (2, 6, 3))):
+        f = np.zeros(shape, np.uint8)
+        f[0, 0, 0] = i
+        cands.append({"index": i, "timestamp": i / 2.0, "frame": f, "hash_distance": 7})
+    kept = m.stage2_clip_filter(np.zeros((8, 8, 3), np.uint8), cands)
+    assert [c["index"] for c in kept] == [3, 9, 12]
+    assert [c["clip_similarity"] for c in kept] == [float(np.float32(0.71)), float(np.float32(0.7001)), float(np.float32(0.95))]
+    assert cands[1]["clip_similarity"] == float(np.float32(0.7)) and cands[4]["clip_similarity"] == float(np.float32(0.2))
+    assert all(c["hash_distance"] == 7 for c in kept) and sorted(batches) == [(2, 2, 6, 3), (3, 4, 4, 3)]
+    assert m.stage2_clip_filter(np.zeros((8, 8, 3), np.uint8), []) == []
