@@ -76,29 +76,57 @@ class FrameExtractor:
         try:
             total = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
             fps = cap.get(cv2.CAP_PROP_FPS) or 30.0
-            sampled = self.sample_indices(total)
-            if not sampled:
-                return None
-            stamps = [i / fps for i in sampled]
-            mid_idx, window_ts = self.window_middles(len(sampled), stamps)
-            if only is not None:
-                if any(w < 0 or w >= len(mid_idx) for w in only):
-                    raise IndexError(f"window index out of range (video has {len(mid_idx)} windows)")
-                mid_idx, window_ts = [mid_idx[w] for w in only], [window_ts[w] for w in only]
-            mid_set = set(mid_idx)
-            got = {}
-            for j in sorted(mid_set | {len(sampled) - 1}):        # + sentinel: the last sampled frame must decode
-                cap.set(cv2.CAP_PROP_POS_FRAMES, sampled[j])
-                ok, frame = cap.read()
-                if not ok:
-                    return None
-                if j in mid_set:
-                    got[j] = frame if bgr else cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
-            if not mid_idx:
-                return np.empty((0, 0, 0, 3), np.uint8), window_ts, len(sampled)
-            return np.stack([got[j] for j in mid_idx]), window_ts, len(sampled)
         finally:
             cap.release()
+        sampled = self.sample_indices(total)
+        if not sampled:
+            return None
+        stamps = [i / fps for i in sampled]
+        mid_idx, window_ts = self.window_middles(len(sampled), stamps)
+        if only is not None:
+            if any(w < 0 or w >= len(mid_idx) for w in only):
+                raise IndexError(f"window index out of range (video has {len(mid_idx)} windows)")
+            mid_idx, window_ts = [mid_idx[w] for w in only], [window_ts[w] for w in only]
+        mid_set = set(mid_idx)
+        need = sorted(mid_set | {len(sampled) - 1})               # + sentinel: the last sampled frame must decode
+
+        def read_some(js):
+            """One decoder handle per worker; the reference's calls (absolute seek + read) per index."""
+            c = cv2.VideoCapture(video_path)
+            out = {}
+            try:
+                if not c.isOpened():
+                    return None
+                for j in js:
+                    c.set(cv2.CAP_PROP_POS_FRAMES, sampled[j])
+                    ok, frame = c.read()
+                    if not ok:
+                        return None
+                    if j in mid_set:
+                        out[j] = frame if bgr else cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+                return out
+            finally:
+                c.release()
+
+        # seeks dominate (a seek decodes forward from the previous key frame), and OpenCV releases the GIL inside
+        # read(): contiguous runs of the needed indices go to B200_DECODE_WORKERS decoder handles in parallel
+        workers = max(1, min(int(settings.B200_DECODE_WORKERS), len(need) // 4 or 1))
+        if workers == 1:
+            parts = [read_some(need)]
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+
+            step = -(-len(need) // workers)
+            with ThreadPoolExecutor(max_workers=workers) as pool:
+                parts = list(pool.map(read_some, [need[i:i + step] for i in range(0, len(need), step)]))
+        if any(p is None for p in parts):
+            return None
+        got = {}
+        for p in parts:
+            got.update(p)
+        if not mid_idx:
+            return np.empty((0, 0, 0, 3), np.uint8), window_ts, len(sampled)
+        return np.stack([got[j] for j in mid_idx]), window_ts, len(sampled)
 
     def window_middles(self, n_frames: int, timestamps: List[float]) -> Tuple[List[int], List[float]]:
         """Index of the frame Phase 1 embeds for every sliding window (`window[len(window)//2]`,

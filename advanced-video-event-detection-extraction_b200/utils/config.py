@@ -43,6 +43,8 @@ class Settings:
         # (FrameExtractor.extract_window_middles; same frames, timestamps and results, 1/8 of the decode work and host
         # memory at the default 16 / 8 windows); 0 = decode every sampled frame like frame_extractor.py:76-104
         self.B200_DECODE_MIDDLES_ONLY = bool(_env("B200_DECODE_MIDDLES_ONLY", 1, int))
+        # decoder handles (threads) the middles-only decode spreads its seeks over (OpenCV releases the GIL while decoding)
+        self.B200_DECODE_WORKERS = _env("B200_DECODE_WORKERS", min(8, os.cpu_count() or 1), int)
         # embed each video once into DATA_DIR/embeddings/*.b2emb and answer later queries from the cache (off = the
         # reference's behaviour: decode + embed on every query)
         self.B200_EMBEDDING_CACHE = bool(_env("B200_EMBEDDING_CACHE", 0, int))
