@@ -30,8 +30,24 @@ class FrameExtractor:
             idx = idx[::step][:cap]
         return idx
 
+    @staticmethod
+    def _video_props(cap, cv2) -> Tuple[int, float]:
+        """(frame count, fps) with the reference's sanity check of the container's fps (frame_extractor.py:134-151)."""
+        total = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        fps = cap.get(cv2.CAP_PROP_FPS)
+        if fps <= 0 or fps > 1000:
+            logger.warning(f"Invalid FPS from OpenCV: {fps}")
+            try:
+                duration_ms = cap.get(cv2.CAP_PROP_POS_MSEC)
+                fps = total / (duration_ms / 1000.0) if duration_ms > 0 else 30.0
+            except Exception:
+                fps = 30.0
+        return total, fps
+
     def extract_frames(self, video_path: str) -> Tuple[np.ndarray, List[float]]:
-        """Decode + sample; timestamps = frame_index / fps (frame_extractor.py:104).  Returns raw RGB frames."""
+        """Decode + sample (frame_extractor.py:128-204, the OpenCV path); a frame's timestamp is the position the decoder
+        reports after the seek divided by fps (:183,201), which is frame_index / fps on well-formed files.  Returns raw
+        RGB frames."""
         try:
             import cv2
         except ImportError as e:  # pragma: no cover
@@ -39,16 +55,16 @@ class FrameExtractor:
         cap = cv2.VideoCapture(video_path)
         if not cap.isOpened():
             raise ValueError(f"Cannot open video: {video_path}")
-        total = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
-        fps = cap.get(cv2.CAP_PROP_FPS) or 30.0
+        total, fps = self._video_props(cap, cv2)
         frames, stamps = [], []
         for i in self.sample_indices(total):
             cap.set(cv2.CAP_PROP_POS_FRAMES, i)
+            actual_pos = cap.get(cv2.CAP_PROP_POS_FRAMES)
             ok, frame = cap.read()
-            if not ok:
+            if not ok or frame is None:
                 continue
             frames.append(cv2.cvtColor(frame, cv2.COLOR_BGR2RGB))
-            stamps.append(i / fps)
+            stamps.append(float(actual_pos) / float(fps))
         cap.release()
         if not frames:
             raise ValueError(f"No frames extracted from video: {video_path}")
@@ -74,19 +90,19 @@ class FrameExtractor:
         if not cap.isOpened():
             raise ValueError(f"Cannot open video: {video_path}")
         try:
-            total = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
-            fps = cap.get(cv2.CAP_PROP_FPS) or 30.0
+            total, fps = self._video_props(cap, cv2)
         finally:
             cap.release()
         sampled = self.sample_indices(total)
         if not sampled:
             return None
-        stamps = [i / fps for i in sampled]
-        mid_idx, window_ts = self.window_middles(len(sampled), stamps)
+        # (nominal stamps only drive the window arithmetic; a window's timestamp is its middle frame's, and that is taken
+        # from the decoder position reported after the seek, like the reference's timestamps list)
+        mid_idx, _ = self.window_middles(len(sampled), [0.0] * len(sampled))
         if only is not None:
             if any(w < 0 or w >= len(mid_idx) for w in only):
                 raise IndexError(f"window index out of range (video has {len(mid_idx)} windows)")
-            mid_idx, window_ts = [mid_idx[w] for w in only], [window_ts[w] for w in only]
+            mid_idx = [mid_idx[w] for w in only]
         mid_set = set(mid_idx)
         need = sorted(mid_set | {len(sampled) - 1})               # + sentinel: the last sampled frame must decode
 
@@ -99,11 +115,12 @@ class FrameExtractor:
                     return None
                 for j in js:
                     c.set(cv2.CAP_PROP_POS_FRAMES, sampled[j])
+                    actual_pos = c.get(cv2.CAP_PROP_POS_FRAMES)
                     ok, frame = c.read()
-                    if not ok:
+                    if not ok or frame is None:
                         return None
                     if j in mid_set:
-                        out[j] = frame if bgr else cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+                        out[j] = (frame if bgr else cv2.cvtColor(frame, cv2.COLOR_BGR2RGB), float(actual_pos) / float(fps))
                 return out
             finally:
                 c.release()
@@ -125,8 +142,8 @@ class FrameExtractor:
         for p in parts:
             got.update(p)
         if not mid_idx:
-            return np.empty((0, 0, 0, 3), np.uint8), window_ts, len(sampled)
-        return np.stack([got[j] for j in mid_idx]), window_ts, len(sampled)
+            return np.empty((0, 0, 0, 3), np.uint8), [], len(sampled)
+        return np.stack([got[j][0] for j in mid_idx]), [got[j][1] for j in mid_idx], len(sampled)
 
     def window_middles(self, n_frames: int, timestamps: List[float]) -> Tuple[List[int], List[float]]:
         """Index of the frame Phase 1 embeds for every sliding window (`window[len(window)//2]`,

@@ -30,3 +30,21 @@ def noise_frames(n: int, h: int, w: int, seed: int = 99) -> np.ndarray:
 
 
 QUERIES = ["a person walks across the street", "red car drives fast", "the dog jumps over a fence"]
+
+
+def write_test_video(path, n: int, w: int = 96, h: int = 64, fps: float = 8.0) -> str:
+    """A small deterministic mp4 (OpenCV's mp4v encoder): per-frame background level, a sliding gradient and a moving
+    block, so that every frame decodes to distinct pixels."""
+    import cv2
+
+    vw = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"mp4v"), fps, (w, h))
+    assert vw.isOpened()
+    xs = np.arange(w)[None, :]
+    for i in range(n):
+        f = np.zeros((h, w, 3), np.uint8)
+        f[:, :, 0] = (3 * i) % 256
+        f[:, :, 1] = ((xs + 5 * i) % 256).astype(np.uint8)
+        f[h // 4:h // 2, (2 * i) % (w - 16):(2 * i) % (w - 16) + 16, 2] = 255
+        vw.write(f)
+    vw.release()
+    return str(path)

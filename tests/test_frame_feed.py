@@ -11,17 +11,9 @@ cv2 = pytest.importorskip("cv2")
 
 
 def _write_video(path, n, w=96, h=64, fps=8.0):
-    vw = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"mp4v"), fps, (w, h))
-    assert vw.isOpened()
-    xs = np.arange(w)[None, :]
-    for i in range(n):
-        f = np.zeros((h, w, 3), np.uint8)
-        f[:, :, 0] = (3 * i) % 256
-        f[:, :, 1] = ((xs + 5 * i) % 256).astype(np.uint8)
-        f[h // 4:h // 2, (2 * i) % (w - 16):(2 * i) % (w - 16) + 16, 2] = 255
-        vw.write(f)
-    vw.release()
-    return str(path)
+    from synth import write_test_video
+
+    return write_test_video(path, n, w, h, fps)
 
 
 def _extractor(monkeypatch, **over):
@@ -99,3 +91,32 @@ def test_unreadable_file_raises_like_extract_frames(tmp_path, monkeypatch):
         fx.extract_window_middles(str(bad))
     with pytest.raises(ValueError, match="Cannot open video"):
         fx.extract_frames(str(bad))
+
+
+def test_decode_semantics_equal_the_reference_frame_extractor(tmp_path, monkeypatch, golden_dir):
+    """tests/golden/frame_extractor.json = the reference's own FrameExtractor (OpenCV path) on mp4 files written by
+    synth.write_test_video (tests/golden/make_golden_frames.py): sampled-frame count (incl. the 1000-frame cap with
+    step 1 and 2), timestamps from the decoder position, window timestamps, and -- after the reference's <= 512 x 512
+    INTER_AREA shrink, which this repository performs inside K1 instead -- the very pixels of every kept frame."""
+    import json
+    import os
+    import zlib
+
+    from oracle.reference_pipeline import resize_frame_for_memory
+    from synth import write_test_video
+
+    cases = json.load(open(os.path.join(golden_dir, "frame_extractor.json")))["cases"]
+    assert len(cases) >= 7
+    for c in cases:
+        fx = _extractor(monkeypatch, FRAME_SAMPLE_RATE=c["sample_rate"])
+        path = write_test_video(tmp_path / f"v_{c['n']}_{c['w']}_{c['sample_rate']}.mp4", c["n"], c["w"], c["h"], c["fps"])
+        frames, stamps = fx.extract_frames(path)
+        assert stamps == c["timestamps"] and len(frames) == c["shape"][0]
+        shrunk = [resize_frame_for_memory(f) for f in frames]
+        assert list(shrunk[0].shape) == c["shape"][1:] and str(shrunk[0].dtype) == c["dtype"]
+        assert [zlib.crc32(np.ascontiguousarray(f).tobytes()) for f in shrunk] == c["frame_crc"]
+        mid_idx, wts = fx.window_middles(len(frames), stamps)
+        assert wts == c["window_timestamps"] and len(wts) == c["windows"]
+        middle, ts, n_sampled = fx.extract_window_middles(path)
+        assert ts == c["window_timestamps"] and n_sampled == c["shape"][0]
+        assert [zlib.crc32(np.ascontiguousarray(resize_frame_for_memory(f)).tobytes()) for f in middle] == [c["frame_crc"][i] for i in mid_idx]
