@@ -95,3 +95,24 @@ def test_merge_oracle_equals_global_sort():
     ms, mi = R.merge_topk_lists(np.stack(cs), np.stack(ci), k)
     want = np.lexsort((np.arange(1000), s))[::-1][:k]
     assert np.array_equal(mi, want) and np.array_equal(ms, s[want])
+
+
+def test_clip_interval_equals_the_reference_clip_extractor(golden_dir):
+    """tests/golden/clip_intervals.json = the reference's own ClipExtractor.extract_clip_with_padding -> extract_clip with
+    ffmpeg replaced by a recorder (tests/golden/make_golden_clips.py): 52 (timestamp, clip duration, video duration)
+    cases incl. the negative-start, empty-interval and past-the-end clamps.  The oracle restatement and the product's
+    host mirror (the K4 kernel's float64 intervals are compared with the oracle in tests/test_gpu_topk.py) must agree."""
+    import json
+    import os
+
+    from b200clip.services.clip_extractor import ClipExtractor
+    from b200clip.utils.config import settings
+
+    cases = json.load(open(os.path.join(golden_dir, "clip_intervals.json")))["cases"]
+    assert len(cases) >= 50
+    ce = ClipExtractor()
+    for c in cases:
+        dur = settings.CLIP_DURATION if c["duration"] is None else c["duration"]
+        for fn in (R.clip_interval, ce.clip_interval):
+            s, e = fn(c["timestamp"], dur, c["video_duration"])
+            assert s == c["start"] and abs(e - c["end"]) <= 1e-9 and abs((e - s) - c["t"]) <= 1e-9, (c, s, e)
