@@ -3,8 +3,8 @@
 Only the text-query path is kept; the other model stacks the reference loads here are out of scope."""
 from __future__ import annotations
 
-import os
 import re
+from pathlib import Path
 from typing import Dict, Optional
 
 from ..pipeline.phase1_mvp import Phase1MVP
@@ -30,10 +30,26 @@ class VideoProcessor:
         """`phase2`: a pipeline.phase2_handoff.Phase2Reranker built around an injected captioning model (BLIP itself is
         outside this path); without one "reranked" / "advanced" fall back to phase 1 like the reference does when its
         phase 2 is unavailable (video_processor.py:436-447)."""
-        self.phase1 = phase1 if phase1 is not None else Phase1MVP()
+        self.phase1 = phase1
         self.clip_extractor = ClipExtractor()
         self.phase2 = phase2
         self.phase2_available = phase2 is not None
+        self._models_loaded = phase1 is not None
+        if not self._models_loaded:
+            # like the reference's constructor (video_processor.py:19-32,145-170): a failed load is logged, the object
+            # survives, and process_query reports it as a 'model_loading_error' dict (:390-402) after one more attempt
+            try:
+                self._load_models()
+            except Exception as e:
+                logger.error(f"Model loading failed: {e}")
+
+    def _load_models(self):
+        self.phase1 = Phase1MVP()
+        self._models_loaded = True
+
+    def _ensure_models_loaded(self):
+        if not self._models_loaded:
+            self._load_models()
 
     def preprocess_query(self, query: str) -> str:
         query = re.sub(r"\s+", " ", query.strip())
@@ -47,18 +63,32 @@ class VideoProcessor:
         return query
 
     def validate_video(self, video_path: str) -> Dict:
-        if not os.path.exists(video_path):
-            return {"valid": False, "error": f"Video file not found: {video_path}"}
-        ext = os.path.splitext(video_path)[1].lower().lstrip(".")
-        if ext not in settings.SUPPORTED_FORMATS:
-            return {"valid": False, "error": f"Unsupported video format: {ext}"}
-        if os.path.getsize(video_path) > settings.MAX_VIDEO_SIZE:
-            return {"valid": False, "error": "Video file too large"}
-        return {"valid": True}
+        """video_processor.py:817-847, message for message (they travel to the caller inside process_query's error
+        dict)."""
+        try:
+            video_file = Path(video_path)
+            if not video_file.exists():
+                return {"valid": False, "error": "Video file does not exist"}
+            file_extension = video_file.suffix.lower().lstrip(".")
+            if file_extension not in settings.SUPPORTED_FORMATS:
+                return {"valid": False,
+                        "error": f"Unsupported format: {file_extension}. Supported: {settings.SUPPORTED_FORMATS}"}
+            file_size = video_file.stat().st_size
+            if file_size > settings.MAX_VIDEO_SIZE:
+                return {"valid": False,
+                        "error": f"Video file too large: {file_size} bytes. Max: {settings.MAX_VIDEO_SIZE} bytes"}
+            return {"valid": True, "format": file_extension, "size": file_size, "path": str(video_file)}
+        except Exception as e:
+            return {"valid": False, "error": f"Error validating video: {str(e)}"}
 
     def process_query(self, video_path: str, query: str, mode: str = "mvp", top_k: Optional[int] = None,
                       threshold: Optional[float] = None, debug_mode: bool = False, merge=None) -> Dict:
         """`merge`: see Phase1MVP.process_video (None = settings.B200_TEMPORAL_MERGE, default off)."""
+        try:
+            self._ensure_models_loaded()
+        except Exception as e:
+            return {"status": "error", "error": f"Failed to load required models: {str(e)}", "query": query, "mode": mode,
+                    "results": [], "error_type": "model_loading_error"}
         if top_k is None:
             top_k = settings.TOP_K_RESULTS
         if threshold is None:
@@ -95,5 +125,7 @@ class VideoProcessor:
                 response["debug_info"] = debug_info
             return response
         except MemoryError as e:
-            return {"status": "error", "error": f"Insufficient memory to process video. Details: {e}",
+            return {"status": "error",
+                    "error": "Insufficient memory to process video. Try using a smaller video or restart the application. "
+                             f"Details: {str(e)}",
                     "query": original_query, "mode": mode, "results": [], "error_type": "memory_error"}

@@ -145,3 +145,49 @@ def test_two_plane_bf16_split_keeps_fp32_like_precision():
         # after L2 normalisation the embeddings are indistinguishable at the parity tolerances
         a, b = two / two.norm(dim=-1, keepdim=True), want / want.norm(dim=-1, keepdim=True)
         assert float((a * b).sum(-1).min()) > 1 - 1e-9
+
+
+def test_validation_and_error_dicts_equal_the_reference(tmp_path, monkeypatch):
+    """tests/golden/validate_video.json = the reference's own VideoProcessor.validate_video and the dicts its
+    process_query returns for a failed validation, a MemoryError out of phase 1 and a model load that fails
+    (tests/golden/make_golden_validate.py).  The boundary caller never raises for these: same keys, same
+    messages."""
+    import json
+    import sys
+
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+    from make_golden_validate import make_files
+
+    from b200clip.services.video_processor import VideoProcessor
+    from b200clip.utils.config import settings
+
+    g = json.load(open(os.path.join(gdir, "validate_video.json")))
+    make_files(str(tmp_path))
+    monkeypatch.setattr(settings, "MAX_VIDEO_SIZE", g["max_video_size"])
+
+    def scrub(x):
+        return json.loads(json.dumps(x).replace(str(tmp_path), "<DIR>"))
+
+    class P1:
+        def process_video(self, *a, **k):
+            raise MemoryError("cannot allocate 12 GB")
+
+    vp = VideoProcessor(phase1=P1())
+    for c in g["validate"]:
+        assert scrub(vp.validate_video(str(tmp_path / c["name"]))) == c["result"], c["name"]
+    for c in g["process_query"]:
+        if "load_error" in c:
+            broken = VideoProcessor.__new__(VideoProcessor)
+            broken.phase1, broken.phase2, broken.phase2_available, broken._models_loaded = None, None, False, False
+            broken._load_models = lambda: (_ for _ in ()).throw(RuntimeError(c["load_error"]))
+            got = broken.process_query(str(tmp_path / c["name"]), c["query"], mode=c["mode"])
+        else:
+            got = vp.process_query(str(tmp_path / c["name"]), c["query"], mode=c["mode"])
+        assert scrub(got) == c["result"], c["name"]
+    # a constructor whose model load fails survives (like the reference's) and reports at query time
+    monkeypatch.setattr(VideoProcessor, "_load_models", lambda self: (_ for _ in ()).throw(RuntimeError("boom")))
+    late = VideoProcessor()
+    out = late.process_query(str(tmp_path / "ok.mp4"), "dog")
+    assert out["status"] == "error" and out["error_type"] == "model_loading_error" and "boom" in out["error"]
