@@ -48,3 +48,16 @@ def write_test_video(path, n: int, w: int = 96, h: int = 64, fps: float = 8.0) -
         vw.write(f)
     vw.release()
     return str(path)
+
+
+def write_frames_video(path, frames: np.ndarray, fps: float = 8.0) -> str:
+    """RGB uint8 frames [N,H,W,3] -> mp4 (OpenCV's mp4v encoder, deterministic for a given OpenCV build)."""
+    import cv2
+
+    h, w = int(frames.shape[1]), int(frames.shape[2])
+    vw = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"mp4v"), fps, (w, h))
+    assert vw.isOpened()
+    for f in frames:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+    vw.release()
+    return str(path)

@@ -193,3 +193,41 @@ def test_phase2_handoff_on_a_real_mp4_through_the_cuda_phase1(phase1, tmp_path):
     for r, (score, w, caption, clip) in zip(out, blended[:3]):
         assert r["window_index"] == w and r["caption"] == caption and r["clip_score"] == clip
         assert r["confidence"] == float(score) and r["timestamp"] == wts[w]
+
+
+def test_process_video_matches_the_reference_on_a_real_mp4(phase1, tmp_path, golden_dir):
+    """tests/golden/phase1_mp4.json = the reference's own Phase1MVP.process_video on an mp4 written by
+    synth.write_frames_video (tests/golden/make_golden_phase1_mp4.py): decode, shrink, windows, embedding, scores,
+    top-k, threshold.  The same file is written here (same encoder, same bytes) and goes through OUR process_video."""
+    pytest.importorskip("cv2")
+    from synth import write_frames_video
+
+    from b200clip.pipeline.phase1_mvp import Phase1MVP
+    from b200clip.utils.config import settings
+
+    g = json.load(open(os.path.join(golden_dir, "phase1_mp4.json")))
+    path = write_frames_video(tmp_path / "clip.mp4", structured_frames(g["n_frames"], g["h"], g["w"], seed=g["seed"]), g["fps"])
+    p1 = Phase1MVP(clip_model=phase1.clip_model)
+    ref_sims = np.array(g["similarities"], np.float32)
+    try:
+        settings.CONFIDENCE_THRESHOLD = -1.0
+        res, debug = p1.process_video(path, g["query"], top_k=g["top_k"], debug_mode=True)
+        p1.debug_mode = False
+        settings.CONFIDENCE_THRESHOLD = g["threshold"]
+        kept = p1.process_video(path, g["query"], top_k=g["top_k"])
+    finally:
+        settings.CONFIDENCE_THRESHOLD = 0.25
+    assert [d["timestamp"] for d in debug] == g["window_timestamps"]
+    sims = np.array([d["similarity"] for d in debug], np.float32)
+    print(f"\n[parity] reference mp4 run: max |dscore| over {len(sims)} windows {np.abs(sims - ref_sims).max():.5f}; "
+          f"reference top-5 {[r['window_index'] for r in g['results']]} ours {[r['window_index'] for r in res]}")
+    assert np.abs(sims - ref_sims).max() <= SCORE_TOL
+    assert len(res) == len(g["results"])
+    assert_topk_equivalent(ref_sims, [r["window_index"] for r in res], [r["confidence"] for r in res], g["top_k"])
+    for r in res:
+        assert r["timestamp"] == g["window_timestamps"][r["window_index"]] and r["phase"] == "phase1_mvp"
+    # thresholded run: a score within 1e-2 of the threshold may flip (as in the synthetic-frame golden)
+    assert abs(len(kept) - len(g["results_thresholded"])) <= 1
+    from oracle.phase1_ref import topk_threshold
+
+    assert [r["window_index"] for r in kept] == [r["window_index"] for r in topk_threshold(sims, g["window_timestamps"], g["top_k"], g["threshold"])]
