@@ -24,6 +24,43 @@ from ..utils.logger import get_logger
 logger = get_logger(__name__)
 
 
+def shrunk_shape(shape) -> tuple:
+    """Shape of a decoded frame after the reference's <= MAX_FRAME_WIDTH x MAX_FRAME_HEIGHT shrink
+    (memory_manager.py:299-312: scale = min(max_w / w, max_h / h, 1), int() truncation) -- the frame phase 1 embeds
+    there and reports as `frame_shape` in debug mode; here the shrink happens inside K1."""
+    h, w = int(shape[0]), int(shape[1])
+    scale = min(settings.MAX_FRAME_WIDTH / w, settings.MAX_FRAME_HEIGHT / h, 1.0)
+    if scale < 1.0:
+        return (int(h * scale), int(w * scale)) + tuple(shape[2:])
+    return tuple(shape)
+
+
+def dump_debug_frames(debug_dir, frames_rgb, window_indices, similarities, n_windows: int) -> list:
+    """phase1_mvp.py:99-102: in debug mode the embedded frame of the first and last five windows is written to
+    DATA_DIR/debug/frame_<i>_sim_<s>.jpg -- the frame AFTER the <= 512 x 512 INTER_AREA shrink, as the reference holds
+    it.  A debugging artefact on the host (at most ten small frames), not part of the query path."""
+    try:
+        import cv2
+    except ImportError:  # pragma: no cover
+        return []
+    from pathlib import Path
+
+    debug_dir = Path(debug_dir)
+    debug_dir.mkdir(parents=True, exist_ok=True)
+    written = []
+    for frame, i, sim in zip(frames_rgb, window_indices, similarities):
+        if not (i < 5 or i >= n_windows - 5):
+            continue
+        frame = np.asarray(frame)
+        hh, ww = shrunk_shape(frame.shape)[:2]
+        if (hh, ww) != frame.shape[:2]:
+            frame = cv2.resize(frame, (ww, hh), interpolation=cv2.INTER_AREA)
+        path = debug_dir / f"frame_{int(i):03d}_sim_{float(sim):.4f}.jpg"
+        cv2.imwrite(str(path), cv2.cvtColor(frame, cv2.COLOR_RGB2BGR))
+        written.append(str(path))
+    return written
+
+
 class Phase1MVP:
     def __init__(self, debug_mode: bool = False, clip_model: OpenCLIPModel | None = None):
         self.clip_model = clip_model if clip_model is not None else OpenCLIPModel()
@@ -193,8 +230,11 @@ class Phase1MVP:
             norms = emb.norm(dim=-1).cpu().numpy()
             debug_info = [{"window_index": lo + j, "timestamp": window_ts[lo + j], "similarity": float(sims[j]),
                            "image_embedding_norm": float(norms[j]),
-                           "frame_shape": tuple(middle.shape[1:])} for j in range(hi - lo)]
+                           "frame_shape": shrunk_shape(middle.shape[1:])} for j in range(hi - lo)]
             if len(sims):
+                edge = [j for j in range(hi - lo) if lo + j < 5 or lo + j >= len(window_ts) - 5]
+                dump_debug_frames(settings.DATA_DIR / "debug", [middle[j][..., ::-1] if bgr else middle[j] for j in edge],
+                                  [lo + j for j in edge], [sims[j] for j in edge], len(window_ts))
                 self._log_debug_analysis(sims, debug_info, query, settings.CONFIDENCE_THRESHOLD)
             return results, debug_info
         return results

@@ -218,6 +218,7 @@ def test_process_video_matches_the_reference_on_a_real_mp4(phase1, tmp_path, gol
     finally:
         settings.CONFIDENCE_THRESHOLD = 0.25
     assert [d["timestamp"] for d in debug] == g["window_timestamps"]
+    assert [list(d["frame_shape"]) for d in debug] == g["frame_shapes"]      # the shape after the reference's shrink
     sims = np.array([d["similarity"] for d in debug], np.float32)
     print(f"\n[parity] reference mp4 run: max |dscore| over {len(sims)} windows {np.abs(sims - ref_sims).max():.5f}; "
           f"reference top-5 {[r['window_index'] for r in g['results']]} ours {[r['window_index'] for r in res]}")

@@ -191,3 +191,29 @@ def test_validation_and_error_dicts_equal_the_reference(tmp_path, monkeypatch):
     late = VideoProcessor()
     out = late.process_query(str(tmp_path / "ok.mp4"), "dog")
     assert out["status"] == "error" and out["error_type"] == "model_loading_error" and "boom" in out["error"]
+
+
+def test_debug_frame_shape_and_frame_dump(tmp_path, monkeypatch):
+    """Debug mode (phase1_mvp.py:90-102): `frame_shape` is the shape AFTER the reference's <= 512 x 512 shrink
+    (memory_manager.py:299-312; int() truncation) and the first / last five windows' frames are written as JPEGs of that
+    shrunk frame -- the same file cv2 writes for the reference's frame."""
+    cv2 = pytest.importorskip("cv2")
+    from b200clip.pipeline.phase1_mvp import dump_debug_frames, shrunk_shape
+    from oracle.preprocess_ref import fit_size
+    from oracle.reference_pipeline import resize_frame_for_memory
+
+    for h, w in ((1080, 1920), (360, 640), (224, 224), (512, 512), (513, 100), (100, 2000), (719, 1279)):
+        fw, fh = fit_size(w, h)
+        assert shrunk_shape((h, w, 3)) == (fh, fw, 3)
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 256, (12, 360, 640, 3), dtype=np.uint8)
+    sims = np.linspace(-0.05, 0.06, 12)
+    written = dump_debug_frames(tmp_path / "debug", frames, list(range(12)), sims, 12)
+    names = sorted(os.path.basename(p) for p in written)
+    assert len(names) == 10 and "frame_000_sim_-0.0500.jpg" in names and "frame_011_sim_0.0600.jpg" in names
+    assert not any(n.startswith("frame_005") or n.startswith("frame_006") for n in names)
+    want = tmp_path / "want.jpg"
+    cv2.imwrite(str(want), cv2.cvtColor(resize_frame_for_memory(frames[0]), cv2.COLOR_RGB2BGR))
+    got = [p for p in written if os.path.basename(p).startswith("frame_000")][0]
+    assert open(got, "rb").read() == open(want, "rb").read()
+    assert cv2.imread(got).shape == (288, 512, 3)
